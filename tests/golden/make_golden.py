@@ -1,0 +1,356 @@
+"""Generate the committed golden vectors by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference is imported through oracle/ref_loader.py (a `dgl` shim is the only addition;
+no reference file is edited or copied).  Inputs are synthetic (igcn_cf_b200.synth, 'tiny'
+shape, seed 2021).  Random draws the reference makes internally are RECORDED, not re-derived:
+`torch.rand` (edge dropout, model.py:267) and `BasicDataset.__getitem__` (triple sampling,
+dataset.py:119-131) are wrapped so every draw lands in the fixture and can be replayed into
+the oracle restatement and the CUDA path.
+
+Outputs (tests/golden/):
+  tiny_data.npz            the split (CSR form)
+  tiny_lightgcn.npz        LightGCN: graph, rep, one fwd/bwd, one epoch, evals
+  tiny_igcn.npz            IGCN: feat, rep (eval + train w/ recorded dropout), fwd/bwd, epoch, anneal, evals
+  tiny_igcn_dropui.npz     train on the dropui split, re-aggregate on the full graph, inductive_eval
+  tiny_igcn_ratio.npz      feature_ratio 0.5 ('sort' ranking): maps, feat, rep
+"""
+import os
+import sys
+import tempfile
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings('ignore')
+
+from igcn_cf_b200 import synth  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+ref = ref_loader.load()
+R_model, R_trainer, R_dataset, R_utils = ref['model'], ref['trainer'], ref['dataset'], ref['utils']
+DEV = torch.device('cpu')
+SEED = 2021
+
+
+class Recorder:
+    """Wraps torch.rand and BasicDataset.__getitem__ (no reference code is changed)."""
+
+    def __init__(self):
+        self.rands, self.main, self.aux = [], [], []
+        self._rand = torch.rand
+        self._getitem = R_dataset.BasicDataset.__getitem__
+
+    def __enter__(self):
+        rec = self
+
+        def rand(*a, **k):
+            out = rec._rand(*a, **k)
+            rec.rands.append(out.clone().numpy())
+            return out
+
+        def getitem(ds, index):
+            out = rec._getitem(ds, index)
+            (rec.aux if isinstance(ds, R_dataset.AuxiliaryDataset) else rec.main).append(out[0].copy())
+            return out
+
+        torch.rand = rand
+        R_dataset.BasicDataset.__getitem__ = getitem
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand = self._rand
+        R_dataset.BasicDataset.__getitem__ = self._getitem
+
+
+def csr_of(lists):
+    ptr = np.zeros(len(lists) + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in lists], out=ptr[1:])
+    items = np.array([i for x in lists for i in x], dtype=np.int64)
+    return ptr, items
+
+
+def load_dataset(split, tmp, name):
+    path = os.path.join(tmp, name)
+    synth.write_split(split, path)
+    return R_dataset.get_dataset({'name': 'ProcessedDataset', 'path': path, 'device': DEV})
+
+
+def lgcn_cfgs():
+    return ({'name': 'LightGCN', 'embedding_size': 64, 'n_layers': 3, 'device': DEV},
+            {'name': 'BPRTrainer', 'optimizer': 'Adam', 'lr': 1.e-3, 'l2_reg': 1.e-4, 'device': DEV,
+             'n_epochs': 1, 'batch_size': 2048, 'dataloader_num_workers': 0, 'test_batch_size': 512,
+             'topks': [5, 20]})
+
+
+def igcn_cfgs(dropout=0.3, ratio=1.):
+    return ({'name': 'IGCN', 'embedding_size': 64, 'n_layers': 3, 'device': DEV, 'dropout': dropout,
+             'feature_ratio': ratio},
+            {'name': 'IGCNTrainer', 'optimizer': 'Adam', 'lr': 1.e-3, 'l2_reg': 0., 'aux_reg': 0.01,
+             'device': DEV, 'n_epochs': 1, 'batch_size': 2048, 'dataloader_num_workers': 0,
+             'test_batch_size': 512, 'topks': [5, 20]})
+
+
+def fixed_triples(ds, n, seed):
+    """A hand-made triple batch (valid: pos in train list, neg not) for the fwd/bwd pins."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((n, 3), dtype=np.int64)
+    for t in range(n):
+        u = int(rng.integers(ds.n_users))
+        while not ds.train_data[u]:
+            u = int(rng.integers(ds.n_users))
+        p = int(rng.choice(ds.train_data[u]))
+        ng = int(rng.integers(ds.n_items))
+        while ng in ds.train_data[u]:
+            ng = int(rng.integers(ds.n_items))
+        out[t] = (u, p, ng)
+    return out
+
+
+def eval_all(trainer, out, prefix):
+    """eval('train'|'val'|'test'): record top-k lists and metrics (trainer.py:140-177)."""
+    captured = {}
+    orig = trainer.calculate_metrics
+
+    def spy(eval_data, rec_items):
+        captured['rec'] = rec_items.copy()
+        return orig(eval_data, rec_items)
+
+    trainer.calculate_metrics = spy
+    for which in ('train', 'val', 'test'):
+        _, metrics = trainer.eval(which)
+        out['%s_%s_rec' % (prefix, which)] = captured['rec']
+        for m in metrics:
+            for k in metrics[m]:
+                out['%s_%s_%s@%d' % (prefix, which, m, k)] = np.float64(metrics[m][k])
+    trainer.calculate_metrics = orig
+
+
+def sparse_parts(sp_t):
+    return sp_t.indices().numpy().copy(), sp_t.values().detach().numpy().copy()
+
+
+def golden_lightgcn(ds, out_path):
+    out = {}
+    mcfg, tcfg = lgcn_cfgs()
+    R_utils.set_seed(SEED)
+    model = R_model.get_model(mcfg, ds)
+    trainer = R_trainer.get_trainer(tcfg, ds, model)
+    out['emb0'] = model.embedding.weight.detach().numpy().copy()
+    out['adj_idx'], out['adj_val'] = sparse_parts(model.norm_adj)
+    model.eval()
+    with torch.no_grad():
+        out['rep0'] = model.get_rep().numpy().copy()
+        users = torch.arange(0, 64, dtype=torch.int64)
+        out['scores0_users'] = users.numpy()
+        out['scores0'] = model.predict(users).numpy().copy()
+
+    # one forward/backward on a fixed batch, no optimizer step (model.py:108-116, trainer.py:238-243)
+    model.train()
+    tri = fixed_triples(ds, 512, 7)
+    out['fb_triples'] = tri
+    t = torch.from_numpy(tri)
+    u_r, p_r, n_r, l2 = model.bpr_forward(t[:, 0], t[:, 1], t[:, 2])
+    pos = torch.sum(u_r * p_r, dim=1)
+    neg = torch.sum(u_r * n_r, dim=1)
+    loss = torch.nn.functional.softplus(neg - pos).mean() + tcfg['l2_reg'] * l2.mean()
+    model.zero_grad()
+    loss.backward()
+    out['fb_users_r'], out['fb_pos_r'], out['fb_neg_r'] = (x.detach().numpy().copy() for x in (u_r, p_r, n_r))
+    out['fb_l2'] = l2.detach().numpy().copy()
+    out['fb_loss'] = np.float64(loss.item())
+    out['fb_grad_emb'] = model.embedding.weight.grad.numpy().copy()
+    model.zero_grad()
+
+    # one epoch with recorded triples (trainer.py:231-248)
+    R_utils.set_seed(SEED + 1)
+    with Recorder() as rec:
+        out['epoch_loss'] = np.float64(trainer.train_one_epoch())
+    out['epoch_triples'] = np.stack(rec.main)
+    out['emb1'] = model.embedding.weight.detach().numpy().copy()
+    model.eval()
+    with torch.no_grad():
+        out['rep1'] = model.get_rep().numpy().copy()
+    eval_all(trainer, out, 'e1')
+    np.savez_compressed(out_path, **out)
+    print('wrote', out_path, len(out), 'arrays')
+
+
+def golden_igcn(ds, out_path):
+    out = {}
+    mcfg, tcfg = igcn_cfgs()
+    R_utils.set_seed(SEED)
+    model = R_model.get_model(mcfg, ds)
+    trainer = R_trainer.get_trainer(tcfg, ds, model)
+    out['emb0'] = model.embedding.weight.detach().numpy().copy()
+    out['w0'] = model.w.detach().numpy().copy()
+    out['adj_idx'], out['adj_val'] = sparse_parts(model.norm_adj)
+    out['feat_idx'], out['feat_val'] = sparse_parts(model.feat_mat)
+    out['feat_shape'] = np.array(model.feat_mat.shape)
+    out['row_sum'] = model.row_sum.numpy().copy()
+    model.eval()
+    with torch.no_grad():
+        out['rep0_eval'] = model.get_rep().numpy().copy()
+    model.train()
+    torch.manual_seed(11)
+    with Recorder() as rec, torch.no_grad():
+        out['rep0_train'] = model.get_rep().numpy().copy()
+    out['rep0_train_rand'] = rec.rands[0]
+
+    # one forward/backward with recorded dropout, fixed main + aux batches (trainer.py:296-313)
+    tri, atri = fixed_triples(ds, 512, 7), fixed_triples(ds, 512, 8)   # ratio 1: template ids == raw ids
+    out['fb_triples'], out['fb_aux_triples'] = tri, atri
+    t, a = torch.from_numpy(tri), torch.from_numpy(atri)
+    torch.manual_seed(12)
+    with Recorder() as rec:
+        u_r, p_r, n_r, l2 = model.bpr_forward(t[:, 0], t[:, 1], t[:, 2])
+    out['fb_rand'] = rec.rands[0]
+    sp_fn = torch.nn.functional.softplus
+    bpr = sp_fn(torch.sum(u_r * n_r, dim=1) - torch.sum(u_r * p_r, dim=1)).mean()
+    t_u = len(model.user_map)
+    au, ap, an = model.embedding(a[:, 0]), model.embedding(a[:, 1] + t_u), model.embedding(a[:, 2] + t_u)
+    aux = sp_fn(torch.sum(au * an * model.w[None, :], dim=1) - torch.sum(au * ap * model.w[None, :], dim=1)).mean()
+    # l2_reg is 0 in the shipped configs; pin a non-zero one here as well so the term is exercised
+    for tag, l2_reg in (('', tcfg['l2_reg']), ('_l2', 1.e-3)):
+        loss = bpr + (l2_reg * l2.mean() + tcfg['aux_reg'] * aux)
+        model.zero_grad()
+        loss.backward(retain_graph=True)
+        out['fb_loss' + tag] = np.float64(loss.item())
+        out['fb_grad_emb' + tag] = model.embedding.weight.grad.numpy().copy()
+        out['fb_grad_w' + tag] = model.w.grad.numpy().copy()
+    out['fb_users_r'], out['fb_pos_r'], out['fb_neg_r'] = (x.detach().numpy().copy() for x in (u_r, p_r, n_r))
+    out['fb_l2'] = l2.detach().numpy().copy()
+    out['fb_bpr'] = np.float64(bpr.item())
+    out['fb_aux'] = np.float64(aux.item())
+    model.zero_grad()
+
+    # one epoch, everything recorded (trainer.py:294-320), then anneal happened once
+    R_utils.set_seed(SEED + 1)
+    with Recorder() as rec:
+        out['epoch_loss'] = np.float64(trainer.train_one_epoch())
+    out['epoch_triples'] = np.stack(rec.main)
+    out['epoch_aux_triples'] = np.stack(rec.aux)
+    for s, r in enumerate(rec.rands):
+        out['epoch_rand_%d' % s] = r
+    out['epoch_n_steps'] = np.int64(len(rec.rands))
+    out['emb1'] = model.embedding.weight.detach().numpy().copy()
+    out['w1'] = model.w.detach().numpy().copy()
+    out['alpha1'] = np.float64(model.alpha)
+    out['feat_val1'] = model.feat_mat.values().numpy().copy()
+    model.eval()
+    with torch.no_grad():
+        out['rep1_eval'] = model.get_rep().numpy().copy()
+        users = torch.arange(0, 64, dtype=torch.int64)
+        out['scores1_users'] = users.numpy()
+        out['scores1'] = model.predict(users).numpy().copy()
+    eval_all(trainer, out, 'e1')
+    np.savez_compressed(out_path, **out)
+    print('wrote', out_path, len(out), 'arrays')
+
+
+def golden_dropui(full_split, tmp, out_path):
+    """run/dropui/igcn_dropui.py:17-35 on the tiny graph."""
+    out = {}
+    small = synth.dropui(full_split, 0.8)
+    ds_small = load_dataset(small, tmp, 'tiny_dropui')
+    ds_full = load_dataset(full_split, tmp, 'tiny_full2')
+    mcfg, tcfg = igcn_cfgs()
+    R_utils.set_seed(SEED)
+    model = R_model.get_model(mcfg, ds_small)
+    trainer = R_trainer.get_trainer(tcfg, ds_small, model)
+    out['emb0'] = model.embedding.weight.detach().numpy().copy()
+    R_utils.set_seed(SEED + 1)
+    with Recorder() as rec:
+        trainer.train_one_epoch()
+    out['epoch_triples'] = np.stack(rec.main)
+    out['epoch_aux_triples'] = np.stack(rec.aux)
+    for s, r in enumerate(rec.rands):
+        out['epoch_rand_%d' % s] = r
+    out['epoch_n_steps'] = np.int64(len(rec.rands))
+    out['emb1'] = model.embedding.weight.detach().numpy().copy()
+    out['alpha1'] = np.float64(model.alpha)
+    out['n_old_users'], out['n_old_items'] = np.int64(ds_small.n_users), np.int64(ds_small.n_items)
+
+    model.config['dataset'] = ds_full
+    model.n_users, model.n_items = ds_full.n_users, ds_full.n_items
+    model.norm_adj = model.generate_graph(ds_full)
+    model.feat_mat, _, _, model.row_sum = model.generate_feat(ds_full, is_updating=True)
+    model.update_feat_mat()
+    out['feat_idx'], out['feat_val'] = sparse_parts(model.feat_mat)
+    out['feat_shape'] = np.array(model.feat_mat.shape)
+    out['row_sum'] = model.row_sum.numpy().copy()
+    model.eval()
+    with torch.no_grad():
+        out['rep_full'] = model.get_rep().numpy().copy()
+    trainer = R_trainer.get_trainer(tcfg, ds_full, model)
+    calls = []
+    orig_cm = trainer.calculate_metrics
+
+    def spy(eval_data, rec_items):
+        res = orig_cm(eval_data, rec_items)
+        calls.append((rec_items.copy(), res))
+        return res
+
+    trainer.calculate_metrics = spy
+    trainer.inductive_eval(ds_small.n_users, ds_small.n_items)
+    for c, (rec_items, res) in enumerate(calls):
+        out['ind%d_rec' % c] = rec_items
+        for m in res:
+            for k in res[m]:
+                out['ind%d_%s@%d' % (c, m, k)] = np.float64(res[m][k])
+    out['n_ind'] = np.int64(len(calls))
+    np.savez_compressed(out_path, **out)
+    print('wrote', out_path, len(out), 'arrays')
+
+
+def golden_ratio(ds, out_path):
+    out = {}
+    mcfg, _ = igcn_cfgs(ratio=0.5)
+    R_utils.set_seed(SEED)
+    model = R_model.get_model(mcfg, ds)
+    out['emb0'] = model.embedding.weight.detach().numpy().copy()
+    um = np.full(ds.n_users, -1, dtype=np.int64)
+    for k, v in model.user_map.items():
+        um[int(k)] = v
+    im = np.full(ds.n_items, -1, dtype=np.int64)
+    for k, v in model.item_map.items():
+        im[int(k)] = v
+    out['user_map'], out['item_map'] = um, im
+    out['feat_idx'], out['feat_val'] = sparse_parts(model.feat_mat)
+    out['feat_shape'] = np.array(model.feat_mat.shape)
+    out['row_sum'] = model.row_sum.numpy().copy()
+    model.eval()
+    with torch.no_grad():
+        out['rep0_eval'] = model.get_rep().numpy().copy()
+    model.train()
+    torch.manual_seed(21)
+    with Recorder() as rec, torch.no_grad():
+        out['rep0_train'] = model.get_rep().numpy().copy()
+    out['rep0_train_rand'] = rec.rands[0]
+    np.savez_compressed(out_path, **out)
+    print('wrote', out_path, len(out), 'arrays')
+
+
+def main():
+    split = synth.gen_named('tiny', seed=SEED)
+    with tempfile.TemporaryDirectory() as tmp:
+        ds = load_dataset(split, tmp, 'tiny')
+        data = {'n_users': np.int64(ds.n_users), 'n_items': np.int64(ds.n_items)}
+        for which in ('train', 'val', 'test'):
+            data[which + '_ptr'], data[which + '_items'] = csr_of(getattr(ds, which + '_data'))
+        np.savez_compressed(os.path.join(HERE, 'tiny_data.npz'), **data)
+        golden_lightgcn(ds, os.path.join(HERE, 'tiny_lightgcn.npz'))
+        golden_igcn(ds, os.path.join(HERE, 'tiny_igcn.npz'))
+        golden_dropui(split, tmp, os.path.join(HERE, 'tiny_igcn_dropui.npz'))
+        golden_ratio(ds, os.path.join(HERE, 'tiny_igcn_ratio.npz'))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,139 @@
+"""Pin the CPU restatement (oracle/restate.py) to outputs of the reference itself.
+
+The golden vectors were produced by tests/golden/make_golden.py running the unmodified
+reference on CPU.  Tolerance 1e-6 relative-to-scale: both sides are fp32 torch CPU code.
+"""
+import numpy as np
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import restate as R
+
+TOL = 1e-6
+
+
+def _t(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+def test_graph_matches_reference(tiny):
+    g = load_golden('tiny_lightgcn')
+    adj = R.normalized_adjacency(tiny['n_users'], tiny['n_items'], tiny['pairs'])
+    assert np.array_equal(adj.indices().numpy(), g['adj_idx'])
+    assert np.array_equal(adj.values().numpy(), g['adj_val'])          # bit-exact fp32
+
+
+def test_lightgcn_rep_fwd_bwd(tiny):
+    g = load_golden('tiny_lightgcn')
+    m = R.OracleLightGCN(tiny['n_users'], tiny['n_items'], tiny['pairs'], 3, g['emb0'], l2_reg=1e-4)
+    assert rel_err(m.get_rep().detach().numpy(), g['rep0']) < TOL
+    assert rel_err(m.predict(_t(g['scores0_users'])).numpy(), g['scores0']) < TOL
+    tri = _t(g['fb_triples'])
+    loss = m.loss(tri[:, 0], tri[:, 1], tri[:, 2])
+    loss.backward()
+    assert abs(loss.item() - float(g['fb_loss'])) < TOL
+    assert rel_err(m.emb.grad.numpy(), g['fb_grad_emb']) < TOL
+
+
+def test_lightgcn_epoch_and_eval(tiny):
+    g = load_golden('tiny_lightgcn')
+    m = R.OracleLightGCN(tiny['n_users'], tiny['n_items'], tiny['pairs'], 3, g['emb0'], l2_reg=1e-4)
+    tri = g['epoch_triples']
+    tot, cnt = 0., 0
+    for lo in range(0, len(tri), 2048):
+        b = _t(tri[lo:lo + 2048])
+        tot += m.train_step(b[:, 0], b[:, 1], b[:, 2]) * len(b)
+        cnt += len(b)
+    assert abs(tot / cnt - float(g['epoch_loss'])) < 1e-6
+    assert rel_err(m.emb.detach().numpy(), g['emb1']) < 1e-5
+    for which in ('train', 'val', 'test'):
+        metrics, rec = R.evaluate(m, which, tiny['train'], tiny['val'], tiny[which], [5, 20])
+        assert np.array_equal(rec, g['e1_%s_rec' % which])
+        for name in ('Precision', 'Recall', 'NDCG'):
+            for k in (5, 20):
+                assert metrics[name][k] == g['e1_%s_%s@%d' % (which, name, k)]
+
+
+def test_igcn_feat_matches_reference(tiny):
+    g = load_golden('tiny_igcn')
+    um, im = R.identity_maps(tiny['n_users'], tiny['n_items'])
+    feat, row_sum = R.template_incidence(tiny['n_users'], tiny['n_items'], tiny['pairs'], um, im)
+    feat = R.feat_values(feat, row_sum, 1.)
+    assert list(feat.shape) == g['feat_shape'].tolist()
+    assert np.array_equal(feat.indices().numpy(), g['feat_idx'])
+    assert np.array_equal(feat.values().numpy(), g['feat_val'])
+    assert np.array_equal(row_sum.numpy(), g['row_sum'])
+
+
+def _igcn(tiny, g, **kw):
+    return R.OracleIGCN(tiny['n_users'], tiny['n_items'], tiny['pairs'], 3, g['emb0'], 0.3, **kw)
+
+
+def test_igcn_rep_eval_and_train(tiny):
+    g = load_golden('tiny_igcn')
+    m = _igcn(tiny, g)
+    assert rel_err(m.get_rep(train=False).detach().numpy(), g['rep0_eval']) < TOL
+    rep = m.get_rep(train=True, rand=_t(g['rep0_train_rand']))
+    assert rel_err(rep.detach().numpy(), g['rep0_train']) < TOL
+
+
+def test_igcn_fwd_bwd(tiny):
+    g = load_golden('tiny_igcn')
+    for tag, l2_reg in (('', 0.), ('_l2', 1e-3)):
+        m = _igcn(tiny, g, l2_reg=l2_reg)
+        t, a = _t(g['fb_triples']), _t(g['fb_aux_triples'])
+        loss = m.loss(t[:, 0], t[:, 1], t[:, 2], a[:, 0], a[:, 1], a[:, 2], rand=_t(g['fb_rand']))
+        loss.backward()
+        assert abs(loss.item() - float(g['fb_loss' + tag])) < TOL
+        assert rel_err(m.emb.grad.numpy(), g['fb_grad_emb' + tag]) < TOL
+        assert rel_err(m.w.grad.numpy(), g['fb_grad_w' + tag]) < TOL
+
+
+def test_igcn_epoch_anneal_eval(tiny):
+    g = load_golden('tiny_igcn')
+    m = _igcn(tiny, g)
+    tri, atri = g['epoch_triples'], g['epoch_aux_triples']
+    tot, cnt = 0., 0
+    for s, lo in enumerate(range(0, len(tri), 2048)):
+        b, a = _t(tri[lo:lo + 2048]), _t(atri[lo:lo + 2048])
+        tot += m.train_step(b[:, 0], b[:, 1], b[:, 2], a[:, 0], a[:, 1], a[:, 2],
+                            rand=_t(g['epoch_rand_%d' % s])) * len(b)
+        cnt += len(b)
+    m.anneal()
+    assert s + 1 == int(g['epoch_n_steps'])
+    assert abs(tot / cnt - float(g['epoch_loss'])) < 1e-6
+    assert rel_err(m.emb.detach().numpy(), g['emb1']) < 1e-5
+    assert rel_err(m.w.detach().numpy(), g['w1']) < 1e-5
+    assert m.alpha == float(g['alpha1'])
+    assert rel_err(m.feat.values().numpy(), g['feat_val1']) < TOL
+    assert rel_err(m.get_rep().detach().numpy(), g['rep1_eval']) < 1e-5
+    assert rel_err(m.predict(_t(g['scores1_users'])).numpy(), g['scores1']) < 1e-5
+    for which in ('train', 'val', 'test'):
+        metrics, rec = R.evaluate(m, which, tiny['train'], tiny['val'], tiny[which], [5, 20])
+        assert np.array_equal(rec, g['e1_%s_rec' % which])
+        for name in ('Precision', 'Recall', 'NDCG'):
+            for k in (5, 20):
+                assert metrics[name][k] == g['e1_%s_%s@%d' % (which, name, k)]
+
+
+def test_igcn_feature_ratio(tiny):
+    g = load_golden('tiny_igcn_ratio')
+    um = {int(u): int(t) for u, t in enumerate(g['user_map']) if t >= 0}
+    im = {int(i): int(t) for i, t in enumerate(g['item_map']) if t >= 0}
+    m = R.OracleIGCN(tiny['n_users'], tiny['n_items'], tiny['pairs'], 3, g['emb0'], 0.3,
+                     user_map=um, item_map=im)
+    assert list(m.feat.shape) == g['feat_shape'].tolist()
+    assert np.array_equal(m.feat.indices().numpy(), g['feat_idx'])
+    assert np.array_equal(m.feat.values().numpy(), g['feat_val'])
+    assert rel_err(m.get_rep().detach().numpy(), g['rep0_eval']) < TOL
+    rep = m.get_rep(train=True, rand=_t(g['rep0_train_rand']))
+    assert rel_err(rep.detach().numpy(), g['rep0_train']) < TOL
+
+
+def test_metrics_edge_cases():
+    # users with empty eval lists are excluded from the means (trainer.py:134-137)
+    rec = np.array([[1, 2, 3], [4, 5, 6], [7, 8, 9]])
+    res = R.calculate_metrics([[1, 9], [], [9]], rec, [1, 3])
+    assert res['Precision'][1] == np.float32(0.5)
+    assert abs(res['Recall'][3] - 0.75) < 1e-12
+    assert res['NDCG'][3].dtype == np.float32
