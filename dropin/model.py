@@ -1,0 +1,4 @@
+"""Top-level alias so reference launchers (`from model import ...`) pick up the B200 implementation."""
+from igcn_cf_b200.model import *  # noqa: F401,F403
+from igcn_cf_b200 import model as _impl
+globals().update({k: v for k, v in vars(_impl).items() if not k.startswith('__')})

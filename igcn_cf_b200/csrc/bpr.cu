@@ -1,0 +1,437 @@
+// The BPR trainer step on B200: sampler, fused gather-dot-softplus forward, deterministic
+// segmented gradient (sort + one owner per touched row, no float atomics), loss finalisation
+// and Adam.  Reference call sites: dataset.py:119-131, model.py:108-116 / 293-299,
+// trainer.py:231-248 / 294-320.  All of it is small gather/scatter work (3*B rows of 256 B).
+#include "common.cuh"
+
+namespace igcn {
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------ sampler
+__global__ void sample_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t col_offset,
+                              int64_t n_users, int64_t n_items, int64_t B, uint64_t key, const uint64_t *step_dev, int64_t *out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B) return;
+    if (step_dev) key = mix64(key ^ mix64(*step_dev + 0x51ed2701ULL));
+    uint64_t ctr = mix64(key ^ ((uint64_t)t * 0x9e3779b97f4a7c15ULL));
+    auto next = [&]() { ctr += 0x9e3779b97f4a7c15ULL; return mix64(ctr); };
+    // multiply-shift maps 64 uniform bits to [0, n) with bias < n / 2^64
+    auto below = [&](uint64_t n) { return (int64_t)__umul64hi(next(), n); };
+    int64_t u, lo, hi;
+    do {
+        u = below((uint64_t)n_users);
+        lo = rowptr[u]; hi = rowptr[u + 1];
+    } while (hi == lo);
+    const int64_t pos = (int64_t)col[lo + below((uint64_t)(hi - lo))] - col_offset;
+    int64_t neg;
+    for (;;) {
+        neg = below((uint64_t)n_items);
+        const int32_t keyc = (int32_t)(neg + col_offset);
+        int64_t a = lo, b = hi;
+        while (a < b) {
+            const int64_t mid = (a + b) >> 1;
+            if (col[mid] < keyc) a = mid + 1; else b = mid;
+        }
+        if (a == hi || col[a] != keyc) break;
+    }
+    out[t * 3 + 0] = u; out[t * 3 + 1] = pos; out[t * 3 + 2] = neg;
+}
+
+// ------------------------------------------------------------------ forward
+template <int LANES>
+__device__ __forceinline__ float group_sum(float v, uint32_t gmask) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o, LANES);
+    return v;
+}
+
+template <int LANES>
+__device__ __forceinline__ uint32_t gmask_of() {
+    if (LANES == 32) return 0xffffffffu;
+    const uint32_t base = (LANES == 16) ? 0xffffu : 0xffu;
+    return base << ((threadIdx.x & 31) & ~(LANES - 1));
+}
+
+__device__ __forceinline__ float dot4(const float4 &a, const float4 &b) {
+    return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(kThreads) bpr_fwd_kernel(const float *__restrict__ T, const float *__restrict__ L2T,
+                                                           const float *__restrict__ w, const int64_t *__restrict__ tri,
+                                                           int64_t B, int64_t off, int D, float *sp, float *sig, float *l2) {
+    const int lane = threadIdx.x % LANES;
+    const uint32_t gmask = gmask_of<LANES>();
+    const int64_t i = (int64_t)blockIdx.x * (kThreads / LANES) + threadIdx.x / LANES;
+    if (i >= B) return;
+    const bool active = lane * 4 < D;
+    const int64_t u = tri[i * 3], p = tri[i * 3 + 1] + off, n = tri[i * 3 + 2] + off;
+    float4 xu = f4zero(), xp = f4zero(), xn = f4zero(), ww = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (active) {
+        xu = ld4(T + u * D + lane * 4); xp = ld4(T + p * D + lane * 4); xn = ld4(T + n * D + lane * 4);
+        if (w) ww = ld4(w + lane * 4);
+    }
+    const float4 uw = make_float4(xu.x * ww.x, xu.y * ww.y, xu.z * ww.z, xu.w * ww.w);
+    const float ps = group_sum<LANES>(dot4(uw, xp), gmask);
+    const float ns = group_sum<LANES>(dot4(uw, xn), gmask);
+    float q = 0.f;
+    if (L2T) {
+        float4 a = xu, b = xp, c = xn;
+        if (L2T != T && active) { a = ld4(L2T + u * D + lane * 4); b = ld4(L2T + p * D + lane * 4); c = ld4(L2T + n * D + lane * 4); }
+        q = group_sum<LANES>(dot4(a, a), gmask) + group_sum<LANES>(dot4(b, b), gmask) + group_sum<LANES>(dot4(c, c), gmask);
+    }
+    if (lane == 0) {
+        const float x = ns - ps;
+        sp[i] = x > 20.f ? x : log1pf(expf(x));      // F.softplus (beta 1, threshold 20)
+        sig[i] = 1.f / (1.f + expf(-x));
+        if (l2) l2[i] = q;
+    }
+}
+
+// ------------------------------------------------------------------ loss finalisation (one CTA, fixed order)
+__device__ float block_sum_ordered(const float *__restrict__ v, int64_t n, float *sm) {
+    // thread t sums a contiguous slice sequentially, then thread 0 adds the 256 partials in order
+    const int64_t per = (n + kThreads - 1) / kThreads;
+    const int64_t lo = (int64_t)threadIdx.x * per, hi = min(n, lo + per);
+    float s = 0.f;
+    for (int64_t k = lo; k < hi; ++k) s += v[k];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    float tot = 0.f;
+    if (threadIdx.x == 0)
+        for (int k = 0; k < kThreads; ++k) tot += sm[k];
+    __syncthreads();
+    return tot;
+}
+
+__global__ void __launch_bounds__(kThreads) loss_finalize_kernel(const float *sp, const float *l2, const float *aux, int64_t B,
+                                                                 int64_t B_aux, float l2_reg, float aux_reg, float *loss, double *acc) {
+    __shared__ float sm[kThreads];
+    const float s0 = block_sum_ordered(sp, B, sm);
+    const float s1 = l2 ? block_sum_ordered(l2, B, sm) : 0.f;
+    const float s2 = aux ? block_sum_ordered(aux, B_aux, sm) : 0.f;
+    if (threadIdx.x == 0) {
+        float v = s0 / (float)B;
+        float reg = 0.f;
+        if (l2) reg = l2_reg * (s1 / (float)B);
+        if (aux) reg += aux_reg * (s2 / (float)B_aux);
+        v += reg;
+        loss[0] = v;
+        if (acc) {   // AverageMeter.update(loss.item(), B): the reference weights by the LAST inputs' batch size
+            const double n = (double)(aux ? B_aux : B);
+            acc[0] += (double)v * n;
+            acc[1] += n;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ scatter plan: bitonic sort of (row id, slot)
+__global__ void __launch_bounds__(1024) plan_kernel(const int64_t *__restrict__ tri, int64_t B, int64_t off, int n_pad,
+                                                    int32_t *order, int32_t *seg_start, int64_t *seg_row, int32_t *n_seg) {
+    extern __shared__ uint64_t keys[];
+    __shared__ int warp_tot[32];
+    const int n = (int)(3 * B);
+    for (int s = threadIdx.x; s < n_pad; s += blockDim.x) {
+        uint64_t k = ~0ULL;
+        if (s < n) {
+            const int kind = s / (int)B, i = s % (int)B;
+            const int64_t id = tri[(int64_t)i * 3 + kind] + (kind ? off : 0);
+            k = ((uint64_t)id << 32) | (uint32_t)s;
+        }
+        keys[s] = k;
+    }
+    __syncthreads();
+    for (int size = 2; size <= n_pad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < n_pad / 2; t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1));   // index with bit `stride` cleared
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const uint64_t a = keys[lo], b = keys[hi];
+                if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    // segment heads + exclusive scan of head flags (thread t owns a contiguous slice)
+    const int per = (n_pad + blockDim.x - 1) / blockDim.x;
+    const int lo = threadIdx.x * per, hi = min(n, lo + per);
+    int cnt = 0;
+    for (int s = lo; s < hi; ++s) cnt += (s == 0 || (keys[s] >> 32) != (keys[s - 1] >> 32));
+    int incl = cnt;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int v = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += x;
+        }
+        warp_tot[lane] = v;
+    }
+    __syncthreads();
+    int seg = incl - cnt + (wid ? warp_tot[wid - 1] : 0);
+    for (int s = lo; s < hi; ++s) {
+        const uint64_t k = keys[s];
+        order[s] = (int32_t)(k & 0xffffffffu);
+        if (s == 0 || (k >> 32) != (keys[s - 1] >> 32)) {
+            seg_start[seg] = s;
+            seg_row[seg] = (int64_t)(k >> 32);
+            ++seg;
+        }
+    }
+    if (threadIdx.x == blockDim.x - 1) {
+        const int total = warp_tot[31];
+        n_seg[0] = total;
+        seg_start[total] = n;
+    }
+}
+
+// ------------------------------------------------------------------ backward: one group per touched row
+template <int LANES>
+__global__ void __launch_bounds__(kThreads) bpr_bwd_kernel(const float *__restrict__ T, const float *__restrict__ w,
+                                                           const int64_t *__restrict__ tri, int64_t B, int64_t off, int D,
+                                                           const float *__restrict__ sig, float cscale, float lam, int l2_on,
+                                                           const int32_t *__restrict__ order, const int32_t *__restrict__ seg_start,
+                                                           const int64_t *__restrict__ seg_row, const int32_t *__restrict__ n_seg,
+                                                           float *G, int accumulate) {
+    const int lane = threadIdx.x % LANES;
+    const int64_t seg = (int64_t)blockIdx.x * (kThreads / LANES) + threadIdx.x / LANES;
+    if (seg >= *n_seg) return;
+    if (lane * 4 >= D) return;
+    const int64_t row = seg_row[seg];
+    const int s0 = seg_start[seg], s1 = seg_start[seg + 1];
+    float4 ww = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (w) ww = ld4(w + lane * 4);
+    const float4 self = ld4(T + row * D + lane * 4);
+    float4 acc = f4zero();
+    for (int s = s0; s < s1; ++s) {
+        const int slot = order[s];
+        const int kind = slot / (int)B, i = slot % (int)B;
+        const float c = cscale * sig[i];
+        float4 g;
+        if (kind == 0) {
+            const int64_t p = tri[(int64_t)i * 3 + 1] + off, n = tri[(int64_t)i * 3 + 2] + off;
+            const float4 xp = ld4(T + p * D + lane * 4), xn = ld4(T + n * D + lane * 4);
+            g = make_float4(c * ww.x * (xn.x - xp.x), c * ww.y * (xn.y - xp.y), c * ww.z * (xn.z - xp.z), c * ww.w * (xn.w - xp.w));
+        } else {
+            const int64_t u = tri[(int64_t)i * 3];
+            const float4 xu = ld4(T + u * D + lane * 4);
+            const float cs = kind == 1 ? -c : c;
+            g = make_float4(cs * ww.x * xu.x, cs * ww.y * xu.y, cs * ww.z * xu.z, cs * ww.w * xu.w);
+        }
+        if (l2_on) fma4(g, lam, self);
+        add4(acc, g);
+    }
+    float *dst = G + row * D + lane * 4;
+    if (accumulate) add4(acc, ld4(dst));
+    st4(dst, acc);
+}
+
+// dw: stage 1 sums 64 triples per CTA in order, stage 2 adds the CTA partials in order.
+__global__ void __launch_bounds__(128) dw_stage1(const float *__restrict__ T, const int64_t *__restrict__ tri, int64_t B, int64_t off,
+                                                 int D, const float *__restrict__ sig, float cscale, float *scratch) {
+    const int d = threadIdx.x;
+    if (d >= D) return;
+    const int64_t lo = (int64_t)blockIdx.x * 64, hi = min(B, lo + 64);
+    float t = 0.f;
+    for (int64_t i = lo; i < hi; ++i) {
+        const int64_t u = tri[i * 3], p = tri[i * 3 + 1] + off, n = tri[i * 3 + 2] + off;
+        t = fmaf(cscale * sig[i] * T[u * D + d], T[n * D + d] - T[p * D + d], t);
+    }
+    scratch[(int64_t)blockIdx.x * D + d] = t;
+}
+
+__global__ void dw_stage2(const float *__restrict__ scratch, int64_t n_blocks, int D, float *dw) {
+    const int d = threadIdx.x;
+    if (d >= D) return;
+    float t = 0.f;
+    for (int64_t b = 0; b < n_blocks; ++b) t += scratch[b * D + d];
+    dw[d] += t;
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(kThreads) l2_rows_kernel(const float *__restrict__ E, float *dE, int D, float coef,
+                                                           const int32_t *__restrict__ seg_start, const int64_t *__restrict__ seg_row,
+                                                           const int32_t *__restrict__ n_seg) {
+    const int lane = threadIdx.x % LANES;
+    const int64_t seg = (int64_t)blockIdx.x * (kThreads / LANES) + threadIdx.x / LANES;
+    if (seg >= *n_seg || lane * 4 >= D) return;
+    const int64_t row = seg_row[seg];
+    const float m = coef * (float)(seg_start[seg + 1] - seg_start[seg]);
+    float4 g = ld4(dE + row * D + lane * 4);
+    fma4(g, m, ld4(E + row * D + lane * 4));
+    st4(dE + row * D + lane * 4, g);
+}
+
+// ------------------------------------------------------------------ Adam
+__global__ void __launch_bounds__(kThreads) adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                                                        float *__restrict__ v, int64_t n4, int64_t n, float b1, float b2,
+                                                        float step_size, float inv_sqrt_bc2, float eps,
+                                                        const igcn_step_state *__restrict__ state) {
+    if (state) { step_size = state->adam_step_size; inv_sqrt_bc2 = state->adam_inv_sqrt_bc2; }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 pp = ld4(p + i * 4), gg = ld4(g + i * 4), mm = ld4(m + i * 4), vv = ld4(v + i * 4);
+#define IGCN_ADAM1(c)                                                      \
+        mm.c = mm.c + (gg.c - mm.c) * (1.f - b1);                          \
+        vv.c = vv.c * b2 + (1.f - b2) * gg.c * gg.c;                       \
+        pp.c = pp.c - step_size * (mm.c / (sqrtf(vv.c) * inv_sqrt_bc2 + eps));
+        IGCN_ADAM1(x) IGCN_ADAM1(y) IGCN_ADAM1(z) IGCN_ADAM1(w)
+        st4(p + i * 4, pp); st4(m + i * 4, mm); st4(v + i * 4, vv);
+    }
+    // tail (n not a multiple of 4)
+    const int64_t t = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0 && t < n) {
+        float mm = m[t], vv = v[t];
+        const float gg = g[t];
+        mm = mm + (gg - mm) * (1.f - b1);
+        vv = vv * b2 + (1.f - b2) * gg * gg;
+        p[t] -= step_size * (mm / (sqrtf(vv) * inv_sqrt_bc2 + eps));
+        m[t] = mm; v[t] = vv;
+    }
+}
+
+__global__ void step_tick_kernel(igcn_step_state *s, float lr, float b1, float b2) {
+    const uint64_t t = s->step + 1;
+    s->step = t;
+    s->adam_step_size = (float)((double)lr / (1.0 - pow((double)b1, (double)t)));
+    s->adam_inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)b2, (double)t)));
+}
+
+template <typename F8, typename F16, typename F32>
+static void by_lanes(int D, F8 f8, F16 f16, F32 f32) {
+    if (D <= 32) f8(); else if (D <= 64) f16(); else f32();
+}
+
+}  // namespace igcn
+
+using namespace igcn;
+
+#define IGCN_CHECK_D(D) IGCN_CHECK_ARG((D) > 0 && (D) <= 128 && !((D)&3), "embedding size unsupported (need D % 4 == 0, D <= 128)")
+
+extern "C" int igcn_sample_triples(const int64_t *rowptr, const int32_t *col, int64_t col_offset, int64_t n_users,
+                                   int64_t n_items, int64_t B, uint64_t seed, uint64_t step, const uint64_t *step_dev, int64_t *out,
+                                   void *stream) {
+    IGCN_CHECK_ARG(rowptr && col && out, "null pointer");
+    IGCN_CHECK_ARG(n_users > 0 && n_items > 0 && B >= 0, "bad sizes");
+    if (B == 0) return 0;
+    const uint64_t key = mix64(seed * 0x9e3779b97f4a7c15ULL + mix64(step + 0x1234567ULL));
+    sample_kernel<<<(unsigned)((B + 127) / 128), 128, 0, as_stream(stream)>>>(rowptr, col, col_offset, n_users, n_items, B, key, step_dev, out);
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_bpr_fwd(const float *table, const float *l2_table, const float *w, const int64_t *triples, int64_t B,
+                            int64_t item_offset, int32_t D, float *sp, float *sig, float *l2, void *stream) {
+    IGCN_CHECK_ARG(table && triples && sp && sig, "null pointer");
+    IGCN_CHECK_D(D);
+    IGCN_CHECK_ARG(!l2_table || l2, "l2_table given without l2 output");
+    if (B <= 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    by_lanes(D,
+             [&] { bpr_fwd_kernel<8><<<(unsigned)((B + 31) / 32), kThreads, 0, st>>>(table, l2_table, w, triples, B, item_offset, D, sp, sig, l2); },
+             [&] { bpr_fwd_kernel<16><<<(unsigned)((B + 15) / 16), kThreads, 0, st>>>(table, l2_table, w, triples, B, item_offset, D, sp, sig, l2); },
+             [&] { bpr_fwd_kernel<32><<<(unsigned)((B + 7) / 8), kThreads, 0, st>>>(table, l2_table, w, triples, B, item_offset, D, sp, sig, l2); });
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_loss_finalize(const float *sp, const float *l2, const float *aux_sp, int64_t B, int64_t B_aux,
+                                  float l2_reg, float aux_reg, float *loss, double *acc, void *stream) {
+    IGCN_CHECK_ARG(sp && loss && B > 0, "null pointer or empty batch");
+    IGCN_CHECK_ARG(!aux_sp || B_aux > 0, "empty aux batch");
+    loss_finalize_kernel<<<1, kThreads, 0, as_stream(stream)>>>(sp, l2, aux_sp, B, B_aux, l2_reg, aux_reg, loss, acc);
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_bpr_plan(const int64_t *triples, int64_t B, int64_t item_offset, int32_t *order, int32_t *seg_start,
+                             int64_t *seg_row, int32_t *n_seg, void *stream) {
+    IGCN_CHECK_ARG(triples && order && seg_start && seg_row && n_seg, "null pointer");
+    IGCN_CHECK_ARG(B > 0 && 3 * B <= 16384, "batch size must satisfy 0 < 3*B <= 16384");
+    int n_pad = 2;
+    while (n_pad < 3 * B) n_pad <<= 1;
+    const size_t smem = (size_t)n_pad * sizeof(uint64_t);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+        if (e != cudaSuccess) { set_error("igcn_bpr_plan: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_done = true;
+    }
+    plan_kernel<<<1, 1024, smem, as_stream(stream)>>>(triples, B, item_offset, n_pad, order, seg_start, seg_row, n_seg);
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_bpr_bwd(const float *table, const float *w, const int64_t *triples, int64_t B, int64_t item_offset,
+                            int32_t D, const float *sig, float scale, float l2_coef, int32_t l2_on_table,
+                            const int32_t *order, const int32_t *seg_start, const int64_t *seg_row, const int32_t *n_seg,
+                            float *G, int32_t accumulate, float *dw, float *dw_scratch, void *stream) {
+    IGCN_CHECK_ARG(table && triples && sig && order && seg_start && seg_row && n_seg && G, "null pointer");
+    IGCN_CHECK_D(D);
+    IGCN_CHECK_ARG(!dw || (w && dw_scratch), "dw needs w and dw_scratch");
+    if (B <= 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    const float cscale = scale / (float)B;
+    const float lam = scale * 2.f * l2_coef / (float)B;
+    const int64_t max_seg = 3 * B;
+#define IGCN_BWD_LAUNCH(L)                                                                                       \
+    bpr_bwd_kernel<L><<<(unsigned)((max_seg + kThreads / L - 1) / (kThreads / L)), kThreads, 0, st>>>(           \
+        table, w, triples, B, item_offset, D, sig, cscale, lam, l2_on_table, order, seg_start, seg_row, n_seg, G, accumulate)
+    by_lanes(D, [&] { IGCN_BWD_LAUNCH(8); }, [&] { IGCN_BWD_LAUNCH(16); }, [&] { IGCN_BWD_LAUNCH(32); });
+    if (dw) {
+        const int64_t nb = (B + 63) / 64;
+        dw_stage1<<<(unsigned)nb, 128, 0, st>>>(table, triples, B, item_offset, D, sig, cscale, dw_scratch);
+        dw_stage2<<<1, 128, 0, st>>>(dw_scratch, nb, D, dw);
+    }
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_l2_rows_bwd(const float *E, float *dE, int32_t D, float coef, const int32_t *seg_start,
+                                const int64_t *seg_row, const int32_t *n_seg, int64_t max_seg, void *stream) {
+    IGCN_CHECK_ARG(E && dE && seg_start && seg_row && n_seg, "null pointer");
+    IGCN_CHECK_D(D);
+    if (max_seg <= 0) return 0;
+    cudaStream_t st = as_stream(stream);
+#define IGCN_L2_LAUNCH(L) \
+    l2_rows_kernel<L><<<(unsigned)((max_seg + kThreads / L - 1) / (kThreads / L)), kThreads, 0, st>>>(E, dE, D, coef, seg_start, seg_row, n_seg)
+    by_lanes(D, [&] { IGCN_L2_LAUNCH(8); }, [&] { IGCN_L2_LAUNCH(16); }, [&] { IGCN_L2_LAUNCH(32); });
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_adam(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2,
+                         float eps, int64_t t, const igcn_step_state *state_dev, void *stream) {
+    IGCN_CHECK_ARG(p && g && m && v, "null pointer");
+    IGCN_CHECK_ARG(state_dev || t >= 1, "step count starts at 1");
+    if (t < 1) t = 1;
+    if (n <= 0) return 0;
+    const double bc1 = 1.0 - pow((double)beta1, (double)t);
+    const double bc2 = 1.0 - pow((double)beta2, (double)t);
+    const float step_size = (float)((double)lr / bc1);
+    const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    const int64_t n4 = n / 4;
+    int64_t blocks = (n4 + kThreads - 1) / kThreads;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    adam_kernel<<<(unsigned)blocks, kThreads, 0, as_stream(stream)>>>(p, g, m, v, n4, n, beta1, beta2, step_size, inv_sqrt_bc2, eps, state_dev);
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_step_tick(igcn_step_state *state_dev, float lr, float beta1, float beta2, void *stream) {
+    IGCN_CHECK_ARG(state_dev, "null pointer");
+    step_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(state_dev, lr, beta1, beta2);
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}

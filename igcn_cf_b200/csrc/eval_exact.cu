@@ -1,0 +1,248 @@
+// Full-ranking evaluation, exact fp32 path: score tile (CUDA-core FMA chain, ascending d) ->
+// threshold filter -> lazy seen-item mask -> per-user running top-k kept in shared memory.
+// The B x I score matrix is never written to HBM.
+//
+// Replaces torch.mm (reference model.py:122), the -inf index_put (trainer.py:149-161) and
+// torch.topk (trainer.py:163).  It defines the score summation order that the tensor-core path's
+// re-scoring step reproduces bit for bit, and it is the fallback for users whose tensor-core
+// candidate bound does not verify.  igcn_hits is the membership test of calculate_metrics
+// (trainer.py:111-115).
+#include <float.h>
+
+#include "common.cuh"
+
+namespace igcn {
+
+constexpr int BM = 64;      // users per CTA
+constexpr int BN = 128;     // items per tile
+constexpr int CAP = 256;    // candidate slots per user (K <= CAP - BN)
+constexpr int EX_THREADS = 256;
+
+__device__ __forceinline__ uint32_t float_order(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float order_float(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+// larger key == better candidate: higher score first, then lower item id
+__device__ __forceinline__ uint64_t cand_key(float score, int32_t item) {
+    return ((uint64_t)float_order(score) << 32) | (uint32_t)(0x7fffffff - item);
+}
+
+__device__ __forceinline__ bool item_masked(int64_t u, int32_t j, const int64_t *__restrict__ mptr,
+                                            const int32_t *__restrict__ mitems, const uint32_t *__restrict__ banned) {
+    if (banned && ((__ldg(banned + (j >> 5)) >> (j & 31)) & 1u)) return true;
+    if (!mptr) return false;
+    int64_t lo = __ldg(mptr + u), hi = __ldg(mptr + u + 1);
+    const int64_t end = hi;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(mitems + mid) < j) lo = mid + 1; else hi = mid;
+    }
+    return lo < end && __ldg(mitems + lo) == j;
+}
+
+// One warp sorts the first `n` (<= CAP) keys of a row descending (bitonic, padded with 0).
+__device__ void warp_sort_desc(uint64_t *keys, int n, int lane) {
+    int n_pad = 32;
+    while (n_pad < n) n_pad <<= 1;
+    for (int s = n + lane; s < n_pad; s += 32) keys[s] = 0ULL;
+    __syncwarp();
+    for (int size = 2; size <= n_pad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = lane; t < n_pad / 2; t += 32) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const uint64_t a = keys[lo], b = keys[hi];
+                if ((a < b) == desc) { keys[lo] = b; keys[hi] = a; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+struct ExactArgs {
+    const float *rep;
+    const int64_t *user_ids;
+    int64_t n_eval, item_row0, n_items;
+    int D;
+    const int64_t *mask_ptr;
+    const int32_t *mask_items;
+    int64_t item_lo, item_hi;
+    const uint32_t *banned;
+    int k;
+    int32_t *out_items;
+    float *out_scores;
+};
+
+// smem: Us[BM][D+4] | Is[BN][min(D,64)+4] | keys[BM][CAP] (u64) | cnt[BM] | thr[BM]
+__global__ void __launch_bounds__(EX_THREADS, 1) score_topk_exact_kernel(const __grid_constant__ ExactArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int D = a.D, DP = D + 4;
+    float *Us = reinterpret_cast<float *>(smem_raw);
+    float *Is = Us + BM * DP;
+    uint64_t *keys = reinterpret_cast<uint64_t *>(Is + BN * (min(D, 64) + 4));
+    int *cnt = reinterpret_cast<int *>(keys + BM * CAP);
+    float *thr = reinterpret_cast<float *>(cnt + BM);
+    __shared__ int need_compact;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tx = tid & 15, ty = tid >> 4;      // 16 item lanes x 16 user groups of 4
+    const int64_t ubase = (int64_t)blockIdx.x * BM;
+    const int d4 = D >> 2;
+
+    for (int idx = tid; idx < BM * d4; idx += EX_THREADS) {
+        const int r = idx / d4, c = idx % d4;
+        float4 v = f4zero();
+        if (ubase + r < a.n_eval) v = ld4(a.rep + __ldg(a.user_ids + ubase + r) * D + c * 4);
+        st4(Us + r * DP + c * 4, v);
+    }
+    if (tid < BM) { cnt[tid] = 0; thr[tid] = -INFINITY; }
+    if (tid == 0) need_compact = 0;
+    __syncthreads();
+
+    const int64_t j_begin = max((int64_t)0, a.item_lo) / BN * BN;
+    const int64_t j_end = min(a.n_items, a.item_hi);
+    const int KC = min(D, 64), KCP = KC + 4;      // item tile holds at most 64 dims at a time
+    for (int64_t j0 = j_begin; j0 < j_end; j0 += BN) {
+        float acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int kb = 0; kb < D; kb += KC) {
+            const int kc4 = min(KC, D - kb) >> 2;
+            if (kb) __syncthreads();
+            for (int idx = tid; idx < BN * kc4; idx += EX_THREADS) {
+                const int r = idx / kc4, c = idx % kc4;
+                float4 v = f4zero();
+                if (j0 + r < a.n_items) v = ld4(a.rep + (a.item_row0 + j0 + r) * D + kb + c * 4);
+                st4(Is + r * KCP + c * 4, v);
+            }
+            __syncthreads();
+            for (int c = 0; c < kc4; ++c) {
+                float4 u[4], it[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) u[i] = ld4(Us + (ty * 4 + i) * DP + kb + c * 4);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) it[j] = ld4(Is + (tx + 16 * j) * KCP + c * 4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float s = acc[i][j];
+                        s = fmaf(u[i].x, it[j].x, s); s = fmaf(u[i].y, it[j].y, s);
+                        s = fmaf(u[i].z, it[j].z, s); s = fmaf(u[i].w, it[j].w, s);
+                        acc[i][j] = s;
+                    }
+            }
+        }
+        // threshold filter (thr is stale-but-valid: never above the true k-th best so far)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = ty * 4 + i;
+            const float t = thr[r];
+            const int64_t urow = ubase + r;
+            if (urow >= a.n_eval) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int64_t item = j0 + tx + 16 * j;
+                const float s = acc[i][j];
+                if (s > t && item >= a.item_lo && item < j_end) {
+                    if (!item_masked(__ldg(a.user_ids + urow), (int32_t)item, a.mask_ptr, a.mask_items, a.banned)) {
+                        const int slot = atomicAdd(cnt + r, 1);
+                        keys[r * CAP + slot] = cand_key(s, (int32_t)item);
+                        if (slot + 1 > CAP - BN) need_compact = 1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (need_compact) {
+            for (int r = wid; r < BM; r += EX_THREADS / 32) {
+                const int n = cnt[r];
+                if (n > CAP - BN) {
+                    warp_sort_desc(keys + r * CAP, n, lane);
+                    if (lane == 0) {
+                        cnt[r] = a.k;   // n > CAP - BN >= k
+                        thr[r] = order_float((uint32_t)(keys[r * CAP + a.k - 1] >> 32));
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) need_compact = 0;
+        }
+        __syncthreads();
+    }
+
+    for (int r = wid; r < BM; r += EX_THREADS / 32) {
+        const int64_t urow = ubase + r;
+        if (urow >= a.n_eval) continue;
+        const int n = cnt[r];
+        warp_sort_desc(keys + r * CAP, n, lane);
+        for (int q = lane; q < a.k; q += 32) {
+            int32_t item = -1;
+            float sc = -INFINITY;
+            if (q < n) {
+                const uint64_t key = keys[r * CAP + q];
+                item = 0x7fffffff - (int32_t)(key & 0xffffffffu);
+                sc = order_float((uint32_t)(key >> 32));
+            }
+            a.out_items[urow * a.k + q] = item;
+            a.out_scores[urow * a.k + q] = sc;
+        }
+    }
+}
+
+__global__ void hits_kernel(const int32_t *__restrict__ rec, int64_t n, int k, const int64_t *__restrict__ ptr,
+                            const int32_t *__restrict__ items, float *hit) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * k) return;
+    const int64_t u = idx / k;
+    const int32_t j = rec[idx];
+    int64_t lo = ptr[u], hi = ptr[u + 1];
+    const int64_t end = hi;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (items[mid] < j) lo = mid + 1; else hi = mid;
+    }
+    hit[idx] = (j >= 0 && lo < end && items[lo] == j) ? 1.f : 0.f;
+}
+
+}  // namespace igcn
+
+using namespace igcn;
+
+extern "C" int igcn_score_topk_exact(const float *rep, const int64_t *user_ids, int64_t n_eval, int64_t item_row0,
+                                     int64_t n_items, int32_t D, const int64_t *mask_ptr, const int32_t *mask_items,
+                                     int64_t item_lo, int64_t item_hi, const uint32_t *banned_bits, int32_t k,
+                                     int32_t *out_items, float *out_scores, void *stream) {
+    IGCN_CHECK_ARG(rep && user_ids && out_items && out_scores, "null pointer");
+    IGCN_CHECK_ARG(D > 0 && D <= 128 && !(D & 3), "embedding size unsupported (need D % 4 == 0, D <= 128)");
+    IGCN_CHECK_ARG(k > 0 && k <= CAP - BN, "k must be in [1, 128]");
+    IGCN_CHECK_ARG(!mask_ptr || mask_items, "mask_ptr without mask_items");
+    IGCN_CHECK_ARG(n_items > 0 && n_items < 0x7fffffff, "n_items out of range");
+    if (n_eval <= 0) return 0;
+    ExactArgs a{rep, user_ids, n_eval, item_row0, n_items, D, mask_ptr, mask_items, item_lo, item_hi, banned_bits, k,
+                out_items, out_scores};
+    const size_t smem = ((size_t)BM * (D + 4) + (size_t)BN * ((D < 64 ? D : 64) + 4)) * sizeof(float) + (size_t)BM * CAP * sizeof(uint64_t) + BM * 8;
+    cudaError_t e = cudaFuncSetAttribute(score_topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("igcn_score_topk_exact: %s", cudaGetErrorString(e)); return (int)e; }
+    const int64_t blocks = (n_eval + BM - 1) / BM;
+    score_topk_exact_kernel<<<(unsigned)blocks, EX_THREADS, smem, as_stream(stream)>>>(a);
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_hits(const int32_t *rec, int64_t n_users, int32_t k, const int64_t *eval_ptr,
+                         const int32_t *eval_items, float *hit, void *stream) {
+    IGCN_CHECK_ARG(rec && eval_ptr && eval_items && hit, "null pointer");
+    IGCN_CHECK_ARG(k > 0, "k must be positive");
+    const int64_t total = n_users * k;
+    if (total <= 0) return 0;
+    hits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(rec, n_users, k, eval_ptr, eval_items, hit);
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}

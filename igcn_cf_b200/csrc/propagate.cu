@@ -1,0 +1,339 @@
+// Embedding propagation on B200: CSR row-split gather kernels.
+//
+//   igcn_spmm       Y = alpha * rowscale .* (A X + sum_j add_j)     K1/K4/K5 of SURVEY.md 2.2
+//   igcn_inmo_fwd   X0 = s .* (F~ E)    template aggregation + dropout fused    K2/K3
+//   igcn_inmo_bwd   dE = F~^T G         transposed, mask regenerated            K4
+//   igcn_colsum_masked   gradient of the two global template rows
+//
+// Work decomposition (all three share it): one group of LANES = D/4 lanes owns one row and
+// walks its non-zeros in CSR order; every lane carries one float4 of the 4*LANES-wide row, so a
+// 64-dim row is one 256-byte gather per neighbour (16 lanes x 128-bit).  Column ids and values
+// are loaded LANES at a time (coalesced) and broadcast with shuffles; 8 gathers are kept in
+// flight per group.  Rows longer than `long_threshold` are pre-cut into chunks on the host
+// (igcn_csr.chunk_*): chunk units come first in the grid, write partial sums, and the last one
+// to arrive (self-resetting counter) adds the partials in chunk order -- deterministic, and
+// independent of how rows are sharded over GPUs.
+//
+// Everything here is HBM/L2-bound gather work; there is no tensor-core shape to it.
+#include "common.cuh"
+
+namespace igcn {
+
+enum { MODE_SPMM = 0, MODE_INMO_FWD = 1, MODE_INMO_BWD = 2 };
+
+struct PropArgs {
+    igcn_csr g;
+    const float *X;   // gathered table (X, E or G)
+    float *Y;         // output rows
+    const float *add[IGCN_MAX_ADD];
+    int n_add;
+    const float *rowscale;
+    float alpha;
+    int D;
+    // INMO only
+    const int32_t *tmpl;
+    igcn_dropout drop;
+    uint32_t thresh;
+    float inv_keep;
+    int64_t row0, n_users, glob_user, glob_item;
+};
+
+constexpr int kThreads = 256;
+constexpr uint32_t kSelfCol = 0xffffffffu;
+
+template <int LANES>
+__device__ __forceinline__ uint32_t group_mask(int lane_in_warp) {
+    if (LANES == 32) return 0xffffffffu;
+    const uint32_t base = (LANES == 16) ? 0xffffu : 0xffu;
+    return base << (lane_in_warp & ~(LANES - 1));
+}
+
+// Sum of the gathered rows of non-zeros [beg, end) of one row, as this lane's float4 slice.
+template <int LANES, int MODE, int DROP>
+__device__ __forceinline__ float4 gather_range(const PropArgs &a, int64_t beg, int64_t end,
+                                               int64_t grow /* global id of this row */,
+                                               int lane, uint32_t gmask, bool active, uint64_t seed) {
+    float4 acc = f4zero();
+    const int32_t *__restrict__ col = a.g.col;
+    const float *__restrict__ val = a.g.val;
+    const float *__restrict__ X = a.X;
+    const int D = a.D;
+    const int shift = (threadIdx.x & 31) & ~(LANES - 1);
+
+    for (int64_t e0 = beg; e0 < end; e0 += LANES) {
+        const int n = (int)min((int64_t)LANES, end - e0);
+        int c = 0;
+        float v = 0.f;
+        bool keep = false;
+        if (lane < n) {
+            const int64_t e = e0 + lane;
+            c = __ldg(col + e);
+            keep = true;
+            if (MODE == MODE_SPMM) {
+                v = val ? __ldg(val + e) : 1.f;
+            } else {
+                if (DROP == 1) {
+                    const uint32_t h = (MODE == MODE_INMO_FWD) ? edge_hash(seed, (uint32_t)grow, (uint32_t)c)
+                                                               : edge_hash(seed, (uint32_t)c, (uint32_t)grow);
+                    keep = h >= a.thresh;
+                } else if (DROP == 2) {
+                    const int64_t b = (MODE == MODE_INMO_FWD) ? e : __ldg(a.drop.tperm + e);
+                    keep = (__ldg(a.drop.edge_keep + (b >> 5)) >> (b & 31)) & 1u;
+                }
+                if (MODE == MODE_INMO_FWD && a.tmpl) {
+                    c = __ldg(a.tmpl + c);
+                    keep = keep && (c >= 0);
+                }
+            }
+        }
+        if (MODE == MODE_SPMM) {
+#pragma unroll
+            for (int j0 = 0; j0 < LANES; j0 += 8) {
+                if (j0 >= n) break;
+                float4 x[8];
+                float w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int cj = __shfl_sync(gmask, c, j0 + j, LANES);
+                    w[j] = __shfl_sync(gmask, v, j0 + j, LANES);
+                    x[j] = (j0 + j < n && active) ? ld4(X + (int64_t)cj * D + lane * 4) : f4zero();
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) fma4(acc, w[j], x[j]);
+            }
+        } else {
+            uint32_t m = (__ballot_sync(gmask, keep) >> shift);
+            m &= (uint32_t)((1ULL << LANES) - 1ULL);
+            while (m) {
+                float4 x[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool ok = m != 0;
+                    const int j = ok ? (__ffs(m) - 1) : 0;
+                    m &= m - 1;   // 0 & anything stays 0
+                    const int cj = __shfl_sync(gmask, c, j, LANES);
+                    x[q] = (ok && active) ? ld4(X + (int64_t)cj * D + lane * 4) : f4zero();
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) add4(acc, x[q]);
+            }
+        }
+    }
+    return acc;
+}
+
+template <int LANES, int MODE, int DROP>
+__device__ __forceinline__ void finish_row(const PropArgs &a, int64_t r, float4 acc, int lane, bool active, uint64_t seed) {
+    if (!active) return;
+    const int D = a.D;
+    const int64_t grow = a.row0 + r;
+    if (MODE == MODE_SPMM) {
+        for (int j = 0; j < a.n_add; ++j) add4(acc, ld4(a.add[j] + r * D + lane * 4));
+        float s = a.alpha;
+        if (a.rowscale) s *= __ldg(a.rowscale + r);
+        st4(a.Y + r * D + lane * 4, scale4(acc, s));
+    } else if (MODE == MODE_INMO_FWD) {
+        bool keep = true;
+        if (DROP == 1) keep = edge_hash(seed, (uint32_t)grow, kSelfCol) >= a.thresh;
+        if (DROP == 2) keep = (__ldg(a.drop.self_keep + (grow >> 5)) >> (grow & 31)) & 1u;
+        if (keep) {
+            const int64_t gt = grow < a.n_users ? a.glob_user : a.glob_item;
+            add4(acc, ld4(a.X + gt * D + lane * 4));
+        }
+        const float s = __ldg(a.rowscale + r) * a.inv_keep;
+        st4(a.Y + r * D + lane * 4, scale4(acc, s));
+    } else {
+        int64_t t = grow;
+        if (a.tmpl) t = __ldg(a.tmpl + grow);
+        if (t >= 0) st4(a.Y + t * D + lane * 4, acc);
+    }
+}
+
+template <int LANES, int MODE, int DROP>
+__global__ void __launch_bounds__(kThreads) prop_kernel(const __grid_constant__ PropArgs a) {
+    constexpr int GROUPS = kThreads / LANES;
+    const int lane = threadIdx.x % LANES;
+    const uint32_t gmask = group_mask<LANES>(threadIdx.x & 31);
+    const int64_t unit = (int64_t)blockIdx.x * GROUPS + threadIdx.x / LANES;
+    const bool active = lane * 4 < a.D;
+    const int64_t n_chunks = a.g.n_chunks;
+    if (unit >= n_chunks + a.g.n_rows) return;
+    uint64_t seed = a.drop.seed;
+    if (DROP == 1 && a.drop.seed_dev) seed = mix64(seed ^ mix64(*a.drop.seed_dev + 0x2545f491ULL));
+
+    if (unit < n_chunks) {
+        // ---- one chunk of a long row
+        const int ch = (int)unit;
+        const int64_t r = a.g.chunk_row[ch];
+        const int64_t beg = a.g.chunk_begin[ch];
+        const int64_t end = beg + a.g.chunk_len[ch];
+        float4 acc = gather_range<LANES, MODE, DROP>(a, beg, end, a.row0 + r, lane, gmask, active, seed);
+        const int first = a.g.chunk_first[ch];
+        const int count = a.g.chunk_count[ch];
+        if (active) st4(a.g.partial + (int64_t)ch * a.D + lane * 4, acc);
+        __threadfence();
+        __syncwarp(gmask);
+        int old = 0;
+        if (lane == 0) old = atomicAdd(a.g.counters + first, 1);
+        old = __shfl_sync(gmask, old, 0, LANES);
+        if (old != count - 1) return;
+        __threadfence();
+        if (lane == 0) a.g.counters[first] = 0;   // self-reset for the next launch
+        float4 tot = f4zero();
+        if (active)
+            for (int k = 0; k < count; ++k)
+                add4(tot, __ldcg(reinterpret_cast<const float4 *>(a.g.partial + (int64_t)(first + k) * a.D + lane * 4)));
+        finish_row<LANES, MODE, DROP>(a, r, tot, lane, active, seed);
+        return;
+    }
+
+    // ---- one whole (short) row
+    const int64_t r = unit - n_chunks;
+    const int64_t beg = __ldg(a.g.rowptr + r), end = __ldg(a.g.rowptr + r + 1);
+    if (n_chunks > 0 && end - beg > a.g.long_threshold) return;   // handled by chunk units
+    float4 acc = gather_range<LANES, MODE, DROP>(a, beg, end, a.row0 + r, lane, gmask, active, seed);
+    finish_row<LANES, MODE, DROP>(a, r, acc, lane, active, seed);
+}
+
+template <int MODE, int DROP>
+static int launch_lanes(const PropArgs &a, cudaStream_t st) {
+    const int64_t units = a.g.n_chunks + a.g.n_rows;
+    if (units == 0) return 0;
+    const int D = a.D;
+    if (D <= 32) {
+        const int64_t blocks = (units + kThreads / 8 - 1) / (kThreads / 8);
+        prop_kernel<8, MODE, DROP><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+    } else if (D <= 64) {
+        const int64_t blocks = (units + kThreads / 16 - 1) / (kThreads / 16);
+        prop_kernel<16, MODE, DROP><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+    } else {
+        const int64_t blocks = (units + kThreads / 32 - 1) / (kThreads / 32);
+        prop_kernel<32, MODE, DROP><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+    }
+    return 0;
+}
+
+template <int MODE>
+static int launch_drop(const PropArgs &a, cudaStream_t st) {
+    switch (a.drop.mode) {
+        case 0: return launch_lanes<MODE, 0>(a, st);
+        case 1: return launch_lanes<MODE, 1>(a, st);
+        default: return launch_lanes<MODE, 2>(a, st);
+    }
+}
+
+static int check_common(const igcn_csr *g, int32_t D) {
+    if (!g) { set_error("null csr"); return -1; }
+    if (D <= 0 || D > 128 || (D & 3)) { set_error("embedding size %d unsupported (need D %% 4 == 0, D <= 128)", D); return -1; }
+    if (g->n_chunks > 0 && (!g->partial || !g->counters || !g->chunk_row)) { set_error("chunk plan incomplete"); return -1; }
+    return 0;
+}
+
+static int fill_drop(PropArgs &a, const igcn_dropout *drop) {
+    if (drop) a.drop = *drop; else { a.drop = igcn_dropout{}; }
+    if (a.drop.mode < 0 || a.drop.mode > 2) { set_error("dropout mode %d", a.drop.mode); return -1; }
+    if (a.drop.mode != 0 && !(a.drop.p >= 0.f && a.drop.p < 1.f)) { set_error("dropout p out of range"); return -1; }
+    if (a.drop.mode == 2 && (!a.drop.edge_keep || !a.drop.self_keep)) { set_error("mode 2 needs keep bits"); return -1; }
+    a.thresh = a.drop.mode == 1 ? drop_threshold(a.drop.p) : 0u;
+    a.inv_keep = a.drop.mode == 0 ? 1.f : 1.f / (1.f - a.drop.p);
+    return 0;
+}
+
+// ------------------------------------------------------------------ masked column sums
+template <int LANES>
+__global__ void __launch_bounds__(kThreads) colsum_stage1(const float *__restrict__ G, int64_t row_begin, int64_t row_end,
+                                                          int D, igcn_dropout drop, uint32_t thresh, float *scratch) {
+    constexpr int GROUPS = kThreads / LANES;
+    __shared__ float4 sm[GROUPS][LANES];
+    const int lane = threadIdx.x % LANES, grp = threadIdx.x / LANES;
+    const bool active = lane * 4 < D;
+    uint64_t seed = drop.seed;
+    if (drop.mode == 1 && drop.seed_dev) seed = mix64(seed ^ mix64(*drop.seed_dev + 0x2545f491ULL));
+    const int64_t base = row_begin + (int64_t)blockIdx.x * 256;
+    const int64_t stop = min(row_end, base + 256);
+    float4 acc = f4zero();
+    for (int64_t r = base + grp; r < stop; r += GROUPS) {
+        bool keep = true;
+        if (drop.mode == 1) keep = edge_hash(seed, (uint32_t)r, kSelfCol) >= thresh;
+        if (drop.mode == 2) keep = (__ldg(drop.self_keep + (r >> 5)) >> (r & 31)) & 1u;
+        if (keep && active) add4(acc, ld4(G + r * D + lane * 4));
+    }
+    sm[grp][lane] = acc;
+    __syncthreads();
+    if (grp == 0 && active) {
+        float4 t = sm[0][lane];
+        for (int k = 1; k < GROUPS; ++k) add4(t, sm[k][lane]);
+        st4(scratch + (int64_t)blockIdx.x * D + lane * 4, t);
+    }
+}
+
+__global__ void colsum_stage2(const float *__restrict__ scratch, int64_t n_blocks, int D, float *out) {
+    const int d = threadIdx.x;
+    if (d >= D) return;
+    float t = 0.f;
+    for (int64_t b = 0; b < n_blocks; ++b) t += scratch[b * D + d];
+    out[d] = t;
+}
+
+}  // namespace igcn
+
+using namespace igcn;
+
+extern "C" int igcn_spmm(const igcn_csr *g, const float *X, float *Y, int32_t D, const float *const *add_host,
+                         int32_t n_add, const float *rowscale, float alpha, void *stream) {
+    if (check_common(g, D)) return -1;
+    IGCN_CHECK_ARG(X && Y, "null X/Y");
+    IGCN_CHECK_ARG(n_add >= 0 && n_add <= IGCN_MAX_ADD, "n_add out of range");
+    PropArgs a{};
+    a.g = *g; a.X = X; a.Y = Y; a.D = D; a.n_add = n_add; a.rowscale = rowscale; a.alpha = alpha;
+    for (int j = 0; j < n_add; ++j) a.add[j] = add_host[j];
+    launch_lanes<MODE_SPMM, 0>(a, as_stream(stream));
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_inmo_fwd(const igcn_csr *g, const int32_t *tmpl, const float *rowscale, const igcn_dropout *drop,
+                             const float *E, float *X0, int32_t D, int64_t row0, int64_t n_users, int64_t glob_user,
+                             int64_t glob_item, void *stream) {
+    if (check_common(g, D)) return -1;
+    IGCN_CHECK_ARG(E && X0 && rowscale, "null E/X0/rowscale");
+    PropArgs a{};
+    a.g = *g; a.X = E; a.Y = X0; a.D = D; a.rowscale = rowscale; a.alpha = 1.f; a.tmpl = tmpl;
+    a.row0 = row0; a.n_users = n_users; a.glob_user = glob_user; a.glob_item = glob_item;
+    if (fill_drop(a, drop)) return -1;
+    launch_drop<MODE_INMO_FWD>(a, as_stream(stream));
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_inmo_bwd(const igcn_csr *g, const int32_t *tmpl, const igcn_dropout *drop, const float *G,
+                             float *dE, int32_t D, int64_t row0, void *stream) {
+    if (check_common(g, D)) return -1;
+    IGCN_CHECK_ARG(G && dE, "null G/dE");
+    PropArgs a{};
+    a.g = *g; a.X = G; a.Y = dE; a.D = D; a.alpha = 1.f; a.tmpl = tmpl; a.row0 = row0;
+    if (fill_drop(a, drop)) return -1;
+    IGCN_CHECK_ARG(a.drop.mode != 2 || a.drop.tperm, "mode 2 backward needs tperm");
+    launch_drop<MODE_INMO_BWD>(a, as_stream(stream));
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_colsum_masked(const float *G, int64_t row_begin, int64_t row_end, int32_t D,
+                                  const igcn_dropout *drop, float *scratch, float *out, void *stream) {
+    IGCN_CHECK_ARG(G && scratch && out, "null pointer");
+    IGCN_CHECK_ARG(D > 0 && D <= 128 && !(D & 3), "embedding size unsupported");
+    IGCN_CHECK_ARG(row_end >= row_begin, "bad row range");
+    PropArgs a{};
+    if (fill_drop(a, drop)) return -1;
+    cudaStream_t st = as_stream(stream);
+    const int64_t n_blocks = (row_end - row_begin + 255) / 256;
+    if (n_blocks > 0) {
+        if (D <= 32) colsum_stage1<8><<<(unsigned)n_blocks, kThreads, 0, st>>>(G, row_begin, row_end, D, a.drop, a.thresh, scratch);
+        else if (D <= 64) colsum_stage1<16><<<(unsigned)n_blocks, kThreads, 0, st>>>(G, row_begin, row_end, D, a.drop, a.thresh, scratch);
+        else colsum_stage1<32><<<(unsigned)n_blocks, kThreads, 0, st>>>(G, row_begin, row_end, D, a.drop, a.thresh, scratch);
+    }
+    colsum_stage2<<<1, 128, 0, st>>>(scratch, n_blocks, D, out);
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}

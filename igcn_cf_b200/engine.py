@@ -1,0 +1,401 @@
+"""Host-side drivers of the sm_100a kernels: propagation forward/backward, the fused BPR training
+step and full-ranking evaluation.  Every arithmetic step is a call into libigcn_b200.so through
+igcn_cf_b200._lib; PyTorch only owns the buffers, the stream and (optionally) the CUDA graph.
+
+Reference call sites are cited on each method.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+BETA1, BETA2, ADAM_EPS = 0.9, 0.999, 1e-8      # torch.optim.Adam defaults (trainer.py:43-45)
+MAX_PLAN = 16384                                # igcn_bpr_plan: 3 * B <= 16384
+
+
+def _drop_struct(drop):
+    """drop: None | dict(mode, p, seed, seed_dev, edge_keep, self_keep, tperm) -> C struct pointer."""
+    if drop is None:
+        return None
+    s = _lib.DropoutStruct(int(drop.get('mode', 0)), float(drop.get('p', 0.)), int(drop.get('seed', 0)),
+                           ptr(drop.get('seed_dev')), ptr(drop.get('edge_keep')), ptr(drop.get('self_keep')),
+                           ptr(drop.get('tperm')))
+    return C.byref(s)
+
+
+class Propagator:
+    """L-layer propagation with the layer mean fused into the last SpMM, and its backward.
+
+    forward:  X_{l+1} = A X_l, rep = mean(X_0..X_L)           (model.py:96-106, 434-446)
+    backward: h_L = g', h_l = A h_{l+1} + g', dX_0 = h_0 with g' = d_rep / (L+1)  (A symmetric)
+    Intermediate layers live in persistent buffers that the backward pass reuses as ping-pong
+    space (the propagation is linear, no activation has to be saved)."""
+
+    def __init__(self, n_nodes, dim, n_layers, device):
+        if n_layers > _lib.MAX_ADD:
+            raise RuntimeError('n_layers > %d is not supported by the fused layer-mean epilogue' % _lib.MAX_ADD)
+        self.n, self.dim, self.n_layers = int(n_nodes), int(dim), int(n_layers)
+        self.device = torch.device(device)
+        mk = lambda: torch.empty((self.n, self.dim), dtype=torch.float32, device=self.device)
+        self.layers = [mk() for _ in range(max(2, self.n_layers - 1))]   # X_1.. / backward ping-pong
+        self.x0 = None          # allocated on demand by the INMO layer
+        self.rep = mk()
+        self._add_arrays = {}
+
+    def x0_buffer(self):
+        if self.x0 is None:
+            self.x0 = torch.empty((self.n, self.dim), dtype=torch.float32, device=self.device)
+        return self.x0
+
+    def _adds(self, tensors):
+        key = tuple(t.data_ptr() for t in tensors)
+        arr = self._add_arrays.get(key)
+        if arr is None:
+            arr = (C.c_void_p * max(1, len(key)))(*key)
+            self._add_arrays[key] = arr
+        return arr
+
+    def spmm(self, adj, x, y, adds=(), rowscale=None, alpha=1.0):
+        call('igcn_spmm', adj.csr.struct(self.dim), ptr(x), ptr(y), self.dim, self._adds(adds), len(adds),
+             ptr(rowscale), float(alpha), stream_ptr())
+
+    def forward(self, adj, x0, out=None):
+        """rep = mean_l A^l x0.  `out` defaults to the persistent rep buffer."""
+        L = self.n_layers
+        rep = self.rep if out is None else out
+        if L == 0:
+            rep.copy_(x0)
+            return rep
+        xs = [x0]
+        for l in range(1, L):
+            self.spmm(adj, xs[-1], self.layers[l - 1])
+            xs.append(self.layers[l - 1])
+        self.spmm(adj, xs[-1], rep, adds=xs, alpha=1.0 / (L + 1))
+        return rep
+
+    def backward(self, adj, gprime, out, rowscale=None, alpha=1.0):
+        """out = alpha * rowscale .* h_0, h from the Horner recurrence above; gprime = d_rep/(L+1)."""
+        L = self.n_layers
+        if L == 0:
+            if rowscale is None:
+                out.copy_(gprime)
+                if alpha != 1.0:
+                    out.mul_(alpha)
+            else:
+                torch.mul(gprime, rowscale[:, None] * alpha, out=out)
+            return out
+        h = gprime
+        for l in range(L - 1, 0, -1):
+            dst = self.layers[l % 2]
+            self.spmm(adj, h, dst, adds=(gprime,))
+            h = dst
+        self.spmm(adj, h, out, adds=(gprime,), rowscale=rowscale, alpha=alpha)
+        return out
+
+
+def inmo_forward(feat, emb, x0, drop, dim):
+    """X0 = F~ E with dropout fused (model.py:423-432 after model.py:435)."""
+    call('igcn_inmo_fwd', feat.csr.struct(dim), ptr(feat.tmpl), ptr(feat.rowscale), _drop_struct(drop), ptr(emb),
+         ptr(x0), dim, 0, feat.n_users, feat.glob_user, feat.glob_item, stream_ptr())
+
+
+def inmo_backward(feat, g_scaled, d_emb, drop, dim, scratch):
+    """dE = F~^T dX0 given g_scaled = rowscale/(1-p) .* dX0 (autograd backward of model.py:430)."""
+    n, u = feat.csr.n_rows, feat.n_users
+    call('igcn_inmo_bwd', feat.csr.struct(dim), ptr(feat.tmpl), _drop_struct(drop), ptr(g_scaled), ptr(d_emb), dim, 0,
+         stream_ptr())
+    d = _drop_struct(drop)
+    call('igcn_colsum_masked', ptr(g_scaled), 0, u, dim, d, ptr(scratch), ptr(d_emb[feat.glob_user]), stream_ptr())
+    call('igcn_colsum_masked', ptr(g_scaled), u, n, dim, d, ptr(scratch), ptr(d_emb[feat.glob_item]), stream_ptr())
+
+
+def colsum_scratch(n_rows, dim, device):
+    return torch.empty(((n_rows + 255) // 256 + 1, dim), dtype=torch.float32, device=device)
+
+
+# --------------------------------------------------------------------------- autograd bridges
+class LightGCNRep(torch.autograd.Function):
+    """get_rep for LightGCN as one autograd node (generic API path; model.py:96-106)."""
+
+    @staticmethod
+    def forward(ctx, emb, model):
+        prop = model._propagator()
+        rep = torch.empty_like(emb)
+        prop.forward(model.norm_adj, emb.detach().contiguous(), out=rep)
+        ctx.model = model
+        return rep
+
+    @staticmethod
+    def backward(ctx, g):
+        model = ctx.model
+        prop = model._propagator()
+        gprime = (g * (1.0 / (prop.n_layers + 1))).contiguous()
+        d_emb = torch.empty_like(gprime)
+        prop.backward(model.norm_adj, gprime, d_emb)
+        return d_emb, None
+
+
+class IGCNRep(torch.autograd.Function):
+    """get_rep for IGCN as one autograd node (model.py:434-446); drop is the mask description."""
+
+    @staticmethod
+    def forward(ctx, emb, model, drop):
+        prop = model._propagator()
+        feat = model.feat_mat
+        x0 = prop.x0_buffer()
+        inmo_forward(feat, emb.detach().contiguous(), x0, drop, prop.dim)
+        rep = torch.empty_like(x0)
+        prop.forward(model.norm_adj, x0, out=rep)
+        ctx.model, ctx.drop, ctx.emb_shape = model, drop, emb.shape
+        return rep
+
+    @staticmethod
+    def backward(ctx, g):
+        model, drop = ctx.model, ctx.drop
+        prop = model._propagator()
+        feat = model.feat_mat
+        gprime = (g * (1.0 / (prop.n_layers + 1))).contiguous()
+        g_scaled = prop.x0_buffer()
+        inv_keep = 1.0 if (drop is None or drop.get('mode', 0) == 0) else 1.0 / (1.0 - drop['p'])
+        prop.backward(model.norm_adj, gprime, g_scaled, rowscale=feat.rowscale, alpha=inv_keep)
+        d_emb = torch.zeros(ctx.emb_shape, dtype=torch.float32, device=g.device)
+        if drop is not None and drop.get('mode', 0) == 2 and drop.get('tperm') is None:
+            drop = dict(drop, tperm=feat.tperm())
+        inmo_backward(feat, g_scaled, d_emb, drop, prop.dim, colsum_scratch(prop.n, prop.dim, g.device))
+        return d_emb, None, None
+
+
+# --------------------------------------------------------------------------- fused training step
+class TrainStep:
+    """One BPR training step with no autograd tape (trainer.py:233-247 and 296-318).
+
+    sample (or take injected) triples -> plan -> propagate -> fused BPR forward -> loss on device
+    -> deterministic gradient rows -> propagate backward -> (INMO transpose) -> Adam.
+    With `use_graph=True` the whole step is captured once into a CUDA graph and replayed; step
+    counter, sampler stream, dropout seed and Adam bias corrections advance on the device."""
+
+    def __init__(self, model, opt, l2_reg, aux_reg=None, batch_size=2048, seed=0, use_graph=False):
+        self.model = model
+        self.opt = opt
+        self.is_igcn = hasattr(model, 'feat_mat')
+        self.lr, self.l2_reg, self.aux_reg = float(opt.param_groups[0]['lr']), float(l2_reg), aux_reg
+        self.B = int(batch_size)
+        if 3 * self.B > MAX_PLAN:
+            raise RuntimeError('batch_size %d too large for the single-CTA scatter plan (3*B <= %d)' % (self.B, MAX_PLAN))
+        self.seed = int(seed)
+        self.use_graph = bool(use_graph)
+        dev = model.embedding.weight.device
+        self.device = dev
+        D = model.embedding_size
+        self.D = D
+        i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)
+        f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        self.triples = torch.zeros((self.B, 3), dtype=torch.int64, device=dev)
+        self.order, self.seg_start = i32(3 * self.B), i32(3 * self.B + 1)
+        self.seg_row = torch.empty(3 * self.B, dtype=torch.int64, device=dev)
+        self.n_seg = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.sp, self.sig, self.l2 = f32(self.B), f32(self.B), f32(self.B)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.acc = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.state = opt.device_state(dev)                                # igcn_step_state
+        n = model.n_users + model.n_items
+        self.gprime = torch.zeros((n, D), dtype=torch.float32, device=dev)
+        self.d_emb = torch.zeros_like(model.embedding.weight.data)
+        self.emb_m, self.emb_v = opt.moments(model.embedding.weight)
+        if self.is_igcn:
+            self.a_triples = torch.zeros((self.B, 3), dtype=torch.int64, device=dev)
+            self.a_order, self.a_seg_start = i32(3 * self.B), i32(3 * self.B + 1)
+            self.a_seg_row = torch.empty(3 * self.B, dtype=torch.int64, device=dev)
+            self.a_n_seg = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.a_sp, self.a_sig = f32(self.B), f32(self.B)
+            self.d_w = torch.zeros_like(model.w.data)
+            self.dw_scratch = f32((self.B + 63) // 64, D)
+            self.w_m, self.w_v = opt.moments(model.w)
+            self.colsum_scratch = colsum_scratch(n, D, dev)
+        self._graphs = {}
+
+    # -- pieces
+    def _sample(self, B):
+        m = self.model
+        csr = m.norm_adj.csr
+        call('igcn_sample_triples', ptr(csr.rowptr), ptr(csr.col), m.n_users, m.n_users, m.n_items, B, self.seed,
+             0, ptr(self.state), ptr(self.triples), stream_ptr())
+        if self.is_igcn:
+            a = m.aux_csr()
+            call('igcn_sample_triples', ptr(a['rowptr']), ptr(a['col']), a['col_offset'], a['n_users'], a['n_items'], B,
+                 self.seed ^ 0x5bd1e995, 0, ptr(self.state), ptr(self.a_triples), stream_ptr())
+
+    def _body(self, B, sample, drop):
+        m, D, st = self.model, self.D, stream_ptr
+        prop = m._propagator()
+        L = prop.n_layers
+        emb = m.embedding.weight.data
+        call('igcn_step_tick', ptr(self.state), self.lr, BETA1, BETA2, st())
+        if sample:
+            self._sample(B)
+        call('igcn_bpr_plan', ptr(self.triples), B, m.n_users, ptr(self.order), ptr(self.seg_start), ptr(self.seg_row),
+             ptr(self.n_seg), st())
+        # forward
+        if self.is_igcn:
+            x0 = prop.x0_buffer()
+            inmo_forward(m.feat_mat, emb, x0, drop, D)
+            rep = prop.forward(m.norm_adj, x0)
+            l2_table = rep
+        else:
+            rep = prop.forward(m.norm_adj, emb)
+            l2_table = emb
+        call('igcn_bpr_fwd', ptr(rep), ptr(l2_table), None, ptr(self.triples), B, m.n_users, D, ptr(self.sp),
+             ptr(self.sig), ptr(self.l2), st())
+        if self.is_igcn:
+            t_u = m.feat_mat.t_users
+            call('igcn_bpr_plan', ptr(self.a_triples), B, t_u, ptr(self.a_order), ptr(self.a_seg_start),
+                 ptr(self.a_seg_row), ptr(self.a_n_seg), st())
+            call('igcn_bpr_fwd', ptr(emb), None, ptr(m.w.data), ptr(self.a_triples), B, t_u, D, ptr(self.a_sp),
+                 ptr(self.a_sig), None, st())
+            call('igcn_loss_finalize', ptr(self.sp), ptr(self.l2), ptr(self.a_sp), B, B, self.l2_reg, self.aux_reg,
+                 ptr(self.loss), ptr(self.acc), st())
+        else:
+            call('igcn_loss_finalize', ptr(self.sp), ptr(self.l2), None, B, 0, self.l2_reg, 0.0, ptr(self.loss),
+                 ptr(self.acc), st())
+        # backward
+        self.gprime.zero_()
+        call('igcn_bpr_bwd', ptr(rep), None, ptr(self.triples), B, m.n_users, D, ptr(self.sig), 1.0 / (L + 1),
+             self.l2_reg if self.is_igcn else 0.0, 1 if self.is_igcn else 0, ptr(self.order), ptr(self.seg_start),
+             ptr(self.seg_row), ptr(self.n_seg), ptr(self.gprime), 0, None, None, st())
+        if self.is_igcn:
+            feat = m.feat_mat
+            g_scaled = prop.x0_buffer()
+            inv_keep = 1.0 if (drop is None or drop.get('mode', 0) == 0) else 1.0 / (1.0 - drop['p'])
+            prop.backward(m.norm_adj, self.gprime, g_scaled, rowscale=feat.rowscale, alpha=inv_keep)
+            if feat.tmpl is not None:
+                self.d_emb.zero_()       # template rows without a node in this graph get no gradient
+            inmo_backward(feat, g_scaled, self.d_emb, drop, D, self.colsum_scratch)
+            self.d_w.zero_()
+            call('igcn_bpr_bwd', ptr(emb), ptr(m.w.data), ptr(self.a_triples), B, feat.t_users, D, ptr(self.a_sig),
+                 float(self.aux_reg), 0.0, 0, ptr(self.a_order), ptr(self.a_seg_start), ptr(self.a_seg_row),
+                 ptr(self.a_n_seg), ptr(self.d_emb), 1, ptr(self.d_w), ptr(self.dw_scratch), st())
+        else:
+            prop.backward(m.norm_adj, self.gprime, self.d_emb)
+            if self.l2_reg != 0.0:
+                call('igcn_l2_rows_bwd', ptr(emb), ptr(self.d_emb), D, 2.0 * self.l2_reg / B, ptr(self.seg_start),
+                     ptr(self.seg_row), ptr(self.n_seg), 3 * B, st())
+        # Adam
+        call('igcn_adam', ptr(emb), ptr(self.d_emb), ptr(self.emb_m), ptr(self.emb_v), emb.numel(), self.lr,
+             BETA1, BETA2, ADAM_EPS, 0, ptr(self.state), st())
+        if self.is_igcn:
+            w = m.w.data
+            call('igcn_adam', ptr(w), ptr(self.d_w), ptr(self.w_m), ptr(self.w_v), w.numel(), self.lr, BETA1,
+                 BETA2, ADAM_EPS, 0, ptr(self.state), st())
+
+    def _production_drop(self):
+        m = self.model
+        if not self.is_igcn or not m.training or m.dropout <= 0.0:
+            return None
+        return {'mode': 1, 'p': m.dropout, 'seed': self.seed * 0x9e3779b97f4a7c15 % (1 << 64), 'seed_dev': self.state}
+
+    # -- public
+    def run(self, triples=None, aux_triples=None, drop='auto', batch=None):
+        """One step.  triples/aux_triples: injected int64 [b,3] device tensors (parity mode) or None
+        to sample `batch` (default batch_size) triples on the device; drop: 'auto' (hash dropout
+        when the model is in training mode) or an explicit dict (see _drop_struct)."""
+        B = self.B if batch is None else int(batch)
+        if B > self.B:
+            raise RuntimeError('batch %d exceeds the step\'s capacity %d' % (B, self.B))
+        sample = triples is None
+        if not sample:
+            B = int(triples.shape[0])
+            self.triples[:B].copy_(triples)
+            if self.is_igcn:
+                self.a_triples[:B].copy_(aux_triples)
+        d = self._production_drop() if isinstance(drop, str) else drop
+        if d is not None and d.get('mode', 0) == 2 and d.get('tperm') is None:
+            d = dict(d, tperm=self.model.feat_mat.tperm())
+        graphable = self.use_graph and (d is None or d.get('mode', 0) != 2)
+        if not graphable:
+            self._body(B, sample, d)
+        else:
+            key = (B, sample, None if d is None else (d['mode'], d['p'], d['seed']), self.model.graph_version())
+            g = self._graphs.get(key)
+            if g is None:
+                if len(self._graphs) >= 8:
+                    self._graphs.clear()
+                g = self._capture(B, sample, d)
+                self._graphs[key] = g
+            g.replay()
+        self.opt.t += 1
+        self.model._bump()
+        return self.loss
+
+    def _capture(self, B, sample, d):
+        torch.cuda.synchronize()
+        state_backup = self.state.clone()
+        snap = self._snapshot()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._body(B, sample, d)       # warm-up outside capture (lazy allocations, func attributes)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._restore(snap, state_backup)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._body(B, sample, d)
+        return g
+
+    def _snapshot(self):
+        ts = [self.model.embedding.weight.data, self.emb_m, self.emb_v, self.acc]
+        if self.is_igcn:
+            ts += [self.model.w.data, self.w_m, self.w_v]
+        return [(t, t.clone()) for t in ts]
+
+    def _restore(self, snap, state_backup):
+        for t, c in snap:
+            t.copy_(c)
+        self.state.copy_(state_backup)
+
+    def reset_meter(self):
+        self.acc.zero_()
+
+    def meter_avg(self):
+        """losses.avg of the reference's AverageMeter (utils.py:126-135); one D2H read per epoch."""
+        s, c = self.acc.tolist()
+        return s / c if c else 0.0
+
+
+# --------------------------------------------------------------------------- evaluation
+def lists_to_csr(lists, device, sort=True):
+    """list-of-lists -> (ptr int64 [n+1], items int32 [nnz]) on `device`, items ascending per row."""
+    lens = np.fromiter((len(x) for x in lists), dtype=np.int64, count=len(lists))
+    ptr_ = np.zeros(len(lists) + 1, dtype=np.int64)
+    np.cumsum(lens, out=ptr_[1:])
+    flat = np.fromiter((i for x in lists for i in x), dtype=np.int64, count=int(ptr_[-1]))
+    if sort and len(flat):
+        rows = np.repeat(np.arange(len(lists), dtype=np.int64), lens)
+        order = np.lexsort((flat, rows))
+        flat = flat[order]
+    return (torch.from_numpy(ptr_).to(device), torch.from_numpy(flat.astype(np.int32)).to(device), lens)
+
+
+def score_topk(rep, user_ids, n_users, n_items, k, mask=None, item_lo=0, item_hi=None, banned_bits=None):
+    """Fused scoring + mask + top-k for `user_ids` (model.py:118-123 + trainer.py:149-164).
+    Returns (items int32 [n, k], scores fp32 [n, k])."""
+    _lib.require_cuda(rep, torch.float32, 'rep')
+    n = int(user_ids.shape[0])
+    out_i = torch.empty((n, k), dtype=torch.int32, device=rep.device)
+    out_s = torch.empty((n, k), dtype=torch.float32, device=rep.device)
+    mptr, mitems = (None, None) if mask is None else (mask[0], mask[1])
+    call('igcn_score_topk_exact', ptr(rep), ptr(user_ids), n, n_users, n_items, rep.shape[1], ptr(mptr), ptr(mitems),
+         int(item_lo), int(n_items if item_hi is None else item_hi), ptr(banned_bits), int(k), ptr(out_i), ptr(out_s),
+         stream_ptr())
+    return out_i, out_s
+
+
+def hit_matrix(rec, eval_csr):
+    """hit[u, j] = rec[u, j] in eval_data[u] (trainer.py:111-115) as fp32 on the device."""
+    n, k = rec.shape
+    hit = torch.empty((n, k), dtype=torch.float32, device=rec.device)
+    call('igcn_hits', ptr(rec), n, k, ptr(eval_csr[0]), ptr(eval_csr[1]), ptr(hit), stream_ptr())
+    return hit

@@ -1,0 +1,261 @@
+"""Device-resident graph structures behind `norm_adj` and `feat_mat`.
+
+`NormAdj` is what `LightGCN.generate_graph` returns here and `TemplateFeat` what
+`IGCN.generate_feat` returns.  Both keep the reference's observable surface (`shape`,
+`indices()`, `values()`, `_nnz()`, `to_sparse_coo()`; reference model.py:85-94, 386-421) but store
+one CSR on the GPU (int64 rowptr, int32 col, fp32 val) plus the long-row chunk plan the kernels
+use (include/igcn_b200.h, `igcn_csr`).  They are built ONCE per generate_* call, not once per
+`get_rep` as the reference's `dgl.graph(...)` is (model.py:99-100, 439-440).
+
+HBM layout: rowptr[N+1] int64 | col[nnz] int32 | val[nnz] fp32 | chunk plan (5 small int arrays)
+| partial[n_chunks, D] fp32 | counters[n_chunks] int32.  The INMO layer reuses rowptr/col (its
+pattern is the adjacency pattern filtered by template membership) and adds
+tmpl[N] int32 (only when some node is not a template) and rowscale[N] fp32.
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _lib
+
+LONG_THRESHOLD = 512     # rows with more non-zeros than this are split ...
+CHUNK = 256              # ... into chunks of this many non-zeros
+
+
+def train_pairs_of(dataset):
+    """[E, 2] int64 array of (user, item) train interactions of a reference-style dataset."""
+    pairs = getattr(dataset, 'train_pairs', None)
+    if pairs is None:
+        pairs = np.asarray(dataset.train_array, dtype=np.int64).reshape(-1, 2)
+    return pairs
+
+
+def build_adjacency(n_users, n_items, pairs):
+    """scipy CSR of the symmetric bipartite adjacency, duplicates summed (utils.py:41-49)."""
+    n = n_users + n_items
+    u, i = pairs[:, 0], pairs[:, 1] + n_users
+    rows = np.concatenate([u, i])
+    cols = np.concatenate([i, u])
+    adj = sp.csr_matrix((np.ones(rows.shape[0], dtype=np.float32), (rows, cols)), shape=(n, n))
+    adj.sum_duplicates()
+    adj.sort_indices()
+    return adj
+
+
+def chunk_plan(rowptr, threshold=LONG_THRESHOLD, chunk=CHUNK):
+    """Split rows longer than `threshold` into chunks of `chunk` non-zeros (host, numpy)."""
+    deg = np.diff(rowptr)
+    long_rows = np.nonzero(deg > threshold)[0]
+    n_ch = (deg[long_rows] + chunk - 1) // chunk
+    total = int(n_ch.sum())
+    first = np.zeros(len(long_rows) + 1, dtype=np.int64)
+    np.cumsum(n_ch, out=first[1:])
+    chunk_row = np.repeat(long_rows, n_ch).astype(np.int32)
+    chunk_first = np.repeat(first[:-1], n_ch).astype(np.int32)
+    chunk_count = np.repeat(n_ch, n_ch).astype(np.int32)
+    k = np.arange(total, dtype=np.int64) - chunk_first
+    chunk_begin = rowptr[chunk_row] + k * chunk
+    chunk_len = np.minimum(chunk, rowptr[chunk_row.astype(np.int64) + 1] - chunk_begin).astype(np.int32)
+    return chunk_row, chunk_begin.astype(np.int64), chunk_len, chunk_first, chunk_count
+
+
+class CsrDevice:
+    """One CSR block on the GPU + chunk plan + per-D scratch; produces the `igcn_csr` struct."""
+
+    def __init__(self, rowptr, col, val, n_cols, device, threshold=LONG_THRESHOLD, chunk=CHUNK):
+        self.device = torch.device(device)   # kernels need CUDA; a CPU device only supports the views
+        self.n_rows = int(len(rowptr) - 1)
+        self.n_cols = int(n_cols)
+        self.nnz = int(rowptr[-1])
+        self.rowptr_host = np.ascontiguousarray(rowptr, dtype=np.int64)
+        self.col_host = np.ascontiguousarray(col, dtype=np.int32)
+        self.rowptr = torch.from_numpy(self.rowptr_host).to(self.device)
+        self.col = torch.from_numpy(self.col_host).to(self.device)
+        self.val = None if val is None else torch.from_numpy(np.ascontiguousarray(val, dtype=np.float32)).to(self.device)
+        self.threshold = int(threshold)
+        plan = chunk_plan(self.rowptr_host, threshold, chunk)
+        self.n_chunks = int(len(plan[0]))
+        self._plan = [torch.from_numpy(np.ascontiguousarray(a)).to(self.device) for a in plan]
+        self.counters = torch.zeros(max(1, self.n_chunks), dtype=torch.int32, device=self.device)
+        self._partial = {}
+        self._structs = {}
+
+    def with_values(self, val):
+        """Same pattern/plan, different (or no) value array; shares index memory."""
+        other = object.__new__(CsrDevice)
+        other.__dict__.update(self.__dict__)
+        other.val = val
+        other.counters = torch.zeros_like(self.counters)
+        other._partial, other._structs = {}, {}
+        return other
+
+    def struct(self, D):
+        s = self._structs.get(D)
+        if s is None:
+            partial = torch.empty((max(1, self.n_chunks), D), dtype=torch.float32, device=self.device)
+            self._partial[D] = partial
+            cr, cb, cl, cf, cc = self._plan
+            s = _lib.CsrStruct(self.n_rows, self.n_cols, self.nnz, self.rowptr.data_ptr(), self.col.data_ptr(),
+                               None if self.val is None else self.val.data_ptr(), self.threshold, self.n_chunks,
+                               cr.data_ptr(), cb.data_ptr(), cl.data_ptr(), cf.data_ptr(), cc.data_ptr(),
+                               partial.data_ptr(), self.counters.data_ptr())
+            self._structs[D] = s
+        return C.byref(s)
+
+
+class _SparseView:
+    """Reference-compatible read-only view (`shape`, `indices()`, `values()`, `_nnz()`)."""
+    shape = None
+
+    def _coo(self):
+        raise NotImplementedError
+
+    def indices(self):
+        return self._coo()[0]
+
+    def values(self):
+        return self._coo()[1]
+
+    def _nnz(self):
+        return int(self._coo()[0].shape[1])
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def to_sparse_coo(self):
+        idx, val = self._coo()
+        return torch.sparse_coo_tensor(idx, val, self.shape, is_coalesced=True)
+
+
+class NormAdj(_SparseView):
+    """D^-1/2 A D^-1/2 (deg clamped to >= 1) as a device CSR; reference model.py:85-94."""
+
+    def __init__(self, n_users, n_items, pairs, device):
+        adj = build_adjacency(n_users, n_items, pairs)
+        deg = np.maximum(1., np.asarray(adj.sum(axis=1)).squeeze()).astype(np.float32)
+        d_inv = np.power(deg, np.float32(-0.5)).astype(np.float32)
+        rows = np.repeat(np.arange(adj.shape[0], dtype=np.int64), np.diff(adj.indptr))
+        # same rounding sequence as d_mat.dot(adj).dot(d_mat) in fp32: (d_r * a) * d_c
+        val = (d_inv[rows] * adj.data.astype(np.float32)) * d_inv[adj.indices]
+        self.n_users, self.n_items = int(n_users), int(n_items)
+        self.shape = torch.Size([adj.shape[0], adj.shape[1]])
+        self.multiplicity_host = adj.data.astype(np.float32)
+        self.csr = CsrDevice(adj.indptr.astype(np.int64), adj.indices.astype(np.int32), val, adj.shape[0], device)
+        self.device = self.csr.device
+        self._coo_cache = None
+
+    def _coo(self):
+        if self._coo_cache is None:
+            rows = torch.repeat_interleave(torch.arange(self.csr.n_rows, device=self.device),
+                                           self.csr.rowptr[1:] - self.csr.rowptr[:-1])
+            self._coo_cache = (torch.stack([rows, self.csr.col.long()]), self.csr.val)
+        return self._coo_cache
+
+
+class TemplateFeat(_SparseView):
+    """The INMO template incidence matrix `feat_mat` (reference model.py:386-421, 374-377).
+
+    Row r holds one entry per neighbour c of r whose node is a template (column tmpl[c]) plus one
+    global-template entry (column T_u+T_i for users, T_u+T_i+1 for items); every entry of row r
+    has the value row_sum[r] ** ((alpha-1)/2 - 1/2).  Stored as: the adjacency pattern CSR (shared
+    layout with NormAdj), tmpl[N] (None when every node is a template and tmpl is the identity),
+    row_sum[N], rowscale[N]."""
+
+    def __init__(self, n_users, n_items, pairs, user_tmpl, item_tmpl, t_users, t_items, device):
+        adj = build_adjacency(n_users, n_items, pairs)
+        n = adj.shape[0]
+        self.n_users, self.n_items = int(n_users), int(n_items)
+        self.t_users, self.t_items = int(t_users), int(t_items)
+        self.shape = torch.Size([n, self.t_users + self.t_items + 2])
+        tmpl = np.concatenate([user_tmpl, np.where(item_tmpl >= 0, item_tmpl + self.t_users, -1)]).astype(np.int32)
+        identity = (self.t_users == n_users and self.t_items == n_items
+                    and np.array_equal(tmpl, np.arange(n, dtype=np.int32)))
+        self.tmpl_host = tmpl
+        # row_sum counts duplicates like feat.sum(axis=1) does (model.py:419); +1 = global template
+        member = (tmpl[adj.indices] >= 0) * adj.data.astype(np.float64)
+        rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(adj.indptr))
+        row_sum = np.bincount(rows, weights=member, minlength=n).astype(np.float32) + np.float32(1.)
+        self.csr = CsrDevice(adj.indptr.astype(np.int64), adj.indices.astype(np.int32), None, n, device)
+        self.device = self.csr.device
+        self.tmpl = None if identity else torch.from_numpy(tmpl).to(self.device)
+        self.row_sum = torch.from_numpy(row_sum.astype(np.float32)).to(self.device)
+        self.rowscale = torch.ones(n, dtype=torch.float32, device=self.device)
+        self.glob_user = self.t_users + self.t_items
+        self.glob_item = self.t_users + self.t_items + 1
+        self._order = None
+        self._tperm = None
+
+    def set_alpha(self, alpha, row_sum=None):
+        """update_feat_mat (model.py:374-377): value of every entry of row r.  Written in place so
+        captured CUDA graphs keep pointing at live memory across the per-epoch anneal."""
+        if row_sum is not None:
+            self.row_sum = row_sum
+        new = torch.pow(self.row_sum, (alpha - 1.) / 2. - 0.5)
+        if new.shape == self.rowscale.shape and new.device == self.rowscale.device:
+            self.rowscale.copy_(new)
+        else:
+            self.rowscale = new.contiguous()
+
+    # ---- reference-order bookkeeping (compat views and replay of recorded dropout draws)
+    def coo_order(self):
+        """Positions of my entries inside the reference's coalesced `feat_mat`.
+
+        Returns (edge_pos[nnz_adj] int64, self_pos[N] int64, idx[2, nnz_feat]): edge_pos[e] is the
+        index, in the reference's (row, column)-sorted nnz order, of adjacency edge e (or -1 when
+        its column node is not a template); self_pos[r] is the index of row r's global entry."""
+        if self._order is None:
+            rp, col, tm = self.csr.rowptr_host, self.csr.col_host, self.tmpl_host
+            n = self.csr.n_rows
+            rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
+            fcol = tm[col].astype(np.int64)
+            keep = fcol >= 0
+            e_rows, e_cols = rows[keep], fcol[keep]
+            s_rows = np.arange(n, dtype=np.int64)
+            s_cols = np.where(s_rows < self.n_users, self.glob_user, self.glob_item).astype(np.int64)
+            all_rows = np.concatenate([e_rows, s_rows])
+            all_cols = np.concatenate([e_cols, s_cols])
+            order = np.lexsort((all_cols, all_rows))
+            pos = np.empty(len(order), dtype=np.int64)
+            pos[order] = np.arange(len(order), dtype=np.int64)
+            edge_pos = np.full(len(col), -1, dtype=np.int64)
+            edge_pos[keep] = pos[:len(e_rows)]
+            self_pos = pos[len(e_rows):]
+            idx = np.stack([all_rows[order], all_cols[order]])
+            self._order = (edge_pos, self_pos, idx)
+        return self._order
+
+    def _coo(self):
+        edge_pos, self_pos, idx = self.coo_order()
+        idx_t = torch.from_numpy(idx).to(self.device)
+        return idx_t, self.rowscale[idx_t[0]]
+
+    def keep_bits(self, keep_ref):
+        """Pack a keep vector given in the reference's nnz order into (edge_keep, self_keep) bit
+        arrays in CSR order -- the `mode 2` dropout of include/igcn_b200.h."""
+        keep_ref = np.asarray(keep_ref).astype(bool)
+        edge_pos, self_pos, _ = self.coo_order()
+        ek = np.zeros(len(edge_pos), dtype=bool)
+        ok = edge_pos >= 0
+        ek[ok] = keep_ref[edge_pos[ok]]
+        sk = keep_ref[self_pos]
+        return _pack_bits(ek, self.device), _pack_bits(sk, self.device)
+
+    def tperm(self):
+        """tperm[e] = CSR position of the reverse edge (for the mode-2 backward pass)."""
+        if self._tperm is None:
+            rp, col = self.csr.rowptr_host, self.csr.col_host.astype(np.int64)
+            n = self.csr.n_rows
+            rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
+            fwd = rows * n + col        # ascending (CSR order, sorted columns)
+            self._tperm = torch.from_numpy(np.searchsorted(fwd, col * n + rows).astype(np.int64)).to(self.device)
+        return self._tperm
+
+
+def _pack_bits(flags, device):
+    n = len(flags)
+    padded = np.zeros((n + 31) // 32 * 32 + 32, dtype=np.uint8)
+    padded[:n] = flags
+    words = np.packbits(padded.reshape(-1, 32)[:, ::-1], axis=1).view('>u4').astype(np.uint32).ravel()
+    return torch.from_numpy(words.view(np.int32).copy()).to(device)

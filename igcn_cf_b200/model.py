@@ -1,0 +1,319 @@
+"""Drop-in model layer: `LightGCN` and `IGCN` (INMO-LightGCN) with the reference's public surface
+(reference model.py:16-49, 75-123, 354-466) on top of the sm_100a kernels.
+
+What is the same: class names, constructor configs, attribute names (`embedding`, `norm_adj`,
+`feat_mat`, `row_sum`, `user_map`, `item_map`, `alpha`, `w`, ...), method names and return values,
+the parameter-initialisation order (so a given torch seed yields the same initial weights), the
+checkpoint format (including the 'sate_dict' key of model.py:455) and the external mutation
+sequence of run/dropui/igcn_dropui.py:28-32.
+
+What differs: `norm_adj` / `feat_mat` are device CSR objects (igcn_cf_b200.graph) built once per
+generate_* call; `get_rep` is a single autograd node backed by libigcn_b200.so; in eval mode the
+representation is cached until a parameter or graph changes (the reference recomputes the full
+propagation for every 512-user batch, model.py:119); there is no CPU path.
+"""
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+import torch.nn as nn
+from torch.nn.init import normal_
+
+from . import engine, graph
+from ._lib import require_cuda
+
+
+def get_model(config, dataset):
+    """Name-dispatched factory (model.py:16-21)."""
+    config = config.copy()
+    config['dataset'] = dataset
+    cls = getattr(sys.modules[__name__], config['name'])
+    return cls(config)
+
+
+def _device_of(cfg):
+    dev = torch.device(cfg['device'])
+    if dev.type != 'cuda':
+        raise RuntimeError('igcn_cf_b200 models run on CUDA devices only (got %s): there is no CPU fallback' % dev)
+    return dev
+
+
+class BasicModel(nn.Module):
+    """model.py:31-49."""
+
+    def __init__(self, model_config):
+        super().__init__()
+        print(model_config)
+        self.config = model_config
+        self.name = model_config['name']
+        self.device = _device_of(model_config)
+        self.n_users = model_config['dataset'].n_users
+        self.n_items = model_config['dataset'].n_items
+        self.trainable = True
+
+    def predict(self, users):
+        raise NotImplementedError
+
+    def save(self, path):
+        torch.save(self.state_dict(), path)
+
+    def load(self, path):
+        self.load_state_dict(torch.load(path, map_location=self.device))
+
+
+class _GraphModel(BasicModel):
+    """Machinery shared by LightGCN and IGCN: propagator buffers, eval-mode cache, predict."""
+    _prop = None
+    _rep_cache = None
+    _param_epoch = 0
+
+    def _bump(self):
+        """Tell the eval-mode cache that parameters were changed behind autograd's back."""
+        self._param_epoch += 1
+
+    def graph_version(self):
+        return (id(self.norm_adj), id(getattr(self, 'feat_mat', None)), self.n_users, self.n_items)
+
+    def _propagator(self):
+        n = self.n_users + self.n_items
+        p = self._prop
+        if p is None or (p.n, p.dim, p.n_layers) != (n, self.embedding_size, self.n_layers):
+            p = engine.Propagator(n, self.embedding_size, self.n_layers, self.device)
+            self._prop = p
+        return p
+
+    def _cache_key(self):
+        w = self.embedding.weight
+        return (self.graph_version(), id(w), w._version, self._param_epoch, getattr(self, 'alpha', None))
+
+    def _check_graph(self):
+        n = self.n_users + self.n_items
+        if self.norm_adj.shape[0] != n:
+            raise RuntimeError('norm_adj has %d rows but the model has %d nodes; regenerate the graph'
+                               % (self.norm_adj.shape[0], n))
+
+    def _cached_rep(self, compute):
+        """Eval mode: the representation is a pure function of parameters and graph (model.py:264-265
+        makes dropout the identity), so compute it once."""
+        if self.training or torch.is_grad_enabled() and self.embedding.weight.requires_grad:
+            return compute()
+        key = self._cache_key()
+        if self._rep_cache is None or self._rep_cache[0] != key:
+            self._rep_cache = (key, compute())
+        return self._rep_cache[1]
+
+    def load(self, path):
+        super().load(path)
+        self._bump()
+
+    def predict(self, users):
+        """LightGCN.predict (model.py:118-123); the trainer's eval() does not come through here, it
+        uses the fused score + mask + top-k kernel on the cached representation."""
+        rep = self.get_rep()
+        users_r = rep[users, :]
+        all_items_r = rep[self.n_users:, :]
+        return torch.mm(users_r, all_items_r.t())
+
+
+class LightGCN(_GraphModel):
+    """model.py:75-123."""
+
+    def __init__(self, model_config):
+        super().__init__(model_config)
+        self.embedding_size = model_config['embedding_size']
+        self.n_layers = model_config['n_layers']
+        self.embedding = nn.Embedding(self.n_users + self.n_items, self.embedding_size)
+        self.norm_adj = self.generate_graph(model_config['dataset'])
+        normal_(self.embedding.weight, std=0.1)
+        self.to(device=self.device)
+
+    def generate_graph(self, dataset):
+        """D^-1/2 A D^-1/2 as a device CSR (model.py:85-94)."""
+        return graph.NormAdj(dataset.n_users, dataset.n_items, graph.train_pairs_of(dataset), self.device)
+
+    def get_rep(self):
+        self._check_graph()
+        require_cuda(self.embedding.weight, torch.float32, 'embedding.weight')
+        return self._cached_rep(lambda: engine.LightGCNRep.apply(self.embedding.weight, self))
+
+    def bpr_forward(self, users, pos_items, neg_items):
+        """model.py:108-116: the L2 term is over RAW embedding rows."""
+        rep = self.get_rep()
+        users_e = self.embedding(users)
+        pos_e, neg_e = self.embedding(self.n_users + pos_items), self.embedding(self.n_users + neg_items)
+        l2_norm_sq = (users_e ** 2).sum(dim=1) + (pos_e ** 2).sum(dim=1) + (neg_e ** 2).sum(dim=1)
+        return rep[users, :], rep[self.n_users + pos_items, :], rep[self.n_users + neg_items, :], l2_norm_sq
+
+
+def graph_rank_nodes(dataset, ranking_metric):
+    """Template ("core") node ranking for feature_ratio < 1 (utils.py:94-123).  Host-side, one-off."""
+    adj = graph.build_adjacency(dataset.n_users, dataset.n_items, graph.train_pairs_of(dataset))
+    n_u = dataset.n_users
+    if ranking_metric == 'degree':
+        deg = np.asarray(adj.sum(axis=1)).squeeze()
+        user_metrics, item_metrics = deg[:n_u], deg[n_u:]
+    elif ranking_metric in ('greedy', 'sort'):
+        from sklearn.preprocessing import normalize
+        walk = normalize(adj, axis=1, norm='l1')
+        user_metrics = np.asarray(walk[:, :n_u].sum(axis=0)).squeeze()
+        item_metrics = np.asarray(walk[:, n_u:].sum(axis=0)).squeeze()
+    elif ranking_metric == 'page_rank':
+        import networkx as nx
+        g = nx.Graph()
+        g.add_edges_from(np.array(adj.nonzero()).T)
+        pr = nx.pagerank(g)
+        pr = np.array([pr[i] for i in range(adj.shape[0])])
+        user_metrics, item_metrics = pr[:n_u], pr[n_u:]
+    else:
+        return None
+    return np.argsort(user_metrics)[::-1].copy(), np.argsort(item_metrics)[::-1].copy()
+
+
+class IGCN(_GraphModel):
+    """INMO-LightGCN (model.py:354-466)."""
+
+    def __init__(self, model_config):
+        super().__init__(model_config)
+        self.embedding_size = model_config['embedding_size']
+        self.n_layers = model_config['n_layers']
+        self.dropout = model_config['dropout']
+        self.feature_ratio = model_config['feature_ratio']
+        self.norm_adj = self.generate_graph(model_config['dataset'])
+        self.alpha = 1.
+        self.delta = model_config.get('delta', 0.99)
+        self.feat_mat, self.user_map, self.item_map, self.row_sum = \
+            self.generate_feat(model_config['dataset'], ranking_metric=model_config.get('ranking_metric', 'sort'))
+        self.update_feat_mat()
+
+        self.embedding = nn.Embedding(self.feat_mat.shape[1], self.embedding_size)
+        self.w = nn.Parameter(torch.ones([self.embedding_size], dtype=torch.float32, device=self.device))
+        normal_(self.embedding.weight, std=0.1)
+        self.to(device=self.device)
+        self._drop_calls = 0
+        self.drop_seed = int(model_config.get('dropout_seed', 0))
+        self.injected_keep = None      # tests: keep vector in the reference's nnz order for the next get_rep
+        self._aux = None
+
+    # ---- graph / template construction
+    def generate_graph(self, dataset):
+        return LightGCN.generate_graph(self, dataset)
+
+    def _maps_to_arrays(self, user_map, item_map):
+        ut = np.full(self.n_users, -1, dtype=np.int64)
+        it = np.full(self.n_items, -1, dtype=np.int64)
+        for arr, mp in ((ut, user_map), (it, item_map)):
+            if len(mp):
+                keys = np.fromiter(mp.keys(), dtype=np.int64, count=len(mp))
+                vals = np.fromiter(mp.values(), dtype=np.int64, count=len(mp))
+                ok = keys < len(arr)
+                arr[keys[ok]] = vals[ok]
+        return ut, it
+
+    def generate_feat(self, dataset, is_updating=False, ranking_metric=None):
+        """Template incidence structure (model.py:386-421).  Returns (feat, user_map, item_map,
+        row_sum) like the reference; `feat` is a graph.TemplateFeat."""
+        if not is_updating:
+            if self.feature_ratio < 1.:
+                ranked_users, ranked_items = graph_rank_nodes(dataset, ranking_metric)
+                core_users = ranked_users[:int(self.n_users * self.feature_ratio)]
+                core_items = ranked_items[:int(self.n_items * self.feature_ratio)]
+            else:
+                core_users = np.arange(self.n_users, dtype=np.int64)
+                core_items = np.arange(self.n_items, dtype=np.int64)
+            user_map = {int(u): t for t, u in enumerate(core_users.tolist())}
+            item_map = {int(i): t for t, i in enumerate(core_items.tolist())}
+        else:
+            user_map, item_map = self.user_map, self.item_map
+        ut, it = self._maps_to_arrays(user_map, item_map)
+        feat = graph.TemplateFeat(self.n_users, self.n_items, graph.train_pairs_of(dataset), ut, it,
+                                  len(user_map), len(item_map), self.device)
+        self._aux = None
+        return feat, user_map, item_map, feat.row_sum
+
+    def update_feat_mat(self):
+        """Entries of row r become row_sum[r] ** ((alpha-1)/2 - 1/2) (model.py:374-377)."""
+        self.feat_mat.set_alpha(self.alpha, self.row_sum)
+
+    def feat_mat_anneal(self):
+        """model.py:379-381."""
+        self.alpha *= self.delta
+        self.update_feat_mat()
+
+    def aux_csr(self):
+        """User-by-item train CSR in TEMPLATE id space for the auxiliary sampler (dataset.py:258-273)."""
+        if self._aux is None:
+            feat, adj = self.feat_mat, self.norm_adj.csr
+            if feat.tmpl is None:
+                self._aux = {'rowptr': adj.rowptr, 'col': adj.col, 'col_offset': self.n_users,
+                             'n_users': self.n_users, 'n_items': self.n_items}
+            else:
+                pairs = graph.train_pairs_of(self.config['dataset'])
+                ut, it = self._maps_to_arrays(self.user_map, self.item_map)
+                tu, ti = ut[pairs[:, 0]], it[pairs[:, 1]]
+                ok = (tu >= 0) & (ti >= 0)
+                m = sp.csr_matrix((np.ones(int(ok.sum()), dtype=np.float32), (tu[ok], ti[ok])),
+                                  shape=(feat.t_users, feat.t_items))
+                m.sum_duplicates()
+                m.sort_indices()
+                self._aux = {'rowptr': torch.from_numpy(m.indptr.astype(np.int64)).to(self.device),
+                             'col': torch.from_numpy(m.indices.astype(np.int32)).to(self.device),
+                             'col_offset': 0, 'n_users': feat.t_users, 'n_items': feat.t_items}
+        return self._aux
+
+    # ---- forward
+    def _next_drop(self):
+        if not self.training:
+            return None                                  # model.py:264-265
+        feat = self.feat_mat
+        if self.injected_keep is not None:
+            ek, sk = feat.keep_bits(self.injected_keep)
+            self.injected_keep = None
+            return {'mode': 2, 'p': self.dropout, 'edge_keep': ek, 'self_keep': sk, 'tperm': feat.tperm()}
+        if self.dropout <= 0.:
+            return None
+        self._drop_calls += 1
+        seed = (self.drop_seed * 0x9e3779b97f4a7c15 + self._drop_calls * 0xd1342543de82ef95) % (1 << 64)
+        return {'mode': 1, 'p': self.dropout, 'seed': seed}
+
+    def inductive_rep_layer(self, feat_mat):
+        """feat_mat @ embedding.weight (model.py:423-432); differentiable through get_rep only."""
+        prop = self._propagator()
+        x0 = torch.empty((feat_mat.shape[0], self.embedding_size), dtype=torch.float32, device=self.device)
+        engine.inmo_forward(feat_mat, self.embedding.weight.detach().contiguous(), x0, None, prop.dim)
+        return x0
+
+    def get_rep(self):
+        """model.py:434-446."""
+        self._check_graph()
+        feat = self.feat_mat
+        if feat.shape[0] != self.n_users + self.n_items or feat.shape[1] != self.embedding.weight.shape[0]:
+            raise RuntimeError('feat_mat %s does not match nodes=%d / templates=%d'
+                               % (tuple(feat.shape), self.n_users + self.n_items, self.embedding.weight.shape[0]))
+        require_cuda(self.embedding.weight, torch.float32, 'embedding.weight')
+        drop = self._next_drop()
+        return self._cached_rep(lambda: engine.IGCNRep.apply(self.embedding.weight, self, drop))
+
+    def bpr_forward(self, users, pos_items, neg_items):
+        """NGCF.bpr_forward (model.py:293-299): the L2 term is over PROPAGATED rows."""
+        rep = self.get_rep()
+        users_r = rep[users, :]
+        pos_r, neg_r = rep[self.n_users + pos_items, :], rep[self.n_users + neg_items, :]
+        l2_norm_sq = (users_r ** 2).sum(dim=1) + (pos_r ** 2).sum(dim=1) + (neg_r ** 2).sum(dim=1)
+        return users_r, pos_r, neg_r, l2_norm_sq
+
+    # ---- checkpoint (model.py:454-466; key spelling kept for file compatibility)
+    def save(self, path):
+        params = {'sate_dict': self.state_dict(), 'user_map': self.user_map,
+                  'item_map': self.item_map, 'alpha': self.alpha}
+        torch.save(params, path)
+
+    def load(self, path):
+        params = torch.load(path, map_location=self.device, weights_only=False)
+        self.load_state_dict(params['sate_dict'])
+        self.user_map = params['user_map']
+        self.item_map = params['item_map']
+        self.alpha = params['alpha']
+        self.feat_mat, _, _, self.row_sum = self.generate_feat(self.config['dataset'], is_updating=True)
+        self.update_feat_mat()
+        self._bump()

@@ -1,0 +1,375 @@
+"""Drop-in trainer layer: `BasicTrainer`, `BPRTrainer`, `IGCNTrainer` with the reference's public
+surface (reference trainer.py:14-219, 222-248, 281-320).
+
+Same: class names and config keys, `train / train_one_epoch / eval / inductive_eval /
+calculate_metrics / record / initialize_optimizer`, the returned result string and metric dict,
+checkpoint naming and early stopping.
+
+Different (B200-native): `train_one_epoch` drives igcn_cf_b200.engine.TrainStep -- sampler,
+propagation, fused BPR loss, deterministic gradient, backward propagation and Adam are sm_100a
+kernels, optionally replayed as one CUDA graph, and the running loss stays on the device until the
+epoch ends (the reference syncs on loss.item() every step, trainer.py:247/318).  `eval` computes the
+representation once and runs the fused score + mask + top-k kernel over all users (the reference
+re-propagates per 512-user batch and round-trips an [512, n_items] score matrix, trainer.py:145-164).
+
+Trainer config extras (all optional): 'sampler': 'device' (default) | 'reference' (host
+DataLoader, same draw sequence as the reference), 'cuda_graph': bool (default True), 'seed': int.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader
+
+from . import engine
+from ._lib import call, ptr, stream_ptr
+from .dataset import AuxiliaryDataset
+from .utils import AverageMeter  # noqa: F401  (re-exported like the reference module does)
+
+
+def get_trainer(config, dataset, model):
+    """Name-dispatched factory (trainer.py:14-20)."""
+    config = config.copy()
+    config['dataset'] = dataset
+    config['model'] = model
+    cls = getattr(sys.modules[__name__], config['name'])
+    return cls(config)
+
+
+class Adam(torch.optim.Optimizer):
+    """torch.optim.Adam semantics (default betas/eps, no weight decay) on the igcn_adam kernel.
+
+    Selected by name from config['optimizer'] like the reference does (trainer.py:43-45).  The
+    moments and the device-resident step counter are shared with the fused TrainStep, so mixing
+    `opt.step()` (generic autograd path) and fused steps keeps one optimizer state."""
+
+    def __init__(self, params, lr=1e-3):
+        super().__init__(params, dict(lr=lr, betas=(engine.BETA1, engine.BETA2), eps=engine.ADAM_EPS))
+        self.t = 0
+        self.step_state = None      # igcn_step_state on the device, created lazily
+
+    def moments(self, p):
+        st = self.state[p]
+        if 'exp_avg' not in st:
+            st['exp_avg'] = torch.zeros_like(p.data)
+            st['exp_avg_sq'] = torch.zeros_like(p.data)
+        return st['exp_avg'], st['exp_avg_sq']
+
+    def device_state(self, device):
+        if self.step_state is None:
+            self.step_state = torch.zeros(16, dtype=torch.uint8, device=device)
+        return self.step_state
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        self.t += 1
+        for group in self.param_groups:
+            b1, b2 = group['betas']
+            for p in group['params']:
+                if p.grad is None:
+                    continue
+                m, v = self.moments(p)
+                g = p.grad.contiguous()
+                call('igcn_adam', ptr(p.data), ptr(g), ptr(m), ptr(v), p.numel(), group['lr'], b1, b2, group['eps'],
+                     self.t, None, stream_ptr())
+        if self.step_state is not None:
+            self._sync_device_step()
+
+    def _sync_device_step(self):
+        self.step_state[:8].copy_(torch.tensor([self.t], dtype=torch.int64).view(torch.uint8))
+
+
+class BasicTrainer:
+    """trainer.py:23-219."""
+
+    def __init__(self, trainer_config):
+        print(trainer_config)
+        self.config = trainer_config
+        self.name = trainer_config['name']
+        self.dataset = trainer_config['dataset']
+        self.model = trainer_config['model']
+        self.topks = trainer_config['topks']
+        self.device = trainer_config['device']
+        self.n_epochs = trainer_config['n_epochs']
+        self.max_patience = trainer_config.get('max_patience', 50)
+        self.val_interval = trainer_config.get('val_interval', 1)
+        self.test_batch_size = trainer_config.get('test_batch_size', 512)
+        self.epoch = 0
+        self.best_ndcg = -np.inf
+        self.save_path = None
+        self.opt = None
+        self._mask_cache = {}
+        self._eval_cache = {}
+        self._last_rec = None
+        self.test_users = torch.arange(self.dataset.n_users, dtype=torch.int64, device=self.device)
+
+    def initialize_optimizer(self):
+        name = self.config['optimizer']
+        if name != 'Adam':
+            raise NotImplementedError('the B200 hot path implements Adam (every shipped config uses it); got ' + name)
+        self.opt = Adam(self.model.parameters(), lr=self.config['lr'])
+
+    def train_one_epoch(self):
+        raise NotImplementedError
+
+    def record(self, writer, stage, metrics):
+        for metric in metrics:
+            for k in self.topks:
+                writer.add_scalar('{:s}_{:s}/{:s}_{:s}@{:d}'.format(self.model.name, self.name, stage, metric, k),
+                                  metrics[metric][k], self.epoch)
+
+    def train(self, verbose=True, writer=None):
+        """Epoch loop, validation, best-NDCG checkpoint, patience (trainer.py:57-107)."""
+        if not self.model.trainable:
+            results, metrics = self.eval('val')
+            if verbose:
+                print('Validation result. {:s}'.format(results))
+            return metrics['NDCG'][self.topks[0]]
+
+        if not os.path.exists('checkpoints'):
+            os.mkdir('checkpoints')
+        patience = self.max_patience
+        for self.epoch in range(self.n_epochs):
+            start_time = time.time()
+            self.model.train()
+            loss = self.train_one_epoch()
+            _, metrics = self.eval('train')
+            consumed_time = time.time() - start_time
+            if verbose:
+                print('Epoch {:d}/{:d}, Loss: {:.6f}, Time: {:.3f}s'.format(self.epoch, self.n_epochs, loss, consumed_time))
+            if writer:
+                writer.add_scalar('{:s}_{:s}/train_loss'.format(self.model.name, self.name), loss, self.epoch)
+                self.record(writer, 'train', metrics)
+            if (self.epoch + 1) % self.val_interval != 0:
+                continue
+
+            start_time = time.time()
+            results, metrics = self.eval('val')
+            consumed_time = time.time() - start_time
+            if verbose:
+                print('Validation result. {:s}Time: {:.3f}s'.format(results, consumed_time))
+            if writer:
+                self.record(writer, 'validation', metrics)
+
+            ndcg = metrics['NDCG'][self.topks[0]]
+            if ndcg > self.best_ndcg:
+                if self.save_path:
+                    os.remove(self.save_path)
+                self.save_path = os.path.join('checkpoints', '{:s}_{:s}_{:s}_{:.3f}.pth'.format(
+                    self.model.name, self.name, self.dataset.name, ndcg * 100))
+                self.best_ndcg = ndcg
+                self.model.save(self.save_path)
+                patience = self.max_patience
+                print('Best NDCG, save model to {:s}'.format(self.save_path))
+            else:
+                patience -= self.val_interval
+                if patience <= 0:
+                    print('Early stopping!')
+                    break
+        self.model.load(self.save_path)
+        return self.best_ndcg
+
+    # ---- metrics (trainer.py:109-138)
+    def _eval_csr(self, eval_data):
+        """Sorted CSR of an eval list-of-lists; rebuilt when any inner list object or length changed
+        (inductive_eval swaps inner lists in place, trainer.py:185-217)."""
+        sig = (tuple(map(id, eval_data)), tuple(map(len, eval_data)))
+        hit = self._eval_cache.get(id(eval_data))
+        if hit is None or hit[0] != sig:
+            hit = (sig, engine.lists_to_csr(eval_data, self.device))
+            self._eval_cache = {id(eval_data): hit}
+        return hit[1]
+
+    def calculate_metrics(self, eval_data, rec_items):
+        """Precision / Recall / NDCG @k with the reference's dtypes: fp32 hit matrix and log2 table,
+        int32 list lengths, users without eval items excluded from the means."""
+        results = {'Precision': {}, 'Recall': {}, 'NDCG': {}}
+        csr = self._eval_csr(eval_data)
+        if self._last_rec is not None and self._last_rec[0] is rec_items:
+            rec_dev = self._last_rec[1]
+        else:
+            rec_dev = torch.as_tensor(np.ascontiguousarray(rec_items), device=self.device).to(torch.int32).contiguous()
+        hit_matrix = engine.hit_matrix(rec_dev, csr).cpu().numpy()
+        eval_data_len = csr[2].astype(np.int32)
+        for k in self.topks:
+            hit_num = np.sum(hit_matrix[:, :k], axis=1)
+            precisions = hit_num / k
+            with np.errstate(invalid='ignore', divide='ignore'):
+                recalls = hit_num / eval_data_len
+            max_hit_num = np.minimum(eval_data_len, k)
+            max_hit_matrix = (np.arange(k)[None, :] < max_hit_num[:, None]).astype(np.float32)
+            denominator = np.log2(np.arange(2, k + 2, dtype=np.float32))[None, :]
+            dcgs = np.sum(hit_matrix[:, :k] / denominator, axis=1)
+            idcgs = np.sum(max_hit_matrix / denominator, axis=1)
+            with np.errstate(invalid='ignore', divide='ignore'):
+                ndcgs = dcgs / idcgs
+            user_masks = (max_hit_num > 0)
+            results['Precision'][k] = precisions[user_masks].mean()
+            results['Recall'][k] = recalls[user_masks].mean()
+            results['NDCG'][k] = ndcgs[user_masks].mean()
+        return results
+
+    # ---- evaluation (trainer.py:140-177)
+    def _mask_csr(self, val_or_test):
+        if val_or_test == 'train':
+            return None
+        ds = self.dataset
+        key = (val_or_test, id(ds.train_data), id(ds.val_data), len(ds.train_data))
+        hit = self._mask_cache.get(val_or_test)
+        if hit is None or hit[0] != key:
+            if val_or_test == 'test':
+                lists = [a + b for a, b in zip(ds.train_data, ds.val_data)]
+            else:
+                lists = ds.train_data
+            hit = (key, engine.lists_to_csr(lists, self.device)[:2])
+            self._mask_cache[val_or_test] = hit
+        return hit[1]
+
+    def _banned(self, banned_items):
+        """banned_items (index array) -> (item_lo, item_hi, bitmap or None)."""
+        n = self.dataset.n_items
+        if banned_items is None:
+            return 0, n, None
+        b = np.unique(np.asarray(torch.as_tensor(banned_items).cpu()).astype(np.int64))
+        if len(b) == 0:
+            return 0, n, None
+        if b[-1] - b[0] + 1 == len(b):              # contiguous: trim the scored range instead
+            if b[0] == 0:
+                return int(b[-1]) + 1, n, None
+            if b[-1] == n - 1:
+                return 0, int(b[0]), None
+        flags = np.zeros(n, dtype=bool)
+        flags[b[(b >= 0) & (b < n)]] = True
+        from .graph import _pack_bits
+        return 0, n, _pack_bits(flags, self.device)
+
+    def recommend(self, val_or_test, banned_items=None, users=None):
+        """Top-max(topks) item ids (device int32 [n, k]) and scores for `users` (default: all)."""
+        self.model.eval()
+        with torch.no_grad():
+            rep = self.model.get_rep().contiguous()
+        users = self.test_users if users is None else users
+        lo, hi, bits = self._banned(banned_items)
+        return engine.score_topk(rep, users, self.model.n_users, self.model.n_items, max(self.topks),
+                                 mask=self._mask_csr(val_or_test), item_lo=lo, item_hi=hi, banned_bits=bits)
+
+    def eval(self, val_or_test, banned_items=None):
+        eval_data = getattr(self.dataset, val_or_test + '_data')
+        rec_dev, _ = self.recommend(val_or_test, banned_items)
+        rec_items = rec_dev.cpu().numpy().astype(np.int64)
+        self._last_rec = (rec_items, rec_dev)
+        metrics = self.calculate_metrics(eval_data, rec_items)
+        self._last_rec = None
+
+        precison = ''
+        recall = ''
+        ndcg = ''
+        for k in self.topks:
+            precison += '{:.3f}%@{:d}, '.format(metrics['Precision'][k] * 100., k)
+            recall += '{:.3f}%@{:d}, '.format(metrics['Recall'][k] * 100., k)
+            ndcg += '{:.3f}%@{:d}, '.format(metrics['NDCG'][k] * 100., k)
+        results = 'Precision: {:s}Recall: {:s}NDCG: {:s}'.format(precison, recall, ndcg)
+        return results, metrics
+
+    def inductive_eval(self, n_old_users, n_old_items):
+        """Six test passes over user/item subsets (trainer.py:179-219)."""
+        ds = self.dataset
+        full = ds.test_data.copy()
+        n_u, n_i = ds.n_users, ds.n_items
+
+        def restrict(users, keep):
+            ds.test_data = full.copy()
+            for user in range(n_u):
+                if user not in users:
+                    ds.test_data[user] = []
+                elif keep is not None:
+                    items = np.array(ds.test_data[user])
+                    ds.test_data[user] = items[keep(items)].tolist()
+
+        all_users, old_users = range(n_u), range(n_old_users)
+        new_users = range(n_old_users, n_u)
+        old_items = lambda it: it < n_old_items
+        new_items = lambda it: it >= n_old_items
+        ban_new, ban_old = np.arange(n_old_items, n_i), np.arange(n_old_items)
+        plan = [('All users and all items', all_users, None, None),
+                ('Old users and all items', old_users, None, None),
+                ('New users and all items', new_users, None, None),
+                ('All users and old items', all_users, old_items, ban_new),
+                ('All users and new items', all_users, new_items, ban_old),
+                ('Old users and old items', old_users, old_items, ban_new)]
+        for title, users, keep, banned in plan:
+            restrict(users, keep)
+            results, _ = self.eval('test', banned_items=banned)
+            print('{:s} result. {:s}'.format(title, results))
+        ds.test_data = full.copy()
+
+
+class _FusedBPRMixin:
+    """Epoch loop shared by BPRTrainer and IGCNTrainer on top of engine.TrainStep."""
+
+    def _init_fused(self, trainer_config, aux_reg=None):
+        self.l2_reg = trainer_config['l2_reg']
+        self.batch_size = trainer_config['batch_size']
+        self.sampler = trainer_config.get('sampler', 'device')
+        self.initialize_optimizer()
+        self.step = engine.TrainStep(self.model, self.opt, self.l2_reg, aux_reg=aux_reg, batch_size=self.batch_size,
+                                     seed=trainer_config.get('seed', 0),
+                                     use_graph=trainer_config.get('cuda_graph', True))
+
+    def _host_batches(self):
+        loaders = [self.dataloader] + ([self.aux_dataloader] if isinstance(self, IGCNTrainer) else [])
+        for batches in zip(*loaders):
+            yield [b[:, 0, :].to(device=self.device, dtype=torch.int64) for b in batches]
+
+    def _run_epoch(self):
+        self.step.reset_meter()
+        if self.sampler == 'reference':
+            for batches in self._host_batches():
+                self.step.run(*batches)
+        else:
+            total, B = len(self.dataset), self.batch_size
+            for lo in range(0, total, B):
+                self.step.run(batch=min(B, total - lo))
+        return self.step.meter_avg()
+
+
+class BPRTrainer(BasicTrainer, _FusedBPRMixin):
+    """trainer.py:222-248."""
+
+    def __init__(self, trainer_config):
+        super().__init__(trainer_config)
+        self.dataloader = DataLoader(self.dataset, batch_size=trainer_config['batch_size'],
+                                     num_workers=trainer_config['dataloader_num_workers'])
+        self._init_fused(trainer_config)
+
+    def train_one_epoch(self):
+        return self._run_epoch()
+
+
+class IGCNTrainer(BasicTrainer, _FusedBPRMixin):
+    """trainer.py:281-320."""
+
+    def __init__(self, trainer_config):
+        super().__init__(trainer_config)
+        self.dataloader = DataLoader(self.dataset, batch_size=trainer_config['batch_size'],
+                                     num_workers=trainer_config['dataloader_num_workers'])
+        self._aux_dataloader = None
+        self.aux_reg = trainer_config['aux_reg']
+        self._init_fused(trainer_config, aux_reg=self.aux_reg)
+
+    @property
+    def aux_dataloader(self):
+        """Host sampler in template-id space (trainer.py:287-289); built on first use because only the
+        'reference' sampler mode needs it (the device sampler reads model.aux_csr())."""
+        if self._aux_dataloader is None:
+            aux = AuxiliaryDataset(self.dataset, self.model.user_map, self.model.item_map)
+            self._aux_dataloader = DataLoader(aux, batch_size=self.config['batch_size'],
+                                              num_workers=self.config['dataloader_num_workers'])
+        return self._aux_dataloader
+
+    def train_one_epoch(self):
+        loss = self._run_epoch()
+        self.model.feat_mat_anneal()
+        return loss

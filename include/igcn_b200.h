@@ -1,0 +1,204 @@
+/*
+ * igcn_b200.h -- C ABI of the B200 (sm_100a) hot-path library for INMO / IGCN collaborative
+ * filtering.  One shared object (libigcn_b200.so), plain pointers and sizes, no torch types.
+ *
+ * The reference (WuYunfan/igcn_cf) is pure Python and has no FFI of its own; every entry point
+ * below replaces a LIBRARY CALL SITE of the reference's hot path (cited per function, paths
+ * relative to the reference root).  The Python host code in igcn_cf_b200/ binds these with
+ * ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - the caller owns all buffers; nothing is retained across calls;
+ *  - return 0 on success, non-zero on failure (cudaError_t value, or a negative code for
+ *    argument errors); igcn_last_error() returns a thread-local message;
+ *  - node rows: users 0..U-1, items U..U+I-1 (reference utils.py:41-49);
+ *  - embeddings are row-major fp32 [rows, D], D % 4 == 0, 16-byte aligned.
+ */
+#ifndef IGCN_B200_H
+#define IGCN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IGCN_ABI_VERSION 1
+#define IGCN_MAX_ADD 8
+
+int igcn_abi_version(void);
+const char *igcn_last_error(void);
+
+/* CSR adjacency of one contiguous block of node rows, plus the long-row split plan that keeps
+ * power-law rows from serialising on one half-warp.  Rows with more than `long_threshold`
+ * non-zeros are cut into chunks (chunk_* arrays, one entry per chunk); each chunk's partial sum
+ * goes to partial[chunk][D] and the last chunk to finish (counters[], self-resetting) adds the
+ * partials IN CHUNK ORDER, so the result does not depend on scheduling or on the GPU count.
+ * Built by igcn_cf_b200/graph.py from the same data LightGCN.generate_graph builds
+ * (model.py:85-94): val[e] = fl32(d_r^-1/2 * d_c^-1/2), columns sorted inside each row. */
+typedef struct igcn_csr {
+    int64_t n_rows;             /* rows in this block                                  */
+    int64_t n_cols;             /* width of the gathered table (global node count)     */
+    int64_t nnz;
+    const int64_t *rowptr;      /* [n_rows + 1]                                        */
+    const int32_t *col;         /* [nnz] global column ids                             */
+    const float *val;           /* [nnz] or NULL (pattern-only: every value is 1)      */
+    int32_t long_threshold;     /* rows with nnz > threshold are chunked               */
+    int32_t n_chunks;
+    const int32_t *chunk_row;   /* [n_chunks] local row id                             */
+    const int64_t *chunk_begin; /* [n_chunks] first nnz of the chunk                   */
+    const int32_t *chunk_len;   /* [n_chunks]                                          */
+    const int32_t *chunk_first; /* [n_chunks] index of the row's first chunk           */
+    const int32_t *chunk_count; /* [n_chunks] number of chunks of the row              */
+    float *partial;             /* [n_chunks, D] scratch                               */
+    int32_t *counters;          /* [n_chunks] scratch, must be zero before first use   */
+} igcn_csr;
+
+/* Edge-dropout description for the INMO layer (reference NGCF.dropout_sp_mat, model.py:263-275,
+ * called from IGCN.get_rep, model.py:435).  mode 0: keep everything (eval mode / p == 0);
+ * mode 1: keep edge (row r, column-node c) iff hash32(seed, r, c) >= p * 2^32 (production:
+ * counter-based, so the transposed backward pass regenerates the same mask); mode 2: explicit
+ * keep bits (parity tests replay the reference's torch.rand draw): bit e of edge_keep for the
+ * e-th non-zero in CSR order, bit r of self_keep for row r's global-template entry.
+ * tperm[e] = CSR position of the reverse edge; only needed for mode 2 in the backward pass. */
+typedef struct igcn_dropout {
+    int32_t mode;
+    float p;
+    uint64_t seed;
+    const uint64_t *seed_dev;   /* optional device counter mixed into seed (CUDA-graph replay)  */
+    const uint32_t *edge_keep;
+    const uint32_t *self_keep;
+    const int64_t *tperm;
+} igcn_dropout;
+
+typedef struct igcn_step_state {
+    uint64_t step;
+    float adam_step_size;       /* lr / (1 - beta1^step)        */
+    float adam_inv_sqrt_bc2;    /* 1 / sqrt(1 - beta2^step)     */
+} igcn_step_state;
+
+/* Y[r] = alpha * rowscale[r] * ( sum_e val[e] * X[col[e]] + sum_j add[j][r] )
+ * Replaces dgl.ops.gspmm(g,'mul','sum',X,A.values()) at model.py:102 and model.py:442 (forward)
+ * and its autograd backward (A is symmetric, so dX = A * dY uses the same CSR); with add[] =
+ * the earlier layers and alpha = 1/(L+1) the last call also produces the layer mean that
+ * torch.stack(...).mean(0) computes at model.py:104-105 / 444-445.
+ * X: [n_cols, D]; Y and add[j]: [n_rows, D] (already offset to this row block); rowscale may be
+ * NULL; add_host is a HOST array of n_add (<= IGCN_MAX_ADD) device pointers. */
+int igcn_spmm(const igcn_csr *g, const float *X, float *Y, int32_t D,
+              const float *const *add_host, int32_t n_add,
+              const float *rowscale, float alpha, void *stream);
+
+/* INMO template aggregation fused with edge dropout (IGCN.inductive_rep_layer, model.py:423-432,
+ * after dropout_sp_mat, model.py:435):
+ *   X0[r] = rowscale[r]/(1-p) * ( sum_{c in adj(r), tmpl[c] >= 0, keep(r,c)} E[tmpl[c]]
+ *                                 + keep_self(r) * E[r < n_users ? glob_user : glob_item] )
+ * where rowscale[r] = row_sum[r]^((alpha-1)/2 - 1/2) (model.py:374-377).  tmpl == NULL means the
+ * identity map (feature_ratio == 1: template id == node id).  row0 = global id of local row 0. */
+int igcn_inmo_fwd(const igcn_csr *g, const int32_t *tmpl, const float *rowscale,
+                  const igcn_dropout *drop, const float *E, float *X0, int32_t D,
+                  int64_t row0, int64_t n_users, int64_t glob_user, int64_t glob_item,
+                  void *stream);
+
+/* Transposed INMO layer for the embedding gradient (autograd backward of model.py:430):
+ *   dE[tmpl[c]] = sum_{r in adj(c), keep(r,c)} G[r]      for local rows c with tmpl[c] >= 0
+ * G must already hold rowscale[r]/(1-p) * dX0[r] (igcn_spmm's rowscale/alpha epilogue does that).
+ * The two global-template rows are produced by igcn_colsum_masked. */
+int igcn_inmo_bwd(const igcn_csr *g, const int32_t *tmpl, const igcn_dropout *drop,
+                  const float *G, float *dE, int32_t D, int64_t row0, void *stream);
+
+/* out[d] = sum over rows r in [row_begin,row_end) with keep_self(r) of G[r][d]; fixed two-stage
+ * order (deterministic).  scratch: [ceil(n/256)+1, D] floats. */
+int igcn_colsum_masked(const float *G, int64_t row_begin, int64_t row_end, int32_t D,
+                       const igcn_dropout *drop, float *scratch, float *out, void *stream);
+
+/* Triple sampler (BasicDataset.__getitem__, dataset.py:119-131, neg_ratio 1): user uniform over
+ * users with a non-empty train list, positive uniform over the user's list, negative uniform over
+ * items rejecting the user's list.  The user-by-item train CSR is passed as rows [0,n_users) of
+ * `rowptr/col` with item = col - col_offset (the adjacency's user rows, col_offset = n_users).
+ * out: int64 [B, 3].  Counter-based: (seed, step [+ *step_dev], triple index) fully determine the
+ * draw; step_dev (may be NULL) is a device counter so a captured CUDA graph advances by itself. */
+int igcn_sample_triples(const int64_t *rowptr, const int32_t *col, int64_t col_offset,
+                        int64_t n_users, int64_t n_items, int64_t B, uint64_t seed,
+                        uint64_t step, const uint64_t *step_dev, int64_t *out, void *stream);
+
+/* Forward of the BPR step on a batch of triples (trainer.py:238-241 / 300-302 and, with w, the
+ * auxiliary loss at trainer.py:304-311; L2 term of model.py:110-113 / 297-298):
+ *   pos_i = <T[u_i] * w, T[off+p_i]>, neg_i = <T[u_i] * w, T[off+n_i]>
+ *   sp[i] = softplus(neg_i - pos_i), sig[i] = sigmoid(neg_i - pos_i)
+ *   l2[i] = |L[u_i]|^2 + |L[off+p_i]|^2 + |L[off+n_i]|^2      (L = l2_table, may be NULL)
+ * triples: int64 [B,3]; w: [D] or NULL. */
+int igcn_bpr_fwd(const float *table, const float *l2_table, const float *w,
+                 const int64_t *triples, int64_t B, int64_t item_offset, int32_t D,
+                 float *sp, float *sig, float *l2, void *stream);
+
+/* loss[0] = mean(sp) + l2_reg * mean(l2) + aux_reg * mean(aux_sp)   (trainer.py:241-243, 313-314)
+ * acc[0] += loss * B ; acc[1] += B   (the AverageMeter of utils.py:126-135, kept on device so
+ * the per-step loss.item() sync of trainer.py:247/318 disappears).  l2 / aux_sp may be NULL. */
+int igcn_loss_finalize(const float *sp, const float *l2, const float *aux_sp, int64_t B,
+                       int64_t B_aux, float l2_reg, float aux_reg, float *loss, double *acc,
+                       void *stream);
+
+/* Deterministic scatter plan for the gradient of a triple batch: slot s = kind * B + i
+ * (kind 0 user, 1 positive, 2 negative) touches row id(s).  Sorts (id, slot) and emits
+ * order[3B] (slots, ascending id then slot), seg_start[n_seg+1], seg_row[n_seg], n_seg[0].
+ * One CTA, shared-memory bitonic sort; 3B <= 16384. */
+int igcn_bpr_plan(const int64_t *triples, int64_t B, int64_t item_offset, int32_t *order,
+                  int32_t *seg_start, int64_t *seg_row, int32_t *n_seg, void *stream);
+
+/* Gradient rows of the BPR step, one half-warp per touched row, contributions added in slot
+ * order (no atomics; replaces the index_put_(accumulate=True) autograd backward of
+ * model.py:114-115 / 295-296):
+ *   d/dT[u_i]   += c_i * w*(T[n_i] - T[p_i]) + lam * L2row
+ *   d/dT[p_i]   += -c_i * w*T[u_i] + lam * L2row      d/dT[n_i] += c_i * w*T[u_i] + lam * L2row
+ * with c_i = scale * sig[i] / B and lam = scale * 2 * l2_coef / B applied to the row itself (only when
+ * l2_on_table != 0).  accumulate == 0: G[row] = sum (G is expected pre-zeroed elsewhere);
+ * accumulate != 0: G[row] += sum.  dw (may be NULL, needs w): dw[d] += scale/B * sum_i sig_i *
+ * T[u_i][d] * (T[n_i][d] - T[p_i][d]) through dw_scratch [ceil(B/64), D]. */
+int igcn_bpr_bwd(const float *table, const float *w, const int64_t *triples, int64_t B,
+                 int64_t item_offset, int32_t D, const float *sig, float scale, float l2_coef,
+                 int32_t l2_on_table, const int32_t *order, const int32_t *seg_start,
+                 const int64_t *seg_row, const int32_t *n_seg, float *G, int32_t accumulate,
+                 float *dw, float *dw_scratch, void *stream);
+
+/* dE[row] += coef * multiplicity(row) * E[row] for every touched row: gradient of
+ * l2_reg * mean(|E[u]|^2 + |E[p]|^2 + |E[n]|^2) over RAW embedding rows (LightGCN.bpr_forward,
+ * model.py:110-113), coef = 2 * l2_reg / B. */
+int igcn_l2_rows_bwd(const float *E, float *dE, int32_t D, float coef, const int32_t *seg_start,
+                     const int64_t *seg_row, const int32_t *n_seg, int64_t max_seg, void *stream);
+
+/* torch.optim.Adam (trainer.py:43-45, 246) with default betas/eps semantics, one fused pass:
+ * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps) */
+int igcn_adam(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1,
+              float beta2, float eps, int64_t t, const igcn_step_state *state_dev, void *stream);
+
+/* Device-resident step counter so that a whole training step can be replayed as one CUDA graph:
+ * state->step += 1 and the Adam bias-correction factors for t = step are refreshed.  When
+ * igcn_adam gets state_dev != NULL it reads the factors from there instead of using `t`. */
+int igcn_step_tick(igcn_step_state *state_dev, float lr, float beta1, float beta2, void *stream);
+
+/* Full-ranking scoring fused with the seen-item mask and per-user top-k; the score matrix never
+ * reaches HBM.  Replaces torch.mm (model.py:122), the -inf index_put (trainer.py:149-161) and
+ * torch.topk (trainer.py:163).
+ *   score(u, j) = sum_{d ascending} rep[user_ids[b]][d] * rep[item_row0 + j][d]   (fp32 FMA chain)
+ * masked when j is in mask_items[mask_ptr[u] .. mask_ptr[u+1]) (sorted ascending per user, may be
+ * NULL), or j outside [item_lo, item_hi), or bit j of banned_bits set (may be NULL).
+ * Output per user: k item ids (int32, -1 when fewer than k candidates) and scores, sorted by
+ * (score descending, item ascending).  This is the exact CUDA-core kernel; it is also the
+ * fallback the tensor-core path uses for users whose candidate bound does not verify. */
+int igcn_score_topk_exact(const float *rep, const int64_t *user_ids, int64_t n_eval,
+                          int64_t item_row0, int64_t n_items, int32_t D,
+                          const int64_t *mask_ptr, const int32_t *mask_items,
+                          int64_t item_lo, int64_t item_hi, const uint32_t *banned_bits,
+                          int32_t k, int32_t *out_items, float *out_scores, void *stream);
+
+/* hit[u][j] = 1 if rec[u][j] is in eval_items[eval_ptr[u] .. eval_ptr[u+1]) (sorted), else 0:
+ * the membership double loop of BasicTrainer.calculate_metrics (trainer.py:111-115). */
+int igcn_hits(const int32_t *rec, int64_t n_users, int32_t k, const int64_t *eval_ptr,
+              const int32_t *eval_items, float *hit, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IGCN_B200_H */

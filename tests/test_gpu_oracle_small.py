@@ -1,0 +1,87 @@
+"""CUDA path vs the CPU oracle on a larger seeded graph ('small': 3000 x 4000, ~90K interactions,
+power-law heads long enough to hit the chunked-row path)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda:0')
+TOL = 1e-5
+
+
+@pytest.fixture(scope='module')
+def small():
+    from igcn_cf_b200 import synth
+    from igcn_cf_b200.dataset import get_dataset
+    split = synth.gen_named('small', seed=11)
+    ds = get_dataset({'name': 'SyntheticDataset', 'split': split, 'device': DEV})
+    return ds
+
+
+def _rand_triples(ds, n, seed):
+    rng = np.random.default_rng(seed)
+    out = np.zeros((n, 3), dtype=np.int64)
+    for t in range(n):
+        u = int(rng.integers(ds.n_users))
+        out[t] = (u, int(rng.choice(ds.train_data[u])), int(rng.integers(ds.n_items)))
+    return out
+
+
+def test_lightgcn_three_steps_and_topk(small):
+    from igcn_cf_b200.model import get_model
+    from igcn_cf_b200.trainer import get_trainer
+    from oracle import restate as R
+    ds = small
+    torch.manual_seed(0)
+    model = get_model({'name': 'LightGCN', 'embedding_size': 64, 'n_layers': 3, 'device': DEV}, ds)
+    assert model.norm_adj.csr.n_chunks > 0                          # long rows present
+    trainer = get_trainer({'name': 'BPRTrainer', 'optimizer': 'Adam', 'lr': 1e-3, 'l2_reg': 1e-4, 'device': DEV,
+                           'n_epochs': 1, 'batch_size': 2048, 'dataloader_num_workers': 0, 'test_batch_size': 512,
+                           'topks': [20], 'cuda_graph': False}, ds, model)
+    emb0 = model.embedding.weight.detach().cpu().numpy()
+    orc = R.OracleLightGCN(ds.n_users, ds.n_items, ds.train_pairs, 3, emb0, l2_reg=1e-4)
+    assert rel_err(model.get_rep().detach().cpu().numpy(), orc.get_rep().detach().numpy()) < TOL
+    model.train()
+    for s in range(3):
+        tri = _rand_triples(ds, 2048, s)
+        t = torch.from_numpy(tri)
+        ref_loss = orc.train_step(t[:, 0], t[:, 1], t[:, 2])
+        loss = trainer.step.run(t.to(DEV)).item()
+        assert abs(loss - ref_loss) < TOL
+    assert rel_err(model.embedding.weight.detach().cpu().numpy(), orc.emb.detach().numpy()) < TOL
+    metrics, rec = R.evaluate(orc, 'test', ds.train_data, ds.val_data, ds.test_data, [20])
+    _, mine = trainer.eval('test')
+    rec_dev, _ = trainer.recommend('test')
+    differing = int((rec_dev.cpu().numpy() != rec).any(axis=1).sum())
+    assert differing <= ds.n_users // 100
+    for name in metrics:
+        assert abs(float(mine[name][20]) - float(metrics[name][20])) < 2e-4
+
+
+def test_igcn_step_with_zero_dropout(small):
+    """Amazon-style config (dropout 0.0, reference config.py:169): train-mode parity needs no mask."""
+    from igcn_cf_b200.model import get_model
+    from igcn_cf_b200.trainer import get_trainer
+    from oracle import restate as R
+    ds = small
+    torch.manual_seed(1)
+    model = get_model({'name': 'IGCN', 'embedding_size': 64, 'n_layers': 3, 'device': DEV, 'dropout': 0.0,
+                       'feature_ratio': 1.}, ds)
+    trainer = get_trainer({'name': 'IGCNTrainer', 'optimizer': 'Adam', 'lr': 1e-3, 'l2_reg': 0., 'aux_reg': 0.01,
+                           'device': DEV, 'n_epochs': 1, 'batch_size': 2048, 'dataloader_num_workers': 0,
+                           'test_batch_size': 512, 'topks': [20], 'cuda_graph': False}, ds, model)
+    emb0 = model.embedding.weight.detach().cpu().numpy()
+    orc = R.OracleIGCN(ds.n_users, ds.n_items, ds.train_pairs, 3, emb0, 0.0)
+    model.train()
+    for s in range(2):
+        t, a = torch.from_numpy(_rand_triples(ds, 2048, s)), torch.from_numpy(_rand_triples(ds, 2048, 100 + s))
+        ref_loss = orc.loss(t[:, 0], t[:, 1], t[:, 2], a[:, 0], a[:, 1], a[:, 2], train=False)
+        orc.opt.zero_grad()
+        ref_loss.backward()
+        orc.opt.step()
+        loss = trainer.step.run(t.to(DEV), a.to(DEV)).item()
+        assert abs(loss - ref_loss.item()) < TOL
+    assert rel_err(model.embedding.weight.detach().cpu().numpy(), orc.emb.detach().numpy()) < TOL
+    assert rel_err(model.w.detach().cpu().numpy(), orc.w.detach().numpy()) < TOL

@@ -1,0 +1,134 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, and the host-built
+graph structures equal the reference's tensors (golden vectors).  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from igcn_cf_b200 import _lib, graph
+from igcn_cf_b200.dataset import AuxiliaryDataset, ListDataset, get_dataset
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, 'include', 'igcn_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(igcn_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_lib.LIB_PATH):
+        from igcn_cf_b200 import build
+        build.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_functions()
+    assert len(declared) >= 16
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(_lib.EXPORTS) == declared          # the ctypes binding covers the whole header
+    lib.igcn_abi_version.restype = ctypes.c_int
+    assert lib.igcn_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_layout_matches_header():
+    # sizes implied by include/igcn_b200.h on LP64
+    assert ctypes.sizeof(_lib.CsrStruct) == 3 * 8 + 3 * 8 + 2 * 4 + 7 * 8
+    assert ctypes.sizeof(_lib.DropoutStruct) == 4 + 4 + 8 + 4 * 8
+
+
+def test_missing_cuda_fails_loudly(tiny):
+    from igcn_cf_b200.model import get_model
+    ds = _dataset(tiny)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        get_model({'name': 'LightGCN', 'embedding_size': 64, 'n_layers': 3, 'device': torch.device('cpu')}, ds)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        _lib.require_cuda(torch.zeros(4), torch.float32, 'x')
+
+
+def _dataset(tiny):
+    return get_dataset({'name': 'ListDataset', 'train': tiny['train'], 'val': tiny['val'], 'test': tiny['test'],
+                        'n_items': tiny['n_items'], 'device': 'cpu'})
+
+
+def test_dataset_mirror(tiny):
+    ds = _dataset(tiny)
+    assert (ds.n_users, ds.n_items) == (tiny['n_users'], tiny['n_items'])
+    assert ds.train_array == tiny['pairs'].tolist()
+    assert len(ds) == len(tiny['pairs'])
+    t = ds[0]
+    assert t.shape == (1, 3) and t.dtype == np.int64
+    u, p, n = t[0]
+    assert p in ds.train_data[u] and n not in ds.train_data[u]
+    aux = AuxiliaryDataset(ds, {u: u for u in range(ds.n_users)}, {i: i for i in range(ds.n_items)})
+    assert aux.train_data == ds.train_data and len(aux) == len(ds)
+
+
+def test_norm_adj_matches_reference(tiny):
+    g = load_golden('tiny_lightgcn')
+    adj = graph.NormAdj(tiny['n_users'], tiny['n_items'], tiny['pairs'], 'cpu')
+    assert np.array_equal(adj.indices().numpy(), g['adj_idx'])
+    assert np.array_equal(adj.values().numpy(), g['adj_val'])      # bit-exact fp32 values
+    assert adj._nnz() == g['adj_val'].shape[0] and tuple(adj.shape) == (700, 700)
+
+
+def _feat(tiny, user_tmpl, item_tmpl, pairs=None, n_users=None, n_items=None):
+    n_users = tiny['n_users'] if n_users is None else n_users
+    n_items = tiny['n_items'] if n_items is None else n_items
+    pairs = tiny['pairs'] if pairs is None else pairs
+    return graph.TemplateFeat(n_users, n_items, pairs, user_tmpl, item_tmpl,
+                              int((user_tmpl >= 0).sum()), int((item_tmpl >= 0).sum()), 'cpu')
+
+
+def test_template_feat_identity_matches_reference(tiny):
+    g = load_golden('tiny_igcn')
+    f = _feat(tiny, np.arange(tiny['n_users']), np.arange(tiny['n_items']))
+    f.set_alpha(1.)
+    assert f.tmpl is None                                           # identity map needs no indirection
+    assert list(f.shape) == g['feat_shape'].tolist()
+    assert np.array_equal(f.indices().numpy(), g['feat_idx'])
+    assert np.array_equal(f.row_sum.numpy(), g['row_sum'])
+    np.testing.assert_allclose(f.values().numpy(), g['feat_val'], rtol=1e-6)
+    f.set_alpha(float(g['alpha1']))
+    np.testing.assert_allclose(f.values().numpy(), g['feat_val1'], rtol=1e-6)
+
+
+def test_template_feat_ratio_matches_reference(tiny):
+    g = load_golden('tiny_igcn_ratio')
+    f = _feat(tiny, g['user_map'], g['item_map'])
+    f.set_alpha(1.)
+    assert f.tmpl is not None
+    assert list(f.shape) == g['feat_shape'].tolist()
+    assert np.array_equal(f.indices().numpy(), g['feat_idx'])
+    assert np.array_equal(f.row_sum.numpy(), g['row_sum'])
+    np.testing.assert_allclose(f.values().numpy(), g['feat_val'], rtol=1e-6)
+
+
+def test_keep_bits_and_tperm(tiny):
+    f = _feat(tiny, np.arange(tiny['n_users']), np.arange(tiny['n_items']))
+    rng = np.random.default_rng(0)
+    keep = rng.random(f._nnz()) < 0.7
+    ek, sk = f.keep_bits(keep)
+    edge_pos, self_pos, _ = f.coo_order()
+    words = ek.numpy().view(np.uint32)
+    for e in (0, 1, 31, 32, 33, len(edge_pos) - 1):
+        assert bool((words[e >> 5] >> (e & 31)) & 1) == bool(keep[edge_pos[e]])
+    words = sk.numpy().view(np.uint32)
+    for r in (0, 5, 299, 300, 699):
+        assert bool((words[r >> 5] >> (r & 31)) & 1) == bool(keep[self_pos[r]])
+    tp = f.tperm().numpy()
+    rp, col = f.csr.rowptr_host, f.csr.col_host
+    rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+    assert np.array_equal(col[tp], rows) and np.array_equal(rows[tp], col)
+
+
+def test_chunk_plan_covers_long_rows():
+    rowptr = np.array([0, 3, 3, 1003, 1010, 1600], dtype=np.int64)
+    row, begin, length, first, count = graph.chunk_plan(rowptr, threshold=512, chunk=256)
+    assert row.tolist() == [2, 2, 2, 2, 4, 4, 4]
+    assert begin.tolist() == [3, 259, 515, 771, 1010, 1266, 1522]
+    assert length.tolist() == [256, 256, 256, 232, 256, 256, 78]
+    assert first.tolist() == [0, 0, 0, 0, 4, 4, 4] and count.tolist() == [4, 4, 4, 4, 3, 3, 3]
+    assert graph.chunk_plan(np.array([0, 5, 9], dtype=np.int64))[0].size == 0
