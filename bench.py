@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the INMO / IGCN hot path on B200 (contract: see the task statement and DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload yelp-lightgcn] [--impl reference]
+
+A "step" is one BPR training step (2,048 triples): sample -> propagate (L SpMM layers + fused mean)
+-> fused BPR loss -> deterministic gradient -> backward propagation -> Adam.  `value` is ms/epoch =
+ms_per_step x ceil(E_train / 2048) with everything resident in HBM (CUDA-graph replay, device
+sampler).  `e2e` is the same metric through the public trainer step with HOST triples in pinned
+memory copied H2D every step and the loss read back D2H every step (what the reference does,
+trainer.py:234/247).  `eval` is the second half of BASELINE.json's metric: full-ranking users/s.
+`roofline` describes the dominant kernel (the CSR SpMM) against the measured HBM peak; `cpu_baseline`
+times the CPU oracle port of the reference's step on this box's host cores (a reported baseline).
+
+--impl reference times that CPU port only (the reference is pure Python/PyTorch; /root/reference is
+not present on the GPU box, so the pinned restatement in oracle/restate.py is what runs).
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (shape, model, l2_reg, dropout)   -- reference config.py hyper-parameters
+    'yelp-lightgcn': ('yelp', 'LightGCN', 1e-4, None),       # BASELINE.json configs[1]
+    'gowalla-igcn': ('gowalla', 'IGCN', 0., 0.3),            # configs[0] (the reference's CPU-runnable case)
+    'gowalla-lightgcn': ('gowalla', 'LightGCN', 1e-4, None),
+    'yelp-igcn': ('yelp', 'IGCN', 0., 0.3),
+    'amazon-igcn': ('amazon', 'IGCN', 0., 0.0),              # configs[2]
+    'small-igcn': ('small', 'IGCN', 0., 0.3),
+    'small-lightgcn': ('small', 'LightGCN', 1e-4, None),
+}
+BATCH = 2048
+METRIC = 'ms/epoch (propagate+BPR)'
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (pynvml, 100 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'sw_thermal_slowdown': 0x20,
+                     'hw_thermal_slowdown': 0x40, 'hw_power_brake': 0x80}
+            self.ok = True
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.1)
+        except Exception as e:          # clocks are evidence, not the product: report the failure
+            self.reasons.add('sampler_error:%s' % type(e).__name__)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(s)}
+
+
+def build_dataset(shape, device):
+    from igcn_cf_b200.dataset import get_dataset
+    return get_dataset({'name': 'SyntheticDataset', 'shape': shape, 'seed': 2021, 'device': device})
+
+
+def build_model(ds, kind, dropout, l2_reg, device, use_graph=True):
+    from igcn_cf_b200.model import get_model
+    from igcn_cf_b200.trainer import get_trainer
+    mcfg = {'name': kind, 'embedding_size': 64, 'n_layers': 3, 'device': device}
+    tcfg = {'optimizer': 'Adam', 'lr': 1e-3, 'l2_reg': l2_reg, 'device': device, 'n_epochs': 1, 'batch_size': BATCH,
+            'dataloader_num_workers': 0, 'test_batch_size': 512, 'topks': [20], 'cuda_graph': use_graph, 'seed': 2021}
+    if kind == 'IGCN':
+        mcfg.update(dropout=dropout, feature_ratio=1.)
+        tcfg.update(name='IGCNTrainer', aux_reg=0.01)
+    else:
+        tcfg.update(name='BPRTrainer')
+    model = get_model(mcfg, ds)
+    return model, get_trainer(tcfg, ds, model)
+
+
+def spmm_bytes(n, nnz, D, n_add):
+    """Algorithmic (compulsory) bytes of one igcn_spmm launch: idx + val, rowptr, read X, write Y,
+    plus one N x D read per fused add operand (rowptr is int64 here)."""
+    return nnz * 8 + (n + 1) * 8 + (2 + n_add) * n * D * 4
+
+
+def profile_kernels(trainer, n, nnz, D, steps):
+    """Per-entry-point device time of the eager (un-graphed) step, CUDA events on the launch stream."""
+    import torch
+    from igcn_cf_b200 import _lib
+    events, open_ev = [], {}
+
+    def hook(name, phase):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        if phase == 0:
+            open_ev[name] = ev
+        else:
+            events.append((name, open_ev.pop(name), ev))
+
+    step = trainer.step
+    use_graph, step.use_graph = step.use_graph, False
+    _lib.profile_hook = hook
+    try:
+        for _ in range(steps):
+            step.run()
+        torch.cuda.synchronize()
+    finally:
+        _lib.profile_hook = None
+        step.use_graph = use_graph
+    per = {}
+    for name, a, b in events:
+        per.setdefault(name, []).append(a.elapsed_time(b))
+    summary = {k: {'launches_per_step': len(v) / steps, 'avg_ms': sum(v) / len(v), 'ms_per_step': sum(v) / steps}
+               for k, v in per.items()}
+    # SpMM roofline: layers 1..L-1 plain, last forward layer adds L operands, backward layers add 1
+    L = trainer.model.n_layers
+    t_spmm = sum(per['igcn_spmm'])
+    n_adds = [0] * (L - 1) + [L] + [1] * L
+    byts = sum(spmm_bytes(n, nnz, D, a) for a in n_adds) * steps
+    return summary, byts / (t_spmm * 1e-3) / 1e9, t_spmm / len(per['igcn_spmm']), byts / len(per['igcn_spmm'])
+
+
+def cpu_step_time(ds, kind, dropout, l2_reg, steps, warmup=1):
+    """Seconds per training step of the CPU oracle port (oracle/restate.py), all host threads."""
+    import numpy as np
+    import torch
+    from oracle import restate as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    rng = np.random.default_rng(0)
+    emb_rows = ds.n_users + ds.n_items + (2 if kind == 'IGCN' else 0)
+    emb0 = (rng.standard_normal((emb_rows, 64)) * 0.1).astype(np.float32)
+    if kind == 'IGCN':
+        m = R.OracleIGCN(ds.n_users, ds.n_items, ds.train_pairs, 3, emb0, dropout, l2_reg=l2_reg)
+    else:
+        m = R.OracleLightGCN(ds.n_users, ds.n_items, ds.train_pairs, 3, emb0, l2_reg=l2_reg)
+    pairs = ds.train_pairs
+    times = []
+    for s in range(warmup + steps):
+        sel = rng.integers(len(pairs), size=BATCH)
+        u = torch.from_numpy(pairs[sel, 0])
+        p = torch.from_numpy(pairs[sel, 1])
+        ng = torch.from_numpy(rng.integers(ds.n_items, size=BATCH))
+        t0 = time.perf_counter()
+        if kind == 'IGCN':
+            m.train_step(u, p, ng, u, p, ng)
+        else:
+            m.train_step(u, p, ng)
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), m
+
+
+def run_reference(args, shape, kind, l2_reg, dropout):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    ds = build_dataset(shape, 'cpu')
+    steps_per_epoch = math.ceil(len(ds) / BATCH)
+    sec, _ = cpu_step_time(ds, kind, dropout if dropout is not None else 0., l2_reg, args.steps, args.warmup)
+    value = sec * 1e3 * steps_per_epoch
+    cores = os.cpu_count() or 1
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'ms', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': False, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': args.workload, 'shape': shape, 'model': kind, 'n_users': ds.n_users, 'n_items': ds.n_items,
+                       'train_interactions': len(ds), 'batch': BATCH, 'steps_per_epoch': steps_per_epoch},
+            'cpu_baseline': {'value': value, 'unit': 'ms', 'cores': cores, 'kind': 'port',
+                             'sample': '%d full train steps of %d per epoch, extrapolated' % (args.steps, steps_per_epoch)},
+            'e2e': {'value': value, 'unit': 'ms', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=None)
+    ap.add_argument('--warmup', type=int, default=None)
+    ap.add_argument('--workload', default='yelp-lightgcn', choices=sorted(WORKLOADS))
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-steps', type=int, default=4)
+    args = ap.parse_args()
+    shape, kind, l2_reg, dropout = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        args.steps = 5 if args.steps is None else args.steps
+        args.warmup = 1 if args.warmup is None else args.warmup
+        return run_reference(args, shape, kind, l2_reg, dropout)
+    args.steps = 200 if args.steps is None else args.steps
+    args.warmup = 20 if args.warmup is None else max(3, args.warmup)
+
+    import torch
+    import torch.distributed as dist
+    from igcn_cf_b200 import _lib
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    ds = build_dataset(shape, dev)
+    model, trainer = build_model(ds, kind, dropout, l2_reg, dev)
+    n, nnz, D = model.n_users + model.n_items, model.norm_adj.csr.nnz, 64
+    steps_per_epoch = math.ceil(len(ds) / BATCH)
+    step = trainer.step
+    model.train()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- launches per step (eager), then warm-up (captures the CUDA graph)
+    step.use_graph = False
+    before = _lib.launch_count
+    step.run()
+    launches_per_step = _lib.launch_count - before
+    step.use_graph = True
+    for _ in range(args.warmup):
+        step.run()
+
+    # ---- timed region: K steps, resident in HBM, device sampler, graph replay
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step.run()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    ms_per_step = ms / args.steps
+
+    # ---- e2e: host triples (pinned) -> H2D every step, loss D2H every step, public step API
+    pairs = ds.train_pairs
+    g = torch.Generator().manual_seed(0)
+    pool = 64
+    sel = torch.randint(len(pairs), (pool, BATCH), generator=g)
+    tp = torch.from_numpy(pairs)
+    host = torch.stack([tp[sel, 0], tp[sel, 1], torch.randint(ds.n_items, (pool, BATCH), generator=g)], dim=2).pin_memory()
+    is_igcn = kind == 'IGCN'
+    for i in range(3):
+        b = host[i].to(dev, non_blocking=True)
+        step.run(b, b if is_igcn else None).item()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        b = host[i % pool].to(dev, non_blocking=True)
+        step.run(b, b if is_igcn else None).item()
+    barrier()
+    e2e_ms_step = (time.perf_counter() - t0) * 1e3 / args.steps
+    h2d = BATCH * 3 * 8
+    if world > 1:
+        t = torch.tensor([e2e_ms_step], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms_step = t.item()
+
+    # ---- full-ranking evaluation (second half of the metric)
+    trainer.eval('val')
+    barrier()
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        model._bump()                          # force the propagation to be recomputed, as after training
+        rec, _ = trainer.recommend('val')
+    e1.record()
+    barrier()
+    eval_ms = e0.elapsed_time(e1) / reps
+    t0 = time.perf_counter()
+    model._bump()
+    trainer.eval('val')
+    torch.cuda.synchronize()
+    eval_e2e_ms = (time.perf_counter() - t0) * 1e3
+
+    # ---- per-kernel profile + roofline of the dominant kernel
+    summary, spmm_gbs, spmm_avg_ms, spmm_avg_bytes = profile_kernels(trainer, n, nnz, D, 10)
+    peak, peak_src = measured_peaks()
+    total = sum(v['ms_per_step'] for v in summary.values())
+    shares = {k: round(v['ms_per_step'] / total, 4) for k, v in sorted(summary.items(), key=lambda kv: -kv[1]['ms_per_step'])}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, _ = cpu_step_time(build_dataset(shape, 'cpu') if False else ds, kind, dropout if dropout is not None else 0.,
+                               l2_reg, args.cpu_steps, 1)
+        cpu = {'value': sec * 1e3 * steps_per_epoch, 'unit': 'ms', 'cores': os.cpu_count() or 1, 'kind': 'port',
+               'sample': '%d full train steps of %d per epoch (oracle/restate.py), extrapolated' % (args.cpu_steps, steps_per_epoch)}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': ms_per_step * steps_per_epoch, 'unit': 'ms', 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': False,
+                'scaling': 'strong' if world > 1 else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': args.workload, 'shape': shape, 'model': kind, 'n_users': ds.n_users,
+                           'n_items': ds.n_items, 'train_interactions': len(ds), 'nnz_adj': nnz, 'dim': D, 'layers': 3,
+                           'batch': BATCH, 'steps_per_epoch': steps_per_epoch, 'sampler': 'device', 'cuda_graph': True,
+                           'l2': 'no explicit flush: a step touches ~%d MB of distinct buffers (> 126 MB L2)'
+                                 % ((8 * n * D * 4 + nnz * 8) // 2 ** 20)},
+                'e2e': {'value': e2e_ms_step * steps_per_epoch, 'unit': 'ms', 'ms_per_step': e2e_ms_step,
+                        'h2d_bytes_per_step': h2d * (2 if is_igcn else 1), 'd2h_bytes_per_step': 4},
+                'gpu_launches': launches_per_step * args.steps,
+                'eval': {'users_per_s': ds.n_users / (eval_ms * 1e-3), 'ms': eval_ms,
+                         'e2e_users_per_s': ds.n_users / (eval_e2e_ms * 1e-3), 'e2e_ms': eval_e2e_ms,
+                         'what': 'propagate once + fused score/mask/top-20 over all %d users x %d items; e2e adds D2H of the lists and host metrics'
+                                 % (ds.n_users, ds.n_items)},
+                'roofline': {'kernel': 'prop_kernel<16,SPMM> (igcn_spmm)', 'bound': 'hbm', 'achieved': spmm_gbs, 'peak': peak,
+                             'unit': 'GB/s', 'frac': spmm_gbs / peak, 'traffic': None, 'peak_source': peak_src,
+                             'avg_launch_ms': spmm_avg_ms, 'algorithmic_bytes_per_launch': spmm_avg_bytes},
+                'kernel_shares': shares, 'kernel_ms_per_step_eager': round(total, 4), 'clocks': clocks}
+        if cpu:
+            line['cpu_baseline'] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

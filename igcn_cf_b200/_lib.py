@@ -97,9 +97,22 @@ def ptr(t):
     return t.data_ptr()
 
 
+# kernels launched per entry point (igcn_bpr_bwd launches 2 more when dw is requested)
+KERNELS_PER_CALL = {'igcn_colsum_masked': 2}
+launch_count = 0          # running total of kernel launches issued through this binding
+profile_hook = None       # optional callable(name, phase) used by bench.py to time launches
+
+
 def call(name, *args):
+    global launch_count
     lib = load()
-    rc = getattr(lib, name)(*args)
+    launch_count += KERNELS_PER_CALL.get(name, 1) + (2 if name == 'igcn_bpr_bwd' and args[16] else 0)
+    if profile_hook is not None:
+        profile_hook(name, 0)
+        rc = getattr(lib, name)(*args)
+        profile_hook(name, 1)
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError('%s failed (%d): %s' % (name, rc, lib.igcn_last_error().decode()))
 
