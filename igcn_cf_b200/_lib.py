@@ -23,7 +23,7 @@ class CsrStruct(C.Structure):
                 ('long_threshold', c_int32), ('n_chunks', c_int32),
                 ('chunk_row', c_void_p), ('chunk_begin', c_void_p), ('chunk_len', c_void_p),
                 ('chunk_first', c_void_p), ('chunk_count', c_void_p),
-                ('partial', c_void_p), ('counters', c_void_p)]
+                ('partial', c_void_p), ('counters', c_void_p), ('row_order', c_void_p)]
 
 
 class DropoutStruct(C.Structure):
@@ -57,7 +57,15 @@ _SIGNATURES = {
                   c_int64, c_void_p, c_void_p],
     'igcn_step_tick': [c_void_p, c_float, c_float, c_float, c_void_p],
     'igcn_score_topk_exact': [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p,
-                              c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p],
+                              c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'igcn_tc_workspace': [c_int64, c_int64, c_int32, c_int32, C.POINTER(c_int64), C.POINTER(c_int64),
+                          C.POINTER(c_int64)],
+    'igcn_tc_pack': [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
+                     c_void_p],
+    'igcn_tc_candidates': [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int64, c_int64, c_void_p,
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'igcn_tc_finalize': [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                         c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'igcn_hits': [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p],
 }
 EXPORTS = ['igcn_abi_version', 'igcn_last_error'] + sorted(_SIGNATURES)
@@ -98,7 +106,7 @@ def ptr(t):
 
 
 # kernels launched per entry point (igcn_bpr_bwd launches 2 more when dw is requested)
-KERNELS_PER_CALL = {'igcn_colsum_masked': 2}
+KERNELS_PER_CALL = {'igcn_colsum_masked': 2, 'igcn_tc_pack': 3, 'igcn_tc_workspace': 0}
 launch_count = 0          # running total of kernel launches issued through this binding
 profile_hook = None       # optional callable(name, phase) used by bench.py to time launches
 

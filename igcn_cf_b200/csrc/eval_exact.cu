@@ -75,6 +75,8 @@ struct ExactArgs {
     int k;
     int32_t *out_items;
     float *out_scores;
+    const int32_t *out_rows;     // optional: output row of entry b (default b)
+    const int32_t *n_eval_dev;   // optional: device-side entry count (<= n_eval)
 };
 
 // smem: Us[BM][D+4] | Is[BN][min(D,64)+4] | keys[BM][CAP] (u64) | cnt[BM] | thr[BM]
@@ -92,11 +94,13 @@ __global__ void __launch_bounds__(EX_THREADS, 1) score_topk_exact_kernel(const _
     const int tx = tid & 15, ty = tid >> 4;      // 16 item lanes x 16 user groups of 4
     const int64_t ubase = (int64_t)blockIdx.x * BM;
     const int d4 = D >> 2;
+    const int64_t n_eval = a.n_eval_dev ? min(a.n_eval, (int64_t)*a.n_eval_dev) : a.n_eval;
+    if (ubase >= n_eval) return;
 
     for (int idx = tid; idx < BM * d4; idx += EX_THREADS) {
         const int r = idx / d4, c = idx % d4;
         float4 v = f4zero();
-        if (ubase + r < a.n_eval) v = ld4(a.rep + __ldg(a.user_ids + ubase + r) * D + c * 4);
+        if (ubase + r < n_eval) v = ld4(a.rep + __ldg(a.user_ids + ubase + r) * D + c * 4);
         st4(Us + r * DP + c * 4, v);
     }
     if (tid < BM) { cnt[tid] = 0; thr[tid] = -INFINITY; }
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) score_topk_exact_kernel(const _
             const int r = ty * 4 + i;
             const float t = thr[r];
             const int64_t urow = ubase + r;
-            if (urow >= a.n_eval) continue;
+            if (urow >= n_eval) continue;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int64_t item = j0 + tx + 16 * j;
@@ -179,8 +183,9 @@ __global__ void __launch_bounds__(EX_THREADS, 1) score_topk_exact_kernel(const _
 
     for (int r = wid; r < BM; r += EX_THREADS / 32) {
         const int64_t urow = ubase + r;
-        if (urow >= a.n_eval) continue;
+        if (urow >= n_eval) continue;
         const int n = cnt[r];
+        const int64_t orow = a.out_rows ? (int64_t)__ldg(a.out_rows + urow) : urow;
         warp_sort_desc(keys + r * CAP, n, lane);
         for (int q = lane; q < a.k; q += 32) {
             int32_t item = -1;
@@ -190,8 +195,8 @@ __global__ void __launch_bounds__(EX_THREADS, 1) score_topk_exact_kernel(const _
                 item = 0x7fffffff - (int32_t)(key & 0xffffffffu);
                 sc = order_float((uint32_t)(key >> 32));
             }
-            a.out_items[urow * a.k + q] = item;
-            a.out_scores[urow * a.k + q] = sc;
+            a.out_items[orow * a.k + q] = item;
+            a.out_scores[orow * a.k + q] = sc;
         }
     }
 }
@@ -218,7 +223,8 @@ using namespace igcn;
 extern "C" int igcn_score_topk_exact(const float *rep, const int64_t *user_ids, int64_t n_eval, int64_t item_row0,
                                      int64_t n_items, int32_t D, const int64_t *mask_ptr, const int32_t *mask_items,
                                      int64_t item_lo, int64_t item_hi, const uint32_t *banned_bits, int32_t k,
-                                     int32_t *out_items, float *out_scores, void *stream) {
+                                     int32_t *out_items, float *out_scores, const int32_t *out_rows,
+                                     const int32_t *n_eval_dev, void *stream) {
     IGCN_CHECK_ARG(rep && user_ids && out_items && out_scores, "null pointer");
     IGCN_CHECK_ARG(D > 0 && D <= 128 && !(D & 3), "embedding size unsupported (need D % 4 == 0, D <= 128)");
     IGCN_CHECK_ARG(k > 0 && k <= CAP - BN, "k must be in [1, 128]");
@@ -226,7 +232,7 @@ extern "C" int igcn_score_topk_exact(const float *rep, const int64_t *user_ids, 
     IGCN_CHECK_ARG(n_items > 0 && n_items < 0x7fffffff, "n_items out of range");
     if (n_eval <= 0) return 0;
     ExactArgs a{rep, user_ids, n_eval, item_row0, n_items, D, mask_ptr, mask_items, item_lo, item_hi, banned_bits, k,
-                out_items, out_scores};
+                out_items, out_scores, out_rows, n_eval_dev};
     const size_t smem = ((size_t)BM * (D + 4) + (size_t)BN * ((D < 64 ? D : 64) + 4)) * sizeof(float) + (size_t)BM * CAP * sizeof(uint64_t) + BM * 8;
     cudaError_t e = cudaFuncSetAttribute(score_topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("igcn_score_topk_exact: %s", cudaGetErrorString(e)); return (int)e; }

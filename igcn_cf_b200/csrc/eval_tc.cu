@@ -1,0 +1,574 @@
+// Full-ranking evaluation on the 5th-generation tensor cores (tcgen05 + TMEM + bulk-TMA).
+//
+// Replaces torch.mm (reference model.py:122) + the -inf index_put (trainer.py:149-161) +
+// torch.topk (trainer.py:163) for whole-catalogue ranking.  The B x I score matrix lives only in
+// tensor memory; what leaves the SM is <= 96 candidate item ids per user.
+//
+// Exactness without an fp32 MMA kind: operands are rounded to fp16 (kind::f16, fp32 accumulate in
+// TMEM) and ONE EXTRA K-BLOCK carries an error bound: user row gets c*|u| (+eps), item row gets
+// |i| (+eps), both rounded UP, so the tensor core itself produces s_hat = s_fp16 + c|u||i| >= s
+// (Cauchy-Schwarz on the fp16 rounding errors, c = 1e-3 > 2^-10 + accumulation slack).  The
+// epilogue keeps, per user, every item whose upper bound s_hat beats a running threshold that is
+// provably <= the 32nd largest s_hat; candidates are re-scored in exact fp32 (same FMA order as
+// eval_exact.cu) by tc_finalize_kernel, and a user is accepted only if its k-th exact score is
+// strictly above every dropped item's upper bound -- otherwise the user goes to the exact kernel.
+//
+// Kernel structure (one CTA per 128-user tile x item-range split, 7 warps):
+//   warp 0  bulk-TMA producer: cp.async.bulk of pre-arranged operand images (no-swizzle K-major
+//           core-matrix layout written by tc_pack_kernel, so a tile is one contiguous copy)
+//   warp 1  TMEM allocator + single-thread tcgen05.mma issuer (M128 x N256 x K16, 5 per tile)
+//   warp 2  mask helper: turns the (user tile, item tile) bucket of seen items, the banned bitmap
+//           and the item range into a 128 x 256 bitmap in shared memory
+//   warp 3-6 epilogue: tcgen05.ld 32x32b (thread = user row), threshold + mask filter, append to the
+//           row's candidate buffer in shared memory, warp-cooperative compaction when it fills.
+// Pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty double buffer (MMA <-> epilogue),
+// bitmap full (helper -> epilogue).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace igcn {
+
+constexpr int TC_BM = 128;        // users per CTA tile (UMMA M)
+constexpr int TC_BN = 256;        // items per tile     (UMMA N)
+constexpr int TC_CAP = 96;        // candidate slots per user row
+constexpr int TC_KEEP = 32;       // the threshold never rises above the TC_KEEP-th best upper bound
+constexpr int TC_STAGES = 2;      // item-tile smem stages
+constexpr int TC_THREADS = 7 * 32;
+constexpr float TC_C = 1.0e-3f;           // relative bound constant (> 2^-10 + 2^-22 + 80 * 2^-23)
+constexpr float TC_EPS_U = 4.76837158e-7f;   // 2^-21, absolute slack in the user bound entry
+constexpr float TC_EPS_I = 4.8828125e-4f;    // 2^-11, absolute slack in the item bound entry
+
+// ------------------------------------------------------------------ small PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// core matrix = 8 rows x 16 bytes, contiguous 128 B; LBO = byte distance between the two K-adjacent
+// core matrices of one MMA, SBO = byte distance between 8-row groups; version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, both operands K-major, M = 128, N = 256.
+__device__ __forceinline__ uint32_t umma_idesc_f16_m128_n256() {
+    return (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t f_order(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float order_f(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
+
+// ------------------------------------------------------------------ operand packing
+__global__ void maxabs_kernel(const float *__restrict__ x, int64_t n, uint32_t *out) {
+    uint32_t m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, __float_as_uint(fabsf(x[i])));
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);   // max is order independent: deterministic
+}
+
+// scale = 2^(9 - floor(log2(maxabs))) so that the largest |element| lands in [512, 1024)
+__device__ __forceinline__ float tc_scale(const uint32_t *maxabs_bits) {
+    const float m = __uint_as_float(*maxabs_bits);
+    if (!(m > 0.f) || !isfinite(m)) return 1.f;
+    int e;
+    frexpf(m, &e);   // m = f * 2^e, f in [0.5, 1)  -> floor(log2 m) = e - 1
+    return ldexpf(1.f, 10 - e);
+}
+
+// One group of 16 lanes converts one row (D <= 64) into its tile image: kcores core matrices of
+// 8 fp16 (16 B) per row; the last K block holds the bound entry in its first element.
+__global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ rep, const int64_t *__restrict__ row_ids,
+                                                      int64_t row0, int64_t n_rows, int D, int tile_rows, int kcores, int is_user,
+                                                      const uint32_t *__restrict__ maxabs_bits, uint8_t *__restrict__ img) {
+    const int lane = threadIdx.x & 15;
+    const int64_t r = (int64_t)blockIdx.x * 16 + (threadIdx.x >> 4);
+    if (r >= n_rows) return;
+    const uint32_t gmask = 0xffffu << ((threadIdx.x & 31) & 16);
+    const float scale = tc_scale(maxabs_bits);
+    const int64_t src = row_ids ? row_ids[r] : row0 + r;
+    float4 v = f4zero();
+    if (lane * 4 < D) v = ld4(rep + src * D + lane * 4);
+    v = scale4(v, scale);
+    float sq = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(gmask, sq, o, 16);
+    const float norm = sqrtf(sq) * 1.000001f;
+    const int64_t tile = r / tile_rows;
+    const int rr = (int)(r % tile_rows);
+    const size_t group_bytes = (size_t)kcores * 128;
+    uint8_t *base = img + (size_t)tile * (tile_rows / 8) * group_bytes + (size_t)(rr >> 3) * group_bytes + (size_t)(rr & 7) * 16;
+    const int dcores = (D + 15) / 16 * 2;      // K cores holding embedding dims (D padded to 16)
+    if ((lane >> 1) < dcores) {
+        __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t *>(&h0);
+        pk.y = *reinterpret_cast<uint32_t *>(&h1);
+        *reinterpret_cast<uint2 *>(base + (size_t)(lane >> 1) * 128 + (lane & 1) * 8) = pk;
+    }
+    if (lane == 0) {
+        const float b = is_user ? (TC_C * norm + TC_EPS_U) : (norm + TC_EPS_I);
+        uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        z.x = (uint32_t)__half_as_ushort(__float2half_ru(b));
+        *reinterpret_cast<uint4 *>(base + (size_t)dcores * 128) = z;
+        *reinterpret_cast<uint4 *>(base + (size_t)(dcores + 1) * 128) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// ------------------------------------------------------------------ candidate kernel
+struct TcArgs {
+    const uint8_t *a_img;
+    const uint8_t *b_img;
+    int n_utiles, n_itiles, n_splits, kcores;
+    int64_t n_eval, n_items, item_lo, item_hi;
+    const uint32_t *banned;
+    const int32_t *mask_tile_ptr;     // [n_utiles, n_itiles + 1] or NULL
+    const uint16_t *mask_entries;     // (row << 8) | col
+    int32_t *cand_items;              // [n_eval, n_splits, TC_CAP]
+    int32_t *cand_cnt;                // [n_eval, n_splits]
+    float *cand_thr;                  // [n_eval, n_splits]   (scaled units; -inf = nothing was dropped)
+    float *dump;                      // optional [n_utiles*128, n_itiles*256] of s_hat (tests)
+};
+
+struct TcSmem {
+    uint64_t full[TC_STAGES], empty[TC_STAGES], a_full, tmem_full[2], tmem_empty[2], mask_full[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t warp_sort_desc(uint32_t x, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+            const bool dir = (lane & k) == 0, lower = (lane & j) == 0;
+            x = (lower == dir) ? max(x, y) : min(x, y);
+        }
+    return x;
+}
+
+// Shrink one row's candidate buffer (n in (64, 96]) keeping every entry whose score is >= a threshold
+// that has at least TC_KEEP entries at or above it.  Returns the new count; thr_key gets the threshold.
+__device__ __forceinline__ int compact_row(uint64_t *buf, int n, int lane, uint32_t &thr_key) {
+    const uint64_t e0 = buf[lane], e1 = buf[lane + 32], e2 = (lane + 64 < n) ? buf[lane + 64] : 0ULL;
+    const uint32_t s0 = (uint32_t)(e0 >> 32), s1 = (uint32_t)(e1 >> 32), s2 = (uint32_t)(e2 >> 32);
+    // second largest of this lane's scores; >= 16 lanes at or above the 16th largest of those
+    // contribute two entries each -> at least 32 entries survive
+    const uint32_t second = max(min(s0, s1), min(max(s0, s1), s2));
+    uint32_t t = __shfl_sync(0xffffffffu, warp_sort_desc(second, lane), 15);
+    bool k0 = s0 >= t, k1 = s1 >= t, k2 = (lane + 64 < n) && s2 >= t;
+    uint32_t b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1), b2 = __ballot_sync(0xffffffffu, k2);
+    int kept = __popc(b0) + __popc(b1) + __popc(b2);
+    __syncwarp();
+    if (kept > TC_CAP - 32) {
+        // rare: too many ties / flat scores -> exact top-TC_KEEP by counting (keys are unique)
+        int r0 = 0, r1 = 0, r2 = 0;
+        for (int j = 0; j < n; ++j) {
+            const uint64_t x = buf[j];
+            r0 += x > e0; r1 += x > e1; r2 += x > e2;
+        }
+        __syncwarp();
+        k0 = r0 < TC_KEEP; k1 = r1 < TC_KEEP; k2 = (lane + 64 < n) && r2 < TC_KEEP;
+        if (k0) buf[r0] = e0;
+        if (k1) buf[r1] = e1;
+        if (k2) buf[r2] = e2;
+        uint32_t last = 0;
+        if (r0 == TC_KEEP - 1) last = s0;
+        if (r1 == TC_KEEP - 1) last = s1;
+        if ((lane + 64 < n) && r2 == TC_KEEP - 1) last = s2;
+        t = __reduce_max_sync(0xffffffffu, last);
+        kept = TC_KEEP;
+    } else {
+        const uint32_t lt = (1u << lane) - 1u;
+        const int p0 = __popc(b0 & lt), p1 = __popc(b0) + __popc(b1 & lt), p2 = __popc(b0) + __popc(b1) + __popc(b2 & lt);
+        if (k0) buf[p0] = e0;
+        if (k1) buf[p1] = e1;
+        if (k2) buf[p2] = e2;
+    }
+    __syncwarp();
+    thr_key = t;
+    return kept;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ TcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t a_bytes = (uint32_t)(TC_BM / 8) * a.kcores * 128;
+    const uint32_t b_bytes = (uint32_t)(TC_BN / 8) * a.kcores * 128;
+    uint8_t *sA = smem_raw;
+    uint8_t *sB = sA + a_bytes;
+    uint64_t *cand = reinterpret_cast<uint64_t *>(sB + (size_t)TC_STAGES * b_bytes);
+    uint32_t *bitmap = reinterpret_cast<uint32_t *>(cand + (size_t)TC_BM * (TC_CAP + 1));
+    TcSmem *sm = reinterpret_cast<TcSmem *>(bitmap + 2 * TC_BM * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ut = blockIdx.x / a.n_splits, sp = blockIdx.x % a.n_splits;
+    // item tiles intersecting [item_lo, item_hi), divided evenly over the splits
+    const int64_t hi_eff = min(a.item_hi, a.n_items);
+    const int t_first = (int)(max((int64_t)0, a.item_lo) / TC_BN);
+    const int t_last = (int)((hi_eff + TC_BN - 1) / TC_BN);                 // exclusive
+    const int n_t = max(0, t_last - t_first);
+    const int per = (n_t + a.n_splits - 1) / a.n_splits;
+    const int t0 = t_first + sp * per, t1 = min(t_last, t0 + per);
+    const int n_it = max(0, t1 - t0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
+        mbar_init(&sm->a_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm->tmem_full[i], 1); mbar_init(&sm->tmem_empty[i], 4); mbar_init(&sm->mask_full[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 2 * TC_BM * 8; i += TC_THREADS) bitmap[i] = 0u;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm->tmem_base;
+
+    if (warp == 0) {
+        // ===== bulk-TMA producer
+        if (lane == 0 && n_it > 0) {
+            mbar_arrive_expect_tx(&sm->a_full, a_bytes);
+            bulk_g2s(sA, a.a_img + (size_t)ut * a_bytes, a_bytes, &sm->a_full);
+            for (int it = 0; it < n_it; ++it) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                mbar_wait(&sm->empty[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&sm->full[s], b_bytes);
+                bulk_g2s(sB + (size_t)s * b_bytes, a.b_img + (size_t)(t0 + it) * b_bytes, b_bytes, &sm->full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread)
+        if (lane == 0 && n_it > 0) {
+            const uint32_t idesc = umma_idesc_f16_m128_n256();
+            const uint32_t sbo = (uint32_t)a.kcores * 128, lbo = 128;
+            const int ksteps = a.kcores / 2;
+            mbar_wait(&sm->a_full, 0);
+            for (int it = 0; it < n_it; ++it) {
+                const int s = it % TC_STAGES, acc = it & 1;
+                mbar_wait(&sm->tmem_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                mbar_wait(&sm->full[s], (uint32_t)(it / TC_STAGES) & 1u);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + (size_t)s * b_bytes);
+                for (int ks = 0; ks < ksteps; ++ks)
+                    tc_mma_f16(tmem_base + (uint32_t)acc * TC_BN, umma_desc(a0 + ks * 256, lbo, sbo), umma_desc(b0 + ks * 256, lbo, sbo),
+                               idesc, ks > 0 ? 1u : 0u);
+                tc_commit(&sm->empty[s]);          // smem stage reusable once these MMAs retire
+                tc_commit(&sm->tmem_full[acc]);    // accumulator ready for the epilogue
+            }
+        }
+    } else if (warp == 2) {
+        // ===== mask helper: seen-item bucket + banned bitmap + item range -> bitmap[acc][row][8 words]
+        for (int it = 0; it < n_it; ++it) {
+            const int acc = it & 1, t = t0 + it;
+            mbar_wait(&sm->tmem_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+            uint32_t *bm = bitmap + (size_t)acc * TC_BM * 8;
+            uint32_t common = 0;
+            if (lane < 8) {
+                const int64_t c0 = (int64_t)t * TC_BN + lane * 32;
+                if (c0 < a.item_lo) common |= (a.item_lo - c0 >= 32) ? 0xffffffffu : ((1u << (a.item_lo - c0)) - 1u);
+                if (c0 + 32 > hi_eff) common |= (c0 >= hi_eff) ? 0xffffffffu : ~((1u << (hi_eff - c0)) - 1u);
+                if (a.banned && c0 < a.n_items) common |= __ldg(a.banned + (c0 >> 5));
+            }
+            if (__any_sync(0xffffffffu, common != 0u)) {
+                for (int w = 0; w < 8; ++w) {
+                    const uint32_t cw = __shfl_sync(0xffffffffu, common, w);
+                    if (cw)
+                        for (int r = lane; r < TC_BM; r += 32) bm[r * 8 + w] |= cw;
+                }
+                __syncwarp();
+            }
+            if (a.mask_tile_ptr) {
+                const int32_t *p = a.mask_tile_ptr + (size_t)ut * (a.n_itiles + 1) + t;
+                const int e0 = __ldg(p), e1 = __ldg(p + 1);
+                for (int e = e0 + lane; e < e1; e += 32) {
+                    const uint32_t ent = a.mask_entries[e];
+                    atomicOr(bm + (ent >> 8) * 8 + ((ent & 255u) >> 5), 1u << (ent & 31u));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm->mask_full[acc]);
+        }
+    } else {
+        // ===== epilogue: thread = user row (TMEM lane), 32 columns per tcgen05.ld
+        const int q = warp & 3;                         // warps 3,4,5,6 -> TMEM lane quarters 3,0,1,2
+        const int row = q * 32 + lane;
+        uint64_t *mybuf = cand + (size_t)row * (TC_CAP + 1);
+        float thr = -INFINITY;
+        int cnt = 0;
+        for (int it = 0; it < n_it; ++it) {
+            const int acc = it & 1, t = t0 + it;
+            const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(&sm->tmem_full[acc], ph);
+            mbar_wait(&sm->mask_full[acc], ph);
+            tc_fence_after();
+            uint32_t *bm = bitmap + ((size_t)acc * TC_BM + row) * 8;
+            const uint4 m_lo = *reinterpret_cast<uint4 *>(bm), m_hi = *reinterpret_cast<uint4 *>(bm + 4);
+            *reinterpret_cast<uint4 *>(bm) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4 *>(bm + 4) = make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t mw[8] = {m_lo.x, m_lo.y, m_lo.z, m_lo.w, m_hi.x, m_hi.y, m_hi.z, m_hi.w};
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_BN;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                uint32_t full_rows = __ballot_sync(0xffffffffu, cnt > TC_CAP - 32);
+                while (full_rows) {
+                    const int r = __ffs(full_rows) - 1;
+                    full_rows &= full_rows - 1;
+                    const int n = __shfl_sync(0xffffffffu, cnt, r);
+                    uint32_t key;
+                    const int kept = compact_row(cand + (size_t)(q * 32 + r) * (TC_CAP + 1), n, lane, key);
+                    if (lane == r) { cnt = kept; thr = order_f(key); }
+                }
+                uint32_t v[32];
+                tc_ld32(taddr + ch * 32, v);
+                tc_wait_ld();
+                const uint32_t m = mw[ch];
+                const int item0 = t * TC_BN + ch * 32;
+                if (a.dump && (int64_t)ut * TC_BM + row < (int64_t)a.n_utiles * TC_BM) {
+                    float *d = a.dump + ((size_t)ut * TC_BM + row) * ((size_t)a.n_itiles * TC_BN) + item0;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) d[c] = __uint_as_float(v[c]);
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float s = __uint_as_float(v[c]);
+                    const bool take = (s > thr) && !((m >> c) & 1u);
+                    if (take) mybuf[cnt] = ((uint64_t)f_order(s) << 32) | (uint32_t)(item0 + c);
+                    cnt += take ? 1 : 0;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm->tmem_empty[acc]);
+        }
+        // dump this row's candidates
+        __syncwarp();
+        for (int r = 0; r < 32; ++r) {
+            const int64_t b = (int64_t)ut * TC_BM + q * 32 + r;
+            if (b >= a.n_eval) break;
+            const int n = __shfl_sync(0xffffffffu, cnt, r);
+            const float th = __shfl_sync(0xffffffffu, thr, r);
+            const uint64_t *src = cand + (size_t)(q * 32 + r) * (TC_CAP + 1);
+            int32_t *dst = a.cand_items + ((size_t)b * a.n_splits + sp) * TC_CAP;
+            for (int e = lane; e < n; e += 32) dst[e] = (int32_t)(uint32_t)(src[e] & 0xffffffffu);
+            if (lane == 0) {
+                a.cand_cnt[b * a.n_splits + sp] = n;
+                a.cand_thr[b * a.n_splits + sp] = th;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
+// ------------------------------------------------------------------ exact re-scoring + verification
+// One warp per user: exact fp32 scores of all candidates (FMA chain, ascending d -- identical to
+// eval_exact.cu), rank by (score desc, item asc), emit top-k, and verify that the k-th exact score
+// is strictly above every dropped item's upper bound.  Unverified users are appended to a list.
+__global__ void __launch_bounds__(256) tc_finalize_kernel(const float *__restrict__ rep, const int64_t *__restrict__ user_ids,
+                                                          int64_t n_eval, int64_t item_row0, int D, int n_splits,
+                                                          const int32_t *__restrict__ cand_items, const int32_t *__restrict__ cand_cnt,
+                                                          const float *__restrict__ cand_thr, const uint32_t *__restrict__ maxabs_bits,
+                                                          int k, int32_t *out_items, float *out_scores, int32_t *fb_count,
+                                                          int64_t *fb_users, int32_t *fb_rows) {
+    extern __shared__ uint64_t fin_keys[];               // [8 warps][n_splits * TC_CAP]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * 8 + wid;
+    if (b >= n_eval) return;
+    const int cap = n_splits * TC_CAP;
+    uint64_t *keys = fin_keys + (size_t)wid * cap;
+    const int64_t u = user_ids[b];
+    const float *urow = rep + u * D;
+    float thr_max = -INFINITY;
+    int n = 0;
+    for (int sp = 0; sp < n_splits; ++sp) {
+        const int c = cand_cnt[b * n_splits + sp];
+        thr_max = fmaxf(thr_max, cand_thr[b * n_splits + sp]);
+        const int32_t *src = cand_items + ((size_t)b * n_splits + sp) * TC_CAP;
+        for (int e = lane; e < c; e += 32) {
+            const int32_t item = src[e];
+            const float *irow = rep + (item_row0 + item) * D;
+            float s = 0.f;
+            for (int d = 0; d < D; d += 4) {
+                const float4 x = ld4(urow + d), y = ld4(irow + d);
+                s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+            }
+            keys[n + e] = ((uint64_t)f_order(s) << 32) | (uint32_t)(0x7fffffff - item);
+        }
+        n += c;
+    }
+    __syncwarp();
+    float kth = -INFINITY;
+    for (int e = lane; e < n; e += 32) {
+        const uint64_t mine = keys[e];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += keys[j] > mine;
+        if (rank < k) {
+            out_items[b * k + rank] = 0x7fffffff - (int32_t)(mine & 0xffffffffu);
+            out_scores[b * k + rank] = order_f((uint32_t)(mine >> 32));
+        }
+        if (rank == k - 1) kth = order_f((uint32_t)(mine >> 32));
+    }
+    for (int q = n + lane; q < k; q += 32) { out_items[b * k + q] = -1; out_scores[b * k + q] = -INFINITY; }
+    kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, 16));
+    kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, 8));
+    kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, 4));
+    kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, 2));
+    kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, 1));
+    if (lane == 0) {
+        const float scale = tc_scale(maxabs_bits);
+        // dropped items satisfy scale^2 * s <= s_hat <= thr_max; scale^2 is a power of two (exact)
+        const bool ok = (thr_max == -INFINITY) || (n >= k && kth * scale * scale > thr_max);
+        if (!ok) {
+            const int slot = atomicAdd(fb_count, 1);
+            fb_users[slot] = u;
+            fb_rows[slot] = (int32_t)b;
+        }
+    }
+}
+
+}  // namespace igcn
+
+using namespace igcn;
+
+static int tc_kcores(int D) { return ((D + 15) / 16) * 2 + 2; }
+
+extern "C" int igcn_tc_workspace(int64_t n_eval, int64_t n_items, int32_t D, int32_t n_splits, int64_t *a_img_bytes,
+                                 int64_t *b_img_bytes, int64_t *cand_slots) {
+    IGCN_CHECK_ARG(D > 0 && D <= 64 && !(D & 3), "tensor-core scoring supports D % 4 == 0, D <= 64");
+    IGCN_CHECK_ARG(n_splits >= 1 && n_splits <= 8, "n_splits must be in [1, 8]");
+    const int64_t kc = tc_kcores(D);
+    *a_img_bytes = (n_eval + TC_BM - 1) / TC_BM * (TC_BM / 8) * kc * 128;
+    *b_img_bytes = (n_items + TC_BN - 1) / TC_BN * (TC_BN / 8) * kc * 128;
+    *cand_slots = n_eval * n_splits * TC_CAP;
+    return 0;
+}
+
+extern "C" int igcn_tc_pack(const float *rep, int64_t n_rep_elems, const int64_t *user_ids, int64_t n_eval, int64_t item_row0,
+                            int64_t n_items, int32_t D, uint32_t *maxabs_bits, uint8_t *a_img, uint8_t *b_img, void *stream) {
+    IGCN_CHECK_ARG(rep && user_ids && maxabs_bits && a_img && b_img, "null pointer");
+    IGCN_CHECK_ARG(D > 0 && D <= 64 && !(D & 3), "tensor-core scoring supports D % 4 == 0, D <= 64");
+    cudaStream_t st = as_stream(stream);
+    const int kc = tc_kcores(D);
+    cudaMemsetAsync(maxabs_bits, 0, sizeof(uint32_t), st);
+    maxabs_kernel<<<148 * 4, 256, 0, st>>>(rep, n_rep_elems, maxabs_bits);
+    if (n_eval > 0)
+        tc_pack_kernel<<<(unsigned)((n_eval + 15) / 16), 256, 0, st>>>(rep, user_ids, 0, n_eval, D, TC_BM, kc, 1, maxabs_bits, a_img);
+    if (n_items > 0)
+        tc_pack_kernel<<<(unsigned)((n_items + 15) / 16), 256, 0, st>>>(rep, nullptr, item_row0, n_items, D, TC_BN, kc, 0, maxabs_bits, b_img);
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, int64_t n_eval, int64_t n_items, int32_t D,
+                                  int32_t n_splits, int64_t item_lo, int64_t item_hi, const uint32_t *banned_bits,
+                                  const int32_t *mask_tile_ptr, const uint16_t *mask_entries, int32_t *cand_items,
+                                  int32_t *cand_cnt, float *cand_thr, float *dump, void *stream) {
+    IGCN_CHECK_ARG(a_img && b_img && cand_items && cand_cnt && cand_thr, "null pointer");
+    IGCN_CHECK_ARG(D > 0 && D <= 64 && !(D & 3), "tensor-core scoring supports D % 4 == 0, D <= 64");
+    IGCN_CHECK_ARG(n_splits >= 1 && n_splits <= 8, "n_splits must be in [1, 8]");
+    IGCN_CHECK_ARG(!mask_tile_ptr || mask_entries, "mask_tile_ptr without mask_entries");
+    if (n_eval <= 0) return 0;
+    TcArgs a{};
+    a.a_img = a_img; a.b_img = b_img;
+    a.n_utiles = (int)((n_eval + TC_BM - 1) / TC_BM);
+    a.n_itiles = (int)((n_items + TC_BN - 1) / TC_BN);
+    a.n_splits = n_splits; a.kcores = tc_kcores(D);
+    a.n_eval = n_eval; a.n_items = n_items; a.item_lo = item_lo; a.item_hi = item_hi;
+    a.banned = banned_bits; a.mask_tile_ptr = mask_tile_ptr; a.mask_entries = mask_entries;
+    a.cand_items = cand_items; a.cand_cnt = cand_cnt; a.cand_thr = cand_thr; a.dump = dump;
+    const size_t smem = (size_t)(TC_BM / 8 + TC_STAGES * (TC_BN / 8)) * a.kcores * 128 + (size_t)TC_BM * (TC_CAP + 1) * 8 +
+                        2 * TC_BM * 8 * 4 + sizeof(TcSmem) + 1024;
+    cudaError_t e = cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("igcn_tc_candidates: %s", cudaGetErrorString(e)); return (int)e; }
+    score_tc_kernel<<<(unsigned)(a.n_utiles * n_splits), TC_THREADS, smem, as_stream(stream)>>>(a);
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_tc_finalize(const float *rep, const int64_t *user_ids, int64_t n_eval, int64_t item_row0, int32_t D,
+                                int32_t n_splits, const int32_t *cand_items, const int32_t *cand_cnt, const float *cand_thr,
+                                const uint32_t *maxabs_bits, int32_t k, int32_t *out_items, float *out_scores,
+                                int32_t *fb_count, int64_t *fb_users, int32_t *fb_rows, void *stream) {
+    IGCN_CHECK_ARG(rep && user_ids && cand_items && cand_cnt && cand_thr && maxabs_bits && out_items && out_scores, "null pointer");
+    IGCN_CHECK_ARG(fb_count && fb_users && fb_rows, "null fallback buffers");
+    IGCN_CHECK_ARG(k > 0 && k <= TC_KEEP - 8, "tensor-core path supports k <= 24");
+    if (n_eval <= 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    cudaMemsetAsync(fb_count, 0, sizeof(int32_t), st);
+    const size_t smem = (size_t)8 * n_splits * TC_CAP * sizeof(uint64_t);
+    cudaError_t e = cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("igcn_tc_finalize: %s", cudaGetErrorString(e)); return (int)e; }
+    tc_finalize_kernel<<<(unsigned)((n_eval + 7) / 8), 256, smem, st>>>(rep, user_ids, n_eval, item_row0, D, n_splits, cand_items,
+                                                                         cand_cnt, cand_thr, maxabs_bits, k, out_items, out_scores,
+                                                                         fb_count, fb_users, fb_rows);
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}

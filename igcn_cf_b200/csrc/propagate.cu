@@ -5,11 +5,13 @@
 //   igcn_inmo_bwd   dE = F~^T G         transposed, mask regenerated            K4
 //   igcn_colsum_masked   gradient of the two global template rows
 //
-// Work decomposition (all three share it): one group of LANES = D/4 lanes owns one row and
-// walks its non-zeros in CSR order; every lane carries one float4 of the 4*LANES-wide row, so a
-// 64-dim row is one 256-byte gather per neighbour (16 lanes x 128-bit).  Column ids and values
-// are loaded LANES at a time (coalesced) and broadcast with shuffles; 8 gathers are kept in
-// flight per group.  Rows longer than `long_threshold` are pre-cut into chunks on the host
+// Work decomposition (all three share it): a group of 8 lanes owns one row (4 rows per warp) and
+// walks its non-zeros in CSR order; for D = 64 every lane carries two float4 accumulators, so one
+// neighbour is two 128-bit loads per lane and each load instruction of a group reads one full
+// 128-byte line.  Column ids and values are loaded 8 at a time (coalesced) and broadcast with
+// shuffles; 4 neighbours (8 loads per lane) are in flight per group.  Rows are visited in
+// degree-descending order (igcn_csr.row_order) so the rows sharing a warp have similar lengths
+// and the longest ones start first.  Rows longer than `long_threshold` are pre-cut into chunks on the host
 // (igcn_csr.chunk_*): chunk units come first in the grid, write partial sums, and the last one
 // to arrive (self-resetting counter) adds the partials in chunk order -- deterministic, and
 // independent of how rows are sharded over GPUs.
@@ -41,37 +43,46 @@ struct PropArgs {
 constexpr int kThreads = 256;
 constexpr uint32_t kSelfCol = 0xffffffffu;
 
-template <int LANES>
-__device__ __forceinline__ uint32_t group_mask(int lane_in_warp) {
-    if (LANES == 32) return 0xffffffffu;
-    const uint32_t base = (LANES == 16) ? 0xffffu : 0xffu;
-    return base << (lane_in_warp & ~(LANES - 1));
+template <int LPR>
+__device__ __forceinline__ uint32_t group_mask() {
+    if (LPR == 32) return 0xffffffffu;
+    const uint32_t base = (LPR == 16) ? 0xffffu : 0xffu;
+    return base << ((threadIdx.x & 31) & ~(LPR - 1));
 }
 
-// Sum of the gathered rows of non-zeros [beg, end) of one row, as this lane's float4 slice.
-template <int LANES, int MODE, int DROP>
-__device__ __forceinline__ float4 gather_range(const PropArgs &a, int64_t beg, int64_t end,
-                                               int64_t grow /* global id of this row */,
-                                               int lane, uint32_t gmask, bool active, uint64_t seed) {
-    float4 acc = f4zero();
+// Thread mapping: LPR lanes own one row, each lane carries V float4 accumulators; vector v of lane
+// l covers floats [v*LPR*4 + l*4, +4), so every load instruction of a group reads one contiguous
+// LPR*16-byte piece (a full 128-byte line for LPR = 8).  EXACT: D == LPR*V*4 (no per-vector guard).
+template <int LPR, int V, bool EXACT>
+struct RowVec {
+    float4 v[V];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < V; ++i) v[i] = f4zero();
+    }
+    static __device__ __forceinline__ bool on(int i, int lane, int D) { return EXACT || (i * LPR + lane) * 4 < D; }
+};
+
+// Sum over non-zeros [beg, end) of one row of w_e * T[col_e] (this lane's slices).
+template <int LPR, int V, bool EXACT, int MODE, int DROP>
+__device__ __forceinline__ void gather_range(const PropArgs &a, RowVec<LPR, V, EXACT> &acc, int64_t beg, int64_t end,
+                                             int64_t grow, int lane, uint32_t gmask, uint64_t seed) {
     const int32_t *__restrict__ col = a.g.col;
     const float *__restrict__ val = a.g.val;
-    const float *__restrict__ X = a.X;
     const int D = a.D;
-    const int shift = (threadIdx.x & 31) & ~(LANES - 1);
+    const float *__restrict__ Tl = a.X + lane * 4;
 
-    for (int64_t e0 = beg; e0 < end; e0 += LANES) {
-        const int n = (int)min((int64_t)LANES, end - e0);
+    for (int64_t e0 = beg; e0 < end; e0 += LPR) {
+        const int n = (int)min((int64_t)LPR, end - e0);
         int c = 0;
-        float v = 0.f;
-        bool keep = false;
+        float w = 0.f;
         if (lane < n) {
             const int64_t e = e0 + lane;
             c = __ldg(col + e);
-            keep = true;
             if (MODE == MODE_SPMM) {
-                v = val ? __ldg(val + e) : 1.f;
+                w = val ? __ldg(val + e) : 1.f;
             } else {
+                bool keep = true;
                 if (DROP == 1) {
                     const uint32_t h = (MODE == MODE_INMO_FWD) ? edge_hash(seed, (uint32_t)grow, (uint32_t)c)
                                                                : edge_hash(seed, (uint32_t)c, (uint32_t)grow);
@@ -84,132 +95,133 @@ __device__ __forceinline__ float4 gather_range(const PropArgs &a, int64_t beg, i
                     c = __ldg(a.tmpl + c);
                     keep = keep && (c >= 0);
                 }
+                w = keep ? 1.f : 0.f;
+                if (!keep) c = 0;
             }
         }
-        if (MODE == MODE_SPMM) {
+        for (int j0 = 0; j0 < n; j0 += 4) {
+            float4 x[4][V];
+            float ww[4];
 #pragma unroll
-            for (int j0 = 0; j0 < LANES; j0 += 8) {
-                if (j0 >= n) break;
-                float4 x[8];
-                float w[8];
+            for (int q = 0; q < 4; ++q) {
+                const int cj = __shfl_sync(gmask, c, j0 + q, LPR);
+                ww[q] = __shfl_sync(gmask, w, j0 + q, LPR);
+                const bool ok = (j0 + q < n) && (MODE == MODE_SPMM || ww[q] != 0.f);
+                const float *p = Tl + (int64_t)cj * D;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int cj = __shfl_sync(gmask, c, j0 + j, LANES);
-                    w[j] = __shfl_sync(gmask, v, j0 + j, LANES);
-                    x[j] = (j0 + j < n && active) ? ld4(X + (int64_t)cj * D + lane * 4) : f4zero();
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) fma4(acc, w[j], x[j]);
+                for (int i = 0; i < V; ++i)
+                    x[q][i] = (ok && RowVec<LPR, V, EXACT>::on(i, lane, D)) ? ld4(p + i * LPR * 4) : f4zero();
             }
-        } else {
-            uint32_t m = (__ballot_sync(gmask, keep) >> shift);
-            m &= (uint32_t)((1ULL << LANES) - 1ULL);
-            while (m) {
-                float4 x[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const bool ok = m != 0;
-                    const int j = ok ? (__ffs(m) - 1) : 0;
-                    m &= m - 1;   // 0 & anything stays 0
-                    const int cj = __shfl_sync(gmask, c, j, LANES);
-                    x[q] = (ok && active) ? ld4(X + (int64_t)cj * D + lane * 4) : f4zero();
-                }
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) add4(acc, x[q]);
-            }
+                for (int i = 0; i < V; ++i) fma4(acc.v[i], ww[q], x[q][i]);
         }
     }
-    return acc;
 }
 
-template <int LANES, int MODE, int DROP>
-__device__ __forceinline__ void finish_row(const PropArgs &a, int64_t r, float4 acc, int lane, bool active, uint64_t seed) {
-    if (!active) return;
+template <int LPR, int V, bool EXACT, int MODE, int DROP>
+__device__ __forceinline__ void finish_row(const PropArgs &a, int64_t r, RowVec<LPR, V, EXACT> &acc, int lane, uint64_t seed) {
     const int D = a.D;
     const int64_t grow = a.row0 + r;
+    float s = 1.f;
+    int64_t out_row = r;
+    bool self = false;
     if (MODE == MODE_SPMM) {
-        for (int j = 0; j < a.n_add; ++j) add4(acc, ld4(a.add[j] + r * D + lane * 4));
-        float s = a.alpha;
+        s = a.alpha;
         if (a.rowscale) s *= __ldg(a.rowscale + r);
-        st4(a.Y + r * D + lane * 4, scale4(acc, s));
     } else if (MODE == MODE_INMO_FWD) {
-        bool keep = true;
-        if (DROP == 1) keep = edge_hash(seed, (uint32_t)grow, kSelfCol) >= a.thresh;
-        if (DROP == 2) keep = (__ldg(a.drop.self_keep + (grow >> 5)) >> (grow & 31)) & 1u;
-        if (keep) {
-            const int64_t gt = grow < a.n_users ? a.glob_user : a.glob_item;
-            add4(acc, ld4(a.X + gt * D + lane * 4));
-        }
-        const float s = __ldg(a.rowscale + r) * a.inv_keep;
-        st4(a.Y + r * D + lane * 4, scale4(acc, s));
+        self = true;
+        if (DROP == 1) self = edge_hash(seed, (uint32_t)grow, kSelfCol) >= a.thresh;
+        if (DROP == 2) self = (__ldg(a.drop.self_keep + (grow >> 5)) >> (grow & 31)) & 1u;
+        s = __ldg(a.rowscale + r) * a.inv_keep;
     } else {
-        int64_t t = grow;
-        if (a.tmpl) t = __ldg(a.tmpl + grow);
-        if (t >= 0) st4(a.Y + t * D + lane * 4, acc);
+        out_row = a.tmpl ? (int64_t)__ldg(a.tmpl + grow) : grow;
+        if (out_row < 0) return;
+    }
+    const int64_t gt = grow < a.n_users ? a.glob_user : a.glob_item;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        if (!RowVec<LPR, V, EXACT>::on(i, lane, D)) continue;
+        const int off = (i * LPR + lane) * 4;
+        float4 t = acc.v[i];
+        if (MODE == MODE_SPMM)
+            for (int j = 0; j < a.n_add; ++j) add4(t, ld4(a.add[j] + r * D + off));
+        if (MODE == MODE_INMO_FWD && self) add4(t, ld4(a.X + gt * D + off));
+        st4(a.Y + out_row * D + off, MODE == MODE_INMO_BWD ? t : scale4(t, s));
     }
 }
 
-template <int LANES, int MODE, int DROP>
+template <int LPR, int V, bool EXACT, int MODE, int DROP>
 __global__ void __launch_bounds__(kThreads) prop_kernel(const __grid_constant__ PropArgs a) {
-    constexpr int GROUPS = kThreads / LANES;
-    const int lane = threadIdx.x % LANES;
-    const uint32_t gmask = group_mask<LANES>(threadIdx.x & 31);
-    const int64_t unit = (int64_t)blockIdx.x * GROUPS + threadIdx.x / LANES;
-    const bool active = lane * 4 < a.D;
+    constexpr int GROUPS = kThreads / LPR;
+    using Vec = RowVec<LPR, V, EXACT>;
+    const int lane = threadIdx.x % LPR;
+    const uint32_t gmask = group_mask<LPR>();
+    const int64_t unit = (int64_t)blockIdx.x * GROUPS + threadIdx.x / LPR;
     const int64_t n_chunks = a.g.n_chunks;
     if (unit >= n_chunks + a.g.n_rows) return;
     uint64_t seed = a.drop.seed;
     if (DROP == 1 && a.drop.seed_dev) seed = mix64(seed ^ mix64(*a.drop.seed_dev + 0x2545f491ULL));
+    const int D = a.D;
+    Vec acc;
+    acc.zero();
 
     if (unit < n_chunks) {
         // ---- one chunk of a long row
         const int ch = (int)unit;
         const int64_t r = a.g.chunk_row[ch];
         const int64_t beg = a.g.chunk_begin[ch];
-        const int64_t end = beg + a.g.chunk_len[ch];
-        float4 acc = gather_range<LANES, MODE, DROP>(a, beg, end, a.row0 + r, lane, gmask, active, seed);
+        gather_range<LPR, V, EXACT, MODE, DROP>(a, acc, beg, beg + a.g.chunk_len[ch], a.row0 + r, lane, gmask, seed);
         const int first = a.g.chunk_first[ch];
         const int count = a.g.chunk_count[ch];
-        if (active) st4(a.g.partial + (int64_t)ch * a.D + lane * 4, acc);
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+            if (Vec::on(i, lane, D)) st4(a.g.partial + (int64_t)ch * D + (i * LPR + lane) * 4, acc.v[i]);
         __threadfence();
         __syncwarp(gmask);
         int old = 0;
         if (lane == 0) old = atomicAdd(a.g.counters + first, 1);
-        old = __shfl_sync(gmask, old, 0, LANES);
+        old = __shfl_sync(gmask, old, 0, LPR);
         if (old != count - 1) return;
         __threadfence();
         if (lane == 0) a.g.counters[first] = 0;   // self-reset for the next launch
-        float4 tot = f4zero();
-        if (active)
-            for (int k = 0; k < count; ++k)
-                add4(tot, __ldcg(reinterpret_cast<const float4 *>(a.g.partial + (int64_t)(first + k) * a.D + lane * 4)));
-        finish_row<LANES, MODE, DROP>(a, r, tot, lane, active, seed);
+        acc.zero();
+        for (int k = 0; k < count; ++k)
+#pragma unroll
+            for (int i = 0; i < V; ++i)
+                if (Vec::on(i, lane, D))
+                    add4(acc.v[i], __ldcg(reinterpret_cast<const float4 *>(a.g.partial + (int64_t)(first + k) * D + (i * LPR + lane) * 4)));
+        finish_row<LPR, V, EXACT, MODE, DROP>(a, r, acc, lane, seed);
         return;
     }
 
-    // ---- one whole (short) row
-    const int64_t r = unit - n_chunks;
+    // ---- one whole (short) row, taken in degree-descending order when a permutation is given
+    int64_t r = unit - n_chunks;
+    if (a.g.row_order) r = __ldg(a.g.row_order + r);
     const int64_t beg = __ldg(a.g.rowptr + r), end = __ldg(a.g.rowptr + r + 1);
     if (n_chunks > 0 && end - beg > a.g.long_threshold) return;   // handled by chunk units
-    float4 acc = gather_range<LANES, MODE, DROP>(a, beg, end, a.row0 + r, lane, gmask, active, seed);
-    finish_row<LANES, MODE, DROP>(a, r, acc, lane, active, seed);
+    gather_range<LPR, V, EXACT, MODE, DROP>(a, acc, beg, end, a.row0 + r, lane, gmask, seed);
+    finish_row<LPR, V, EXACT, MODE, DROP>(a, r, acc, lane, seed);
+}
+
+template <int LPR, int V, bool EXACT, int MODE, int DROP>
+static void launch_one(const PropArgs &a, cudaStream_t st) {
+    const int64_t units = a.g.n_chunks + a.g.n_rows;
+    constexpr int GROUPS = kThreads / LPR;
+    prop_kernel<LPR, V, EXACT, MODE, DROP><<<(unsigned)((units + GROUPS - 1) / GROUPS), kThreads, 0, st>>>(a);
 }
 
 template <int MODE, int DROP>
 static int launch_lanes(const PropArgs &a, cudaStream_t st) {
-    const int64_t units = a.g.n_chunks + a.g.n_rows;
-    if (units == 0) return 0;
+    if (a.g.n_chunks + a.g.n_rows == 0) return 0;
     const int D = a.D;
-    if (D <= 32) {
-        const int64_t blocks = (units + kThreads / 8 - 1) / (kThreads / 8);
-        prop_kernel<8, MODE, DROP><<<(unsigned)blocks, kThreads, 0, st>>>(a);
-    } else if (D <= 64) {
-        const int64_t blocks = (units + kThreads / 16 - 1) / (kThreads / 16);
-        prop_kernel<16, MODE, DROP><<<(unsigned)blocks, kThreads, 0, st>>>(a);
-    } else {
-        const int64_t blocks = (units + kThreads / 32 - 1) / (kThreads / 32);
-        prop_kernel<32, MODE, DROP><<<(unsigned)blocks, kThreads, 0, st>>>(a);
-    }
+    if (D == 64) launch_one<8, 2, true, MODE, DROP>(a, st);
+    else if (D == 32) launch_one<8, 1, true, MODE, DROP>(a, st);
+    else if (D == 128) launch_one<16, 2, true, MODE, DROP>(a, st);
+    else if (D < 32) launch_one<8, 1, false, MODE, DROP>(a, st);
+    else if (D < 64) launch_one<8, 2, false, MODE, DROP>(a, st);
+    else launch_one<16, 2, false, MODE, DROP>(a, st);
     return 0;
 }
 

@@ -216,6 +216,7 @@ class TrainStep:
             self.w_m, self.w_v = opt.moments(model.w)
             self.colsum_scratch = colsum_scratch(n, D, dev)
         self._graphs = {}
+        self._side = torch.cuda.Stream(device=dev)
 
     # -- pieces
     def _sample(self, B):
@@ -236,8 +237,16 @@ class TrainStep:
         call('igcn_step_tick', ptr(self.state), self.lr, BETA1, BETA2, st())
         if sample:
             self._sample(B)
-        call('igcn_bpr_plan', ptr(self.triples), B, m.n_users, ptr(self.order), ptr(self.seg_start), ptr(self.seg_row),
-             ptr(self.n_seg), st())
+        # the scatter plans depend on the triples only: sort them on a side stream while the forward
+        # propagation runs (one CTA each; joins before the gradient kernels)
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            call('igcn_bpr_plan', ptr(self.triples), B, m.n_users, ptr(self.order), ptr(self.seg_start),
+                 ptr(self.seg_row), ptr(self.n_seg), st())
+            if self.is_igcn:
+                call('igcn_bpr_plan', ptr(self.a_triples), B, m.feat_mat.t_users, ptr(self.a_order), ptr(self.a_seg_start),
+                     ptr(self.a_seg_row), ptr(self.a_n_seg), st())
         # forward
         if self.is_igcn:
             x0 = prop.x0_buffer()
@@ -251,8 +260,6 @@ class TrainStep:
              ptr(self.sig), ptr(self.l2), st())
         if self.is_igcn:
             t_u = m.feat_mat.t_users
-            call('igcn_bpr_plan', ptr(self.a_triples), B, t_u, ptr(self.a_order), ptr(self.a_seg_start),
-                 ptr(self.a_seg_row), ptr(self.a_n_seg), st())
             call('igcn_bpr_fwd', ptr(emb), None, ptr(m.w.data), ptr(self.a_triples), B, t_u, D, ptr(self.a_sp),
                  ptr(self.a_sig), None, st())
             call('igcn_loss_finalize', ptr(self.sp), ptr(self.l2), ptr(self.a_sp), B, B, self.l2_reg, self.aux_reg,
@@ -261,6 +268,7 @@ class TrainStep:
             call('igcn_loss_finalize', ptr(self.sp), ptr(self.l2), None, B, 0, self.l2_reg, 0.0, ptr(self.loss),
                  ptr(self.acc), st())
         # backward
+        main.wait_stream(self._side)
         self.gprime.zero_()
         call('igcn_bpr_bwd', ptr(rep), None, ptr(self.triples), B, m.n_users, D, ptr(self.sig), 1.0 / (L + 1),
              self.l2_reg if self.is_igcn else 0.0, 1 if self.is_igcn else 0, ptr(self.order), ptr(self.seg_start),
@@ -366,31 +374,153 @@ class TrainStep:
 
 
 # --------------------------------------------------------------------------- evaluation
+class ListCSR:
+    """Per-user item lists as a sorted CSR on the device (+ host copies for the tile bucketing)."""
+
+    def __init__(self, lists, device, sort=True):
+        lens = np.fromiter((len(x) for x in lists), dtype=np.int64, count=len(lists))
+        ptr_ = np.zeros(len(lists) + 1, dtype=np.int64)
+        np.cumsum(lens, out=ptr_[1:])
+        flat = np.fromiter((i for x in lists for i in x), dtype=np.int64, count=int(ptr_[-1]))
+        if sort and len(flat):
+            rows = np.repeat(np.arange(len(lists), dtype=np.int64), lens)
+            flat = flat[np.lexsort((flat, rows))]
+        self.lens = lens
+        self.ptr_host, self.items_host = ptr_, flat.astype(np.int32)
+        self.ptr = torch.from_numpy(ptr_).to(device)
+        self.items = torch.from_numpy(self.items_host).to(device)
+        self.device = device
+        self._tiles = {}
+
+    def __getitem__(self, i):          # (ptr, items, lens) tuple view used by older call sites
+        return (self.ptr, self.items, self.lens)[i]
+
+    def tiles(self, n_items, users_host=None):
+        """Seen-item pairs bucketed by (128-user tile, 256-item tile) for the tensor-core kernel:
+        (tile_ptr int32 [n_utiles, n_itiles + 1], entries uint16 ((row << 8) | col))."""
+        key = (int(n_items), None if users_host is None else users_host.tobytes())
+        hit = self._tiles.get(key)
+        if hit is None:
+            ptr_, items = self.ptr_host, self.items_host.astype(np.int64)
+            if users_host is None:
+                n_eval = len(ptr_) - 1
+                pos = np.repeat(np.arange(n_eval, dtype=np.int64), np.diff(ptr_))
+            else:
+                n_eval = len(users_host)
+                lens = ptr_[users_host + 1] - ptr_[users_host]
+                pos = np.repeat(np.arange(n_eval, dtype=np.int64), lens)
+                start = np.repeat(ptr_[users_host], lens)
+                off = np.arange(len(pos), dtype=np.int64) - np.repeat(np.cumsum(lens) - lens, lens)
+                items = items[start + off]
+            n_ut, n_it = (n_eval + 127) // 128, (n_items + 255) // 256
+            keyv = (pos // 128) * n_it + items // 256
+            order = np.argsort(keyv, kind='stable')
+            ent = (((pos % 128) << 8) | (items % 256)).astype(np.uint16)[order]
+            counts = np.bincount(keyv, minlength=n_ut * n_it)
+            excl = np.zeros(n_ut * n_it + 1, dtype=np.int64)
+            np.cumsum(counts, out=excl[1:])
+            tile_ptr = np.empty((n_ut, n_it + 1), dtype=np.int32)
+            tile_ptr[:, :n_it] = excl[:-1].reshape(n_ut, n_it)
+            tile_ptr[:, n_it] = excl[np.arange(1, n_ut + 1) * n_it]
+            hit = (torch.from_numpy(tile_ptr).to(self.device),
+                   torch.from_numpy(ent.view(np.int16).copy()).to(self.device))
+            self._tiles = {key: hit}
+        return hit
+
+
 def lists_to_csr(lists, device, sort=True):
-    """list-of-lists -> (ptr int64 [n+1], items int32 [nnz]) on `device`, items ascending per row."""
-    lens = np.fromiter((len(x) for x in lists), dtype=np.int64, count=len(lists))
-    ptr_ = np.zeros(len(lists) + 1, dtype=np.int64)
-    np.cumsum(lens, out=ptr_[1:])
-    flat = np.fromiter((i for x in lists for i in x), dtype=np.int64, count=int(ptr_[-1]))
-    if sort and len(flat):
-        rows = np.repeat(np.arange(len(lists), dtype=np.int64), lens)
-        order = np.lexsort((flat, rows))
-        flat = flat[order]
-    return (torch.from_numpy(ptr_).to(device), torch.from_numpy(flat.astype(np.int32)).to(device), lens)
+    """list-of-lists -> ListCSR (indexable as (ptr, items, lens))."""
+    return ListCSR(lists, device, sort)
 
 
-def score_topk(rep, user_ids, n_users, n_items, k, mask=None, item_lo=0, item_hi=None, banned_bits=None):
-    """Fused scoring + mask + top-k for `user_ids` (model.py:118-123 + trainer.py:149-164).
-    Returns (items int32 [n, k], scores fp32 [n, k])."""
-    _lib.require_cuda(rep, torch.float32, 'rep')
+def score_topk_exact(rep, user_ids, n_users, n_items, k, mask=None, item_lo=0, item_hi=None, banned_bits=None,
+                     out=None, out_rows=None, n_eval_dev=None):
+    """Exact CUDA-core kernel (also the tensor-core path's fallback)."""
     n = int(user_ids.shape[0])
-    out_i = torch.empty((n, k), dtype=torch.int32, device=rep.device)
-    out_s = torch.empty((n, k), dtype=torch.float32, device=rep.device)
+    if out is None:
+        out = (torch.empty((n, k), dtype=torch.int32, device=rep.device),
+               torch.empty((n, k), dtype=torch.float32, device=rep.device))
     mptr, mitems = (None, None) if mask is None else (mask[0], mask[1])
     call('igcn_score_topk_exact', ptr(rep), ptr(user_ids), n, n_users, n_items, rep.shape[1], ptr(mptr), ptr(mitems),
-         int(item_lo), int(n_items if item_hi is None else item_hi), ptr(banned_bits), int(k), ptr(out_i), ptr(out_s),
-         stream_ptr())
-    return out_i, out_s
+         int(item_lo), int(n_items if item_hi is None else item_hi), ptr(banned_bits), int(k), ptr(out[0]), ptr(out[1]),
+         ptr(out_rows), ptr(n_eval_dev), stream_ptr())
+    return out
+
+
+class TcScorer:
+    """tcgen05 scoring pipeline: pack -> candidates -> finalize -> exact fallback (engine-owned buffers)."""
+
+    def __init__(self):
+        self._ws = {}
+        self.last_fallback = None       # device int32[1]: users sent to the exact kernel by the last call
+
+    def _workspace(self, n_eval, n_items, D, n_splits, k, device):
+        key = (n_eval, n_items, D, n_splits, k, str(device))
+        ws = self._ws.get(key)
+        if ws is None:
+            a_b, b_b, slots = C.c_int64(), C.c_int64(), C.c_int64()
+            call('igcn_tc_workspace', n_eval, n_items, D, n_splits, C.byref(a_b), C.byref(b_b), C.byref(slots))
+            z = lambda n, dt: torch.zeros(n, dtype=dt, device=device)
+            ws = {'a_img': z(a_b.value, torch.uint8), 'b_img': z(b_b.value, torch.uint8),
+                  'cand_items': z(slots.value, torch.int32), 'cand_cnt': z(n_eval * n_splits, torch.int32),
+                  'cand_thr': z(n_eval * n_splits, torch.float32), 'maxabs': z(1, torch.int32),
+                  'fb_count': z(1, torch.int32), 'fb_users': z(n_eval, torch.int64), 'fb_rows': z(n_eval, torch.int32)}
+            self._ws = {key: ws}
+        return ws
+
+    def topk(self, rep, user_ids, n_users, n_items, k, mask=None, item_lo=0, item_hi=None, banned_bits=None,
+             users_host=None, n_splits=None, dump=False):
+        n_eval, D = int(user_ids.shape[0]), int(rep.shape[1])
+        item_hi = n_items if item_hi is None else item_hi
+        if n_splits is None:
+            n_splits = int(min(8, max(1, -(-296 // max(1, (n_eval + 127) // 128)))))
+        ws = self._workspace(n_eval, n_items, D, n_splits, k, rep.device)
+        st = stream_ptr
+        call('igcn_tc_pack', ptr(rep), rep.numel(), ptr(user_ids), n_eval, n_users, n_items, D, ptr(ws['maxabs']),
+             ptr(ws['a_img']), ptr(ws['b_img']), st())
+        tile_ptr, entries = (None, None)
+        if mask is not None:
+            tile_ptr, entries = mask.tiles(n_items, users_host)
+        dump_t = None
+        if dump:
+            dump_t = torch.zeros(((n_eval + 127) // 128 * 128, (n_items + 255) // 256 * 256), dtype=torch.float32,
+                                 device=rep.device)
+        call('igcn_tc_candidates', ptr(ws['a_img']), ptr(ws['b_img']), n_eval, n_items, D, n_splits, int(item_lo),
+             int(item_hi), ptr(banned_bits), ptr(tile_ptr), ptr(entries), ptr(ws['cand_items']), ptr(ws['cand_cnt']),
+             ptr(ws['cand_thr']), ptr(dump_t), st())
+        out_i = torch.empty((n_eval, k), dtype=torch.int32, device=rep.device)
+        out_s = torch.empty((n_eval, k), dtype=torch.float32, device=rep.device)
+        call('igcn_tc_finalize', ptr(rep), ptr(user_ids), n_eval, n_users, D, n_splits, ptr(ws['cand_items']),
+             ptr(ws['cand_cnt']), ptr(ws['cand_thr']), ptr(ws['maxabs']), int(k), ptr(out_i), ptr(out_s),
+             ptr(ws['fb_count']), ptr(ws['fb_users']), ptr(ws['fb_rows']), st())
+        # users whose bound did not verify: exact kernel on the device-side list (no host sync)
+        score_topk_exact(rep, ws['fb_users'], n_users, n_items, k, mask, item_lo, item_hi, banned_bits,
+                         out=(out_i, out_s), out_rows=ws['fb_rows'], n_eval_dev=ws['fb_count'])
+        self.last_fallback = ws['fb_count']
+        if dump:
+            return out_i, out_s, dump_t, ws
+        return out_i, out_s
+
+
+_tc_scorer = TcScorer()
+
+
+def score_topk(rep, user_ids, n_users, n_items, k, mask=None, item_lo=0, item_hi=None, banned_bits=None,
+               users_host=None, impl='auto'):
+    """Fused scoring + seen-item mask + top-k for `user_ids` (model.py:118-123 + trainer.py:149-164).
+    Returns (items int32 [n, k], scores fp32 [n, k]), sorted by (score desc, item asc); slots without
+    a candidate hold -1 / -inf.  impl: 'tc' (tcgen05 path, D <= 64 and k <= 24), 'exact', or 'auto'."""
+    _lib.require_cuda(rep, torch.float32, 'rep')
+    tc_ok = rep.shape[1] <= 64 and k <= 24 and (mask is None or isinstance(mask, ListCSR))
+    if impl == 'tc' and not tc_ok:
+        raise RuntimeError('tensor-core scoring needs D <= 64, k <= 24 and a ListCSR mask')
+    if impl == 'exact' or not tc_ok:
+        return score_topk_exact(rep, user_ids, n_users, n_items, k, mask, item_lo, item_hi, banned_bits)
+    if mask is not None and users_host is None:
+        n = int(user_ids.shape[0])
+        if n != len(mask.ptr_host) - 1 or not bool((user_ids == torch.arange(n, device=user_ids.device)).all()):
+            users_host = user_ids.cpu().numpy()
+    return _tc_scorer.topk(rep, user_ids, n_users, n_items, k, mask, item_lo, item_hi, banned_bits, users_host)
 
 
 def hit_matrix(rec, eval_csr):

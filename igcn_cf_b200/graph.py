@@ -20,8 +20,8 @@ import torch
 
 from . import _lib
 
-LONG_THRESHOLD = 512     # rows with more non-zeros than this are split ...
-CHUNK = 256              # ... into chunks of this many non-zeros
+LONG_THRESHOLD = 256     # rows with more non-zeros than this are split ...
+CHUNK = 128              # ... into chunks of this many non-zeros
 
 
 def train_pairs_of(dataset):
@@ -79,6 +79,9 @@ class CsrDevice:
         self.n_chunks = int(len(plan[0]))
         self._plan = [torch.from_numpy(np.ascontiguousarray(a)).to(self.device) for a in plan]
         self.counters = torch.zeros(max(1, self.n_chunks), dtype=torch.int32, device=self.device)
+        # visiting order: longest rows first, ties by row id (stable) -> rows sharing a warp are alike
+        deg = np.diff(self.rowptr_host)
+        self.row_order = torch.from_numpy(np.argsort(-deg, kind='stable').astype(np.int32)).to(self.device)
         self._partial = {}
         self._structs = {}
 
@@ -100,7 +103,7 @@ class CsrDevice:
             s = _lib.CsrStruct(self.n_rows, self.n_cols, self.nnz, self.rowptr.data_ptr(), self.col.data_ptr(),
                                None if self.val is None else self.val.data_ptr(), self.threshold, self.n_chunks,
                                cr.data_ptr(), cb.data_ptr(), cl.data_ptr(), cf.data_ptr(), cc.data_ptr(),
-                               partial.data_ptr(), self.counters.data_ptr())
+                               partial.data_ptr(), self.counters.data_ptr(), self.row_order.data_ptr())
             self._structs[D] = s
         return C.byref(s)
 

@@ -192,7 +192,7 @@ class BasicTrainer:
         else:
             rec_dev = torch.as_tensor(np.ascontiguousarray(rec_items), device=self.device).to(torch.int32).contiguous()
         hit_matrix = engine.hit_matrix(rec_dev, csr).cpu().numpy()
-        eval_data_len = csr[2].astype(np.int32)
+        eval_data_len = csr.lens.astype(np.int32)
         for k in self.topks:
             hit_num = np.sum(hit_matrix[:, :k], axis=1)
             precisions = hit_num / k
@@ -223,7 +223,7 @@ class BasicTrainer:
                 lists = [a + b for a, b in zip(ds.train_data, ds.val_data)]
             else:
                 lists = ds.train_data
-            hit = (key, engine.lists_to_csr(lists, self.device)[:2])
+            hit = (key, engine.lists_to_csr(lists, self.device))
             self._mask_cache[val_or_test] = hit
         return hit[1]
 
@@ -253,7 +253,8 @@ class BasicTrainer:
         users = self.test_users if users is None else users
         lo, hi, bits = self._banned(banned_items)
         return engine.score_topk(rep, users, self.model.n_users, self.model.n_items, max(self.topks),
-                                 mask=self._mask_csr(val_or_test), item_lo=lo, item_hi=hi, banned_bits=bits)
+                                 mask=self._mask_csr(val_or_test), item_lo=lo, item_hi=hi, banned_bits=bits,
+                                 impl=self.config.get('score_impl', 'auto'))
 
     def eval(self, val_or_test, banned_items=None):
         eval_data = getattr(self.dataset, val_or_test + '_data')

@@ -54,6 +54,7 @@ typedef struct igcn_csr {
     const int32_t *chunk_count; /* [n_chunks] number of chunks of the row              */
     float *partial;             /* [n_chunks, D] scratch                               */
     int32_t *counters;          /* [n_chunks] scratch, must be zero before first use   */
+    const int32_t *row_order;   /* [n_rows] visiting order (degree-descending) or NULL */
 } igcn_csr;
 
 /* Edge-dropout description for the INMO layer (reference NGCF.dropout_sp_mat, model.py:263-275,
@@ -186,12 +187,42 @@ int igcn_step_tick(igcn_step_state *state_dev, float lr, float beta1, float beta
  * NULL), or j outside [item_lo, item_hi), or bit j of banned_bits set (may be NULL).
  * Output per user: k item ids (int32, -1 when fewer than k candidates) and scores, sorted by
  * (score descending, item ascending).  This is the exact CUDA-core kernel; it is also the
- * fallback the tensor-core path uses for users whose candidate bound does not verify. */
+ * fallback the tensor-core path uses for users whose candidate bound does not verify: out_rows
+ * (may be NULL) gives the output row of entry b, n_eval_dev (may be NULL) a device-side count. */
 int igcn_score_topk_exact(const float *rep, const int64_t *user_ids, int64_t n_eval,
                           int64_t item_row0, int64_t n_items, int32_t D,
                           const int64_t *mask_ptr, const int32_t *mask_items,
                           int64_t item_lo, int64_t item_hi, const uint32_t *banned_bits,
-                          int32_t k, int32_t *out_items, float *out_scores, void *stream);
+                          int32_t k, int32_t *out_items, float *out_scores,
+                          const int32_t *out_rows, const int32_t *n_eval_dev, void *stream);
+
+/* ---- tensor-core scoring (tcgen05 / TMEM / bulk TMA), D <= 64, k <= 24 ------------------------
+ * Same contract as igcn_score_topk_exact, split in three launches the host chains on one stream:
+ *   igcn_tc_pack        fp32 rep rows -> fp16 operand images in the UMMA core-matrix layout, with one
+ *                       extra K block carrying the rounding-error bound (c*|u| for users, |i| for items)
+ *   igcn_tc_candidates  tcgen05.mma M128 x N256 tiles, accumulators in TMEM; the epilogue filters
+ *                       s_hat >= running threshold and !masked into <= 96 candidates per (user, split)
+ *   igcn_tc_finalize    exact fp32 re-scoring (same FMA order as the exact kernel), top-k, and the
+ *                       proof check; users that fail it are appended to (fb_users, fb_rows, fb_count)
+ *                       for igcn_score_topk_exact.
+ * a_img / b_img must be zero-initialised by the caller (padding rows); sizes from igcn_tc_workspace.
+ * mask_tile_ptr [ceil(n_eval/128), ceil(n_items/256)+1] + mask_entries ((row<<8)|col, uint16) is the
+ * seen-item CSR bucketed by (user tile, item tile); dump (tests only) receives every s_hat. */
+int igcn_tc_workspace(int64_t n_eval, int64_t n_items, int32_t D, int32_t n_splits,
+                      int64_t *a_img_bytes, int64_t *b_img_bytes, int64_t *cand_slots);
+int igcn_tc_pack(const float *rep, int64_t n_rep_elems, const int64_t *user_ids, int64_t n_eval,
+                 int64_t item_row0, int64_t n_items, int32_t D, uint32_t *maxabs_bits,
+                 uint8_t *a_img, uint8_t *b_img, void *stream);
+int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, int64_t n_eval, int64_t n_items,
+                       int32_t D, int32_t n_splits, int64_t item_lo, int64_t item_hi,
+                       const uint32_t *banned_bits, const int32_t *mask_tile_ptr,
+                       const uint16_t *mask_entries, int32_t *cand_items, int32_t *cand_cnt,
+                       float *cand_thr, float *dump, void *stream);
+int igcn_tc_finalize(const float *rep, const int64_t *user_ids, int64_t n_eval, int64_t item_row0,
+                     int32_t D, int32_t n_splits, const int32_t *cand_items,
+                     const int32_t *cand_cnt, const float *cand_thr, const uint32_t *maxabs_bits,
+                     int32_t k, int32_t *out_items, float *out_scores, int32_t *fb_count,
+                     int64_t *fb_users, int32_t *fb_rows, void *stream);
 
 /* hit[u][j] = 1 if rec[u][j] is in eval_items[eval_ptr[u] .. eval_ptr[u+1]) (sorted), else 0:
  * the membership double loop of BasicTrainer.calculate_metrics (trainer.py:111-115). */

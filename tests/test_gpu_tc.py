@@ -1,0 +1,109 @@
+"""tcgen05 scoring path: (1) the tensor core really produces an UPPER BOUND of the exact score
+(validates operand packing, UMMA descriptors and the error-bound K block), (2) its final top-k is
+bit-identical to the exact CUDA-core kernel (items and scores), including masks, banned ranges and
+bitmaps, odd sizes and the fallback path for users whose bound cannot be verified."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda:0')
+
+
+def _case(n_users, n_items, D, seed, mask_deg=6, scale=0.1):
+    g = torch.Generator().manual_seed(seed)
+    rep = (torch.randn(n_users + n_items, D, generator=g) * scale).to(DEV)
+    rng = np.random.default_rng(seed)
+    lists = [sorted(rng.choice(n_items, size=int(rng.integers(0, mask_deg * 2 + 1)), replace=False).tolist())
+             for _ in range(n_users)]
+    return rep, lists
+
+
+def _both(rep, n_users, k, lists=None, lo=0, hi=None, banned=None, users=None):
+    from igcn_cf_b200 import engine
+    from igcn_cf_b200.graph import _pack_bits
+    n_items = rep.shape[0] - n_users
+    mask = None if lists is None else engine.lists_to_csr(lists, DEV)
+    bits = None
+    if banned is not None:
+        flags = np.zeros(n_items, dtype=bool)
+        flags[list(banned)] = True
+        bits = _pack_bits(flags, DEV)
+    u = torch.arange(n_users, device=DEV) if users is None else torch.tensor(users, dtype=torch.int64, device=DEV)
+    ex = engine.score_topk(rep, u, n_users, n_items, k, mask, lo, hi, bits, impl='exact')
+    tc = engine.score_topk(rep, u, n_users, n_items, k, mask, lo, hi, bits, impl='tc')
+    torch.cuda.synchronize()
+    return ex, tc, int(engine._tc_scorer.last_fallback.item())
+
+
+def test_tensor_core_scores_are_upper_bounds():
+    from igcn_cf_b200 import engine
+    n_users, n_items, D = 200, 700, 64
+    rep, _ = _case(n_users, n_items, D, seed=5)
+    u = torch.arange(n_users, device=DEV)
+    scorer = engine.TcScorer()
+    _, _, dump, ws = scorer.topk(rep, u, n_users, n_items, 20, dump=True, n_splits=2)
+    torch.cuda.synchronize()
+    maxabs = ws['maxabs'].view(torch.float32).item()
+    assert maxabs == rep.abs().max().item()
+    scale = 2.0 ** (9 - int(np.floor(np.log2(maxabs))))
+    exact = (rep[:n_users].double() @ rep[n_users:].double().t()).cpu().numpy()
+    s_hat = dump[:n_users, :n_items].double().cpu().numpy() / scale ** 2
+    nu = rep[:n_users].double().norm(dim=1).cpu().numpy()[:, None]
+    ni = rep[n_users:].double().norm(dim=1).cpu().numpy()[None, :]
+    slack = s_hat - exact
+    assert slack.min() >= 0.0, slack.min()                      # never below the exact score
+    assert (slack <= 2.2e-3 * nu * ni + 1e-6).all()             # and not wastefully loose (c = 1e-3)
+    assert (slack >= 0.2e-3 * nu * ni).mean() > 0.99            # the bound block is really in the MMA
+
+
+@pytest.mark.parametrize('n_users,n_items,D,k', [(300, 1000, 64, 20), (129, 257, 64, 5), (64, 3000, 32, 24),
+                                                 (1000, 5000, 64, 20), (5, 40, 64, 20)])
+def test_tc_equals_exact(n_users, n_items, D, k):
+    rep, lists = _case(n_users, n_items, D, seed=n_items + 1)
+    ex, tc, fb = _both(rep, n_users, k, lists)
+    assert torch.equal(ex[0], tc[0]) and torch.equal(ex[1], tc[1])
+    assert fb <= max(2, n_users // 50)
+
+
+def test_tc_unmasked_and_user_subset():
+    rep, lists = _case(400, 900, 64, seed=9)
+    ex, tc, _ = _both(rep, 400, 20)
+    assert torch.equal(ex[0], tc[0]) and torch.equal(ex[1], tc[1])
+    users = [3, 399, 0, 77, 77, 200]
+    ex, tc, _ = _both(rep, 400, 20, lists, users=users)
+    assert torch.equal(ex[0], tc[0]) and torch.equal(ex[1], tc[1])
+
+
+@pytest.mark.parametrize('lo,hi', [(0, 700), (300, 1000), (250, 260), (256, 512)])
+def test_tc_item_ranges(lo, hi):
+    rep, lists = _case(150, 1000, 64, seed=2)
+    ex, tc, _ = _both(rep, 150, 20, lists, lo=lo, hi=hi)
+    assert torch.equal(ex[0], tc[0]) and torch.equal(ex[1], tc[1])
+    ok = tc[0][tc[0] >= 0]
+    assert int(ok.min()) >= lo and int(ok.max()) < hi
+
+
+def test_tc_banned_bitmap_and_exhaustion():
+    rep, lists = _case(70, 300, 64, seed=3, mask_deg=100)
+    ex, tc, _ = _both(rep, 70, 24, lists, banned=range(0, 300, 2))
+    assert torch.equal(ex[0], tc[0]) and torch.equal(ex[1], tc[1])
+    assert bool((tc[0] == -1).any())
+
+
+def test_tc_fallback_on_ties():
+    """Duplicated item rows -> more than 32 exactly tied scores: the bound cannot separate them, the
+    user must go through the exact kernel, and the answer is still identical."""
+    rep, lists = _case(130, 600, 64, seed=4)
+    rep[130 + 100:130 + 200] = rep[130 + 7]
+    ex, tc, fb = _both(rep, 130, 20, lists)
+    assert torch.equal(ex[0], tc[0]) and torch.equal(ex[1], tc[1])
+    assert fb > 0
+
+
+def test_tc_large_dynamic_range():
+    rep, lists = _case(256, 2048, 64, seed=6, scale=30.0)
+    rep[256 + 5] *= 40.0          # one huge-norm item
+    rep[10] *= 1e-4               # one tiny-norm user
+    ex, tc, _ = _both(rep, 256, 20, lists)
+    assert torch.equal(ex[0], tc[0]) and torch.equal(ex[1], tc[1])
