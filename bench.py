@@ -42,12 +42,41 @@ METRIC = 'ms/epoch (propagate+BPR)'
 
 
 def measured_peaks():
+    """(HBM GB/s, bf16 TFLOP/s burst, source)."""
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
-    return 6650.0, 'fallback (B200_PROFILING.md)'
+        return float(p['hbm_gbs']), float(p['bf16_tflops']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 1590.0, 'fallback (B200_PROFILING.md)'
+
+
+def profile_eval(trainer, reps=5):
+    """Device time of each entry point of one full-ranking evaluation (CUDA events, eager)."""
+    import torch
+    from igcn_cf_b200 import _lib
+    events, open_ev = [], {}
+
+    def hook(name, phase):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        if phase == 0:
+            open_ev[name] = ev
+        else:
+            events.append((name, open_ev.pop(name), ev))
+
+    _lib.profile_hook = hook
+    try:
+        for _ in range(reps):
+            trainer.model._bump()
+            trainer.recommend('val')
+        torch.cuda.synchronize()
+    finally:
+        _lib.profile_hook = None
+    per = {}
+    for name, a, b in events:
+        per.setdefault(name, []).append(a.elapsed_time(b))
+    return {k: sum(v) / reps for k, v in per.items()}
 
 
 class ClockSampler(threading.Thread):
@@ -77,7 +106,7 @@ class ClockSampler(threading.Thread):
                 for k, bit in names.items():
                     if r & bit:
                         self.reasons.add(k)
-                time.sleep(0.1)
+                time.sleep(0.05)
         except Exception as e:          # clocks are evidence, not the product: report the failure
             self.reasons.add('sampler_error:%s' % type(e).__name__)
 
@@ -217,7 +246,7 @@ def main():
         args.steps = 5 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup
         return run_reference(args, shape, kind, l2_reg, dropout)
-    args.steps = 200 if args.steps is None else args.steps
+    args.steps = 1000 if args.steps is None else args.steps
     args.warmup = 20 if args.warmup is None else max(3, args.warmup)
 
     import torch
@@ -313,7 +342,10 @@ def main():
 
     # ---- per-kernel profile + roofline of the dominant kernel
     summary, spmm_gbs, spmm_avg_ms, spmm_avg_bytes = profile_kernels(trainer, n, nnz, D, 10)
-    peak, peak_src = measured_peaks()
+    peak, tc_peak, peak_src = measured_peaks()
+    ev_ms = profile_eval(trainer)
+    tc_ms = ev_ms.get('igcn_tc_candidates')
+    tc_flops = 2.0 * ds.n_users * ds.n_items * 80     # K = 64 dims + the 16-wide error-bound block
     total = sum(v['ms_per_step'] for v in summary.values())
     shares = {k: round(v['ms_per_step'] / total, 4) for k, v in sorted(summary.items(), key=lambda kv: -kv[1]['ms_per_step'])}
 
@@ -339,7 +371,13 @@ def main():
                 'eval': {'users_per_s': ds.n_users / (eval_ms * 1e-3), 'ms': eval_ms,
                          'e2e_users_per_s': ds.n_users / (eval_e2e_ms * 1e-3), 'e2e_ms': eval_e2e_ms,
                          'what': 'propagate once + fused score/mask/top-20 over all %d users x %d items; e2e adds D2H of the lists and host metrics'
-                                 % (ds.n_users, ds.n_items)},
+                                 % (ds.n_users, ds.n_items),
+                         'kernel_ms': {k: round(v, 4) for k, v in sorted(ev_ms.items(), key=lambda kv: -kv[1])},
+                         'roofline': None if not tc_ms else {
+                             'kernel': 'score_tc_kernel (igcn_tc_candidates, tcgen05 kind::f16)', 'bound': 'tensor',
+                             'achieved': tc_flops / (tc_ms * 1e-3) / 1e12, 'peak': tc_peak, 'unit': 'TFLOP/s',
+                             'frac': tc_flops / (tc_ms * 1e-3) / 1e12 / tc_peak, 'traffic': None,
+                             'flops_counted': '2*U*I*80 (64 dims + 16-wide bound block)'}},
                 'roofline': {'kernel': 'prop_kernel<16,SPMM> (igcn_spmm)', 'bound': 'hbm', 'achieved': spmm_gbs, 'peak': peak,
                              'unit': 'GB/s', 'frac': spmm_gbs / peak, 'traffic': None, 'peak_source': peak_src,
                              'avg_launch_ms': spmm_avg_ms, 'algorithmic_bytes_per_launch': spmm_avg_bytes},

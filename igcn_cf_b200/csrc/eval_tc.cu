@@ -207,11 +207,16 @@ __device__ __forceinline__ uint32_t warp_sort_desc(uint32_t x, int lane) {
     return x;
 }
 
+// Candidate buffer entry: low word = raw fp32 score bits, high word = item id (what the predicated
+// epilogue store writes).  Keys used for ordering: (ordered score << 32) | item.
+__device__ __forceinline__ uint64_t entry_key(uint64_t e) { return ((uint64_t)f_order(__uint_as_float((uint32_t)e)) << 32) | (e >> 32); }
+
 // Shrink one row's candidate buffer (n in (64, 96]) keeping every entry whose score is >= a threshold
 // that has at least TC_KEEP entries at or above it.  Returns the new count; thr_key gets the threshold.
 __device__ __forceinline__ int compact_row(uint64_t *buf, int n, int lane, uint32_t &thr_key) {
     const uint64_t e0 = buf[lane], e1 = buf[lane + 32], e2 = (lane + 64 < n) ? buf[lane + 64] : 0ULL;
-    const uint32_t s0 = (uint32_t)(e0 >> 32), s1 = (uint32_t)(e1 >> 32), s2 = (uint32_t)(e2 >> 32);
+    const uint32_t s0 = f_order(__uint_as_float((uint32_t)e0)), s1 = f_order(__uint_as_float((uint32_t)e1));
+    const uint32_t s2 = (lane + 64 < n) ? f_order(__uint_as_float((uint32_t)e2)) : 0u;
     // second largest of this lane's scores; >= 16 lanes at or above the 16th largest of those
     // contribute two entries each -> at least 32 entries survive
     const uint32_t second = max(min(s0, s1), min(max(s0, s1), s2));
@@ -222,10 +227,11 @@ __device__ __forceinline__ int compact_row(uint64_t *buf, int n, int lane, uint3
     __syncwarp();
     if (kept > TC_CAP - 32) {
         // rare: too many ties / flat scores -> exact top-TC_KEEP by counting (keys are unique)
+        const uint64_t q0 = entry_key(e0), q1 = entry_key(e1), q2 = entry_key(e2);
         int r0 = 0, r1 = 0, r2 = 0;
         for (int j = 0; j < n; ++j) {
-            const uint64_t x = buf[j];
-            r0 += x > e0; r1 += x > e1; r2 += x > e2;
+            const uint64_t x = entry_key(buf[j]);
+            r0 += x > q0; r1 += x > q1; r2 += x > q2;
         }
         __syncwarp();
         k0 = r0 < TC_KEEP; k1 = r1 < TC_KEEP; k2 = (lane + 64 < n) && r2 < TC_KEEP;
@@ -248,6 +254,20 @@ __device__ __forceinline__ int compact_row(uint64_t *buf, int n, int lane, uint3
     __syncwarp();
     thr_key = t;
     return kept;
+}
+
+// Branch-free conditional append: if (score > thr) { *(slot) = {score bits, item}; slot += 8 bytes }.
+__device__ __forceinline__ void append_if_gt(uint32_t vbits, float thr, uint32_t &slot, uint32_t item) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.gt.f32 p, %1, %2;\n\t"
+        "@p st.shared.v2.b32 [%0], {%3, %4};\n\t"
+        "@p add.u32 %0, %0, 8;\n\t"
+        "}"
+        : "+r"(slot)
+        : "f"(__uint_as_float(vbits)), "f"(thr), "r"(vbits), "r"(item)
+        : "memory");
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ TcArgs a) {
@@ -353,10 +373,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             if (lane == 0) mbar_arrive(&sm->mask_full[acc]);
         }
     } else {
-        // ===== epilogue: thread = user row (TMEM lane), 32 columns per tcgen05.ld
+        // ===== epilogue: thread = user row (TMEM lane), 32 columns per tcgen05.ld, branch-free filter
         const int q = warp & 3;                         // warps 3,4,5,6 -> TMEM lane quarters 3,0,1,2
         const int row = q * 32 + lane;
         uint64_t *mybuf = cand + (size_t)row * (TC_CAP + 1);
+        const uint32_t buf0 = smem_u32(mybuf);
         float thr = -INFINITY;
         int cnt = 0;
         for (int it = 0; it < n_it; ++it) {
@@ -366,13 +387,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             mbar_wait(&sm->mask_full[acc], ph);
             tc_fence_after();
             uint32_t *bm = bitmap + ((size_t)acc * TC_BM + row) * 8;
-            const uint4 m_lo = *reinterpret_cast<uint4 *>(bm), m_hi = *reinterpret_cast<uint4 *>(bm + 4);
-            *reinterpret_cast<uint4 *>(bm) = make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4 *>(bm + 4) = make_uint4(0u, 0u, 0u, 0u);
-            const uint32_t mw[8] = {m_lo.x, m_lo.y, m_lo.z, m_lo.w, m_hi.x, m_hi.y, m_hi.z, m_hi.w};
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_BN;
-#pragma unroll
+            uint32_t v[32];
             for (int ch = 0; ch < 8; ++ch) {
+                tc_ld32(taddr + ch * 32, v);
                 uint32_t full_rows = __ballot_sync(0xffffffffu, cnt > TC_CAP - 32);
                 while (full_rows) {
                     const int r = __ffs(full_rows) - 1;
@@ -382,24 +400,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                     const int kept = compact_row(cand + (size_t)(q * 32 + r) * (TC_CAP + 1), n, lane, key);
                     if (lane == r) { cnt = kept; thr = order_f(key); }
                 }
-                uint32_t v[32];
-                tc_ld32(taddr + ch * 32, v);
+                const uint32_t m = bm[ch];
+                const uint32_t item0 = (uint32_t)(t * TC_BN + ch * 32);
                 tc_wait_ld();
-                const uint32_t m = mw[ch];
-                const int item0 = t * TC_BN + ch * 32;
-                if (a.dump && (int64_t)ut * TC_BM + row < (int64_t)a.n_utiles * TC_BM) {
+                if (a.dump) {
                     float *d = a.dump + ((size_t)ut * TC_BM + row) * ((size_t)a.n_itiles * TC_BN) + item0;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) d[c] = __uint_as_float(v[c]);
                 }
+                if (__any_sync(0xffffffffu, m != 0u)) {             // masked / banned / out-of-range columns
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float s = __uint_as_float(v[c]);
-                    const bool take = (s > thr) && !((m >> c) & 1u);
-                    if (take) mybuf[cnt] = ((uint64_t)f_order(s) << 32) | (uint32_t)(item0 + c);
-                    cnt += take ? 1 : 0;
+                    for (int c = 0; c < 32; ++c)
+                        if ((m >> c) & 1u) v[c] = 0xff800000u;      // -inf never passes the filter
                 }
+                uint32_t slot = buf0 + (uint32_t)cnt * 8u;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) append_if_gt(v[c], thr, slot, item0 + c);
+                cnt = (int)((slot - buf0) >> 3);
             }
+            *reinterpret_cast<uint4 *>(bm) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4 *>(bm + 4) = make_uint4(0u, 0u, 0u, 0u);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm->tmem_empty[acc]);
@@ -413,7 +433,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             const float th = __shfl_sync(0xffffffffu, thr, r);
             const uint64_t *src = cand + (size_t)(q * 32 + r) * (TC_CAP + 1);
             int32_t *dst = a.cand_items + ((size_t)b * a.n_splits + sp) * TC_CAP;
-            for (int e = lane; e < n; e += 32) dst[e] = (int32_t)(uint32_t)(src[e] & 0xffffffffu);
+            for (int e = lane; e < n; e += 32) dst[e] = (int32_t)(uint32_t)(src[e] >> 32);
             if (lane == 0) {
                 a.cand_cnt[b * a.n_splits + sp] = n;
                 a.cand_thr[b * a.n_splits + sp] = th;

@@ -85,7 +85,7 @@ def test_tc_item_ranges(lo, hi):
 
 
 def test_tc_banned_bitmap_and_exhaustion():
-    rep, lists = _case(70, 300, 64, seed=3, mask_deg=100)
+    rep, lists = _case(70, 300, 64, seed=3, mask_deg=148)
     ex, tc, _ = _both(rep, 70, 24, lists, banned=range(0, 300, 2))
     assert torch.equal(ex[0], tc[0]) and torch.equal(ex[1], tc[1])
     assert bool((tc[0] == -1).any())
