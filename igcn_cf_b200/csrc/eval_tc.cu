@@ -208,52 +208,45 @@ __device__ __forceinline__ uint32_t warp_sort_desc(uint32_t x, int lane) {
 }
 
 // Candidate buffer entry: low word = raw fp32 score bits, high word = item id (what the predicated
-// epilogue store writes).  Keys used for ordering: (ordered score << 32) | item.
-__device__ __forceinline__ uint64_t entry_key(uint64_t e) { return ((uint64_t)f_order(__uint_as_float((uint32_t)e)) << 32) | (e >> 32); }
+// epilogue store writes).
+__device__ __forceinline__ float entry_score(uint64_t e) { return __uint_as_float((uint32_t)e); }
 
-// Shrink one row's candidate buffer (n in (64, 96]) keeping every entry whose score is >= a threshold
-// that has at least TC_KEEP entries at or above it.  Returns the new count; thr_key gets the threshold.
-__device__ __forceinline__ int compact_row(uint64_t *buf, int n, int lane, uint32_t &thr_key) {
-    const uint64_t e0 = buf[lane], e1 = buf[lane + 32], e2 = (lane + 64 < n) ? buf[lane + 64] : 0ULL;
-    const uint32_t s0 = f_order(__uint_as_float((uint32_t)e0)), s1 = f_order(__uint_as_float((uint32_t)e1));
-    const uint32_t s2 = (lane + 64 < n) ? f_order(__uint_as_float((uint32_t)e2)) : 0u;
-    // second largest of this lane's scores; >= 16 lanes at or above the 16th largest of those
-    // contribute two entries each -> at least 32 entries survive
-    const uint32_t second = max(min(s0, s1), min(max(s0, s1), s2));
-    uint32_t t = __shfl_sync(0xffffffffu, warp_sort_desc(second, lane), 15);
-    bool k0 = s0 >= t, k1 = s1 >= t, k2 = (lane + 64 < n) && s2 >= t;
-    uint32_t b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1), b2 = __ballot_sync(0xffffffffu, k2);
-    int kept = __popc(b0) + __popc(b1) + __popc(b2);
-    __syncwarp();
-    if (kept > TC_CAP - 32) {
-        // rare: too many ties / flat scores -> exact top-TC_KEEP by counting (keys are unique)
-        const uint64_t q0 = entry_key(e0), q1 = entry_key(e1), q2 = entry_key(e2);
-        int r0 = 0, r1 = 0, r2 = 0;
-        for (int j = 0; j < n; ++j) {
-            const uint64_t x = entry_key(buf[j]);
-            r0 += x > q0; r1 += x > q1; r2 += x > q2;
+// Lane-parallel compaction: every lane shrinks ITS OWN row's buffer, no cross-lane traffic except
+// the common loop bound.  A float bisection between the current threshold and the row maximum finds
+// lo with count(score >= lo) >= TC_KEEP (8 halvings: within a few entries of TC_KEEP); entries below
+// lo are dropped and lo becomes the row's threshold.  A row that cannot be shrunk (ties) gives up:
+// thr = +inf makes the finalize kernel route that user to the exact kernel.
+__device__ __forceinline__ void compact_lanes(uint64_t *mybuf, int &cnt, float &thr) {
+    const bool act = cnt > TC_KEEP + 8;
+    const int n = act ? cnt : 0;
+    const int nmax = __reduce_max_sync(0xffffffffu, n);
+    float vmax = -INFINITY, vmin = INFINITY;
+    for (int j = 0; j < nmax; ++j)
+        if (j < n) {
+            const float v = entry_score(mybuf[j]);
+            vmax = fmaxf(vmax, v);
+            vmin = fminf(vmin, v);
         }
-        __syncwarp();
-        k0 = r0 < TC_KEEP; k1 = r1 < TC_KEEP; k2 = (lane + 64 < n) && r2 < TC_KEEP;
-        if (k0) buf[r0] = e0;
-        if (k1) buf[r1] = e1;
-        if (k2) buf[r2] = e2;
-        uint32_t last = 0;
-        if (r0 == TC_KEEP - 1) last = s0;
-        if (r1 == TC_KEEP - 1) last = s1;
-        if ((lane + 64 < n) && r2 == TC_KEEP - 1) last = s2;
-        t = __reduce_max_sync(0xffffffffu, last);
-        kept = TC_KEEP;
-    } else {
-        const uint32_t lt = (1u << lane) - 1u;
-        const int p0 = __popc(b0 & lt), p1 = __popc(b0) + __popc(b1 & lt), p2 = __popc(b0) + __popc(b1) + __popc(b2 & lt);
-        if (k0) buf[p0] = e0;
-        if (k1) buf[p1] = e1;
-        if (k2) buf[p2] = e2;
+    float lo = (thr == -INFINITY) ? vmin : thr;      // count(score >= lo) == n >= TC_KEEP
+    float hi = vmax;
+#pragma unroll 1
+    for (int round = 0; round < 8; ++round) {
+        const float mid = 0.5f * lo + 0.5f * hi;
+        int c = 0;
+        for (int j = 0; j < nmax; ++j)
+            if (j < n) c += entry_score(mybuf[j]) >= mid ? 1 : 0;
+        if (c >= TC_KEEP) lo = mid; else hi = mid;
     }
-    __syncwarp();
-    thr_key = t;
-    return kept;
+    int w = 0;
+    for (int j = 0; j < nmax; ++j)
+        if (j < n) {
+            const uint64_t e = mybuf[j];
+            if (entry_score(e) >= lo) mybuf[w++] = e;
+        }
+    if (act) {
+        if (w > TC_CAP - 32) { cnt = 0; thr = INFINITY; }   // flat scores: hand the user to the exact kernel
+        else { cnt = w; thr = lo; }
+    }
 }
 
 // Branch-free conditional append: if (score > thr) { *(slot) = {score bits, item}; slot += 8 bytes }.
@@ -391,15 +384,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             uint32_t v[32];
             for (int ch = 0; ch < 8; ++ch) {
                 tc_ld32(taddr + ch * 32, v);
-                uint32_t full_rows = __ballot_sync(0xffffffffu, cnt > TC_CAP - 32);
-                while (full_rows) {
-                    const int r = __ffs(full_rows) - 1;
-                    full_rows &= full_rows - 1;
-                    const int n = __shfl_sync(0xffffffffu, cnt, r);
-                    uint32_t key;
-                    const int kept = compact_row(cand + (size_t)(q * 32 + r) * (TC_CAP + 1), n, lane, key);
-                    if (lane == r) { cnt = kept; thr = order_f(key); }
-                }
+                if (__any_sync(0xffffffffu, cnt > TC_CAP - 32)) compact_lanes(mybuf, cnt, thr);
                 const uint32_t m = bm[ch];
                 const uint32_t item0 = (uint32_t)(t * TC_BN + ch * 32);
                 tc_wait_ld();
