@@ -324,16 +324,26 @@ def main():
         e2e_ms_step = t.item()
 
     # ---- full-ranking evaluation (second half of the metric)
-    trainer.eval('val')
+    for _ in range(3):                         # warm: allocator blocks, mask tiles, workspaces
+        model._bump()
+        trainer.eval('val')
     barrier()
     reps = 5
     e0.record()
+    walls = []
     for _ in range(reps):
+        tw = time.perf_counter()
         model._bump()                          # force the propagation to be recomputed, as after training
         rec, _ = trainer.recommend('val')
+        if os.environ.get('IGCN_BENCH_DEBUG'):
+            torch.cuda.synchronize()
+            walls.append(round((time.perf_counter() - tw) * 1e3, 3))
     e1.record()
     barrier()
     eval_ms = e0.elapsed_time(e1) / reps
+    if walls:
+        from igcn_cf_b200 import engine as _e
+        sys.stderr.write('eval walls %s fallback users %d\n' % (walls, int(_e._tc_scorer.last_fallback.item())))
     t0 = time.perf_counter()
     model._bump()
     trainer.eval('val')

@@ -35,6 +35,7 @@ constexpr int TC_CAP = 96;        // candidate slots per user row
 constexpr int TC_KEEP = 32;       // the threshold never rises above the TC_KEEP-th best upper bound
 constexpr int TC_STAGES = 2;      // item-tile smem stages
 constexpr int TC_THREADS = 7 * 32;
+constexpr int TC_STAGE_W = 36;    // words per row of the chunk staging area (16 B aligned, conflict-free)
 constexpr float TC_C = 1.0e-3f;           // relative bound constant (> 2^-10 + 2^-22 + 80 * 2^-23)
 constexpr float TC_EPS_U = 4.76837158e-7f;   // 2^-21, absolute slack in the user bound entry
 constexpr float TC_EPS_I = 4.8828125e-4f;    // 2^-11, absolute slack in the item bound entry
@@ -227,15 +228,22 @@ __device__ __forceinline__ void compact_lanes(uint64_t *mybuf, int &cnt, float &
             vmax = fmaxf(vmax, v);
             vmin = fminf(vmin, v);
         }
-    float lo = (thr == -INFINITY) ? vmin : thr;      // count(score >= lo) == n >= TC_KEEP
+    float lo = (thr == -INFINITY) ? vmin : thr;      // invariant: count(score >= lo) >= TC_KEEP
     float hi = vmax;
 #pragma unroll 1
-    for (int round = 0; round < 8; ++round) {
-        const float mid = 0.5f * lo + 0.5f * hi;
-        int c = 0;
+    for (int round = 0; round < 4; ++round) {          // 4-ary search: 4 rounds = 1/256 of the range
+        const float q = 0.25f * (hi - lo);
+        const float m1 = lo + q, m2 = lo + 2.f * q, m3 = lo + 3.f * q;
+        int c1 = 0, c2 = 0, c3 = 0;
         for (int j = 0; j < nmax; ++j)
-            if (j < n) c += entry_score(mybuf[j]) >= mid ? 1 : 0;
-        if (c >= TC_KEEP) lo = mid; else hi = mid;
+            if (j < n) {
+                const float v = entry_score(mybuf[j]);
+                c1 += v >= m1 ? 1 : 0; c2 += v >= m2 ? 1 : 0; c3 += v >= m3 ? 1 : 0;
+            }
+        if (c3 >= TC_KEEP) lo = m3;
+        else if (c2 >= TC_KEEP) { lo = m2; hi = m3; }
+        else if (c1 >= TC_KEEP) { lo = m1; hi = m2; }
+        else hi = m1;
     }
     int w = 0;
     for (int j = 0; j < nmax; ++j)
@@ -249,20 +257,19 @@ __device__ __forceinline__ void compact_lanes(uint64_t *mybuf, int &cnt, float &
     }
 }
 
-// Branch-free conditional append: if (score > thr) { *(slot) = {score bits, item}; slot += 8 bytes }.
-__device__ __forceinline__ void append_if_gt(uint32_t vbits, float thr, uint32_t &slot, uint32_t item) {
+// hit |= (score > thr) << bit   -- two instructions (FSETP + predicated LOP3), no branch
+__device__ __forceinline__ void hit_if_gt(uint32_t vbits, float thr, uint32_t &hits, uint32_t bit) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.gt.f32 p, %1, %2;\n\t"
-        "@p st.shared.v2.b32 [%0], {%3, %4};\n\t"
-        "@p add.u32 %0, %0, 8;\n\t"
+        "@p or.b32 %0, %0, %3;\n\t"
         "}"
-        : "+r"(slot)
-        : "f"(__uint_as_float(vbits)), "f"(thr), "r"(vbits), "r"(item)
-        : "memory");
+        : "+r"(hits)
+        : "f"(__uint_as_float(vbits)), "f"(thr), "r"(bit));
 }
 
+template <bool DUMP>
 __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t a_bytes = (uint32_t)(TC_BM / 8) * a.kcores * 128;
@@ -271,7 +278,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
     uint8_t *sB = sA + a_bytes;
     uint64_t *cand = reinterpret_cast<uint64_t *>(sB + (size_t)TC_STAGES * b_bytes);
     uint32_t *bitmap = reinterpret_cast<uint32_t *>(cand + (size_t)TC_BM * (TC_CAP + 1));
-    TcSmem *sm = reinterpret_cast<TcSmem *>(bitmap + 2 * TC_BM * 8);
+    uint32_t *stage = bitmap + 2 * TC_BM * 8;                       // [128 rows][TC_STAGE_W] chunk staging
+    TcSmem *sm = reinterpret_cast<TcSmem *>(stage + TC_BM * TC_STAGE_W);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ut = blockIdx.x / a.n_splits, sp = blockIdx.x % a.n_splits;
@@ -366,11 +374,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             if (lane == 0) mbar_arrive(&sm->mask_full[acc]);
         }
     } else {
-        // ===== epilogue: thread = user row (TMEM lane), 32 columns per tcgen05.ld, branch-free filter
+        // ===== epilogue: thread = user row (TMEM lane).  Per 32-column chunk: tcgen05.ld -> stage the
+        // 32 scores in shared memory (8 x STS.128) -> build a hit mask with FSETP + predicated OR (no
+        // branches, 4 independent chains) -> clear masked columns with one AND -> rare slow path
+        // appends the hits from the staged copy.
         const int q = warp & 3;                         // warps 3,4,5,6 -> TMEM lane quarters 3,0,1,2
         const int row = q * 32 + lane;
         uint64_t *mybuf = cand + (size_t)row * (TC_CAP + 1);
-        const uint32_t buf0 = smem_u32(mybuf);
+        uint32_t *mystage = stage + (size_t)row * TC_STAGE_W;
         float thr = -INFINITY;
         int cnt = 0;
         for (int it = 0; it < n_it; ++it) {
@@ -382,26 +393,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             uint32_t *bm = bitmap + ((size_t)acc * TC_BM + row) * 8;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_BN;
             uint32_t v[32];
+#pragma unroll 1
             for (int ch = 0; ch < 8; ++ch) {
                 tc_ld32(taddr + ch * 32, v);
                 if (__any_sync(0xffffffffu, cnt > TC_CAP - 32)) compact_lanes(mybuf, cnt, thr);
                 const uint32_t m = bm[ch];
                 const uint32_t item0 = (uint32_t)(t * TC_BN + ch * 32);
                 tc_wait_ld();
-                if (a.dump) {
+                if (DUMP) {
                     float *d = a.dump + ((size_t)ut * TC_BM + row) * ((size_t)a.n_itiles * TC_BN) + item0;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) d[c] = __uint_as_float(v[c]);
                 }
-                if (__any_sync(0xffffffffu, m != 0u)) {             // masked / banned / out-of-range columns
 #pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        if ((m >> c) & 1u) v[c] = 0xff800000u;      // -inf never passes the filter
+                for (int c = 0; c < 32; c += 4)
+                    *reinterpret_cast<uint4 *>(mystage + c) = make_uint4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    hit_if_gt(v[c], thr, h0, 1u << c);
+                    hit_if_gt(v[c + 8], thr, h1, 1u << (c + 8));
+                    hit_if_gt(v[c + 16], thr, h2, 1u << (c + 16));
+                    hit_if_gt(v[c + 24], thr, h3, 1u << (c + 24));
                 }
-                uint32_t slot = buf0 + (uint32_t)cnt * 8u;
-#pragma unroll
-                for (int c = 0; c < 32; ++c) append_if_gt(v[c], thr, slot, item0 + c);
-                cnt = (int)((slot - buf0) >> 3);
+                uint32_t hits = (h0 | h1 | h2 | h3) & ~m;        // seen / banned / out-of-range columns never pass
+                while (hits) {                                   // rare: ~1 % of the elements
+                    const int c = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    mybuf[cnt++] = ((uint64_t)(item0 + c) << 32) | mystage[c];
+                }
             }
             *reinterpret_cast<uint4 *>(bm) = make_uint4(0u, 0u, 0u, 0u);
             *reinterpret_cast<uint4 *>(bm + 4) = make_uint4(0u, 0u, 0u, 0u);
@@ -550,10 +570,11 @@ extern "C" int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, in
     a.banned = banned_bits; a.mask_tile_ptr = mask_tile_ptr; a.mask_entries = mask_entries;
     a.cand_items = cand_items; a.cand_cnt = cand_cnt; a.cand_thr = cand_thr; a.dump = dump;
     const size_t smem = (size_t)(TC_BM / 8 + TC_STAGES * (TC_BN / 8)) * a.kcores * 128 + (size_t)TC_BM * (TC_CAP + 1) * 8 +
-                        2 * TC_BM * 8 * 4 + sizeof(TcSmem) + 1024;
-    cudaError_t e = cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                        2 * TC_BM * 8 * 4 + (size_t)TC_BM * TC_STAGE_W * 4 + sizeof(TcSmem) + 64;
+    auto kern = dump ? score_tc_kernel<true> : score_tc_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("igcn_tc_candidates: %s", cudaGetErrorString(e)); return (int)e; }
-    score_tc_kernel<<<(unsigned)(a.n_utiles * n_splits), TC_THREADS, smem, as_stream(stream)>>>(a);
+    kern<<<(unsigned)(a.n_utiles * n_splits), TC_THREADS, smem, as_stream(stream)>>>(a);
     IGCN_CHECK_LAUNCH();
     return 0;
 }
