@@ -220,14 +220,17 @@ __device__ __forceinline__ float entry_score(uint64_t e) { return __uint_as_floa
 __device__ __forceinline__ void compact_lanes(uint64_t *mybuf, int &cnt, float &thr) {
     const bool act = cnt > TC_KEEP + 8;
     const int n = act ? cnt : 0;
-    const int nmax = __reduce_max_sync(0xffffffffu, n);
+    const int nmax = (__reduce_max_sync(0xffffffffu, n) + 3) & ~3;       // loops run in groups of 4 (TC_CAP % 4 == 0)
+    const float *sc = reinterpret_cast<const float *>(mybuf);          // score of entry j at sc[2 * j]
     float vmax = -INFINITY, vmin = INFINITY;
-    for (int j = 0; j < nmax; ++j)
-        if (j < n) {
-            const float v = entry_score(mybuf[j]);
-            vmax = fmaxf(vmax, v);
-            vmin = fminf(vmin, v);
-        }
+    for (int j = 0; j < nmax; j += 4) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = sc[2 * (j + u)];             // 4 independent loads in flight
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (j + u < n) { vmax = fmaxf(vmax, v[u]); vmin = fminf(vmin, v[u]); }
+    }
     float lo = (thr == -INFINITY) ? vmin : thr;      // invariant: count(score >= lo) >= TC_KEEP
     float hi = vmax;
 #pragma unroll 1
@@ -235,22 +238,27 @@ __device__ __forceinline__ void compact_lanes(uint64_t *mybuf, int &cnt, float &
         const float q = 0.25f * (hi - lo);
         const float m1 = lo + q, m2 = lo + 2.f * q, m3 = lo + 3.f * q;
         int c1 = 0, c2 = 0, c3 = 0;
-        for (int j = 0; j < nmax; ++j)
-            if (j < n) {
-                const float v = entry_score(mybuf[j]);
-                c1 += v >= m1 ? 1 : 0; c2 += v >= m2 ? 1 : 0; c3 += v >= m3 ? 1 : 0;
-            }
+        for (int j = 0; j < nmax; j += 4) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (j + u < n) ? sc[2 * (j + u)] : -INFINITY;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { c1 += v[u] >= m1 ? 1 : 0; c2 += v[u] >= m2 ? 1 : 0; c3 += v[u] >= m3 ? 1 : 0; }
+        }
         if (c3 >= TC_KEEP) lo = m3;
         else if (c2 >= TC_KEEP) { lo = m2; hi = m3; }
         else if (c1 >= TC_KEEP) { lo = m1; hi = m2; }
         else hi = m1;
     }
     int w = 0;
-    for (int j = 0; j < nmax; ++j)
-        if (j < n) {
-            const uint64_t e = mybuf[j];
-            if (entry_score(e) >= lo) mybuf[w++] = e;
-        }
+    for (int j = 0; j < nmax; j += 4) {
+        uint64_t e[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) e[u] = mybuf[j + u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (j + u < n && entry_score(e[u]) >= lo) mybuf[w++] = e[u];
+    }
     if (act) {
         if (w > TC_CAP - 32) { cnt = 0; thr = INFINITY; }   // flat scores: hand the user to the exact kernel
         else { cnt = w; thr = lo; }
@@ -342,7 +350,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             }
         }
     } else if (warp == 2) {
-        // ===== mask helper: seen-item bucket + banned bitmap + item range -> bitmap[acc][row][8 words]
+        // ===== mask helper: seen-item bucket + banned bitmap + item range -> bitmap[acc][8 words][128 rows]
         for (int it = 0; it < n_it; ++it) {
             const int acc = it & 1, t = t0 + it;
             mbar_wait(&sm->tmem_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
@@ -358,7 +366,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 for (int w = 0; w < 8; ++w) {
                     const uint32_t cw = __shfl_sync(0xffffffffu, common, w);
                     if (cw)
-                        for (int r = lane; r < TC_BM; r += 32) bm[r * 8 + w] |= cw;
+                        for (int r = lane; r < TC_BM; r += 32) bm[w * TC_BM + r] |= cw;
                 }
                 __syncwarp();
             }
@@ -367,7 +375,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 const int e0 = __ldg(p), e1 = __ldg(p + 1);
                 for (int e = e0 + lane; e < e1; e += 32) {
                     const uint32_t ent = a.mask_entries[e];
-                    atomicOr(bm + (ent >> 8) * 8 + ((ent & 255u) >> 5), 1u << (ent & 31u));
+                    atomicOr(bm + ((ent & 255u) >> 5) * TC_BM + (ent >> 8), 1u << (ent & 31u));
                 }
             }
             __syncwarp();
@@ -390,16 +398,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             mbar_wait(&sm->tmem_full[acc], ph);
             mbar_wait(&sm->mask_full[acc], ph);
             tc_fence_after();
-            uint32_t *bm = bitmap + ((size_t)acc * TC_BM + row) * 8;
+            uint32_t *bm = bitmap + (size_t)acc * TC_BM * 8 + row;          // word w of this row at bm[w * 128]
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_BN;
-            uint32_t v[32];
-#pragma unroll 1
-            for (int ch = 0; ch < 8; ++ch) {
-                tc_ld32(taddr + ch * 32, v);
+            uint32_t va[32], vb[32];
+            tc_ld32(taddr, va);
+            // two chunks per iteration so the next TMEM load is always in flight behind the filter
+            auto filter = [&](uint32_t (&v)[32], int ch) {
                 if (__any_sync(0xffffffffu, cnt > TC_CAP - 32)) compact_lanes(mybuf, cnt, thr);
-                const uint32_t m = bm[ch];
+                const uint32_t m = bm[ch * TC_BM];
+                bm[ch * TC_BM] = 0u;
                 const uint32_t item0 = (uint32_t)(t * TC_BN + ch * 32);
-                tc_wait_ld();
                 if (DUMP) {
                     float *d = a.dump + ((size_t)ut * TC_BM + row) * ((size_t)a.n_itiles * TC_BN) + item0;
 #pragma unroll
@@ -422,9 +430,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                     hits &= hits - 1;
                     mybuf[cnt++] = ((uint64_t)(item0 + c) << 32) | mystage[c];
                 }
+            };
+#pragma unroll 1
+            for (int ch = 0; ch < 8; ch += 2) {
+                tc_wait_ld();
+                tc_ld32(taddr + (ch + 1) * 32, vb);
+                filter(va, ch);
+                tc_wait_ld();
+                if (ch + 2 < 8) tc_ld32(taddr + (ch + 2) * 32, va);
+                filter(vb, ch + 1);
             }
-            *reinterpret_cast<uint4 *>(bm) = make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4 *>(bm + 4) = make_uint4(0u, 0u, 0u, 0u);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm->tmem_empty[acc]);
