@@ -69,7 +69,7 @@ def profile_eval(trainer, reps=5):
     try:
         for _ in range(reps):
             trainer.model._bump()
-            trainer.recommend('val')
+            trainer.recommend_local('val')
         torch.cuda.synchronize()
     finally:
         _lib.profile_hook = None
@@ -138,13 +138,15 @@ def build_model(ds, kind, dropout, l2_reg, device, use_graph=True):
     return model, get_trainer(tcfg, ds, model)
 
 
-def spmm_bytes(n, nnz, D, n_add):
-    """Algorithmic (compulsory) bytes of one igcn_spmm launch: idx + val, rowptr, read X, write Y,
-    plus one N x D read per fused add operand (rowptr is int64 here)."""
-    return nnz * 8 + (n + 1) * 8 + (2 + n_add) * n * D * 4
+def spmm_bytes(n, nnz, D, n_add, n_total=None):
+    """Algorithmic (compulsory) bytes of one igcn_spmm launch over a block of n rows: idx + val, rowptr,
+    read X (all n_total rows can be gathered), write Y, plus one n x D read per fused add operand
+    (rowptr is int64 here)."""
+    n_total = n if n_total is None else n_total
+    return nnz * 8 + (n + 1) * 8 + n_total * D * 4 + (1 + n_add) * n * D * 4
 
 
-def profile_kernels(trainer, n, nnz, D, steps):
+def profile_kernels(trainer, n, nnz, D, steps, n_total=None):
     """Per-entry-point device time of the eager (un-graphed) step, CUDA events on the launch stream."""
     import torch
     from igcn_cf_b200 import _lib
@@ -177,7 +179,7 @@ def profile_kernels(trainer, n, nnz, D, steps):
     L = trainer.model.n_layers
     t_spmm = sum(per['igcn_spmm'])
     n_adds = [0] * (L - 1) + [L] + [1] * L
-    byts = sum(spmm_bytes(n, nnz, D, a) for a in n_adds) * steps
+    byts = sum(spmm_bytes(n, nnz, D, a, n_total) for a in n_adds) * steps
     return summary, byts / (t_spmm * 1e-3) / 1e9, t_spmm / len(per['igcn_spmm']), byts / len(per['igcn_spmm'])
 
 
@@ -257,12 +259,16 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    peers = None
     if world > 1:
+        from igcn_cf_b200 import dist as idist
         dist.init_process_group('nccl', device_id=dev)
+        peers = idist.init_peers()        # rows of the propagation sharded over the ranks, fused peer-store all-gather
 
     ds = build_dataset(shape, dev)
     model, trainer = build_model(ds, kind, dropout, l2_reg, dev)
-    n, nnz, D = model.n_users + model.n_items, model.norm_adj.csr.nnz, 64
+    n, nnz, D = model.n_users + model.n_items, model.norm_adj.nnz, 64
+    n_local, nnz_local = model.norm_adj.csr.n_rows, model.norm_adj.csr.nnz
     steps_per_epoch = math.ceil(len(ds) / BATCH)
     step = trainer.step
     model.train()
@@ -334,13 +340,17 @@ def main():
     for _ in range(reps):
         tw = time.perf_counter()
         model._bump()                          # force the propagation to be recomputed, as after training
-        rec, _ = trainer.recommend('val')
+        rec = trainer.recommend_local('val')
         if os.environ.get('IGCN_BENCH_DEBUG'):
             torch.cuda.synchronize()
             walls.append(round((time.perf_counter() - tw) * 1e3, 3))
     e1.record()
     barrier()
     eval_ms = e0.elapsed_time(e1) / reps
+    if world > 1:
+        t = torch.tensor([eval_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        eval_ms = t.item()
     if walls:
         from igcn_cf_b200 import engine as _e
         sys.stderr.write('eval walls %s fallback users %d\n' % (walls, int(_e._tc_scorer.last_fallback.item())))
@@ -349,13 +359,18 @@ def main():
     trainer.eval('val')
     torch.cuda.synchronize()
     eval_e2e_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([eval_e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        eval_e2e_ms = t.item()
 
     # ---- per-kernel profile + roofline of the dominant kernel
-    summary, spmm_gbs, spmm_avg_ms, spmm_avg_bytes = profile_kernels(trainer, n, nnz, D, 10)
+    summary, spmm_gbs, spmm_avg_ms, spmm_avg_bytes = profile_kernels(trainer, n_local, nnz_local, D, 10, n)
     peak, tc_peak, peak_src = measured_peaks()
     ev_ms = profile_eval(trainer)
     tc_ms = ev_ms.get('igcn_tc_candidates')
-    tc_flops = 2.0 * ds.n_users * ds.n_items * 80     # K = 64 dims + the 16-wide error-bound block
+    n_eval_local = ds.n_users if peers is None else (lambda r: r[1] - r[0])(idist.split_range(ds.n_users, rank, world))
+    tc_flops = 2.0 * n_eval_local * ds.n_items * 80     # K = 64 dims + the 16-wide error-bound block (this rank's users)
     total = sum(v['ms_per_step'] for v in summary.values())
     shares = {k: round(v['ms_per_step'] / total, 4) for k, v in sorted(summary.items(), key=lambda kv: -kv[1]['ms_per_step'])}
 
@@ -369,10 +384,13 @@ def main():
     if rank == 0:
         line = {'metric': METRIC, 'value': ms_per_step * steps_per_epoch, 'unit': 'ms', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': False,
-                'scaling': 'strong' if world > 1 else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                 'config': {'workload': args.workload, 'shape': shape, 'model': kind, 'n_users': ds.n_users,
                            'n_items': ds.n_items, 'train_interactions': len(ds), 'nnz_adj': nnz, 'dim': D, 'layers': 3,
                            'batch': BATCH, 'steps_per_epoch': steps_per_epoch, 'sampler': 'device', 'cuda_graph': True,
+                           'parallelism': 'single GPU' if world == 1 else
+                           'propagation rows sharded over %d GPUs (fused NVLink peer-store all-gather per layer), '
+                           'BPR step + Adam replicated, eval users sharded' % world,
                            'l2': 'no explicit flush: a step touches ~%d MB of distinct buffers (> 126 MB L2)'
                                  % ((8 * n * D * 4 + nnz * 8) // 2 ** 20)},
                 'e2e': {'value': e2e_ms_step * steps_per_epoch, 'unit': 'ms', 'ms_per_step': e2e_ms_step,
@@ -396,6 +414,9 @@ def main():
             line['cpu_baseline'] = cpu
         print(json.dumps(line))
     if world > 1:
+        peers.check()
+        from igcn_cf_b200 import dist as idist
+        idist.shutdown()
         dist.destroy_process_group()
 
 

@@ -13,6 +13,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'libigcn_b200.so')
 ABI_VERSION = 1
 MAX_ADD = 8
+MAX_PEERS = 8
 
 c_void_p, c_int32, c_int64, c_uint64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
 
@@ -34,11 +35,11 @@ class DropoutStruct(C.Structure):
 # name -> argtypes; every function returns int (0 == ok) except the two accessors.
 _SIGNATURES = {
     'igcn_spmm': [C.POINTER(CsrStruct), c_void_p, c_void_p, c_int32, C.POINTER(c_void_p), c_int32,
-                  c_void_p, c_float, c_void_p],
+                  c_void_p, c_float, C.POINTER(c_void_p), c_int32, c_void_p],
     'igcn_inmo_fwd': [C.POINTER(CsrStruct), c_void_p, c_void_p, C.POINTER(DropoutStruct), c_void_p,
-                      c_void_p, c_int32, c_int64, c_int64, c_int64, c_int64, c_void_p],
+                      c_void_p, c_int32, c_int64, c_int64, c_int64, c_int64, C.POINTER(c_void_p), c_int32, c_void_p],
     'igcn_inmo_bwd': [C.POINTER(CsrStruct), c_void_p, C.POINTER(DropoutStruct), c_void_p, c_void_p,
-                      c_int32, c_int64, c_void_p],
+                      c_int32, c_int64, C.POINTER(c_void_p), c_int32, c_void_p],
     'igcn_colsum_masked': [c_void_p, c_int64, c_int64, c_int32, C.POINTER(DropoutStruct), c_void_p,
                            c_void_p, c_void_p],
     'igcn_sample_triples': [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_uint64, c_uint64,
@@ -67,6 +68,11 @@ _SIGNATURES = {
     'igcn_tc_finalize': [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                          c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'igcn_hits': [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p],
+    'igcn_peer_alloc': [c_int64, C.POINTER(c_void_p), c_void_p],
+    'igcn_peer_open': [c_void_p, C.POINTER(c_void_p)],
+    'igcn_peer_close': [c_void_p],
+    'igcn_peer_free': [c_void_p],
+    'igcn_peer_barrier': [C.POINTER(c_void_p), c_int32, c_int32, c_void_p, c_void_p, c_void_p],
 }
 EXPORTS = ['igcn_abi_version', 'igcn_last_error'] + sorted(_SIGNATURES)
 
@@ -106,7 +112,8 @@ def ptr(t):
 
 
 # kernels launched per entry point (igcn_bpr_bwd launches 2 more when dw is requested)
-KERNELS_PER_CALL = {'igcn_colsum_masked': 2, 'igcn_tc_pack': 3, 'igcn_tc_workspace': 0}
+KERNELS_PER_CALL = {'igcn_colsum_masked': 2, 'igcn_tc_pack': 3, 'igcn_tc_workspace': 0, 'igcn_peer_alloc': 0,
+                    'igcn_peer_open': 0, 'igcn_peer_close': 0, 'igcn_peer_free': 0}
 launch_count = 0          # running total of kernel launches issued through this binding
 profile_hook = None       # optional callable(name, phase) used by bench.py to time launches
 

@@ -1,0 +1,120 @@
+// Peer memory over NVLink 5 / NVSwitch for the row-sharded propagation.
+//
+// One process per GPU.  Every rank allocates the same set of buffers with igcn_peer_alloc, ships the
+// 64-byte IPC handles to the other ranks (the host code uses torch.distributed for that) and maps
+// theirs with igcn_peer_open.  The propagation kernels then store every finished row into all ranks'
+// copies (igcn_spmm's peer list): the all-gather that would follow a layer is part of the SpMM.
+// igcn_peer_barrier is the only synchronisation between layers: a one-CTA kernel that publishes this
+// rank's epoch in every rank's flag array (st.release.sys) and waits until every rank has published
+// the same epoch (ld.acquire.sys).  It lives on the launch stream, so it can be captured in the
+// step's CUDA graph; a bounded spin turns a lost peer into an error flag instead of a hung GPU.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace igcn {
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct BarrierArgs {
+    uint32_t *flags[IGCN_MAX_PEERS];   // flags[p] = rank p's flag array [IGCN_MAX_PEERS]
+    int n_peers, rank;
+    uint32_t *epoch;                   // local counter
+    uint32_t *status;                  // local: set to 1 when the spin timed out
+    long long timeout_cycles;
+};
+
+__global__ void peer_barrier_kernel(const __grid_constant__ BarrierArgs a) {
+    __shared__ uint32_t e_sh;
+    if (threadIdx.x == 0) e_sh = *a.epoch + 1;
+    __syncthreads();
+    const uint32_t e = e_sh;
+    const int p = threadIdx.x;
+    if (p < a.n_peers) {
+        // everything this stream did before the barrier happens-before the release store
+        __threadfence_system();
+        st_release_sys(a.flags[p] + a.rank, e);
+        const uint32_t *mine = a.flags[a.rank] + p;
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
+            if (clock64() - t0 > a.timeout_cycles) { *a.status = 1u; break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *a.epoch = e;
+}
+
+}  // namespace igcn
+
+using namespace igcn;
+
+#define IGCN_CUDA(call)                                                            \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) {                                                  \
+            igcn::set_error("%s: %s", __func__, cudaGetErrorString(e__));          \
+            return (int)e__;                                                       \
+        }                                                                          \
+    } while (0)
+
+extern "C" int igcn_peer_alloc(int64_t bytes, void **ptr_out, uint8_t *handle_out) {
+    IGCN_CHECK_ARG(bytes > 0 && ptr_out && handle_out, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == IGCN_PEER_HANDLE_BYTES, "IPC handle size");
+    void *p = nullptr;
+    IGCN_CUDA(cudaMalloc(&p, (size_t)bytes));
+    IGCN_CUDA(cudaMemset(p, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        set_error("igcn_peer_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    IGCN_CUDA(cudaDeviceSynchronize());
+    memcpy(handle_out, &h, sizeof(h));
+    *ptr_out = p;
+    return 0;
+}
+
+extern "C" int igcn_peer_open(const uint8_t *handle, void **ptr_out) {
+    IGCN_CHECK_ARG(handle && ptr_out, "bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    IGCN_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr_out = p;
+    return 0;
+}
+
+extern "C" int igcn_peer_close(void *ptr) {
+    IGCN_CHECK_ARG(ptr, "null pointer");
+    IGCN_CUDA(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+
+extern "C" int igcn_peer_free(void *ptr) {
+    IGCN_CHECK_ARG(ptr, "null pointer");
+    IGCN_CUDA(cudaFree(ptr));
+    return 0;
+}
+
+extern "C" int igcn_peer_barrier(uint32_t *const *flags_host, int32_t n_peers, int32_t rank, uint32_t *epoch_dev,
+                                 uint32_t *status_dev, void *stream) {
+    IGCN_CHECK_ARG(flags_host && epoch_dev && status_dev, "null pointer");
+    IGCN_CHECK_ARG(n_peers >= 1 && n_peers <= IGCN_MAX_PEERS && rank >= 0 && rank < n_peers, "bad rank / peer count");
+    BarrierArgs a{};
+    for (int p = 0; p < n_peers; ++p) a.flags[p] = flags_host[p];
+    a.n_peers = n_peers; a.rank = rank; a.epoch = epoch_dev; a.status = status_dev;
+    a.timeout_cycles = 4000000000LL;    // ~2 s at 1.9 GHz
+    peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(a);
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}

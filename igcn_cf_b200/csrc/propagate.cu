@@ -32,6 +32,8 @@ struct PropArgs {
     const float *rowscale;
     float alpha;
     int D;
+    float *peer[IGCN_MAX_PEERS];   // row-sharded multi-GPU: the same output buffer on every rank (self included)
+    int n_peers;                   // 0 = single GPU (write a.Y only)
     // INMO only
     const int32_t *tmpl;
     igcn_dropout drop;
@@ -148,7 +150,13 @@ __device__ __forceinline__ void finish_row(const PropArgs &a, int64_t r, RowVec<
         if (MODE == MODE_SPMM)
             for (int j = 0; j < a.n_add; ++j) add4(t, ld4(a.add[j] + r * D + off));
         if (MODE == MODE_INMO_FWD && self) add4(t, ld4(a.X + gt * D + off));
-        st4(a.Y + out_row * D + off, MODE == MODE_INMO_BWD ? t : scale4(t, s));
+        const float4 o = MODE == MODE_INMO_BWD ? t : scale4(t, s);
+        if (a.n_peers == 0) {
+            st4(a.Y + out_row * D + off, o);
+        } else {
+            // fused all-gather: the row goes straight into every rank's copy over NVLink (peer stores)
+            for (int p = 0; p < a.n_peers; ++p) st4(a.peer[p] + out_row * D + off, o);
+        }
     }
 }
 
@@ -291,12 +299,21 @@ __global__ void colsum_stage2(const float *__restrict__ scratch, int64_t n_block
 
 using namespace igcn;
 
+static int fill_peers(PropArgs &a, float *const *peer_host, int32_t n_peers) {
+    if (n_peers < 0 || n_peers > IGCN_MAX_PEERS || (n_peers > 0 && !peer_host)) { set_error("bad peer list"); return -1; }
+    a.n_peers = n_peers;
+    for (int p = 0; p < n_peers; ++p) a.peer[p] = peer_host[p];
+    return 0;
+}
+
 extern "C" int igcn_spmm(const igcn_csr *g, const float *X, float *Y, int32_t D, const float *const *add_host,
-                         int32_t n_add, const float *rowscale, float alpha, void *stream) {
+                         int32_t n_add, const float *rowscale, float alpha, float *const *peer_y_host, int32_t n_peers,
+                         void *stream) {
     if (check_common(g, D)) return -1;
     IGCN_CHECK_ARG(X && Y, "null X/Y");
     IGCN_CHECK_ARG(n_add >= 0 && n_add <= IGCN_MAX_ADD, "n_add out of range");
     PropArgs a{};
+    if (fill_peers(a, peer_y_host, n_peers)) return -1;
     a.g = *g; a.X = X; a.Y = Y; a.D = D; a.n_add = n_add; a.rowscale = rowscale; a.alpha = alpha;
     for (int j = 0; j < n_add; ++j) a.add[j] = add_host[j];
     launch_lanes<MODE_SPMM, 0>(a, as_stream(stream));
@@ -306,10 +323,11 @@ extern "C" int igcn_spmm(const igcn_csr *g, const float *X, float *Y, int32_t D,
 
 extern "C" int igcn_inmo_fwd(const igcn_csr *g, const int32_t *tmpl, const float *rowscale, const igcn_dropout *drop,
                              const float *E, float *X0, int32_t D, int64_t row0, int64_t n_users, int64_t glob_user,
-                             int64_t glob_item, void *stream) {
+                             int64_t glob_item, float *const *peer_x0_host, int32_t n_peers, void *stream) {
     if (check_common(g, D)) return -1;
     IGCN_CHECK_ARG(E && X0 && rowscale, "null E/X0/rowscale");
     PropArgs a{};
+    if (fill_peers(a, peer_x0_host, n_peers)) return -1;
     a.g = *g; a.X = E; a.Y = X0; a.D = D; a.rowscale = rowscale; a.alpha = 1.f; a.tmpl = tmpl;
     a.row0 = row0; a.n_users = n_users; a.glob_user = glob_user; a.glob_item = glob_item;
     if (fill_drop(a, drop)) return -1;
@@ -319,10 +337,11 @@ extern "C" int igcn_inmo_fwd(const igcn_csr *g, const int32_t *tmpl, const float
 }
 
 extern "C" int igcn_inmo_bwd(const igcn_csr *g, const int32_t *tmpl, const igcn_dropout *drop, const float *G,
-                             float *dE, int32_t D, int64_t row0, void *stream) {
+                             float *dE, int32_t D, int64_t row0, float *const *peer_de_host, int32_t n_peers, void *stream) {
     if (check_common(g, D)) return -1;
     IGCN_CHECK_ARG(G && dE, "null G/dE");
     PropArgs a{};
+    if (fill_peers(a, peer_de_host, n_peers)) return -1;
     a.g = *g; a.X = G; a.Y = dE; a.D = D; a.alpha = 1.f; a.tmpl = tmpl; a.row0 = row0;
     if (fill_drop(a, drop)) return -1;
     IGCN_CHECK_ARG(a.drop.mode != 2 || a.drop.tperm, "mode 2 backward needs tperm");

@@ -26,32 +26,73 @@ def _drop_struct(drop):
     return C.byref(s)
 
 
+class Shard:
+    """This rank's row block [row0, row1) of a row-sharded propagation plus the registry of symmetric
+    (peer-mapped) buffers the kernels may store into.  `None` stands for the single-GPU case."""
+
+    def __init__(self, ctx, row0, row1):
+        self.ctx, self.row0, self.row1 = ctx, int(row0), int(row1)
+        self._bufs = {}
+
+    def new_buffer(self, rows, dim):
+        buf = self.ctx.alloc((rows, dim), torch.float32)
+        self._bufs[buf.tensor.data_ptr()] = buf
+        return buf.tensor
+
+    def peers(self, t, byte_offset):
+        buf = self._bufs.get(t.data_ptr())
+        if buf is None:
+            raise RuntimeError('row-sharded propagation writes into symmetric buffers only '
+                               '(allocate the output with Propagator.new_buffer)')
+        return buf.peer_array(byte_offset), self.ctx.world
+
+
+def _peer_args(shard, t, byte_offset):
+    return (None, 0) if shard is None else shard.peers(t, byte_offset)
+
+
 class Propagator:
     """L-layer propagation with the layer mean fused into the last SpMM, and its backward.
 
     forward:  X_{l+1} = A X_l, rep = mean(X_0..X_L)           (model.py:96-106, 434-446)
     backward: h_L = g', h_l = A h_{l+1} + g', dX_0 = h_0 with g' = d_rep / (L+1)  (A symmetric)
     Intermediate layers live in persistent buffers that the backward pass reuses as ping-pong
-    space (the propagation is linear, no activation has to be saved)."""
+    space (the propagation is linear, no activation has to be saved).
 
-    def __init__(self, n_nodes, dim, n_layers, device):
+    With a `shard` every rank computes its own row block and the kernel epilogue stores each row into
+    all ranks' buffers (fused all-gather over NVLink); a device-side barrier follows every layer."""
+
+    def __init__(self, n_nodes, dim, n_layers, device, shard=None):
         if n_layers > _lib.MAX_ADD:
             raise RuntimeError('n_layers > %d is not supported by the fused layer-mean epilogue' % _lib.MAX_ADD)
         self.n, self.dim, self.n_layers = int(n_nodes), int(dim), int(n_layers)
         self.device = torch.device(device)
-        mk = lambda: torch.empty((self.n, self.dim), dtype=torch.float32, device=self.device)
-        self.layers = [mk() for _ in range(max(2, self.n_layers - 1))]   # X_1.. / backward ping-pong
+        self.shard = shard
+        self.layers = [self.new_buffer(self.n) for _ in range(max(2, self.n_layers - 1))]   # X_1.. / backward ping-pong
         self.x0 = None          # allocated on demand by the INMO layer
-        self.rep = mk()
+        self.rep = self.new_buffer(self.n)
+        self._out = None
         self._add_arrays = {}
+
+    def new_buffer(self, rows):
+        """[rows, dim] fp32 buffer a propagation kernel may write: symmetric when row-sharded."""
+        if self.shard is not None:
+            return self.shard.new_buffer(rows, self.dim)
+        return torch.empty((rows, self.dim), dtype=torch.float32, device=self.device)
 
     def x0_buffer(self):
         if self.x0 is None:
-            self.x0 = torch.empty((self.n, self.dim), dtype=torch.float32, device=self.device)
+            self.x0 = self.new_buffer(self.n)
         return self.x0
 
-    def _adds(self, tensors):
-        key = tuple(t.data_ptr() for t in tensors)
+    def out_buffer(self):
+        """Scratch output for the autograd bridges (the fused TrainStep owns its own)."""
+        if self._out is None:
+            self._out = self.new_buffer(self.n)
+        return self._out
+
+    def _adds(self, tensors, off):
+        key = tuple(t.data_ptr() + off for t in tensors)
         arr = self._add_arrays.get(key)
         if arr is None:
             arr = (C.c_void_p * max(1, len(key)))(*key)
@@ -59,8 +100,14 @@ class Propagator:
         return arr
 
     def spmm(self, adj, x, y, adds=(), rowscale=None, alpha=1.0):
-        call('igcn_spmm', adj.csr.struct(self.dim), ptr(x), ptr(y), self.dim, self._adds(adds), len(adds),
-             ptr(rowscale), float(alpha), stream_ptr())
+        sh = self.shard
+        row0 = 0 if sh is None else sh.row0
+        off = row0 * self.dim * 4
+        peers, n_peers = _peer_args(sh, y, off)
+        call('igcn_spmm', adj.csr.struct(self.dim), ptr(x), ptr(y) + off, self.dim, self._adds(adds, off), len(adds),
+             None if rowscale is None else ptr(rowscale) + row0 * 4, float(alpha), peers, n_peers, stream_ptr())
+        if sh is not None:
+            sh.ctx.barrier()
 
     def forward(self, adj, x0, out=None):
         """rep = mean_l A^l x0.  `out` defaults to the persistent rep buffer."""
@@ -96,20 +143,31 @@ class Propagator:
         return out
 
 
-def inmo_forward(feat, emb, x0, drop, dim):
+def inmo_forward(feat, emb, x0, drop, dim, shard=None):
     """X0 = F~ E with dropout fused (model.py:423-432 after model.py:435)."""
-    call('igcn_inmo_fwd', feat.csr.struct(dim), ptr(feat.tmpl), ptr(feat.rowscale), _drop_struct(drop), ptr(emb),
-         ptr(x0), dim, 0, feat.n_users, feat.glob_user, feat.glob_item, stream_ptr())
+    row0 = 0 if shard is None else shard.row0
+    off = row0 * dim * 4
+    peers, n_peers = _peer_args(shard, x0, off)
+    call('igcn_inmo_fwd', feat.csr.struct(dim), ptr(feat.tmpl), ptr(feat.rowscale) + row0 * 4, _drop_struct(drop), ptr(emb),
+         ptr(x0) + off, dim, row0, feat.n_users, feat.glob_user, feat.glob_item, peers, n_peers, stream_ptr())
+    if shard is not None:
+        shard.ctx.barrier()
 
 
-def inmo_backward(feat, g_scaled, d_emb, drop, dim, scratch):
-    """dE = F~^T dX0 given g_scaled = rowscale/(1-p) .* dX0 (autograd backward of model.py:430)."""
-    n, u = feat.csr.n_rows, feat.n_users
-    call('igcn_inmo_bwd', feat.csr.struct(dim), ptr(feat.tmpl), _drop_struct(drop), ptr(g_scaled), ptr(d_emb), dim, 0,
-         stream_ptr())
+def inmo_backward(feat, g_scaled, d_emb, drop, dim, scratch, shard=None):
+    """dE = F~^T dX0 given g_scaled = rowscale/(1-p) .* dX0 (autograd backward of model.py:430).
+    Row-sharded: each rank produces the template rows of its own node block and stores them into every
+    rank's d_emb; the two global-template rows are column sums every rank computes for itself."""
+    n, u = feat.shape[0], feat.n_users
+    row0 = 0 if shard is None else shard.row0
+    peers, n_peers = _peer_args(shard, d_emb, 0)
+    call('igcn_inmo_bwd', feat.csr.struct(dim), ptr(feat.tmpl), _drop_struct(drop), ptr(g_scaled), ptr(d_emb), dim, row0,
+         peers, n_peers, stream_ptr())
     d = _drop_struct(drop)
     call('igcn_colsum_masked', ptr(g_scaled), 0, u, dim, d, ptr(scratch), ptr(d_emb[feat.glob_user]), stream_ptr())
     call('igcn_colsum_masked', ptr(g_scaled), u, n, dim, d, ptr(scratch), ptr(d_emb[feat.glob_item]), stream_ptr())
+    if shard is not None:
+        shard.ctx.barrier()
 
 
 def colsum_scratch(n_rows, dim, device):
@@ -123,8 +181,7 @@ class LightGCNRep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, emb, model):
         prop = model._propagator()
-        rep = torch.empty_like(emb)
-        prop.forward(model.norm_adj, emb.detach().contiguous(), out=rep)
+        rep = prop.forward(model.norm_adj, emb.detach().contiguous()).clone()
         ctx.model = model
         return rep
 
@@ -133,9 +190,8 @@ class LightGCNRep(torch.autograd.Function):
         model = ctx.model
         prop = model._propagator()
         gprime = (g * (1.0 / (prop.n_layers + 1))).contiguous()
-        d_emb = torch.empty_like(gprime)
-        prop.backward(model.norm_adj, gprime, d_emb)
-        return d_emb, None
+        d_emb = prop.backward(model.norm_adj, gprime, prop.out_buffer())
+        return d_emb.clone(), None
 
 
 class IGCNRep(torch.autograd.Function):
@@ -146,9 +202,8 @@ class IGCNRep(torch.autograd.Function):
         prop = model._propagator()
         feat = model.feat_mat
         x0 = prop.x0_buffer()
-        inmo_forward(feat, emb.detach().contiguous(), x0, drop, prop.dim)
-        rep = torch.empty_like(x0)
-        prop.forward(model.norm_adj, x0, out=rep)
+        inmo_forward(feat, emb.detach().contiguous(), x0, drop, prop.dim, prop.shard)
+        rep = prop.forward(model.norm_adj, x0).clone()
         ctx.model, ctx.drop, ctx.emb_shape = model, drop, emb.shape
         return rep
 
@@ -161,11 +216,16 @@ class IGCNRep(torch.autograd.Function):
         g_scaled = prop.x0_buffer()
         inv_keep = 1.0 if (drop is None or drop.get('mode', 0) == 0) else 1.0 / (1.0 - drop['p'])
         prop.backward(model.norm_adj, gprime, g_scaled, rowscale=feat.rowscale, alpha=inv_keep)
-        d_emb = torch.zeros(ctx.emb_shape, dtype=torch.float32, device=g.device)
+        if prop.shard is None:
+            d_emb = torch.zeros(ctx.emb_shape, dtype=torch.float32, device=g.device)
+        else:
+            d_emb = model._grad_buffer(ctx.emb_shape[0])
+            d_emb.zero_()
+            prop.shard.ctx.barrier()          # nobody stores template rows before every copy is zeroed
         if drop is not None and drop.get('mode', 0) == 2 and drop.get('tperm') is None:
             drop = dict(drop, tperm=feat.tperm())
-        inmo_backward(feat, g_scaled, d_emb, drop, prop.dim, colsum_scratch(prop.n, prop.dim, g.device))
-        return d_emb, None, None
+        inmo_backward(feat, g_scaled, d_emb, drop, prop.dim, colsum_scratch(prop.n, prop.dim, g.device), prop.shard)
+        return (d_emb if prop.shard is None else d_emb.clone()), None, None
 
 
 # --------------------------------------------------------------------------- fused training step
@@ -203,7 +263,10 @@ class TrainStep:
         self.state = opt.device_state(dev)                                # igcn_step_state
         n = model.n_users + model.n_items
         self.gprime = torch.zeros((n, D), dtype=torch.float32, device=dev)
-        self.d_emb = torch.zeros_like(model.embedding.weight.data)
+        prop = model._propagator()
+        self.shard = prop.shard
+        self.d_emb = prop.new_buffer(model.embedding.weight.shape[0])     # symmetric when row-sharded
+        self.d_emb.zero_()
         self.emb_m, self.emb_v = opt.moments(model.embedding.weight)
         if self.is_igcn:
             self.a_triples = torch.zeros((self.B, 3), dtype=torch.int64, device=dev)
@@ -221,8 +284,8 @@ class TrainStep:
     # -- pieces
     def _sample(self, B):
         m = self.model
-        csr = m.norm_adj.csr
-        call('igcn_sample_triples', ptr(csr.rowptr), ptr(csr.col), m.n_users, m.n_users, m.n_items, B, self.seed,
+        rowptr, col = m.norm_adj.sampler_csr()
+        call('igcn_sample_triples', ptr(rowptr), ptr(col), m.n_users, m.n_users, m.n_items, B, self.seed,
              0, ptr(self.state), ptr(self.triples), stream_ptr())
         if self.is_igcn:
             a = m.aux_csr()
@@ -250,7 +313,7 @@ class TrainStep:
         # forward
         if self.is_igcn:
             x0 = prop.x0_buffer()
-            inmo_forward(m.feat_mat, emb, x0, drop, D)
+            inmo_forward(m.feat_mat, emb, x0, drop, D, self.shard)
             rep = prop.forward(m.norm_adj, x0)
             l2_table = rep
         else:
@@ -270,6 +333,10 @@ class TrainStep:
         # backward
         main.wait_stream(self._side)
         self.gprime.zero_()
+        if self.is_igcn and m.feat_mat.tmpl is not None:
+            # template rows without a node in this graph get no gradient; zeroed here, one barrier or more
+            # before any rank stores template rows into this copy
+            self.d_emb.zero_()
         call('igcn_bpr_bwd', ptr(rep), None, ptr(self.triples), B, m.n_users, D, ptr(self.sig), 1.0 / (L + 1),
              self.l2_reg if self.is_igcn else 0.0, 1 if self.is_igcn else 0, ptr(self.order), ptr(self.seg_start),
              ptr(self.seg_row), ptr(self.n_seg), ptr(self.gprime), 0, None, None, st())
@@ -278,9 +345,7 @@ class TrainStep:
             g_scaled = prop.x0_buffer()
             inv_keep = 1.0 if (drop is None or drop.get('mode', 0) == 0) else 1.0 / (1.0 - drop['p'])
             prop.backward(m.norm_adj, self.gprime, g_scaled, rowscale=feat.rowscale, alpha=inv_keep)
-            if feat.tmpl is not None:
-                self.d_emb.zero_()       # template rows without a node in this graph get no gradient
-            inmo_backward(feat, g_scaled, self.d_emb, drop, D, self.colsum_scratch)
+            inmo_backward(feat, g_scaled, self.d_emb, drop, D, self.colsum_scratch, self.shard)
             self.d_w.zero_()
             call('igcn_bpr_bwd', ptr(emb), ptr(m.w.data), ptr(self.a_triples), B, feat.t_users, D, ptr(self.a_sig),
                  float(self.aux_reg), 0.0, 0, ptr(self.a_order), ptr(self.a_seg_start), ptr(self.a_seg_row),

@@ -132,10 +132,26 @@ class _SparseView:
         return torch.sparse_coo_tensor(idx, val, self.shape, is_coalesced=True)
 
 
+def _row_block(rowptr, shard):
+    """(bounds, row0, row1) of this rank's contiguous row block; shard = (rank, world) or None."""
+    n = len(rowptr) - 1
+    if shard is None:
+        return np.array([0, n], dtype=np.int64), 0, n
+    from .dist import shard_bounds
+    rank, world = shard
+    bounds = shard_bounds(rowptr, world)
+    return bounds, int(bounds[rank]), int(bounds[rank + 1])
+
+
+def _block_csr(rowptr, col, val, row0, row1, n_cols, device):
+    lo, hi = int(rowptr[row0]), int(rowptr[row1])
+    return CsrDevice(rowptr[row0:row1 + 1] - lo, col[lo:hi], None if val is None else val[lo:hi], n_cols, device)
+
+
 class NormAdj(_SparseView):
     """D^-1/2 A D^-1/2 (deg clamped to >= 1) as a device CSR; reference model.py:85-94."""
 
-    def __init__(self, n_users, n_items, pairs, device):
+    def __init__(self, n_users, n_items, pairs, device, shard=None):
         adj = build_adjacency(n_users, n_items, pairs)
         deg = np.maximum(1., np.asarray(adj.sum(axis=1)).squeeze()).astype(np.float32)
         d_inv = np.power(deg, np.float32(-0.5)).astype(np.float32)
@@ -145,15 +161,33 @@ class NormAdj(_SparseView):
         self.n_users, self.n_items = int(n_users), int(n_items)
         self.shape = torch.Size([adj.shape[0], adj.shape[1]])
         self.multiplicity_host = adj.data.astype(np.float32)
-        self.csr = CsrDevice(adj.indptr.astype(np.int64), adj.indices.astype(np.int32), val, adj.shape[0], device)
+        self.rowptr_full = adj.indptr.astype(np.int64)
+        self.col_full = adj.indices.astype(np.int32)
+        self.val_full = val
+        self.nnz = int(self.rowptr_full[-1])
+        self.bounds, self.row0, self.row1 = _row_block(self.rowptr_full, shard)
+        self.csr = _block_csr(self.rowptr_full, self.col_full, val, self.row0, self.row1, adj.shape[0], device)
         self.device = self.csr.device
         self._coo_cache = None
+        self._sampler = None
+
+    def sampler_csr(self):
+        """(rowptr, col) on the device covering ALL user rows: the triple sampler is replicated on every
+        rank, so a row-sharded adjacency keeps a separate copy of the user half of the pattern."""
+        if self._sampler is None:
+            if self.row0 == 0 and self.row1 >= self.n_users:
+                self._sampler = (self.csr.rowptr, self.csr.col)
+            else:
+                rp = self.rowptr_full[:self.n_users + 1]
+                self._sampler = (torch.from_numpy(rp.copy()).to(self.device),
+                                 torch.from_numpy(self.col_full[:rp[-1]].copy()).to(self.device))
+        return self._sampler
 
     def _coo(self):
         if self._coo_cache is None:
-            rows = torch.repeat_interleave(torch.arange(self.csr.n_rows, device=self.device),
-                                           self.csr.rowptr[1:] - self.csr.rowptr[:-1])
-            self._coo_cache = (torch.stack([rows, self.csr.col.long()]), self.csr.val)
+            rows = np.repeat(np.arange(self.shape[0], dtype=np.int64), np.diff(self.rowptr_full))
+            idx = torch.from_numpy(np.stack([rows, self.col_full.astype(np.int64)])).to(self.device)
+            self._coo_cache = (idx, torch.from_numpy(self.val_full).to(self.device))
         return self._coo_cache
 
 
@@ -166,7 +200,7 @@ class TemplateFeat(_SparseView):
     layout with NormAdj), tmpl[N] (None when every node is a template and tmpl is the identity),
     row_sum[N], rowscale[N]."""
 
-    def __init__(self, n_users, n_items, pairs, user_tmpl, item_tmpl, t_users, t_items, device):
+    def __init__(self, n_users, n_items, pairs, user_tmpl, item_tmpl, t_users, t_items, device, shard=None):
         adj = build_adjacency(n_users, n_items, pairs)
         n = adj.shape[0]
         self.n_users, self.n_items = int(n_users), int(n_items)
@@ -180,7 +214,10 @@ class TemplateFeat(_SparseView):
         member = (tmpl[adj.indices] >= 0) * adj.data.astype(np.float64)
         rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(adj.indptr))
         row_sum = np.bincount(rows, weights=member, minlength=n).astype(np.float32) + np.float32(1.)
-        self.csr = CsrDevice(adj.indptr.astype(np.int64), adj.indices.astype(np.int32), None, n, device)
+        self.rowptr_full = adj.indptr.astype(np.int64)
+        self.col_full = adj.indices.astype(np.int32)
+        self.bounds, self.row0, self.row1 = _row_block(self.rowptr_full, shard)
+        self.csr = _block_csr(self.rowptr_full, self.col_full, None, self.row0, self.row1, n, device)
         self.device = self.csr.device
         self.tmpl = None if identity else torch.from_numpy(tmpl).to(self.device)
         self.row_sum = torch.from_numpy(row_sum.astype(np.float32)).to(self.device)
@@ -209,8 +246,8 @@ class TemplateFeat(_SparseView):
         index, in the reference's (row, column)-sorted nnz order, of adjacency edge e (or -1 when
         its column node is not a template); self_pos[r] is the index of row r's global entry."""
         if self._order is None:
-            rp, col, tm = self.csr.rowptr_host, self.csr.col_host, self.tmpl_host
-            n = self.csr.n_rows
+            rp, col, tm = self.rowptr_full, self.col_full, self.tmpl_host
+            n = len(rp) - 1
             rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
             fcol = tm[col].astype(np.int64)
             keep = fcol >= 0
@@ -248,8 +285,8 @@ class TemplateFeat(_SparseView):
     def tperm(self):
         """tperm[e] = CSR position of the reverse edge (for the mode-2 backward pass)."""
         if self._tperm is None:
-            rp, col = self.csr.rowptr_host, self.csr.col_host.astype(np.int64)
-            n = self.csr.n_rows
+            rp, col = self.rowptr_full, self.col_full.astype(np.int64)
+            n = len(rp) - 1
             rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
             fwd = rows * n + col        # ascending (CSR order, sorted columns)
             self._tperm = torch.from_numpy(np.searchsorted(fwd, col * n + rows).astype(np.int64)).to(self.device)

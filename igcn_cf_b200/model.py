@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 from torch.nn.init import normal_
 
-from . import engine, graph
+from . import dist, engine, graph
 from ._lib import require_cuda
 
 
@@ -51,6 +51,8 @@ class BasicModel(nn.Module):
         self.n_users = model_config['dataset'].n_users
         self.n_items = model_config['dataset'].n_items
         self.trainable = True
+        # row-sharded multi-GPU mode: on when igcn_cf_b200.dist.init_peers() was called (world > 1)
+        self._peers = dist.current() if model_config.get('shard', True) else None
 
     def predict(self, users):
         raise NotImplementedError
@@ -75,13 +77,27 @@ class _GraphModel(BasicModel):
     def graph_version(self):
         return (id(self.norm_adj), id(getattr(self, 'feat_mat', None)), self.n_users, self.n_items)
 
+    def _shard_arg(self):
+        return None if self._peers is None else (self._peers.rank, self._peers.world)
+
     def _propagator(self):
         n = self.n_users + self.n_items
+        adj = self.norm_adj
+        block = (adj.row0, adj.row1)
         p = self._prop
-        if p is None or (p.n, p.dim, p.n_layers) != (n, self.embedding_size, self.n_layers):
-            p = engine.Propagator(n, self.embedding_size, self.n_layers, self.device)
+        if p is None or (p.n, p.dim, p.n_layers, p.block) != (n, self.embedding_size, self.n_layers, block):
+            shard = None if self._peers is None else engine.Shard(self._peers, *block)
+            p = engine.Propagator(n, self.embedding_size, self.n_layers, self.device, shard)
+            p.block = block
             self._prop = p
+            self._grad_buf = None
         return p
+
+    def _grad_buffer(self, rows):
+        """Symmetric [rows, D] gradient buffer for the autograd bridge of the row-sharded INMO layer."""
+        if getattr(self, '_grad_buf', None) is None or self._grad_buf.shape[0] != rows:
+            self._grad_buf = self._propagator().new_buffer(rows)
+        return self._grad_buf
 
     def _cache_key(self):
         w = self.embedding.weight
@@ -130,7 +146,8 @@ class LightGCN(_GraphModel):
 
     def generate_graph(self, dataset):
         """D^-1/2 A D^-1/2 as a device CSR (model.py:85-94)."""
-        return graph.NormAdj(dataset.n_users, dataset.n_items, graph.train_pairs_of(dataset), self.device)
+        return graph.NormAdj(dataset.n_users, dataset.n_items, graph.train_pairs_of(dataset), self.device,
+                             shard=self._shard_arg())
 
     def get_rep(self):
         self._check_graph()
@@ -227,7 +244,7 @@ class IGCN(_GraphModel):
             user_map, item_map = self.user_map, self.item_map
         ut, it = self._maps_to_arrays(user_map, item_map)
         feat = graph.TemplateFeat(self.n_users, self.n_items, graph.train_pairs_of(dataset), ut, it,
-                                  len(user_map), len(item_map), self.device)
+                                  len(user_map), len(item_map), self.device, shard=self._shard_arg())
         self._aux = None
         return feat, user_map, item_map, feat.row_sum
 
@@ -243,9 +260,10 @@ class IGCN(_GraphModel):
     def aux_csr(self):
         """User-by-item train CSR in TEMPLATE id space for the auxiliary sampler (dataset.py:258-273)."""
         if self._aux is None:
-            feat, adj = self.feat_mat, self.norm_adj.csr
+            feat = self.feat_mat
             if feat.tmpl is None:
-                self._aux = {'rowptr': adj.rowptr, 'col': adj.col, 'col_offset': self.n_users,
+                rowptr, col = self.norm_adj.sampler_csr()
+                self._aux = {'rowptr': rowptr, 'col': col, 'col_offset': self.n_users,
                              'n_users': self.n_users, 'n_items': self.n_items}
             else:
                 pairs = graph.train_pairs_of(self.config['dataset'])
@@ -267,6 +285,8 @@ class IGCN(_GraphModel):
             return None                                  # model.py:264-265
         feat = self.feat_mat
         if self.injected_keep is not None:
+            if self._peers is not None:
+                raise RuntimeError('replaying an explicit dropout mask is a single-GPU test facility')
             ek, sk = feat.keep_bits(self.injected_keep)
             self.injected_keep = None
             return {'mode': 2, 'p': self.dropout, 'edge_keep': ek, 'self_keep': sk, 'tperm': feat.tperm()}
@@ -280,8 +300,10 @@ class IGCN(_GraphModel):
         """feat_mat @ embedding.weight (model.py:423-432); differentiable through get_rep only."""
         prop = self._propagator()
         x0 = torch.empty((feat_mat.shape[0], self.embedding_size), dtype=torch.float32, device=self.device)
-        engine.inmo_forward(feat_mat, self.embedding.weight.detach().contiguous(), x0, None, prop.dim)
-        return x0
+        if prop.shard is not None:
+            x0 = prop.x0_buffer()
+        engine.inmo_forward(feat_mat, self.embedding.weight.detach().contiguous(), x0, None, prop.dim, prop.shard)
+        return x0 if prop.shard is None else x0.clone()
 
     def get_rep(self):
         """model.py:434-446."""

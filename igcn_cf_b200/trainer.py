@@ -23,7 +23,7 @@ import numpy as np
 import torch
 from torch.utils.data import DataLoader
 
-from . import engine
+from . import dist, engine
 from ._lib import call, ptr, stream_ptr
 from .dataset import AuxiliaryDataset
 from .utils import AverageMeter  # noqa: F401  (re-exported like the reference module does)
@@ -256,9 +256,22 @@ class BasicTrainer:
                                  mask=self._mask_csr(val_or_test), item_lo=lo, item_hi=hi, banned_bits=bits,
                                  impl=self.config.get('score_impl', 'auto'))
 
+    def recommend_local(self, val_or_test, banned_items=None):
+        """Top-k lists of the users this rank evaluates: all of them on one GPU, an even contiguous
+        slice per rank when row-sharded (users are independent: no communication while scoring)."""
+        peers = getattr(self.model, '_peers', None)
+        if peers is None:
+            return self.recommend(val_or_test, banned_items)[0]
+        lo, hi = dist.split_range(self.dataset.n_users, peers.rank, peers.world)
+        return self.recommend(val_or_test, banned_items, users=self.test_users[lo:hi])[0]
+
     def eval(self, val_or_test, banned_items=None):
         eval_data = getattr(self.dataset, val_or_test + '_data')
-        rec_dev, _ = self.recommend(val_or_test, banned_items)
+        peers = getattr(self.model, '_peers', None)
+        rec_dev = self.recommend_local(val_or_test, banned_items)
+        if peers is not None:
+            # the top-k lists are gathered so that every rank reports the same metrics
+            rec_dev = dist.gather_rows(rec_dev, self.dataset.n_users, peers.group)
         rec_items = rec_dev.cpu().numpy().astype(np.int64)
         self._last_rec = (rec_items, rec_dev)
         metrics = self.calculate_metrics(eval_data, rec_items)

@@ -27,6 +27,7 @@ extern "C" {
 
 #define IGCN_ABI_VERSION 1
 #define IGCN_MAX_ADD 8
+#define IGCN_MAX_PEERS 8
 
 int igcn_abi_version(void);
 const char *igcn_last_error(void);
@@ -86,10 +87,17 @@ typedef struct igcn_step_state {
  * the earlier layers and alpha = 1/(L+1) the last call also produces the layer mean that
  * torch.stack(...).mean(0) computes at model.py:104-105 / 444-445.
  * X: [n_cols, D]; Y and add[j]: [n_rows, D] (already offset to this row block); rowscale may be
- * NULL; add_host is a HOST array of n_add (<= IGCN_MAX_ADD) device pointers. */
+ * NULL; add_host is a HOST array of n_add (<= IGCN_MAX_ADD) device pointers.
+ *
+ * Multi-GPU (rows sharded over one NVSwitch box): pass n_peers > 0 and peer_y_host[p] = the address of
+ * the SAME output buffer on rank p (self included; peer-mapped symmetric memory).  Every finished row
+ * is then stored into all n_peers copies from the kernel epilogue -- the all-gather that would follow
+ * is fused into the SpMM as NVLink peer stores; the caller only needs a cross-rank barrier before
+ * the next layer.  igcn_inmo_fwd / igcn_inmo_bwd take the same two arguments. */
 int igcn_spmm(const igcn_csr *g, const float *X, float *Y, int32_t D,
               const float *const *add_host, int32_t n_add,
-              const float *rowscale, float alpha, void *stream);
+              const float *rowscale, float alpha,
+              float *const *peer_y_host, int32_t n_peers, void *stream);
 
 /* INMO template aggregation fused with edge dropout (IGCN.inductive_rep_layer, model.py:423-432,
  * after dropout_sp_mat, model.py:435):
@@ -100,14 +108,15 @@ int igcn_spmm(const igcn_csr *g, const float *X, float *Y, int32_t D,
 int igcn_inmo_fwd(const igcn_csr *g, const int32_t *tmpl, const float *rowscale,
                   const igcn_dropout *drop, const float *E, float *X0, int32_t D,
                   int64_t row0, int64_t n_users, int64_t glob_user, int64_t glob_item,
-                  void *stream);
+                  float *const *peer_x0_host, int32_t n_peers, void *stream);
 
 /* Transposed INMO layer for the embedding gradient (autograd backward of model.py:430):
  *   dE[tmpl[c]] = sum_{r in adj(c), keep(r,c)} G[r]      for local rows c with tmpl[c] >= 0
  * G must already hold rowscale[r]/(1-p) * dX0[r] (igcn_spmm's rowscale/alpha epilogue does that).
  * The two global-template rows are produced by igcn_colsum_masked. */
 int igcn_inmo_bwd(const igcn_csr *g, const int32_t *tmpl, const igcn_dropout *drop,
-                  const float *G, float *dE, int32_t D, int64_t row0, void *stream);
+                  const float *G, float *dE, int32_t D, int64_t row0,
+                  float *const *peer_de_host, int32_t n_peers, void *stream);
 
 /* out[d] = sum over rows r in [row_begin,row_end) with keep_self(r) of G[r][d]; fixed two-stage
  * order (deterministic).  scratch: [ceil(n/256)+1, D] floats. */
@@ -223,6 +232,26 @@ int igcn_tc_finalize(const float *rep, const int64_t *user_ids, int64_t n_eval, 
                      const int32_t *cand_cnt, const float *cand_thr, const uint32_t *maxabs_bits,
                      int32_t k, int32_t *out_items, float *out_scores, int32_t *fb_count,
                      int64_t *fb_users, int32_t *fb_rows, void *stream);
+
+/* ---- peer memory for the row-sharded multi-GPU path (one process per GPU, one NVSwitch box) ------
+ * The reference has no distributed code at all; these entry points exist so that the
+ * all-gather after each propagation layer can be fused into the SpMM as NVLink peer stores.
+ *   igcn_peer_alloc    cudaMalloc + zero-fill `bytes`, return the pointer and its 64-byte IPC handle
+ *   igcn_peer_open     map another rank's allocation from its handle (peer access enabled lazily)
+ *   igcn_peer_close    unmap;    igcn_peer_free   release an igcn_peer_alloc allocation
+ *   igcn_peer_barrier  device-side barrier on `stream` across n_peers ranks: flags_host[p] is rank p's
+ *                      flag array (uint32 [IGCN_MAX_PEERS], peer-mapped, zero-initialised), epoch_dev a
+ *                      local counter, status_dev a local word set to 1 if a peer did not arrive within
+ *                      ~2 s (the kernel then returns instead of hanging the GPU).  CUDA-graph capturable.
+ * Buffers from igcn_peer_alloc are owned by the library until igcn_peer_free; everything else in this
+ * header operates on caller-owned memory. */
+#define IGCN_PEER_HANDLE_BYTES 64
+int igcn_peer_alloc(int64_t bytes, void **ptr_out, uint8_t *handle_out);
+int igcn_peer_open(const uint8_t *handle, void **ptr_out);
+int igcn_peer_close(void *ptr);
+int igcn_peer_free(void *ptr);
+int igcn_peer_barrier(uint32_t *const *flags_host, int32_t n_peers, int32_t rank,
+                      uint32_t *epoch_dev, uint32_t *status_dev, void *stream);
 
 /* hit[u][j] = 1 if rec[u][j] is in eval_items[eval_ptr[u] .. eval_ptr[u+1]) (sorted), else 0:
  * the membership double loop of BasicTrainer.calculate_metrics (trainer.py:111-115). */
