@@ -57,7 +57,7 @@ def profile_eval(trainer, reps=5):
     from igcn_cf_b200 import _lib
     events, open_ev = [], {}
 
-    def hook(name, phase):
+    def hook(name, phase, args):
         ev = torch.cuda.Event(enable_timing=True)
         ev.record()
         if phase == 0:
@@ -150,15 +150,17 @@ def profile_kernels(trainer, n, nnz, D, steps, n_total=None):
     """Per-entry-point device time of the eager (un-graphed) step, CUDA events on the launch stream."""
     import torch
     from igcn_cf_b200 import _lib
-    events, open_ev = [], {}
+    events, open_ev, spmm_adds = [], {}, []
 
-    def hook(name, phase):
+    def hook(name, phase, args):
         ev = torch.cuda.Event(enable_timing=True)
         ev.record()
         if phase == 0:
             open_ev[name] = ev
         else:
             events.append((name, open_ev.pop(name), ev))
+            if name == 'igcn_spmm':
+                spmm_adds.append(int(args[5]))          # n_add of this launch
 
     step = trainer.step
     use_graph, step.use_graph = step.use_graph, False
@@ -175,11 +177,11 @@ def profile_kernels(trainer, n, nnz, D, steps, n_total=None):
         per.setdefault(name, []).append(a.elapsed_time(b))
     summary = {k: {'launches_per_step': len(v) / steps, 'avg_ms': sum(v) / len(v), 'ms_per_step': sum(v) / steps}
                for k, v in per.items()}
-    # SpMM roofline: layers 1..L-1 plain, last forward layer adds L operands, backward layers add 1
-    L = trainer.model.n_layers
+    # SpMM roofline over the FULL-layer launches (igcn_spmm): forward layers 1..L-1 carry no add operand, the
+    # backward layers one; the last forward / first backward layer are the partial variants igcn_spmm_rows /
+    # igcn_spmm_cols and are reported in kernel_shares only
     t_spmm = sum(per['igcn_spmm'])
-    n_adds = [0] * (L - 1) + [L] + [1] * L
-    byts = sum(spmm_bytes(n, nnz, D, a, n_total) for a in n_adds) * steps
+    byts = sum(spmm_bytes(n, nnz, D, a, n_total) for a in spmm_adds)
     return summary, byts / (t_spmm * 1e-3) / 1e9, t_spmm / len(per['igcn_spmm']), byts / len(per['igcn_spmm'])
 
 
@@ -406,7 +408,7 @@ def main():
                              'achieved': tc_flops / (tc_ms * 1e-3) / 1e12, 'peak': tc_peak, 'unit': 'TFLOP/s',
                              'frac': tc_flops / (tc_ms * 1e-3) / 1e12 / tc_peak, 'traffic': None,
                              'flops_counted': '2*U*I*80 (64 dims + 16-wide bound block)'}},
-                'roofline': {'kernel': 'prop_kernel<16,SPMM> (igcn_spmm)', 'bound': 'hbm', 'achieved': spmm_gbs, 'peak': peak,
+                'roofline': {'kernel': 'prop_kernel<8,2,SPMM> (igcn_spmm, full layers)', 'bound': 'hbm', 'achieved': spmm_gbs, 'peak': peak,
                              'unit': 'GB/s', 'frac': spmm_gbs / peak, 'traffic': None, 'peak_source': peak_src,
                              'avg_launch_ms': spmm_avg_ms, 'algorithmic_bytes_per_launch': spmm_avg_bytes},
                 'kernel_shares': shares, 'kernel_ms_per_step_eager': round(total, 4), 'clocks': clocks}

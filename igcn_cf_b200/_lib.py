@@ -48,7 +48,11 @@ _SIGNATURES = {
                      c_void_p, c_void_p, c_void_p],
     'igcn_loss_finalize': [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_float, c_void_p,
                            c_void_p, c_void_p],
-    'igcn_bpr_plan': [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'igcn_bpr_plan': [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'igcn_spmm_rows': [C.POINTER(CsrStruct), c_void_p, c_void_p, c_int32, C.POINTER(c_void_p), c_int32,
+                       c_void_p, c_float, c_void_p, c_void_p, c_int64, c_int64, C.POINTER(c_void_p), c_int32, c_void_p],
+    'igcn_spmm_cols': [C.POINTER(CsrStruct), c_void_p, c_void_p, c_int32, C.POINTER(c_void_p), c_int32,
+                       c_void_p, c_float, c_void_p, C.POINTER(c_void_p), c_int32, c_void_p],
     'igcn_bpr_bwd': [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_float, c_float,
                      c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
                      c_void_p, c_void_p],
@@ -115,7 +119,7 @@ def ptr(t):
 KERNELS_PER_CALL = {'igcn_colsum_masked': 2, 'igcn_tc_pack': 3, 'igcn_tc_workspace': 0, 'igcn_peer_alloc': 0,
                     'igcn_peer_open': 0, 'igcn_peer_close': 0, 'igcn_peer_free': 0}
 launch_count = 0          # running total of kernel launches issued through this binding
-profile_hook = None       # optional callable(name, phase) used by bench.py to time launches
+profile_hook = None       # optional callable(name, phase, args) used by bench.py to time launches
 
 
 def call(name, *args):
@@ -123,9 +127,9 @@ def call(name, *args):
     lib = load()
     launch_count += KERNELS_PER_CALL.get(name, 1) + (2 if name == 'igcn_bpr_bwd' and args[16] else 0)
     if profile_hook is not None:
-        profile_hook(name, 0)
+        profile_hook(name, 0, args)
         rc = getattr(lib, name)(*args)
-        profile_hook(name, 1)
+        profile_hook(name, 1, args)
     else:
         rc = getattr(lib, name)(*args)
     if rc != 0:

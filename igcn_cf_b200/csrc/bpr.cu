@@ -128,10 +128,13 @@ __global__ void __launch_bounds__(kThreads) loss_finalize_kernel(const float *sp
 
 // ------------------------------------------------------------------ scatter plan: bitonic sort of (row id, slot)
 __global__ void __launch_bounds__(1024) plan_kernel(const int64_t *__restrict__ tri, int64_t B, int64_t off, int n_pad,
-                                                    int32_t *order, int32_t *seg_start, int64_t *seg_row, int32_t *n_seg) {
+                                                    int32_t *order, int32_t *seg_start, int64_t *seg_row, int32_t *n_seg,
+                                                    uint32_t *touched, int64_t touched_words) {
     extern __shared__ uint64_t keys[];
     __shared__ int warp_tot[32];
     const int n = (int)(3 * B);
+    if (touched)
+        for (int64_t i = threadIdx.x; i < touched_words; i += blockDim.x) touched[i] = 0u;
     for (int s = threadIdx.x; s < n_pad; s += blockDim.x) {
         uint64_t k = ~0ULL;
         if (s < n) {
@@ -185,10 +188,134 @@ __global__ void __launch_bounds__(1024) plan_kernel(const int64_t *__restrict__ 
         if (s == 0 || (k >> 32) != (keys[s - 1] >> 32)) {
             seg_start[seg] = s;
             seg_row[seg] = (int64_t)(k >> 32);
+            if (touched) atomicOr(touched + (k >> 37), 1u << ((k >> 32) & 31));   // OR is order independent
             ++seg;
         }
     }
     if (threadIdx.x == blockDim.x - 1) {
+        const int total = warp_tot[31];
+        n_seg[0] = total;
+        seg_start[total] = n;
+    }
+}
+
+// Fast path (3B <= 8192, ids < 2^19): 32-bit keys (id << 13 | slot), ITEMS keys per thread in registers.
+// Bitonic network: strides below ITEMS are register exchanges, strides inside a warp are shuffles, only
+// the strides across warps go through shared memory (15 of the 91 steps at 8192 keys).
+constexpr int kPlanSlotBits = 13;
+
+__device__ __forceinline__ void cmpx(uint32_t &a, uint32_t &b, bool up) {
+    const uint32_t lo = min(a, b), hi = max(a, b);
+    a = up ? lo : hi;
+    b = up ? hi : lo;
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(1024) plan_fast_kernel(const int64_t *__restrict__ tri, int64_t B, int64_t off, int32_t *order,
+                                                         int32_t *seg_start, int64_t *seg_row, int32_t *n_seg, uint32_t *touched,
+                                                         int64_t touched_words) {
+    __shared__ uint32_t sm[ITEMS * 1024];
+    __shared__ uint32_t last_key[1024];
+    __shared__ int warp_tot[32];
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int n = (int)(3 * B);
+    constexpr int n_pad = ITEMS * 1024;
+    if (touched)
+        for (int64_t i = t; i < touched_words; i += 1024) touched[i] = 0u;
+    uint32_t key[ITEMS];
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+        const int s = t * ITEMS + r;
+        uint32_t k = 0xffffffffu;
+        if (s < n) {
+            const int kind = s / (int)B, i = s % (int)B;
+            const int64_t id = tri[(int64_t)i * 3 + kind] + (kind ? off : 0);
+            k = ((uint32_t)id << kPlanSlotBits) | (uint32_t)s;
+        }
+        key[r] = k;
+    }
+    for (int size = 2; size <= n_pad; size <<= 1) {
+        int stride = size >> 1;
+        for (; stride >= ITEMS; stride >>= 1) {
+            const int m = stride / ITEMS;                     // partner thread = t ^ m, same register
+            const bool lower = (t & m) == 0;
+            if (m < 32) {
+#pragma unroll
+                for (int r = 0; r < ITEMS; ++r) {
+                    const uint32_t other = __shfl_xor_sync(0xffffffffu, key[r], m);
+                    const bool up = (((t * ITEMS + r) & size) == 0);
+                    key[r] = (lower == up) ? min(key[r], other) : max(key[r], other);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < ITEMS; ++r) sm[r * 1024 + t] = key[r];
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < ITEMS; ++r) {
+                    const uint32_t other = sm[r * 1024 + (t ^ m)];
+                    const bool up = (((t * ITEMS + r) & size) == 0);
+                    key[r] = (lower == up) ? min(key[r], other) : max(key[r], other);
+                }
+                __syncthreads();
+            }
+        }
+#pragma unroll
+        for (int s = ITEMS / 2; s > 0; s >>= 1) {
+            if (s < size) {
+#pragma unroll
+                for (int r = 0; r < ITEMS; ++r)
+                    if ((r & s) == 0) cmpx(key[r], key[r | s], (((t * ITEMS + r) & size) == 0));
+            }
+        }
+    }
+    // thread t now owns sorted positions [t * ITEMS, +ITEMS)
+    last_key[t] = key[ITEMS - 1];
+    __syncthreads();
+    uint32_t prev_id = t ? (last_key[t - 1] >> kPlanSlotBits) : 0xffffffffu;
+    int cnt = 0;
+    bool head[ITEMS];
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+        const int s = t * ITEMS + r;
+        const uint32_t id = key[r] >> kPlanSlotBits;
+        head[r] = s < n && (s == 0 || id != prev_id);
+        cnt += head[r] ? 1 : 0;
+        prev_id = id;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int v = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += x;
+        }
+        warp_tot[lane] = v;
+    }
+    __syncthreads();
+    int seg = incl - cnt + (wid ? warp_tot[wid - 1] : 0);
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+        const int s = t * ITEMS + r;
+        if (s < n) {
+            order[s] = (int32_t)(key[r] & ((1u << kPlanSlotBits) - 1u));
+            if (head[r]) {
+                const uint32_t id = key[r] >> kPlanSlotBits;
+                seg_start[seg] = s;
+                seg_row[seg] = (int64_t)id;
+                if (touched) atomicOr(touched + (id >> 5), 1u << (id & 31));
+                ++seg;
+            }
+        }
+    }
+    if (t == 1023) {
         const int total = warp_tot[31];
         n_seg[0] = total;
         seg_start[total] = n;
@@ -354,10 +481,22 @@ extern "C" int igcn_loss_finalize(const float *sp, const float *l2, const float 
     return 0;
 }
 
-extern "C" int igcn_bpr_plan(const int64_t *triples, int64_t B, int64_t item_offset, int32_t *order, int32_t *seg_start,
-                             int64_t *seg_row, int32_t *n_seg, void *stream) {
+extern "C" int igcn_bpr_plan(const int64_t *triples, int64_t B, int64_t item_offset, int64_t n_rows, int32_t *order,
+                             int32_t *seg_start, int64_t *seg_row, int32_t *n_seg, uint32_t *touched_bits, void *stream) {
     IGCN_CHECK_ARG(triples && order && seg_start && seg_row && n_seg, "null pointer");
     IGCN_CHECK_ARG(B > 0 && 3 * B <= 16384, "batch size must satisfy 0 < 3*B <= 16384");
+    IGCN_CHECK_ARG(n_rows > 0, "n_rows (upper bound of the row ids) must be positive");
+    const int64_t words = (n_rows + 31) / 32;
+    if (3 * B <= 8192 && n_rows <= (1 << (32 - kPlanSlotBits))) {
+        cudaStream_t st = as_stream(stream);
+        const int64_t n = 3 * B;
+        if (n <= 1024) plan_fast_kernel<1><<<1, 1024, 0, st>>>(triples, B, item_offset, order, seg_start, seg_row, n_seg, touched_bits, words);
+        else if (n <= 2048) plan_fast_kernel<2><<<1, 1024, 0, st>>>(triples, B, item_offset, order, seg_start, seg_row, n_seg, touched_bits, words);
+        else if (n <= 4096) plan_fast_kernel<4><<<1, 1024, 0, st>>>(triples, B, item_offset, order, seg_start, seg_row, n_seg, touched_bits, words);
+        else plan_fast_kernel<8><<<1, 1024, 0, st>>>(triples, B, item_offset, order, seg_start, seg_row, n_seg, touched_bits, words);
+        IGCN_CHECK_LAUNCH();
+        return 0;
+    }
     int n_pad = 2;
     while (n_pad < 3 * B) n_pad <<= 1;
     const size_t smem = (size_t)n_pad * sizeof(uint64_t);
@@ -367,7 +506,8 @@ extern "C" int igcn_bpr_plan(const int64_t *triples, int64_t B, int64_t item_off
         if (e != cudaSuccess) { set_error("igcn_bpr_plan: %s", cudaGetErrorString(e)); return (int)e; }
         attr_done = true;
     }
-    plan_kernel<<<1, 1024, smem, as_stream(stream)>>>(triples, B, item_offset, n_pad, order, seg_start, seg_row, n_seg);
+    plan_kernel<<<1, 1024, smem, as_stream(stream)>>>(triples, B, item_offset, n_pad, order, seg_start, seg_row, n_seg,
+                                                      touched_bits, words);
     IGCN_CHECK_LAUNCH();
     return 0;
 }

@@ -34,6 +34,11 @@ struct PropArgs {
     int D;
     float *peer[IGCN_MAX_PEERS];   // row-sharded multi-GPU: the same output buffer on every rank (self included)
     int n_peers;                   // 0 = single GPU (write a.Y only)
+    // SPMM variants (template parameter DROP doubles as the variant: 1 = row list, 2 = column filter)
+    const int64_t *row_list;       // ascending GLOBAL row ids to compute
+    const int32_t *n_list;         // device-side length of row_list
+    const uint32_t *col_bits;      // bitmap over columns: non-zeros with a clear bit are skipped
+    int64_t max_list;
     // INMO only
     const int32_t *tmpl;
     igcn_dropout drop;
@@ -66,6 +71,8 @@ struct RowVec {
 };
 
 // Sum over non-zeros [beg, end) of one row of w_e * T[col_e] (this lane's slices).
+// Column ids / values are fetched LPR at a time, one batch AHEAD of the batch being gathered, so a row
+// costs one dependent memory round trip per batch instead of two.
 template <int LPR, int V, bool EXACT, int MODE, int DROP>
 __device__ __forceinline__ void gather_range(const PropArgs &a, RowVec<LPR, V, EXACT> &acc, int64_t beg, int64_t end,
                                              int64_t grow, int lane, uint32_t gmask, uint64_t seed) {
@@ -73,16 +80,31 @@ __device__ __forceinline__ void gather_range(const PropArgs &a, RowVec<LPR, V, E
     const float *__restrict__ val = a.g.val;
     const int D = a.D;
     const float *__restrict__ Tl = a.X + lane * 4;
+    constexpr bool COLS = (MODE == MODE_SPMM && DROP == 2);
+    constexpr int Q = (V == 1) ? 8 : 4;                 // neighbour rows in flight per group (8 x 16 B per lane)
+    const int gshift = (threadIdx.x & 31) & ~(LPR - 1);
 
+    int c_next = 0;
+    float v_next = 1.f;
+    if (beg + lane < end) {
+        c_next = __ldg(col + beg + lane);
+        if (MODE == MODE_SPMM && val) v_next = __ldg(val + beg + lane);
+    }
     for (int64_t e0 = beg; e0 < end; e0 += LPR) {
         const int n = (int)min((int64_t)LPR, end - e0);
-        int c = 0;
-        float w = 0.f;
+        int c = c_next;
+        float w = v_next;
+        {   // prefetch the next batch
+            const int64_t e = e0 + LPR + lane;
+            if (e < end) {
+                c_next = __ldg(col + e);
+                if (MODE == MODE_SPMM && val) v_next = __ldg(val + e);
+            }
+        }
         if (lane < n) {
             const int64_t e = e0 + lane;
-            c = __ldg(col + e);
             if (MODE == MODE_SPMM) {
-                w = val ? __ldg(val + e) : 1.f;
+                if (COLS && !((__ldg(a.col_bits + (c >> 5)) >> (c & 31)) & 1u)) w = 0.f;   // X[c] is an exact zero row
             } else {
                 bool keep = true;
                 if (DROP == 1) {
@@ -100,12 +122,40 @@ __device__ __forceinline__ void gather_range(const PropArgs &a, RowVec<LPR, V, E
                 w = keep ? 1.f : 0.f;
                 if (!keep) c = 0;
             }
+        } else {
+            w = 0.f;
+            c = 0;
         }
-        for (int j0 = 0; j0 < n; j0 += 4) {
-            float4 x[4][V];
-            float ww[4];
+        if (COLS) {
+            // few columns survive the filter: visit only those, still in ascending order, 4 gathers in flight
+            uint32_t km = (__ballot_sync(gmask, w != 0.f) >> gshift) & ((1u << LPR) - 1u);
+            while (km) {
+                float4 x[Q][V];
+                float ww[Q];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < Q; ++q) {
+                    const bool ok = km != 0u;
+                    const int j = ok ? __ffs(km) - 1 : 0;
+                    km &= km - 1u;
+                    const int cj = __shfl_sync(gmask, c, j, LPR);
+                    ww[q] = ok ? __shfl_sync(gmask, w, j, LPR) : 0.f;
+                    const float *p = Tl + (int64_t)cj * D;
+#pragma unroll
+                    for (int i = 0; i < V; ++i)
+                        x[q][i] = (ok && RowVec<LPR, V, EXACT>::on(i, lane, D)) ? ld4(p + i * LPR * 4) : f4zero();
+                }
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+#pragma unroll
+                    for (int i = 0; i < V; ++i) fma4(acc.v[i], ww[q], x[q][i]);
+            }
+            continue;
+        }
+        for (int j0 = 0; j0 < n; j0 += Q) {
+            float4 x[Q][V];
+            float ww[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
                 const int cj = __shfl_sync(gmask, c, j0 + q, LPR);
                 ww[q] = __shfl_sync(gmask, w, j0 + q, LPR);
                 const bool ok = (j0 + q < n) && (MODE == MODE_SPMM || ww[q] != 0.f);
@@ -115,7 +165,7 @@ __device__ __forceinline__ void gather_range(const PropArgs &a, RowVec<LPR, V, E
                     x[q][i] = (ok && RowVec<LPR, V, EXACT>::on(i, lane, D)) ? ld4(p + i * LPR * 4) : f4zero();
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < Q; ++q)
 #pragma unroll
                 for (int i = 0; i < V; ++i) fma4(acc.v[i], ww[q], x[q][i]);
         }
@@ -161,14 +211,15 @@ __device__ __forceinline__ void finish_row(const PropArgs &a, int64_t r, RowVec<
 }
 
 template <int LPR, int V, bool EXACT, int MODE, int DROP>
-__global__ void __launch_bounds__(kThreads) prop_kernel(const __grid_constant__ PropArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) prop_kernel(const __grid_constant__ PropArgs a) {
     constexpr int GROUPS = kThreads / LPR;
     using Vec = RowVec<LPR, V, EXACT>;
     const int lane = threadIdx.x % LPR;
     const uint32_t gmask = group_mask<LPR>();
     const int64_t unit = (int64_t)blockIdx.x * GROUPS + threadIdx.x / LPR;
     const int64_t n_chunks = a.g.n_chunks;
-    if (unit >= n_chunks + a.g.n_rows) return;
+    constexpr bool ROWS = (MODE == MODE_SPMM && DROP == 1);
+    if (!ROWS && unit >= n_chunks + a.g.n_rows) return;
     uint64_t seed = a.drop.seed;
     if (DROP == 1 && a.drop.seed_dev) seed = mix64(seed ^ mix64(*a.drop.seed_dev + 0x2545f491ULL));
     const int D = a.D;
@@ -179,6 +230,16 @@ __global__ void __launch_bounds__(kThreads) prop_kernel(const __grid_constant__ 
         // ---- one chunk of a long row
         const int ch = (int)unit;
         const int64_t r = a.g.chunk_row[ch];
+        if (ROWS) {
+            // is this long row on the list?  (ascending ids: binary search, same answer on every lane)
+            const int64_t want = a.row0 + r;
+            int lo = 0, hi = *a.n_list;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(a.row_list + mid) < want) lo = mid + 1; else hi = mid;
+            }
+            if (lo >= *a.n_list || __ldg(a.row_list + lo) != want) return;
+        }
         const int64_t beg = a.g.chunk_begin[ch];
         gather_range<LPR, V, EXACT, MODE, DROP>(a, acc, beg, beg + a.g.chunk_len[ch], a.row0 + r, lane, gmask, seed);
         const int first = a.g.chunk_first[ch];
@@ -195,18 +256,34 @@ __global__ void __launch_bounds__(kThreads) prop_kernel(const __grid_constant__ 
         __threadfence();
         if (lane == 0) a.g.counters[first] = 0;   // self-reset for the next launch
         acc.zero();
-        for (int k = 0; k < count; ++k)
+        for (int k0 = 0; k0 < count; k0 += 4) {           // 4 partials in flight, added in chunk order
+            float4 pp[4][V];
 #pragma unroll
-            for (int i = 0; i < V; ++i)
-                if (Vec::on(i, lane, D))
-                    add4(acc.v[i], __ldcg(reinterpret_cast<const float4 *>(a.g.partial + (int64_t)(first + k) * D + (i * LPR + lane) * 4)));
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int i = 0; i < V; ++i)
+                    pp[q][i] = (k0 + q < count && Vec::on(i, lane, D))
+                                   ? __ldcg(reinterpret_cast<const float4 *>(a.g.partial + (int64_t)(first + k0 + q) * D + (i * LPR + lane) * 4))
+                                   : f4zero();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (k0 + q < count)
+#pragma unroll
+                    for (int i = 0; i < V; ++i) add4(acc.v[i], pp[q][i]);
+        }
         finish_row<LPR, V, EXACT, MODE, DROP>(a, r, acc, lane, seed);
         return;
     }
 
     // ---- one whole (short) row, taken in degree-descending order when a permutation is given
     int64_t r = unit - n_chunks;
-    if (a.g.row_order) r = __ldg(a.g.row_order + r);
+    if (ROWS) {
+        if (r >= *a.n_list) return;
+        r = __ldg(a.row_list + r) - a.row0;
+        if (r < 0 || r >= a.g.n_rows) return;            // another rank's row
+    } else if (a.g.row_order) {
+        r = __ldg(a.g.row_order + r);
+    }
     const int64_t beg = __ldg(a.g.rowptr + r), end = __ldg(a.g.rowptr + r + 1);
     if (n_chunks > 0 && end - beg > a.g.long_threshold) return;   // handled by chunk units
     gather_range<LPR, V, EXACT, MODE, DROP>(a, acc, beg, end, a.row0 + r, lane, gmask, seed);
@@ -215,16 +292,19 @@ __global__ void __launch_bounds__(kThreads) prop_kernel(const __grid_constant__ 
 
 template <int LPR, int V, bool EXACT, int MODE, int DROP>
 static void launch_one(const PropArgs &a, cudaStream_t st) {
-    const int64_t units = a.g.n_chunks + a.g.n_rows;
+    const int64_t units = a.g.n_chunks + ((MODE == MODE_SPMM && DROP == 1) ? a.max_list : a.g.n_rows);
     constexpr int GROUPS = kThreads / LPR;
     prop_kernel<LPR, V, EXACT, MODE, DROP><<<(unsigned)((units + GROUPS - 1) / GROUPS), kThreads, 0, st>>>(a);
 }
 
 template <int MODE, int DROP>
 static int launch_lanes(const PropArgs &a, cudaStream_t st) {
-    if (a.g.n_chunks + a.g.n_rows == 0) return 0;
+    if (a.g.n_chunks + ((MODE == MODE_SPMM && DROP == 1) ? a.max_list : a.g.n_rows) == 0) return 0;
     const int D = a.D;
-    if (D == 64) launch_one<8, 2, true, MODE, DROP>(a, st);
+    // the two partial-layer variants run far below one wave: fewer, longer dependent chains matter more than
+    // line-sized loads, so a row gets 16 lanes (one float4 each, 8 neighbour rows in flight)
+    if (D == 64 && MODE == MODE_SPMM && DROP != 0) launch_one<16, 1, true, MODE, DROP>(a, st);
+    else if (D == 64) launch_one<8, 2, true, MODE, DROP>(a, st);
     else if (D == 32) launch_one<8, 1, true, MODE, DROP>(a, st);
     else if (D == 128) launch_one<16, 2, true, MODE, DROP>(a, st);
     else if (D < 32) launch_one<8, 1, false, MODE, DROP>(a, st);
@@ -317,6 +397,42 @@ extern "C" int igcn_spmm(const igcn_csr *g, const float *X, float *Y, int32_t D,
     a.g = *g; a.X = X; a.Y = Y; a.D = D; a.n_add = n_add; a.rowscale = rowscale; a.alpha = alpha;
     for (int j = 0; j < n_add; ++j) a.add[j] = add_host[j];
     launch_lanes<MODE_SPMM, 0>(a, as_stream(stream));
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+static int spmm_common(PropArgs &a, const igcn_csr *g, const float *X, float *Y, int32_t D, const float *const *add_host,
+                       int32_t n_add, const float *rowscale, float alpha, float *const *peer_y_host, int32_t n_peers) {
+    if (check_common(g, D)) return -1;
+    IGCN_CHECK_ARG(X && Y, "null X/Y");
+    IGCN_CHECK_ARG(n_add >= 0 && n_add <= IGCN_MAX_ADD, "n_add out of range");
+    if (fill_peers(a, peer_y_host, n_peers)) return -1;
+    a.g = *g; a.X = X; a.Y = Y; a.D = D; a.n_add = n_add; a.rowscale = rowscale; a.alpha = alpha;
+    for (int j = 0; j < n_add; ++j) a.add[j] = add_host[j];
+    return 0;
+}
+
+extern "C" int igcn_spmm_rows(const igcn_csr *g, const float *X, float *Y, int32_t D, const float *const *add_host,
+                              int32_t n_add, const float *rowscale, float alpha, const int64_t *row_list,
+                              const int32_t *n_list, int64_t max_list, int64_t row0, float *const *peer_y_host,
+                              int32_t n_peers, void *stream) {
+    PropArgs a{};
+    if (spmm_common(a, g, X, Y, D, add_host, n_add, rowscale, alpha, peer_y_host, n_peers)) return -1;
+    IGCN_CHECK_ARG(row_list && n_list && max_list >= 0, "row list missing");
+    a.row_list = row_list; a.n_list = n_list; a.max_list = max_list; a.row0 = row0;
+    launch_lanes<MODE_SPMM, 1>(a, as_stream(stream));
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_spmm_cols(const igcn_csr *g, const float *X, float *Y, int32_t D, const float *const *add_host,
+                              int32_t n_add, const float *rowscale, float alpha, const uint32_t *col_bits,
+                              float *const *peer_y_host, int32_t n_peers, void *stream) {
+    PropArgs a{};
+    if (spmm_common(a, g, X, Y, D, add_host, n_add, rowscale, alpha, peer_y_host, n_peers)) return -1;
+    IGCN_CHECK_ARG(col_bits, "column bitmap missing");
+    a.col_bits = col_bits;
+    launch_lanes<MODE_SPMM, 2>(a, as_stream(stream));
     IGCN_CHECK_LAUNCH();
     return 0;
 }

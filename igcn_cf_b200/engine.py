@@ -99,18 +99,28 @@ class Propagator:
             self._add_arrays[key] = arr
         return arr
 
-    def spmm(self, adj, x, y, adds=(), rowscale=None, alpha=1.0):
+    def spmm(self, adj, x, y, adds=(), rowscale=None, alpha=1.0, rows=None, cols=None):
+        """One layer.  rows = (row_list int64, n_list int32[1], max_list): compute the listed rows only
+        (igcn_spmm_rows); cols = bitmap of the columns whose X row is non-zero (igcn_spmm_cols)."""
         sh = self.shard
         row0 = 0 if sh is None else sh.row0
         off = row0 * self.dim * 4
         peers, n_peers = _peer_args(sh, y, off)
-        call('igcn_spmm', adj.csr.struct(self.dim), ptr(x), ptr(y) + off, self.dim, self._adds(adds, off), len(adds),
-             None if rowscale is None else ptr(rowscale) + row0 * 4, float(alpha), peers, n_peers, stream_ptr())
+        head = (adj.csr.struct(self.dim), ptr(x), ptr(y) + off, self.dim, self._adds(adds, off), len(adds),
+                None if rowscale is None else ptr(rowscale) + row0 * 4, float(alpha))
+        if rows is not None:
+            call('igcn_spmm_rows', *head, ptr(rows[0]), ptr(rows[1]), int(rows[2]), row0, peers, n_peers, stream_ptr())
+        elif cols is not None:
+            call('igcn_spmm_cols', *head, ptr(cols), peers, n_peers, stream_ptr())
+        else:
+            call('igcn_spmm', *head, peers, n_peers, stream_ptr())
         if sh is not None:
             sh.ctx.barrier()
 
-    def forward(self, adj, x0, out=None):
-        """rep = mean_l A^l x0.  `out` defaults to the persistent rep buffer."""
+    def forward(self, adj, x0, out=None, rows=None, before_last=None):
+        """rep = mean_l A^l x0.  `out` defaults to the persistent rep buffer.  With `rows` the last layer
+        (and with it the layer mean) is only evaluated on the listed rows -- a training step reads
+        nothing else; `before_last` runs right before that layer is enqueued (stream join)."""
         L = self.n_layers
         rep = self.rep if out is None else out
         if L == 0:
@@ -120,11 +130,14 @@ class Propagator:
         for l in range(1, L):
             self.spmm(adj, xs[-1], self.layers[l - 1])
             xs.append(self.layers[l - 1])
-        self.spmm(adj, xs[-1], rep, adds=xs, alpha=1.0 / (L + 1))
+        if before_last is not None:
+            before_last()
+        self.spmm(adj, xs[-1], rep, adds=xs, alpha=1.0 / (L + 1), rows=rows)
         return rep
 
-    def backward(self, adj, gprime, out, rowscale=None, alpha=1.0):
-        """out = alpha * rowscale .* h_0, h from the Horner recurrence above; gprime = d_rep/(L+1)."""
+    def backward(self, adj, gprime, out, rowscale=None, alpha=1.0, gprime_rows=None):
+        """out = alpha * rowscale .* h_0, h from the Horner recurrence above; gprime = d_rep/(L+1).
+        gprime_rows: bitmap of the rows where gprime is non-zero (first layer skips the other columns)."""
         L = self.n_layers
         if L == 0:
             if rowscale is None:
@@ -135,11 +148,12 @@ class Propagator:
                 torch.mul(gprime, rowscale[:, None] * alpha, out=out)
             return out
         h = gprime
+        cols = gprime_rows
         for l in range(L - 1, 0, -1):
             dst = self.layers[l % 2]
-            self.spmm(adj, h, dst, adds=(gprime,))
-            h = dst
-        self.spmm(adj, h, out, adds=(gprime,), rowscale=rowscale, alpha=alpha)
+            self.spmm(adj, h, dst, adds=(gprime,), cols=cols)
+            h, cols = dst, None
+        self.spmm(adj, h, out, adds=(gprime,), rowscale=rowscale, alpha=alpha, cols=cols)
         return out
 
 
@@ -257,6 +271,8 @@ class TrainStep:
         self.order, self.seg_start = i32(3 * self.B), i32(3 * self.B + 1)
         self.seg_row = torch.empty(3 * self.B, dtype=torch.int64, device=dev)
         self.n_seg = torch.zeros(1, dtype=torch.int32, device=dev)
+        n_nodes = model.n_users + model.n_items
+        self.touched = torch.zeros((n_nodes + 31) // 32 + 1, dtype=torch.int32, device=dev)   # bitmap of the batch's rows
         self.sp, self.sig, self.l2 = f32(self.B), f32(self.B), f32(self.B)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.acc = torch.zeros(2, dtype=torch.float64, device=dev)
@@ -305,20 +321,27 @@ class TrainStep:
         main = torch.cuda.current_stream()
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
-            call('igcn_bpr_plan', ptr(self.triples), B, m.n_users, ptr(self.order), ptr(self.seg_start),
-                 ptr(self.seg_row), ptr(self.n_seg), st())
-            if self.is_igcn:
-                call('igcn_bpr_plan', ptr(self.a_triples), B, m.feat_mat.t_users, ptr(self.a_order), ptr(self.a_seg_start),
-                     ptr(self.a_seg_row), ptr(self.a_n_seg), st())
-        # forward
+            call('igcn_bpr_plan', ptr(self.triples), B, m.n_users, m.n_users + m.n_items, ptr(self.order),
+                 ptr(self.seg_start), ptr(self.seg_row), ptr(self.n_seg), ptr(self.touched), st())
+        # forward: full layers 1..L-1, then the last layer + layer mean on the batch's rows only (the plan's
+        # sorted unique row list); the aux plan is only needed by the gradient kernels
+        rows = (self.seg_row, self.n_seg, 3 * B)
+        join = lambda: main.wait_stream(self._side)
         if self.is_igcn:
             x0 = prop.x0_buffer()
             inmo_forward(m.feat_mat, emb, x0, drop, D, self.shard)
-            rep = prop.forward(m.norm_adj, x0)
+            rep = prop.forward(m.norm_adj, x0, rows=rows, before_last=join)
             l2_table = rep
         else:
-            rep = prop.forward(m.norm_adj, emb)
+            rep = prop.forward(m.norm_adj, emb, rows=rows, before_last=join)
             l2_table = emb
+        if L == 0:
+            join()
+        if self.is_igcn:
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                call('igcn_bpr_plan', ptr(self.a_triples), B, m.feat_mat.t_users, m.embedding.weight.shape[0],
+                     ptr(self.a_order), ptr(self.a_seg_start), ptr(self.a_seg_row), ptr(self.a_n_seg), None, st())
         call('igcn_bpr_fwd', ptr(rep), ptr(l2_table), None, ptr(self.triples), B, m.n_users, D, ptr(self.sp),
              ptr(self.sig), ptr(self.l2), st())
         if self.is_igcn:
@@ -344,14 +367,15 @@ class TrainStep:
             feat = m.feat_mat
             g_scaled = prop.x0_buffer()
             inv_keep = 1.0 if (drop is None or drop.get('mode', 0) == 0) else 1.0 / (1.0 - drop['p'])
-            prop.backward(m.norm_adj, self.gprime, g_scaled, rowscale=feat.rowscale, alpha=inv_keep)
+            prop.backward(m.norm_adj, self.gprime, g_scaled, rowscale=feat.rowscale, alpha=inv_keep,
+                          gprime_rows=self.touched)
             inmo_backward(feat, g_scaled, self.d_emb, drop, D, self.colsum_scratch, self.shard)
             self.d_w.zero_()
             call('igcn_bpr_bwd', ptr(emb), ptr(m.w.data), ptr(self.a_triples), B, feat.t_users, D, ptr(self.a_sig),
                  float(self.aux_reg), 0.0, 0, ptr(self.a_order), ptr(self.a_seg_start), ptr(self.a_seg_row),
                  ptr(self.a_n_seg), ptr(self.d_emb), 1, ptr(self.d_w), ptr(self.dw_scratch), st())
         else:
-            prop.backward(m.norm_adj, self.gprime, self.d_emb)
+            prop.backward(m.norm_adj, self.gprime, self.d_emb, gprime_rows=self.touched)
             if self.l2_reg != 0.0:
                 call('igcn_l2_rows_bwd', ptr(emb), ptr(self.d_emb), D, 2.0 * self.l2_reg / B, ptr(self.seg_start),
                      ptr(self.seg_row), ptr(self.n_seg), 3 * B, st())

@@ -99,6 +99,25 @@ int igcn_spmm(const igcn_csr *g, const float *X, float *Y, int32_t D,
               const float *rowscale, float alpha,
               float *const *peer_y_host, int32_t n_peers, void *stream);
 
+/* The two places where a training step does not need a full layer (same arguments as igcn_spmm plus
+ * the selection; results for the selected rows are bit-identical to igcn_spmm's):
+ *   igcn_spmm_rows  computes only the rows listed in row_list[0 .. *n_list) (GLOBAL row ids, ascending,
+ *                   device-side count, at most max_list): the LAST forward layer of a training step,
+ *                   whose output bpr_forward reads at the <= 3B rows of the batch only
+ *                   (model.py:114-115 / 295-296).  Rows outside this block are skipped.
+ *   igcn_spmm_cols  skips every non-zero whose column is not set in col_bits (bitmap over the n_cols
+ *                   columns): the FIRST backward layer, whose input d_rep/(L+1) is non-zero on the
+ *                   touched rows only -- the skipped terms are exact zeros. */
+int igcn_spmm_rows(const igcn_csr *g, const float *X, float *Y, int32_t D,
+                   const float *const *add_host, int32_t n_add,
+                   const float *rowscale, float alpha,
+                   const int64_t *row_list, const int32_t *n_list, int64_t max_list, int64_t row0,
+                   float *const *peer_y_host, int32_t n_peers, void *stream);
+int igcn_spmm_cols(const igcn_csr *g, const float *X, float *Y, int32_t D,
+                   const float *const *add_host, int32_t n_add,
+                   const float *rowscale, float alpha, const uint32_t *col_bits,
+                   float *const *peer_y_host, int32_t n_peers, void *stream);
+
 /* INMO template aggregation fused with edge dropout (IGCN.inductive_rep_layer, model.py:423-432,
  * after dropout_sp_mat, model.py:435):
  *   X0[r] = rowscale[r]/(1-p) * ( sum_{c in adj(r), tmpl[c] >= 0, keep(r,c)} E[tmpl[c]]
@@ -152,10 +171,13 @@ int igcn_loss_finalize(const float *sp, const float *l2, const float *aux_sp, in
 
 /* Deterministic scatter plan for the gradient of a triple batch: slot s = kind * B + i
  * (kind 0 user, 1 positive, 2 negative) touches row id(s).  Sorts (id, slot) and emits
- * order[3B] (slots, ascending id then slot), seg_start[n_seg+1], seg_row[n_seg], n_seg[0].
- * One CTA, shared-memory bitonic sort; 3B <= 16384. */
-int igcn_bpr_plan(const int64_t *triples, int64_t B, int64_t item_offset, int32_t *order,
-                  int32_t *seg_start, int64_t *seg_row, int32_t *n_seg, void *stream);
+ * order[3B] (slots, ascending id then slot), seg_start[n_seg+1], seg_row[n_seg] (ascending), n_seg[0].
+ * n_rows = exclusive upper bound of the row ids.  touched_bits (may be NULL): bitmap of n_rows bits,
+ * cleared and then set for every touched row -- igcn_spmm_cols uses it in the backward pass.
+ * One CTA bitonic sort (registers + shuffles + shared memory); 3B <= 16384. */
+int igcn_bpr_plan(const int64_t *triples, int64_t B, int64_t item_offset, int64_t n_rows,
+                  int32_t *order, int32_t *seg_start, int64_t *seg_row, int32_t *n_seg,
+                  uint32_t *touched_bits, void *stream);
 
 /* Gradient rows of the BPR step, one half-warp per touched row, contributions added in slot
  * order (no atomics; replaces the index_put_(accumulate=True) autograd backward of
