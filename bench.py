@@ -37,6 +37,13 @@ WORKLOADS = {
     'small-igcn': ('small', 'IGCN', 0., 0.3),
     'small-lightgcn': ('small', 'LightGCN', 1e-4, None),
 }
+SCALEOUT = {
+    # BASELINE.json configs[4]: propagation + fused scoring/top-k only (per-step full-graph training is
+    # meaningless at this size)
+    'scaleout': (10_000_000, 1_000_000, 500_000_000),
+    'scaleout-mid': (1_000_000, 200_000, 50_000_000),
+    'scaleout-small': (100_000, 50_000, 5_000_000),
+}
 BATCH = 2048
 METRIC = 'ms/epoch (propagate+BPR)'
 
@@ -235,16 +242,120 @@ def run_reference(args, shape, kind, l2_reg, dropout):
     print(json.dumps(line))
 
 
+def run_scaleout(args):
+    """BASELINE.json configs[4]: IGCN propagation + fused scoring/top-k on a power-law graph generated on the
+    device; rows of the propagation and users of the ranking are sharded over the ranks."""
+    import torch
+    import torch.distributed as dist
+    from igcn_cf_b200 import dist as idist
+    from igcn_cf_b200.dataset import get_dataset
+    from igcn_cf_b200.model import get_model
+    from igcn_cf_b200.trainer import BasicTrainer
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    peers = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+        peers = idist.init_peers()
+    steps = 3 if args.steps is None else args.steps
+    warmup = 1 if args.warmup is None else args.warmup
+    t0 = time.perf_counter()
+    ds = get_dataset({'name': 'DeviceSyntheticDataset', 'shape': SCALEOUT[args.workload], 'seed': 2021, 'device': dev})
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+    model = get_model({'name': 'IGCN', 'embedding_size': 64, 'n_layers': 3, 'device': dev, 'dropout': 0.3,
+                       'feature_ratio': 1.}, ds)
+    trainer = BasicTrainer({'name': 'BasicTrainer', 'device': dev, 'n_epochs': 0, 'topks': [20], 'test_batch_size': 512,
+                            'dataset': ds, 'model': model})
+    model.eval()
+    n, nnz, D, L = ds.n_users + ds.n_items, model.norm_adj.nnz, 64, 3
+    lo, hi = idist.split_range(ds.n_users, rank, world)
+    if args.eval_users:
+        hi = min(hi, lo + args.eval_users)
+    users = trainer.test_users[lo:hi]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, reps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / reps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    def propagate():
+        model._bump()
+        with torch.no_grad():
+            return model.get_rep()
+
+    for _ in range(warmup):
+        propagate()
+        trainer.recommend('train', users=users)
+    sampler = ClockSampler(local)
+    sampler.start()
+    prop_ms = timed(propagate, steps)
+    score_ms = timed(lambda: trainer.recommend('train', users=users), steps)
+    clocks = sampler.stop()
+    peak, tc_peak, peak_src = measured_peaks()
+    n_local, nnz_local = model.norm_adj.csr.n_rows, model.norm_adj.csr.nnz
+    # algorithmic bytes of one propagation on this rank (SURVEY.md 8d): INMO layer + L adjacency layers + mean
+    b_adj = nnz_local * 8 + (n_local + 1) * 8 + n * D * 4 + n_local * D * 4
+    b_feat = nnz_local * 4 + (n_local + 1) * 8 + n_local * 4 + (n + 2) * D * 4 + n_local * D * 4
+    alg = b_feat + L * b_adj + L * n_local * D * 4
+    n_scored = int(users.shape[0])
+    total_scored = n_scored * world if args.eval_users else ds.n_users
+    flops = 2.0 * n_scored * ds.n_items * 80
+    if rank == 0:
+        line = {'metric': 'full-rank eval users/s (propagate + fused score/top-k)', 'value': total_scored / ((prop_ms + score_ms) * 1e-3),
+                'unit': 'users/s', 'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ms_per_step': prop_ms + score_ms,
+                'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': args.workload, 'model': 'IGCN', 'n_users': ds.n_users, 'n_items': ds.n_items,
+                           'interactions': len(ds), 'nnz_adj': nnz, 'dim': D, 'layers': L, 'users_scored': total_scored,
+                           'generated_on_device_s': round(gen_s, 2),
+                           'l2': 'inputs larger than L2 (layer table %d MB)' % (n * D * 4 // 2 ** 20),
+                           'parallelism': 'single GPU' if world == 1 else 'rows and users sharded over %d GPUs' % world},
+                'propagate_ms': prop_ms, 'score_topk_ms': score_ms,
+                'roofline': {'kernel': 'propagation (igcn_inmo_fwd + %d x igcn_spmm)' % L, 'bound': 'hbm', 'achieved': alg / (prop_ms * 1e-3) / 1e9,
+                             'peak': peak, 'unit': 'GB/s', 'frac': alg / (prop_ms * 1e-3) / 1e9 / peak, 'traffic': None,
+                             'peak_source': peak_src, 'algorithmic_bytes': alg,
+                             'gather_model_bytes': (L + 1) * nnz_local * D * 4},
+                'eval': {'roofline': {'kernel': 'score_tc_kernel (tcgen05 kind::f16)', 'bound': 'tensor', 'achieved': flops / (score_ms * 1e-3) / 1e12,
+                                      'peak': tc_peak, 'unit': 'TFLOP/s', 'frac': flops / (score_ms * 1e-3) / 1e12 / tc_peak}},
+                'gpu_launches': steps * (1 + L + 7), 'clocks': clocks}
+        print(json.dumps(line))
+    if world > 1:
+        peers.check()
+        idist.shutdown()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=None)
     ap.add_argument('--warmup', type=int, default=None)
-    ap.add_argument('--workload', default='yelp-lightgcn', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='yelp-lightgcn', choices=sorted(WORKLOADS) + sorted(SCALEOUT))
+    ap.add_argument('--eval-users', type=int, default=None, help='scale-out: users scored per rank (default: all of its share)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-steps', type=int, default=4)
     args = ap.parse_args()
+    if args.workload in SCALEOUT:
+        return run_scaleout(args)
     shape, kind, l2_reg, dropout = WORKLOADS[args.workload]
     if args.impl == 'reference':
         args.steps = 5 if args.steps is None else args.steps

@@ -136,6 +136,25 @@ class SyntheticDataset(BasicDataset):
         self._finish()
 
 
+class DeviceSyntheticDataset(BasicDataset):
+    """Scale-out synthetic graph generated on the GPU and kept there as a CSR (`device_graph`); there are no
+    Python per-user lists, so only propagation and unmasked full-ranking run on it (BASELINE.json config 5).
+    config: {'name': 'DeviceSyntheticDataset', 'shape': (U, I, E) or a synth.SHAPES name, 'seed', 'device'}."""
+
+    def __init__(self, dataset_config):
+        super().__init__(dataset_config)
+        shape = dataset_config['shape']
+        u, i, e = synth.SHAPES[shape] if isinstance(shape, str) else shape
+        self.device_graph = synth.gen_device(u, i, e, dataset_config['device'], seed=dataset_config.get('seed', 2021))
+        self.n_users, self.n_items = self.device_graph.n_users, self.device_graph.n_items
+
+    def __len__(self):
+        return self.device_graph.n_interactions
+
+    def __getitem__(self, index):
+        raise RuntimeError('DeviceSyntheticDataset has no host-side sampler; use the device sampler')
+
+
 class ListDataset(BasicDataset):
     """Dataset from in-memory per-user lists.  config: {'name': 'ListDataset', 'train': [[...], ...],
     'val': [...], 'test': [...], 'n_items': int (optional), 'device': ...}."""

@@ -65,15 +65,22 @@ class CsrDevice:
     """One CSR block on the GPU + chunk plan + per-D scratch; produces the `igcn_csr` struct."""
 
     def __init__(self, rowptr, col, val, n_cols, device, threshold=LONG_THRESHOLD, chunk=CHUNK):
+        """rowptr: host int64 array; col / val: host arrays, or tensors already on `device` (scale-out
+        graphs are generated on the GPU and never visit the host)."""
         self.device = torch.device(device)   # kernels need CUDA; a CPU device only supports the views
         self.n_rows = int(len(rowptr) - 1)
         self.n_cols = int(n_cols)
         self.nnz = int(rowptr[-1])
         self.rowptr_host = np.ascontiguousarray(rowptr, dtype=np.int64)
-        self.col_host = np.ascontiguousarray(col, dtype=np.int32)
         self.rowptr = torch.from_numpy(self.rowptr_host).to(self.device)
-        self.col = torch.from_numpy(self.col_host).to(self.device)
-        self.val = None if val is None else torch.from_numpy(np.ascontiguousarray(val, dtype=np.float32)).to(self.device)
+        if torch.is_tensor(col):
+            self.col_host = None
+            self.col = col.to(device=self.device, dtype=torch.int32).contiguous()
+            self.val = None if val is None else val.to(device=self.device, dtype=torch.float32).contiguous()
+        else:
+            self.col_host = np.ascontiguousarray(col, dtype=np.int32)
+            self.col = torch.from_numpy(self.col_host).to(self.device)
+            self.val = None if val is None else torch.from_numpy(np.ascontiguousarray(val, dtype=np.float32)).to(self.device)
         self.threshold = int(threshold)
         plan = chunk_plan(self.rowptr_host, threshold, chunk)
         self.n_chunks = int(len(plan[0]))
@@ -148,8 +155,54 @@ def _block_csr(rowptr, col, val, row0, row1, n_cols, device):
     return CsrDevice(rowptr[row0:row1 + 1] - lo, col[lo:hi], None if val is None else val[lo:hi], n_cols, device)
 
 
+class DeviceGraph:
+    """A bipartite train graph that already is a symmetric CSR ON THE DEVICE: rowptr int64 [N+1] (also kept
+    on the host for the chunk plan and the shard bounds), col int32 [nnz] sorted inside each row, users
+    first.  Produced by igcn_cf_b200.synth.gen_device for graphs too large to pass through Python lists
+    (BASELINE.json config 5: 10 M users, 1 M items, 500 M interactions)."""
+
+    def __init__(self, n_users, n_items, rowptr, col):
+        self.n_users, self.n_items = int(n_users), int(n_items)
+        self.rowptr, self.col = rowptr, col
+        self.rowptr_host = rowptr.cpu().numpy()
+        self.device = col.device
+
+    @property
+    def n_interactions(self):
+        return int(self.rowptr_host[self.n_users])
+
+    def block(self, row0, row1):
+        lo, hi = int(self.rowptr_host[row0]), int(self.rowptr_host[row1])
+        return self.rowptr_host[row0:row1 + 1] - lo, self.col[lo:hi], lo, hi
+
+
 class NormAdj(_SparseView):
     """D^-1/2 A D^-1/2 (deg clamped to >= 1) as a device CSR; reference model.py:85-94."""
+
+    @classmethod
+    def from_device(cls, dg, shard=None):
+        """Same object from a DeviceGraph: values computed on the GPU with the reference's rounding order
+        ((d_r * 1) * d_c in fp32), only this rank's row block is kept."""
+        self = object.__new__(cls)
+        n = dg.n_users + dg.n_items
+        self.n_users, self.n_items = dg.n_users, dg.n_items
+        self.shape = torch.Size([n, n])
+        self.rowptr_full = dg.rowptr_host
+        self.col_full = self.val_full = self.multiplicity_host = None
+        self.nnz = int(self.rowptr_full[-1])
+        self.bounds, self.row0, self.row1 = _row_block(self.rowptr_full, shard)
+        rp, col, lo, hi = dg.block(self.row0, self.row1)
+        deg = (dg.rowptr[1:] - dg.rowptr[:-1]).clamp_(min=1).to(torch.float32)
+        d_inv = torch.pow(deg, -0.5)
+        rows = torch.repeat_interleave(torch.arange(self.row0, self.row1, device=dg.device),
+                                       dg.rowptr[self.row0 + 1:self.row1 + 1] - dg.rowptr[self.row0:self.row1])
+        val = d_inv[rows] * d_inv[col.long()]
+        del rows
+        self.csr = CsrDevice(rp, col, val, n, dg.device)
+        self.device = self.csr.device
+        self._coo_cache = None
+        self._sampler = (dg.rowptr[:dg.n_users + 1], dg.col[:dg.n_interactions])
+        return self
 
     def __init__(self, n_users, n_items, pairs, device, shard=None):
         adj = build_adjacency(n_users, n_items, pairs)
@@ -199,6 +252,31 @@ class TemplateFeat(_SparseView):
     has the value row_sum[r] ** ((alpha-1)/2 - 1/2).  Stored as: the adjacency pattern CSR (shared
     layout with NormAdj), tmpl[N] (None when every node is a template and tmpl is the identity),
     row_sum[N], rowscale[N]."""
+
+    @classmethod
+    def from_device(cls, dg, adj=None, shard=None):
+        """feature_ratio == 1 template structure of a DeviceGraph (identity template map); shares the index
+        arrays of `adj` (a NormAdj built from the same graph and shard) when given."""
+        self = object.__new__(cls)
+        n = dg.n_users + dg.n_items
+        self.n_users, self.n_items = dg.n_users, dg.n_items
+        self.t_users, self.t_items = dg.n_users, dg.n_items
+        self.shape = torch.Size([n, n + 2])
+        self.tmpl_host = None
+        self.rowptr_full, self.col_full = dg.rowptr_host, None
+        self.bounds, self.row0, self.row1 = _row_block(self.rowptr_full, shard)
+        if adj is not None and (adj.row0, adj.row1) == (self.row0, self.row1):
+            self.csr = adj.csr.with_values(None)
+        else:
+            rp, col, _, _ = dg.block(self.row0, self.row1)
+            self.csr = CsrDevice(rp, col, None, n, dg.device)
+        self.device = self.csr.device
+        self.tmpl = None
+        self.row_sum = (dg.rowptr[1:] - dg.rowptr[:-1]).to(torch.float32) + 1.0
+        self.rowscale = torch.ones(n, dtype=torch.float32, device=self.device)
+        self.glob_user, self.glob_item = n, n + 1
+        self._order = self._tperm = None
+        return self
 
     def __init__(self, n_users, n_items, pairs, user_tmpl, item_tmpl, t_users, t_items, device, shard=None):
         adj = build_adjacency(n_users, n_items, pairs)

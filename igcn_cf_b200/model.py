@@ -146,6 +146,9 @@ class LightGCN(_GraphModel):
 
     def generate_graph(self, dataset):
         """D^-1/2 A D^-1/2 as a device CSR (model.py:85-94)."""
+        dg = getattr(dataset, 'device_graph', None)
+        if dg is not None:
+            return graph.NormAdj.from_device(dg, shard=self._shard_arg())
         return graph.NormAdj(dataset.n_users, dataset.n_items, graph.train_pairs_of(dataset), self.device,
                              shard=self._shard_arg())
 
@@ -161,6 +164,32 @@ class LightGCN(_GraphModel):
         pos_e, neg_e = self.embedding(self.n_users + pos_items), self.embedding(self.n_users + neg_items)
         l2_norm_sq = (users_e ** 2).sum(dim=1) + (pos_e ** 2).sum(dim=1) + (neg_e ** 2).sum(dim=1)
         return rep[users, :], rep[self.n_users + pos_items, :], rep[self.n_users + neg_items, :], l2_norm_sq
+
+
+class IdentityMap:
+    """user_map / item_map of feature_ratio == 1 (model.py:392-401) without materialising n dict entries."""
+
+    def __init__(self, n):
+        self.n = int(n)
+
+    def __len__(self):
+        return self.n
+
+    def __contains__(self, k):
+        return 0 <= k < self.n
+
+    def __getitem__(self, k):
+        if not 0 <= k < self.n:
+            raise KeyError(k)
+        return k
+
+    def keys(self):
+        return range(self.n)
+
+    values = keys
+
+    def items(self):
+        return ((k, k) for k in range(self.n))
 
 
 def graph_rank_nodes(dataset, ranking_metric):
@@ -230,6 +259,14 @@ class IGCN(_GraphModel):
     def generate_feat(self, dataset, is_updating=False, ranking_metric=None):
         """Template incidence structure (model.py:386-421).  Returns (feat, user_map, item_map,
         row_sum) like the reference; `feat` is a graph.TemplateFeat."""
+        dg = getattr(dataset, 'device_graph', None)
+        if dg is not None:
+            if is_updating or self.feature_ratio < 1.:
+                raise RuntimeError('device-resident graphs support feature_ratio == 1 without template updates')
+            adj = self.norm_adj if self.norm_adj.shape[0] == dg.n_users + dg.n_items else None
+            feat = graph.TemplateFeat.from_device(dg, adj=adj, shard=self._shard_arg())
+            self._aux = None
+            return feat, IdentityMap(dg.n_users), IdentityMap(dg.n_items), feat.row_sum
         if not is_updating:
             if self.feature_ratio < 1.:
                 ranked_users, ranked_items = graph_rank_nodes(dataset, ranking_metric)

@@ -173,3 +173,49 @@ def dropit(split, ratio=0.8):
     return SynthSplit(split.n_users, split.n_items, np.array(ptrs, dtype=np.int64),
                       np.concatenate(chunks), np.array(n_tr, dtype=np.int64),
                       np.array(n_va, dtype=np.int64))
+
+
+def gen_device(n_users, n_items, n_inter, device, seed=2021, min_degree=10, chunk=1 << 26):
+    """The same generative model as gen_synth, evaluated with torch ops ON THE DEVICE and returned as a
+    symmetric CSR (igcn_cf_b200.graph.DeviceGraph) -- for graphs that are too large for Python lists
+    (BASELINE.json config 5).  Every interaction is a train interaction (that config only asks for
+    propagation + scoring).  Duplicate (user, item) draws are dropped, so the interaction count comes out a
+    few per cent under n_inter."""
+    import torch
+    from .graph import DeviceGraph
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(int(seed))
+    raw = torch.empty(n_users, dtype=torch.float64, device=dev).log_normal_(0.0, 1.0, generator=g)
+    deg = torch.clamp(torch.round(raw / raw.sum() * n_inter), min=min_degree, max=max(min_degree, n_items // 4)).long()
+    del raw
+    pop = torch.arange(1, n_items + 1, dtype=torch.float64, device=dev) ** -0.8
+    pop = pop[torch.randperm(n_items, generator=g, device=dev)]
+    cdf = torch.cumsum(pop / pop.sum(), 0)
+    cdf[-1] = 1.0
+    del pop
+    users = torch.repeat_interleave(torch.arange(n_users, device=dev), deg)
+    total = int(users.shape[0])
+    keys = torch.empty(total, dtype=torch.int64, device=dev)
+    for lo in range(0, total, chunk):
+        hi = min(total, lo + chunk)
+        r = torch.rand(hi - lo, dtype=torch.float64, device=dev, generator=g)
+        items = torch.searchsorted(cdf, r, right=True).clamp_(max=n_items - 1)
+        keys[lo:hi] = users[lo:hi] * n_items + items
+        del r, items
+    del users, cdf, deg
+    keys = torch.unique(keys)                                     # sorted by (user, item), duplicates dropped
+    u = torch.div(keys, n_items, rounding_mode='floor')
+    it = keys - u * n_items
+    del keys
+    deg_u = torch.bincount(u, minlength=n_users)
+    deg_i = torch.bincount(it, minlength=n_items)
+    # item rows: sort the transposed pairs by (item, user)
+    keys_t = torch.sort(it * n_users + u).values
+    col_u = (it + n_users).to(torch.int32)
+    del it, u
+    col_i = (keys_t - torch.div(keys_t, n_users, rounding_mode='floor') * n_users).to(torch.int32)
+    del keys_t
+    rowptr = torch.zeros(n_users + n_items + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(torch.cat([deg_u, deg_i]), 0, out=rowptr[1:])
+    col = torch.cat([col_u, col_i])
+    return DeviceGraph(n_users, n_items, rowptr, col)
