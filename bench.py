@@ -311,7 +311,7 @@ def run_scaleout(args):
     score_ms = timed(lambda: trainer.recommend('train', users=users), steps)
     clocks = sampler.stop()
     peak, tc_peak, peak_src = measured_peaks()
-    n_local, nnz_local = model.norm_adj.csr.n_rows, model.norm_adj.csr.nnz
+    n_local, nnz_local = model.norm_adj.local_rows, model.norm_adj.local_nnz
     # algorithmic bytes of one propagation on this rank: INMO layer + L adjacency layers + mean
     b_adj = nnz_local * 8 + (n_local + 1) * 8 + n * D * 4 + n_local * D * 4
     b_feat = nnz_local * 4 + (n_local + 1) * 8 + n_local * 4 + (n + 2) * D * 4 + n_local * D * 4
@@ -381,7 +381,7 @@ def main():
     ds = build_dataset(shape, dev)
     model, trainer = build_model(ds, kind, dropout, l2_reg, dev)
     n, nnz, D = model.n_users + model.n_items, model.norm_adj.nnz, 64
-    n_local, nnz_local = model.norm_adj.csr.n_rows, model.norm_adj.csr.nnz
+    n_local, nnz_local = model.norm_adj.local_rows, model.norm_adj.local_nnz
     steps_per_epoch = math.ceil(len(ds) / BATCH)
     step = trainer.step
     model.train()

@@ -24,7 +24,8 @@ class CsrStruct(C.Structure):
                 ('long_threshold', c_int32), ('n_chunks', c_int32),
                 ('chunk_row', c_void_p), ('chunk_begin', c_void_p), ('chunk_len', c_void_p),
                 ('chunk_first', c_void_p), ('chunk_count', c_void_p),
-                ('partial', c_void_p), ('counters', c_void_p), ('row_order', c_void_p)]
+                ('partial', c_void_p), ('counters', c_void_p), ('row_order', c_void_p),
+                ('n_long_rows', c_int32), ('n_medium_rows', c_int32)]
 
 
 class DropoutStruct(C.Structure):

@@ -5,16 +5,17 @@
 //   igcn_inmo_bwd   dE = F~^T G         transposed, mask regenerated            K4
 //   igcn_colsum_masked   gradient of the two global template rows
 //
-// Work decomposition (all three share it): a group of 8 lanes owns one row (4 rows per warp) and
-// walks its non-zeros in CSR order; for D = 64 every lane carries two float4 accumulators, so one
-// neighbour is two 128-bit loads per lane and each load instruction of a group reads one full
-// 128-byte line.  Column ids and values are loaded 8 at a time (coalesced) and broadcast with
-// shuffles; 4 neighbours (8 loads per lane) are in flight per group.  Rows are visited in
-// degree-descending order (igcn_csr.row_order) so the rows sharing a warp have similar lengths
-// and the longest ones start first.  Rows longer than `long_threshold` are pre-cut into chunks on the host
-// (igcn_csr.chunk_*): chunk units come first in the grid, write partial sums, and the last one
-// to arrive (self-resetting counter) adds the partials in chunk order -- deterministic, and
-// independent of how rows are sharded over GPUs.
+// Work decomposition (all three share it): a group of 8 lanes walks a run of non-zeros in CSR order;
+// for D = 64 every lane carries two float4 accumulators, so one neighbour is two 128-bit loads per
+// lane and each load instruction of a group reads one full 128-byte line.  Column ids and values
+// are loaded 8 at a time (coalesced, one batch ahead) and broadcast with shuffles; 4 neighbours
+// (8 loads per lane) are in flight per group.  Rows are visited in degree-descending order
+// (igcn_csr.row_order).  A short row (<= IGCN_MEDIUM_NNZ non-zeros) is one group's work, a medium row
+// is shared by the 4 groups of a warp (quarter each, ordered shuffle combine), a long row (>
+// long_threshold) is pre-cut into chunks on the host (igcn_csr.chunk_*): chunk warps come first in
+// the grid, write partial sums, and the last one to arrive (self-resetting counter) adds the
+// partials in chunk order.  The dependent-load chain of any unit is thus <= 8 batches, and how a row
+// is summed depends on its length only -- deterministic, independent of how rows are sharded over GPUs.
 //
 // Everything here is HBM/L2-bound gather work; there is no tensor-core shape to it.
 #include "common.cuh"
@@ -210,25 +211,61 @@ __device__ __forceinline__ void finish_row(const PropArgs &a, int64_t r, RowVec<
     }
 }
 
+// Ordered in-warp combine: subgroup 0 ends up with ((p0 + p1) + p2) + ... of the SUB subgroup accumulators.
+template <int LPR, int V, bool EXACT>
+__device__ __forceinline__ void combine_subgroups(RowVec<LPR, V, EXACT> &acc, int lane, int sub) {
+    constexpr int SUB = 32 / LPR;
+#pragma unroll
+    for (int s = 1; s < SUB; ++s) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            float4 o;
+            o.x = __shfl_sync(0xffffffffu, acc.v[i].x, lane + s * LPR);
+            o.y = __shfl_sync(0xffffffffu, acc.v[i].y, lane + s * LPR);
+            o.z = __shfl_sync(0xffffffffu, acc.v[i].z, lane + s * LPR);
+            o.w = __shfl_sync(0xffffffffu, acc.v[i].w, lane + s * LPR);
+            if (sub == 0) add4(acc.v[i], o);
+        }
+    }
+}
+
+// This subgroup's slice of the non-zero range [beg, end) when a whole warp shares it (LPR-aligned pieces).
+template <int LPR>
+__device__ __forceinline__ void split_range(int64_t &beg, int64_t &end, int sub) {
+    constexpr int SUB = 32 / LPR;
+    const int64_t q = (((end - beg) + SUB - 1) / SUB + LPR - 1) & ~(int64_t)(LPR - 1);
+    const int64_t b = beg + sub * q;
+    end = min(end, b + q);
+    beg = min(b, end);
+}
+
+// Work units are WARPS, in this order (rows are visited by non-zero count, descending -- igcn_csr.row_order):
+//   [0, n_chunks)                 one chunk of a long row (> long_threshold non-zeros): the warp's subgroups share
+//                                 the chunk, the combined partial goes to g.partial and the last chunk of the row
+//                                 to finish adds the partials in chunk order
+//   [n_chunks, +n_medium_rows)    one medium row (> IGCN_MEDIUM_NNZ non-zeros) per warp, subgroups share it
+//   the rest                      one short row per LPR-lane subgroup
+// How a row is summed depends on its length only, never on the grid, the row block or the GPU count.
 template <int LPR, int V, bool EXACT, int MODE, int DROP>
 __global__ void __launch_bounds__(kThreads, 4) prop_kernel(const __grid_constant__ PropArgs a) {
-    constexpr int GROUPS = kThreads / LPR;
+    constexpr int SUB = 32 / LPR;
+    constexpr bool ROWS = (MODE == MODE_SPMM && DROP == 1);
     using Vec = RowVec<LPR, V, EXACT>;
     const int lane = threadIdx.x % LPR;
+    const int sub = (threadIdx.x & 31) / LPR;
     const uint32_t gmask = group_mask<LPR>();
-    const int64_t unit = (int64_t)blockIdx.x * GROUPS + threadIdx.x / LPR;
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
     const int64_t n_chunks = a.g.n_chunks;
-    constexpr bool ROWS = (MODE == MODE_SPMM && DROP == 1);
-    if (!ROWS && unit >= n_chunks + a.g.n_rows) return;
+    const int64_t n_long = a.g.row_order ? a.g.n_long_rows : 0, n_med = a.g.row_order ? a.g.n_medium_rows : 0;
     uint64_t seed = a.drop.seed;
-    if (DROP == 1 && a.drop.seed_dev) seed = mix64(seed ^ mix64(*a.drop.seed_dev + 0x2545f491ULL));
+    if (MODE != MODE_SPMM && DROP == 1 && a.drop.seed_dev) seed = mix64(seed ^ mix64(*a.drop.seed_dev + 0x2545f491ULL));
     const int D = a.D;
     Vec acc;
     acc.zero();
 
-    if (unit < n_chunks) {
+    if (warp < n_chunks) {
         // ---- one chunk of a long row
-        const int ch = (int)unit;
+        const int ch = (int)warp;
         const int64_t r = a.g.chunk_row[ch];
         if (ROWS) {
             // is this long row on the list?  (ascending ids: binary search, same answer on every lane)
@@ -240,8 +277,11 @@ __global__ void __launch_bounds__(kThreads, 4) prop_kernel(const __grid_constant
             }
             if (lo >= *a.n_list || __ldg(a.row_list + lo) != want) return;
         }
-        const int64_t beg = a.g.chunk_begin[ch];
-        gather_range<LPR, V, EXACT, MODE, DROP>(a, acc, beg, beg + a.g.chunk_len[ch], a.row0 + r, lane, gmask, seed);
+        int64_t beg = a.g.chunk_begin[ch], end = beg + a.g.chunk_len[ch];
+        split_range<LPR>(beg, end, sub);
+        gather_range<LPR, V, EXACT, MODE, DROP>(a, acc, beg, end, a.row0 + r, lane, gmask, seed);
+        combine_subgroups<LPR, V, EXACT>(acc, lane, sub);
+        if (sub != 0) return;
         const int first = a.g.chunk_first[ch];
         const int count = a.g.chunk_count[ch];
 #pragma unroll
@@ -275,36 +315,62 @@ __global__ void __launch_bounds__(kThreads, 4) prop_kernel(const __grid_constant
         return;
     }
 
-    // ---- one whole (short) row, taken in degree-descending order when a permutation is given
-    int64_t r = unit - n_chunks;
+    int64_t r;
+    bool shared_row;                                    // does the whole warp work on row r?
     if (ROWS) {
-        if (r >= *a.n_list) return;
-        r = __ldg(a.row_list + r) - a.row0;
-        if (r < 0 || r >= a.g.n_rows) return;            // another rank's row
-    } else if (a.g.row_order) {
-        r = __ldg(a.g.row_order + r);
+        // one listed row per warp; its length decides how it is summed (same rule as the full kernel)
+        const int64_t idx = warp - n_chunks;
+        if (idx >= *a.n_list) return;
+        r = __ldg(a.row_list + idx) - a.row0;
+        if (r < 0 || r >= a.g.n_rows) return;           // another block's row
+        shared_row = true;
+    } else if (warp < n_chunks + n_med) {
+        r = __ldg(a.g.row_order + n_long + (warp - n_chunks));
+        shared_row = true;
+    } else {
+        const int64_t idx = n_long + n_med + (warp - n_chunks - n_med) * SUB + sub;
+        if (idx >= a.g.n_rows) return;
+        r = a.g.row_order ? (int64_t)__ldg(a.g.row_order + idx) : idx;
+        shared_row = false;
     }
-    const int64_t beg = __ldg(a.g.rowptr + r), end = __ldg(a.g.rowptr + r + 1);
-    if (n_chunks > 0 && end - beg > a.g.long_threshold) return;   // handled by chunk units
-    gather_range<LPR, V, EXACT, MODE, DROP>(a, acc, beg, end, a.row0 + r, lane, gmask, seed);
+    int64_t beg = __ldg(a.g.rowptr + r), end = __ldg(a.g.rowptr + r + 1);
+    if (ROWS) {
+        const int64_t nnz = end - beg;
+        if (n_chunks > 0 && nnz > a.g.long_threshold) return;          // the chunk warps own it
+        if (!(a.g.row_order && nnz > IGCN_MEDIUM_NNZ)) {                // short row: subgroup 0 alone, like the full kernel
+            if (sub != 0) return;
+            shared_row = false;
+        }
+    }
+    if (shared_row) {
+        split_range<LPR>(beg, end, sub);
+        gather_range<LPR, V, EXACT, MODE, DROP>(a, acc, beg, end, a.row0 + r, lane, gmask, seed);
+        combine_subgroups<LPR, V, EXACT>(acc, lane, sub);
+        if (sub != 0) return;
+    } else {
+        gather_range<LPR, V, EXACT, MODE, DROP>(a, acc, beg, end, a.row0 + r, lane, gmask, seed);
+    }
     finish_row<LPR, V, EXACT, MODE, DROP>(a, r, acc, lane, seed);
+}
+
+static int64_t warp_units(const PropArgs &a, int sub, bool rows_variant) {
+    if (rows_variant) return a.g.n_chunks + a.max_list;
+    const int64_t n_long = a.g.row_order ? a.g.n_long_rows : 0, n_med = a.g.row_order ? a.g.n_medium_rows : 0;
+    return a.g.n_chunks + n_med + (a.g.n_rows - n_long - n_med + sub - 1) / sub;
 }
 
 template <int LPR, int V, bool EXACT, int MODE, int DROP>
 static void launch_one(const PropArgs &a, cudaStream_t st) {
-    const int64_t units = a.g.n_chunks + ((MODE == MODE_SPMM && DROP == 1) ? a.max_list : a.g.n_rows);
-    constexpr int GROUPS = kThreads / LPR;
-    prop_kernel<LPR, V, EXACT, MODE, DROP><<<(unsigned)((units + GROUPS - 1) / GROUPS), kThreads, 0, st>>>(a);
+    const int64_t warps = warp_units(a, 32 / LPR, MODE == MODE_SPMM && DROP == 1);
+    constexpr int WPB = kThreads / 32;
+    prop_kernel<LPR, V, EXACT, MODE, DROP><<<(unsigned)((warps + WPB - 1) / WPB), kThreads, 0, st>>>(a);
 }
 
 template <int MODE, int DROP>
 static int launch_lanes(const PropArgs &a, cudaStream_t st) {
     if (a.g.n_chunks + ((MODE == MODE_SPMM && DROP == 1) ? a.max_list : a.g.n_rows) == 0) return 0;
     const int D = a.D;
-    // the two partial-layer variants run far below one wave: fewer, longer dependent chains matter more than
-    // line-sized loads, so a row gets 16 lanes (one float4 each, 8 neighbour rows in flight)
-    if (D == 64 && MODE == MODE_SPMM && DROP != 0) launch_one<16, 1, true, MODE, DROP>(a, st);
-    else if (D == 64) launch_one<8, 2, true, MODE, DROP>(a, st);
+    if (D == 64) launch_one<8, 2, true, MODE, DROP>(a, st);
     else if (D == 32) launch_one<8, 1, true, MODE, DROP>(a, st);
     else if (D == 128) launch_one<16, 2, true, MODE, DROP>(a, st);
     else if (D < 32) launch_one<8, 1, false, MODE, DROP>(a, st);
@@ -326,6 +392,10 @@ static int check_common(const igcn_csr *g, int32_t D) {
     if (!g) { set_error("null csr"); return -1; }
     if (D <= 0 || D > 128 || (D & 3)) { set_error("embedding size %d unsupported (need D %% 4 == 0, D <= 128)", D); return -1; }
     if (g->n_chunks > 0 && (!g->partial || !g->counters || !g->chunk_row)) { set_error("chunk plan incomplete"); return -1; }
+    if (g->n_long_rows < 0 || g->n_medium_rows < 0 || (int64_t)g->n_long_rows + g->n_medium_rows > g->n_rows) {
+        set_error("row class counts out of range"); return -1;
+    }
+    if (!g->row_order && g->n_chunks > 0) { set_error("a chunk plan needs row_order"); return -1; }
     return 0;
 }
 

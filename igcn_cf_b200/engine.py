@@ -27,11 +27,12 @@ def _drop_struct(drop):
 
 
 class Shard:
-    """This rank's row block [row0, row1) of a row-sharded propagation plus the registry of symmetric
-    (peer-mapped) buffers the kernels may store into.  `None` stands for the single-GPU case."""
+    """Row-sharded propagation: the peer context plus the registry of symmetric (peer-mapped) buffers the
+    kernels may store into.  Which rows this rank computes is a property of the graph objects
+    (`adj.blocks`).  `None` stands for the single-GPU case."""
 
-    def __init__(self, ctx, row0, row1):
-        self.ctx, self.row0, self.row1 = ctx, int(row0), int(row1)
+    def __init__(self, ctx):
+        self.ctx = ctx
         self._bufs = {}
 
     def new_buffer(self, rows, dim):
@@ -103,17 +104,18 @@ class Propagator:
         """One layer.  rows = (row_list int64, n_list int32[1], max_list): compute the listed rows only
         (igcn_spmm_rows); cols = bitmap of the columns whose X row is non-zero (igcn_spmm_cols)."""
         sh = self.shard
-        row0 = 0 if sh is None else sh.row0
-        off = row0 * self.dim * 4
-        peers, n_peers = _peer_args(sh, y, off)
-        head = (adj.csr.struct(self.dim), ptr(x), ptr(y) + off, self.dim, self._adds(adds, off), len(adds),
-                None if rowscale is None else ptr(rowscale) + row0 * 4, float(alpha))
-        if rows is not None:
-            call('igcn_spmm_rows', *head, ptr(rows[0]), ptr(rows[1]), int(rows[2]), row0, peers, n_peers, stream_ptr())
-        elif cols is not None:
-            call('igcn_spmm_cols', *head, ptr(cols), peers, n_peers, stream_ptr())
-        else:
-            call('igcn_spmm', *head, peers, n_peers, stream_ptr())
+        for blk in adj.blocks:
+            row0 = blk.row0
+            off = row0 * self.dim * 4
+            peers, n_peers = _peer_args(sh, y, off)
+            head = (blk.csr.struct(self.dim), ptr(x), ptr(y) + off, self.dim, self._adds(adds, off), len(adds),
+                    None if rowscale is None else ptr(rowscale) + row0 * 4, float(alpha))
+            if rows is not None:
+                call('igcn_spmm_rows', *head, ptr(rows[0]), ptr(rows[1]), int(rows[2]), row0, peers, n_peers, stream_ptr())
+            elif cols is not None:
+                call('igcn_spmm_cols', *head, ptr(cols), peers, n_peers, stream_ptr())
+            else:
+                call('igcn_spmm', *head, peers, n_peers, stream_ptr())
         if sh is not None:
             sh.ctx.barrier()
 
@@ -159,11 +161,12 @@ class Propagator:
 
 def inmo_forward(feat, emb, x0, drop, dim, shard=None):
     """X0 = F~ E with dropout fused (model.py:423-432 after model.py:435)."""
-    row0 = 0 if shard is None else shard.row0
-    off = row0 * dim * 4
-    peers, n_peers = _peer_args(shard, x0, off)
-    call('igcn_inmo_fwd', feat.csr.struct(dim), ptr(feat.tmpl), ptr(feat.rowscale) + row0 * 4, _drop_struct(drop), ptr(emb),
-         ptr(x0) + off, dim, row0, feat.n_users, feat.glob_user, feat.glob_item, peers, n_peers, stream_ptr())
+    for blk in feat.blocks:
+        row0 = blk.row0
+        off = row0 * dim * 4
+        peers, n_peers = _peer_args(shard, x0, off)
+        call('igcn_inmo_fwd', blk.csr.struct(dim), ptr(feat.tmpl), ptr(feat.rowscale) + row0 * 4, _drop_struct(drop),
+             ptr(emb), ptr(x0) + off, dim, row0, feat.n_users, feat.glob_user, feat.glob_item, peers, n_peers, stream_ptr())
     if shard is not None:
         shard.ctx.barrier()
 
@@ -173,10 +176,10 @@ def inmo_backward(feat, g_scaled, d_emb, drop, dim, scratch, shard=None):
     Row-sharded: each rank produces the template rows of its own node block and stores them into every
     rank's d_emb; the two global-template rows are column sums every rank computes for itself."""
     n, u = feat.shape[0], feat.n_users
-    row0 = 0 if shard is None else shard.row0
     peers, n_peers = _peer_args(shard, d_emb, 0)
-    call('igcn_inmo_bwd', feat.csr.struct(dim), ptr(feat.tmpl), _drop_struct(drop), ptr(g_scaled), ptr(d_emb), dim, row0,
-         peers, n_peers, stream_ptr())
+    for blk in feat.blocks:
+        call('igcn_inmo_bwd', blk.csr.struct(dim), ptr(feat.tmpl), _drop_struct(drop), ptr(g_scaled), ptr(d_emb), dim,
+             blk.row0, peers, n_peers, stream_ptr())
     d = _drop_struct(drop)
     call('igcn_colsum_masked', ptr(g_scaled), 0, u, dim, d, ptr(scratch), ptr(d_emb[feat.glob_user]), stream_ptr())
     call('igcn_colsum_masked', ptr(g_scaled), u, n, dim, d, ptr(scratch), ptr(d_emb[feat.glob_item]), stream_ptr())
@@ -605,7 +608,9 @@ def score_topk(rep, user_ids, n_users, n_items, k, mask=None, item_lo=0, item_hi
         raise RuntimeError('tensor-core scoring needs D <= 64, k <= 24 and a ListCSR mask')
     if impl == 'exact' or not tc_ok:
         return score_topk_exact(rep, user_ids, n_users, n_items, k, mask, item_lo, item_hi, banned_bits)
-    if mask is not None and users_host is None:
+    if isinstance(users_host, str):          # 'identity': the caller vouches for user_ids == arange(len(mask))
+        users_host = None
+    elif mask is not None and users_host is None:
         n = int(user_ids.shape[0])
         if n != len(mask.ptr_host) - 1 or not bool((user_ids == torch.arange(n, device=user_ids.device)).all()):
             users_host = user_ids.cpu().numpy()

@@ -22,6 +22,7 @@ from . import _lib
 
 LONG_THRESHOLD = 256     # rows with more non-zeros than this are split ...
 CHUNK = 128              # ... into chunks of this many non-zeros
+MEDIUM_NNZ = 64          # IGCN_MEDIUM_NNZ: rows above it (and not long) get a whole warp
 
 
 def train_pairs_of(dataset):
@@ -89,6 +90,8 @@ class CsrDevice:
         # visiting order: longest rows first, ties by row id (stable) -> rows sharing a warp are alike
         deg = np.diff(self.rowptr_host)
         self.row_order = torch.from_numpy(np.argsort(-deg, kind='stable').astype(np.int32)).to(self.device)
+        self.n_long = int((deg > self.threshold).sum())
+        self.n_medium = max(0, int((deg > MEDIUM_NNZ).sum()) - self.n_long)
         self._partial = {}
         self._structs = {}
 
@@ -110,7 +113,8 @@ class CsrDevice:
             s = _lib.CsrStruct(self.n_rows, self.n_cols, self.nnz, self.rowptr.data_ptr(), self.col.data_ptr(),
                                None if self.val is None else self.val.data_ptr(), self.threshold, self.n_chunks,
                                cr.data_ptr(), cb.data_ptr(), cl.data_ptr(), cf.data_ptr(), cc.data_ptr(),
-                               partial.data_ptr(), self.counters.data_ptr(), self.row_order.data_ptr())
+                               partial.data_ptr(), self.counters.data_ptr(), self.row_order.data_ptr(),
+                               self.n_long, self.n_medium)
             self._structs[D] = s
         return C.byref(s)
 
@@ -139,20 +143,53 @@ class _SparseView:
         return torch.sparse_coo_tensor(idx, val, self.shape, is_coalesced=True)
 
 
-def _row_block(rowptr, shard):
-    """(bounds, row0, row1) of this rank's contiguous row block; shard = (rank, world) or None."""
+class RowBlock:
+    """Rows [row0, row1) of a graph as their own CSR."""
+
+    def __init__(self, row0, row1, csr):
+        self.row0, self.row1, self.csr = int(row0), int(row1), csr
+
+
+def _row_ranges(rowptr, n_users, shard):
+    """Row ranges this rank computes; shard = (rank, world) or None (everything).  A rank gets one slice of
+    the USER rows and one slice of the ITEM rows, each balanced by non-zeros: the two halves of the
+    bipartite adjacency cost differently per non-zero (user rows gather from the item table, item rows from
+    the usually much larger user table), so balancing them separately balances the ranks."""
     n = len(rowptr) - 1
     if shard is None:
-        return np.array([0, n], dtype=np.int64), 0, n
+        return [(0, n)]
     from .dist import shard_bounds
     rank, world = shard
-    bounds = shard_bounds(rowptr, world)
-    return bounds, int(bounds[rank]), int(bounds[rank + 1])
+    ub = shard_bounds(rowptr[:n_users + 1], world)
+    ib = shard_bounds(rowptr[n_users:] - rowptr[n_users], world) + n_users
+    return [(int(ub[rank]), int(ub[rank + 1])), (int(ib[rank]), int(ib[rank + 1]))]
 
 
 def _block_csr(rowptr, col, val, row0, row1, n_cols, device):
     lo, hi = int(rowptr[row0]), int(rowptr[row1])
     return CsrDevice(rowptr[row0:row1 + 1] - lo, col[lo:hi], None if val is None else val[lo:hi], n_cols, device)
+
+
+class _Blocked:
+    """Mixin: `blocks` (list of RowBlock) + single-block compatibility attributes."""
+    blocks = ()
+
+    def _set_blocks(self, blocks):
+        self.blocks = blocks
+        self.csr = blocks[0].csr                     # single-GPU view (tests, sampler, chunk statistics)
+        self.row0, self.row1 = blocks[0].row0, blocks[0].row1
+        self.device = self.csr.device
+
+    @property
+    def local_rows(self):
+        return sum(b.csr.n_rows for b in self.blocks)
+
+    @property
+    def local_nnz(self):
+        return sum(b.csr.nnz for b in self.blocks)
+
+    def block_key(self):
+        return tuple((b.row0, b.row1) for b in self.blocks)
 
 
 class DeviceGraph:
@@ -176,7 +213,7 @@ class DeviceGraph:
         return self.rowptr_host[row0:row1 + 1] - lo, self.col[lo:hi], lo, hi
 
 
-class NormAdj(_SparseView):
+class NormAdj(_SparseView, _Blocked):
     """D^-1/2 A D^-1/2 (deg clamped to >= 1) as a device CSR; reference model.py:85-94."""
 
     @classmethod
@@ -190,16 +227,17 @@ class NormAdj(_SparseView):
         self.rowptr_full = dg.rowptr_host
         self.col_full = self.val_full = self.multiplicity_host = None
         self.nnz = int(self.rowptr_full[-1])
-        self.bounds, self.row0, self.row1 = _row_block(self.rowptr_full, shard)
-        rp, col, lo, hi = dg.block(self.row0, self.row1)
         deg = (dg.rowptr[1:] - dg.rowptr[:-1]).clamp_(min=1).to(torch.float32)
         d_inv = torch.pow(deg, -0.5)
-        rows = torch.repeat_interleave(torch.arange(self.row0, self.row1, device=dg.device),
-                                       dg.rowptr[self.row0 + 1:self.row1 + 1] - dg.rowptr[self.row0:self.row1])
-        val = d_inv[rows] * d_inv[col.long()]
-        del rows
-        self.csr = CsrDevice(rp, col, val, n, dg.device)
-        self.device = self.csr.device
+        blocks = []
+        for row0, row1 in _row_ranges(self.rowptr_full, dg.n_users, shard):
+            rp, col, lo, hi = dg.block(row0, row1)
+            rows = torch.repeat_interleave(torch.arange(row0, row1, device=dg.device),
+                                           dg.rowptr[row0 + 1:row1 + 1] - dg.rowptr[row0:row1])
+            val = d_inv[rows] * d_inv[col.long()]
+            del rows
+            blocks.append(RowBlock(row0, row1, CsrDevice(rp, col, val, n, dg.device)))
+        self._set_blocks(blocks)
         self._coo_cache = None
         self._sampler = (dg.rowptr[:dg.n_users + 1], dg.col[:dg.n_interactions])
         return self
@@ -218,9 +256,8 @@ class NormAdj(_SparseView):
         self.col_full = adj.indices.astype(np.int32)
         self.val_full = val
         self.nnz = int(self.rowptr_full[-1])
-        self.bounds, self.row0, self.row1 = _row_block(self.rowptr_full, shard)
-        self.csr = _block_csr(self.rowptr_full, self.col_full, val, self.row0, self.row1, adj.shape[0], device)
-        self.device = self.csr.device
+        self._set_blocks([RowBlock(r0, r1, _block_csr(self.rowptr_full, self.col_full, val, r0, r1, adj.shape[0], device))
+                          for r0, r1 in _row_ranges(self.rowptr_full, n_users, shard)])
         self._coo_cache = None
         self._sampler = None
 
@@ -228,7 +265,7 @@ class NormAdj(_SparseView):
         """(rowptr, col) on the device covering ALL user rows: the triple sampler is replicated on every
         rank, so a row-sharded adjacency keeps a separate copy of the user half of the pattern."""
         if self._sampler is None:
-            if self.row0 == 0 and self.row1 >= self.n_users:
+            if len(self.blocks) == 1 and self.row0 == 0 and self.row1 >= self.n_users:
                 self._sampler = (self.csr.rowptr, self.csr.col)
             else:
                 rp = self.rowptr_full[:self.n_users + 1]
@@ -244,7 +281,7 @@ class NormAdj(_SparseView):
         return self._coo_cache
 
 
-class TemplateFeat(_SparseView):
+class TemplateFeat(_SparseView, _Blocked):
     """The INMO template incidence matrix `feat_mat` (reference model.py:386-421, 374-377).
 
     Row r holds one entry per neighbour c of r whose node is a template (column tmpl[c]) plus one
@@ -264,13 +301,13 @@ class TemplateFeat(_SparseView):
         self.shape = torch.Size([n, n + 2])
         self.tmpl_host = None
         self.rowptr_full, self.col_full = dg.rowptr_host, None
-        self.bounds, self.row0, self.row1 = _row_block(self.rowptr_full, shard)
-        if adj is not None and (adj.row0, adj.row1) == (self.row0, self.row1):
-            self.csr = adj.csr.with_values(None)
+        ranges = _row_ranges(self.rowptr_full, dg.n_users, shard)
+        if adj is not None and list(adj.block_key()) == ranges:
+            blocks = [RowBlock(b.row0, b.row1, b.csr.with_values(None)) for b in adj.blocks]
         else:
-            rp, col, _, _ = dg.block(self.row0, self.row1)
-            self.csr = CsrDevice(rp, col, None, n, dg.device)
-        self.device = self.csr.device
+            blocks = [RowBlock(r0, r1, CsrDevice(dg.block(r0, r1)[0], dg.block(r0, r1)[1], None, n, dg.device))
+                      for r0, r1 in ranges]
+        self._set_blocks(blocks)
         self.tmpl = None
         self.row_sum = (dg.rowptr[1:] - dg.rowptr[:-1]).to(torch.float32) + 1.0
         self.rowscale = torch.ones(n, dtype=torch.float32, device=self.device)
@@ -294,9 +331,8 @@ class TemplateFeat(_SparseView):
         row_sum = np.bincount(rows, weights=member, minlength=n).astype(np.float32) + np.float32(1.)
         self.rowptr_full = adj.indptr.astype(np.int64)
         self.col_full = adj.indices.astype(np.int32)
-        self.bounds, self.row0, self.row1 = _row_block(self.rowptr_full, shard)
-        self.csr = _block_csr(self.rowptr_full, self.col_full, None, self.row0, self.row1, n, device)
-        self.device = self.csr.device
+        self._set_blocks([RowBlock(r0, r1, _block_csr(self.rowptr_full, self.col_full, None, r0, r1, n, device))
+                          for r0, r1 in _row_ranges(self.rowptr_full, n_users, shard)])
         self.tmpl = None if identity else torch.from_numpy(tmpl).to(self.device)
         self.row_sum = torch.from_numpy(row_sum.astype(np.float32)).to(self.device)
         self.rowscale = torch.ones(n, dtype=torch.float32, device=self.device)

@@ -82,11 +82,10 @@ class _GraphModel(BasicModel):
 
     def _propagator(self):
         n = self.n_users + self.n_items
-        adj = self.norm_adj
-        block = (adj.row0, adj.row1)
+        block = self.norm_adj.block_key()
         p = self._prop
         if p is None or (p.n, p.dim, p.n_layers, p.block) != (n, self.embedding_size, self.n_layers, block):
-            shard = None if self._peers is None else engine.Shard(self._peers, *block)
+            shard = None if self._peers is None else engine.Shard(self._peers)
             p = engine.Propagator(n, self.embedding_size, self.n_layers, self.device, shard)
             p.block = block
             self._prop = p

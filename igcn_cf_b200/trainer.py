@@ -245,16 +245,18 @@ class BasicTrainer:
         from .graph import _pack_bits
         return 0, n, _pack_bits(flags, self.device)
 
-    def recommend(self, val_or_test, banned_items=None, users=None):
-        """Top-max(topks) item ids (device int32 [n, k]) and scores for `users` (default: all)."""
+    def recommend(self, val_or_test, banned_items=None, users=None, users_host=None):
+        """Top-max(topks) item ids (device int32 [n, k]) and scores for `users` (default: all).
+        users_host: the same ids as a numpy array when the caller has them (saves a D2H sync)."""
         self.model.eval()
         with torch.no_grad():
             rep = self.model.get_rep().contiguous()
-        users = self.test_users if users is None else users
+        if users is None:
+            users, users_host = self.test_users, 'identity'
         lo, hi, bits = self._banned(banned_items)
         return engine.score_topk(rep, users, self.model.n_users, self.model.n_items, max(self.topks),
                                  mask=self._mask_csr(val_or_test), item_lo=lo, item_hi=hi, banned_bits=bits,
-                                 impl=self.config.get('score_impl', 'auto'))
+                                 users_host=users_host, impl=self.config.get('score_impl', 'auto'))
 
     def recommend_local(self, val_or_test, banned_items=None):
         """Top-k lists of the users this rank evaluates: all of them on one GPU, an even contiguous
@@ -263,7 +265,8 @@ class BasicTrainer:
         if peers is None:
             return self.recommend(val_or_test, banned_items)[0]
         lo, hi = dist.split_range(self.dataset.n_users, peers.rank, peers.world)
-        return self.recommend(val_or_test, banned_items, users=self.test_users[lo:hi])[0]
+        return self.recommend(val_or_test, banned_items, users=self.test_users[lo:hi],
+                              users_host=np.arange(lo, hi, dtype=np.int64))[0]
 
     def eval(self, val_or_test, banned_items=None):
         eval_data = getattr(self.dataset, val_or_test + '_data')

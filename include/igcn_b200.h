@@ -28,6 +28,7 @@ extern "C" {
 #define IGCN_ABI_VERSION 1
 #define IGCN_MAX_ADD 8
 #define IGCN_MAX_PEERS 8
+#define IGCN_MEDIUM_NNZ 64
 
 int igcn_abi_version(void);
 const char *igcn_last_error(void);
@@ -56,6 +57,9 @@ typedef struct igcn_csr {
     float *partial;             /* [n_chunks, D] scratch                               */
     int32_t *counters;          /* [n_chunks] scratch, must be zero before first use   */
     const int32_t *row_order;   /* [n_rows] visiting order (degree-descending) or NULL */
+    int32_t n_long_rows;        /* leading entries of row_order with nnz > long_threshold          */
+    int32_t n_medium_rows;      /* following entries with IGCN_MEDIUM_NNZ < nnz <= long_threshold:  */
+                                /* one warp per row; both counts are ignored when row_order is NULL */
 } igcn_csr;
 
 /* Edge-dropout description for the INMO layer (reference NGCF.dropout_sp_mat, model.py:263-275,

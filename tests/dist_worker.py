@@ -71,7 +71,7 @@ def check_gpu(rank, world):
             trainers.append(get_trainer(tcfg, ds, m))
         sharded, single = models
         assert sharded._peers is peers and single._peers is None
-        assert (sharded.norm_adj.row0, sharded.norm_adj.row1) != (0, ds.n_users + ds.n_items)
+        assert len(sharded.norm_adj.blocks) == 2 and len(single.norm_adj.blocks) == 1
         assert torch.equal(sharded.embedding.weight, single.embedding.weight)
         # eval-mode representation
         for m in models:

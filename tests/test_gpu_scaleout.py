@@ -37,8 +37,10 @@ def test_device_graph_is_the_host_graph(device_ds):
     assert rel_err(dev.csr.val.cpu().numpy(), host.csr.val.cpu().numpy()) < 1e-6
     # a row block of the sharded constructor is a slice of the whole
     part = graph.NormAdj.from_device(dg, shard=(1, 3))
-    lo, hi = int(dev.csr.rowptr_host[part.row0]), int(dev.csr.rowptr_host[part.row1])
-    assert torch.equal(part.csr.col, dev.csr.col[lo:hi]) and torch.equal(part.csr.val, dev.csr.val[lo:hi])
+    assert len(part.blocks) == 2 and part.blocks[0].row1 <= dg.n_users <= part.blocks[1].row0
+    for b in part.blocks:
+        lo, hi = int(dev.csr.rowptr_host[b.row0]), int(dev.csr.rowptr_host[b.row1])
+        assert torch.equal(b.csr.col, dev.csr.col[lo:hi]) and torch.equal(b.csr.val, dev.csr.val[lo:hi])
 
 
 def test_igcn_on_device_graph_matches_list_path(device_ds):

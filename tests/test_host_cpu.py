@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     # sizes implied by include/igcn_b200.h on LP64
-    assert ctypes.sizeof(_lib.CsrStruct) == 3 * 8 + 3 * 8 + 2 * 4 + 8 * 8
+    assert ctypes.sizeof(_lib.CsrStruct) == 3 * 8 + 3 * 8 + 2 * 4 + 8 * 8 + 2 * 4
     assert ctypes.sizeof(_lib.DropoutStruct) == 4 + 4 + 8 + 4 * 8
 
 
