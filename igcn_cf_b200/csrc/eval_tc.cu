@@ -63,6 +63,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "WAIT_DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Wait used by the helper warps (TMA producer, MMA issuer, mask builder): the suspend-time hint parks the
+// thread in hardware instead of spinning through issue slots the epilogue warps on the same scheduler need.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "PARK_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "@P1 bra PARK_DONE;\n\t"
+        "bra PARK_LOOP;\n\t"
+        "PARK_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -324,7 +337,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             for (int it = 0; it < n_it; ++it) {
                 const int s = it % TC_STAGES;
                 const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
-                mbar_wait(&sm->empty[s], ph ^ 1u);
+                mbar_wait_parked(&sm->empty[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&sm->full[s], b_bytes);
                 bulk_g2s(sB + (size_t)s * b_bytes, a.b_img + (size_t)(t0 + it) * b_bytes, b_bytes, &sm->full[s]);
             }
@@ -335,11 +348,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             const uint32_t idesc = umma_idesc_f16_m128_n256();
             const uint32_t sbo = (uint32_t)a.kcores * 128, lbo = 128;
             const int ksteps = a.kcores / 2;
-            mbar_wait(&sm->a_full, 0);
+            mbar_wait_parked(&sm->a_full, 0);
             for (int it = 0; it < n_it; ++it) {
                 const int s = it % TC_STAGES, acc = it & 1;
-                mbar_wait(&sm->tmem_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
-                mbar_wait(&sm->full[s], (uint32_t)(it / TC_STAGES) & 1u);
+                mbar_wait_parked(&sm->tmem_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                mbar_wait_parked(&sm->full[s], (uint32_t)(it / TC_STAGES) & 1u);
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + (size_t)s * b_bytes);
                 for (int ks = 0; ks < ksteps; ++ks)
@@ -353,7 +366,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         // ===== mask helper: seen-item bucket + banned bitmap + item range -> bitmap[acc][8 words][128 rows]
         for (int it = 0; it < n_it; ++it) {
             const int acc = it & 1, t = t0 + it;
-            mbar_wait(&sm->tmem_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+            mbar_wait_parked(&sm->tmem_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
             uint32_t *bm = bitmap + (size_t)acc * TC_BM * 8;
             uint32_t common = 0;
             if (lane < 8) {
@@ -425,10 +438,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                     hit_if_gt(v[c + 24], thr, h3, 1u << (c + 24));
                 }
                 uint32_t hits = (h0 | h1 | h2 | h3) & ~m;        // seen / banned / out-of-range columns never pass
-                while (hits) {                                   // rare: ~1 % of the elements
-                    const int c = __ffs(hits) - 1;
+                while (hits) {                                   // rare: ~1 % of the elements; two per trip so that
+                    const int c0 = __ffs(hits) - 1;              // both staged scores are in flight together
                     hits &= hits - 1;
-                    mybuf[cnt++] = ((uint64_t)(item0 + c) << 32) | mystage[c];
+                    const bool two = hits != 0u;
+                    const int c1 = two ? __ffs(hits) - 1 : c0;
+                    hits &= hits - 1;
+                    const uint32_t s0 = mystage[c0], s1 = mystage[c1];
+                    mybuf[cnt] = ((uint64_t)(item0 + c0) << 32) | s0;
+                    if (two) mybuf[cnt + 1] = ((uint64_t)(item0 + c1) << 32) | s1;
+                    cnt += two ? 2 : 1;
                 }
             };
 #pragma unroll 1
