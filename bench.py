@@ -58,6 +58,17 @@ def measured_peaks():
     return 6650.0, 1590.0, 'fallback (B200_PROFILING.md)'
 
 
+def measured_traffic(workload):
+    """DRAM bytes per launch of the dominant kernels from the committed ncu capture (profiles/*_traffic.json,
+    produced by tools/ncu_traffic.py); only valid for the workload the capture was taken on."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_traffic.json')))
+    if not files or workload != 'yelp-lightgcn':
+        return {}
+    with open(files[-1]) as f:
+        return {k: v['dram_bytes_per_launch'] for k, v in json.load(f)['kernels'].items()}
+
+
 def profile_eval(trainer, reps=5):
     """Device time of each entry point of one full-ranking evaluation (CUDA events, eager)."""
     import torch
@@ -480,6 +491,7 @@ def main():
     # ---- per-kernel profile + roofline of the dominant kernel
     summary, spmm_gbs, spmm_avg_ms, spmm_avg_bytes = profile_kernels(trainer, n_local, nnz_local, D, 10, n)
     peak, tc_peak, peak_src = measured_peaks()
+    traffic = measured_traffic(args.workload) if world == 1 else {}
     ev_ms = profile_eval(trainer)
     tc_ms = ev_ms.get('igcn_tc_candidates')
     n_eval_local = ds.n_users if peers is None else (lambda r: r[1] - r[0])(idist.split_range(ds.n_users, rank, world))
@@ -517,10 +529,11 @@ def main():
                          'roofline': None if not tc_ms else {
                              'kernel': 'score_tc_kernel (igcn_tc_candidates, tcgen05 kind::f16)', 'bound': 'tensor',
                              'achieved': tc_flops / (tc_ms * 1e-3) / 1e12, 'peak': tc_peak, 'unit': 'TFLOP/s',
-                             'frac': tc_flops / (tc_ms * 1e-3) / 1e12 / tc_peak, 'traffic': None,
+                             'frac': tc_flops / (tc_ms * 1e-3) / 1e12 / tc_peak,
+                             'traffic': traffic.get('igcn_tc_candidates'),
                              'flops_counted': '2*U*I*80 (64 dims + 16-wide bound block)'}},
                 'roofline': {'kernel': 'prop_kernel<8,2,SPMM> (igcn_spmm, full layers)', 'bound': 'hbm', 'achieved': spmm_gbs, 'peak': peak,
-                             'unit': 'GB/s', 'frac': spmm_gbs / peak, 'traffic': None, 'peak_source': peak_src,
+                             'unit': 'GB/s', 'frac': spmm_gbs / peak, 'traffic': traffic.get('igcn_spmm'), 'peak_source': peak_src,
                              'avg_launch_ms': spmm_avg_ms, 'algorithmic_bytes_per_launch': spmm_avg_bytes},
                 'kernel_shares': shares, 'kernel_ms_per_step_eager': round(total, 4), 'clocks': clocks}
         if cpu:

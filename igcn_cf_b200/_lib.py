@@ -67,11 +67,11 @@ _SIGNATURES = {
     'igcn_tc_workspace': [c_int64, c_int64, c_int32, c_int32, C.POINTER(c_int64), C.POINTER(c_int64),
                           C.POINTER(c_int64)],
     'igcn_tc_pack': [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
-                     c_void_p],
+                     c_void_p, c_void_p, c_void_p],
     'igcn_tc_candidates': [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int64, c_int64, c_void_p,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'igcn_tc_finalize': [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
-                         c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+                         c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'igcn_hits': [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p],
     'igcn_peer_alloc': [c_int64, C.POINTER(c_void_p), c_void_p],
     'igcn_peer_open': [c_void_p, C.POINTER(c_void_p)],
@@ -117,7 +117,7 @@ def ptr(t):
 
 
 # kernels launched per entry point (igcn_bpr_bwd launches 2 more when dw is requested)
-KERNELS_PER_CALL = {'igcn_colsum_masked': 2, 'igcn_tc_pack': 3, 'igcn_tc_workspace': 0, 'igcn_peer_alloc': 0,
+KERNELS_PER_CALL = {'igcn_colsum_masked': 2, 'igcn_tc_pack': 5, 'igcn_tc_workspace': 0, 'igcn_peer_alloc': 0,
                     'igcn_peer_open': 0, 'igcn_peer_close': 0, 'igcn_peer_free': 0}
 launch_count = 0          # running total of kernel launches issued through this binding
 profile_hook = None       # optional callable(name, phase, args) used by bench.py to time launches

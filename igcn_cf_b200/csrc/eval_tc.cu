@@ -13,6 +13,10 @@
 // eval_exact.cu) by tc_finalize_kernel, and a user is accepted only if its k-th exact score is
 // strictly above every dropped item's upper bound -- otherwise the user goes to the exact kernel.
 //
+// Items are packed RELATIVE TO THE MEAN ITEM ROW m: <u, i - m> = <u, i> - <u, m> ranks a user's items exactly
+// like <u, i> does, but the bound c|u||i - m| no longer pays for a component all items share (propagated
+// embeddings have a large one: every node aggregates the same hubs).  The verification adds <u, m> back.
+//
 // Kernel structure (one CTA per 128-user tile x item-range split, 7 warps):
 //   warp 0  bulk-TMA producer: cp.async.bulk of pre-arranged operand images (no-swizzle K-major
 //           core-matrix layout written by tc_pack_kernel, so a tile is one contiguous copy)
@@ -153,7 +157,8 @@ __device__ __forceinline__ float tc_scale(const uint32_t *maxabs_bits) {
 // 8 fp16 (16 B) per row; the last K block holds the bound entry in its first element.
 __global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ rep, const int64_t *__restrict__ row_ids,
                                                       int64_t row0, int64_t n_rows, int D, int tile_rows, int kcores, int is_user,
-                                                      const uint32_t *__restrict__ maxabs_bits, uint8_t *__restrict__ img) {
+                                                      const uint32_t *__restrict__ maxabs_bits, const float *__restrict__ center_sum,
+                                                      float inv_n, uint8_t *__restrict__ img) {
     const int lane = threadIdx.x & 15;
     const int64_t r = (int64_t)blockIdx.x * 16 + (threadIdx.x >> 4);
     if (r >= n_rows) return;
@@ -161,7 +166,13 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ 
     const float scale = tc_scale(maxabs_bits);
     const int64_t src = row_ids ? row_ids[r] : row0 + r;
     float4 v = f4zero();
-    if (lane * 4 < D) v = ld4(rep + src * D + lane * 4);
+    if (lane * 4 < D) {
+        v = ld4(rep + src * D + lane * 4);
+        if (!is_user) {          // items are packed relative to the mean item row (see the header comment)
+            const float4 m = ld4(center_sum + lane * 4);
+            v.x -= m.x * inv_n; v.y -= m.y * inv_n; v.z -= m.z * inv_n; v.w -= m.w * inv_n;
+        }
+    }
     v = scale4(v, scale);
     float sq = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
 #pragma unroll
@@ -495,6 +506,7 @@ __global__ void __launch_bounds__(256) tc_finalize_kernel(const float *__restric
                                                           int64_t n_eval, int64_t item_row0, int D, int n_splits,
                                                           const int32_t *__restrict__ cand_items, const int32_t *__restrict__ cand_cnt,
                                                           const float *__restrict__ cand_thr, const uint32_t *__restrict__ maxabs_bits,
+                                                          const float *__restrict__ center_sum, float inv_n,
                                                           int k, int32_t *out_items, float *out_scores, int32_t *fb_count,
                                                           int64_t *fb_users, int32_t *fb_rows) {
     extern __shared__ uint64_t fin_keys[];               // [8 warps][n_splits * TC_CAP]
@@ -541,10 +553,20 @@ __global__ void __launch_bounds__(256) tc_finalize_kernel(const float *__restric
     kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, 4));
     kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, 2));
     kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, 1));
+    // <u, m> and sum |u_d m_d| (m = mean item row): the tensor core scored u . (i - m)
+    float um = 0.f, uam = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        const float p = urow[d] * (center_sum[d] * inv_n);
+        um += p; uam += fabsf(p);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { um += __shfl_xor_sync(0xffffffffu, um, o); uam += __shfl_xor_sync(0xffffffffu, uam, o); }
     if (lane == 0) {
         const float scale = tc_scale(maxabs_bits);
-        // dropped items satisfy scale^2 * s <= s_hat <= thr_max; scale^2 is a power of two (exact)
-        const bool ok = (thr_max == -INFINITY) || (n >= k && kth * scale * scale > thr_max);
+        // a dropped item j satisfies scale^2 * <u, i_j - m> <= s_hat_j <= thr_max, i.e. s_j <= thr_max / scale^2 + <u, m>;
+        // scale^2 is a power of two (exact).  err covers the fp32 rounding of um, of the mean and of kth itself.
+        const float err = 1e-5f * (uam + fabsf(kth));
+        const bool ok = (thr_max == -INFINITY) || (n >= k && (kth - um - err) * scale * scale > thr_max);
         if (!ok) {
             const int slot = atomicAdd(fb_count, 1);
             fb_users[slot] = u;
@@ -571,17 +593,23 @@ extern "C" int igcn_tc_workspace(int64_t n_eval, int64_t n_items, int32_t D, int
 }
 
 extern "C" int igcn_tc_pack(const float *rep, int64_t n_rep_elems, const int64_t *user_ids, int64_t n_eval, int64_t item_row0,
-                            int64_t n_items, int32_t D, uint32_t *maxabs_bits, uint8_t *a_img, uint8_t *b_img, void *stream) {
-    IGCN_CHECK_ARG(rep && user_ids && maxabs_bits && a_img && b_img, "null pointer");
+                            int64_t n_items, int32_t D, uint32_t *maxabs_bits, uint8_t *a_img, uint8_t *b_img, float *center_sum,
+                            float *center_scratch, void *stream) {
+    IGCN_CHECK_ARG(rep && user_ids && maxabs_bits && a_img && b_img && center_sum && center_scratch, "null pointer");
     IGCN_CHECK_ARG(D > 0 && D <= 64 && !(D & 3), "tensor-core scoring supports D % 4 == 0, D <= 64");
     cudaStream_t st = as_stream(stream);
     const int kc = tc_kcores(D);
     cudaMemsetAsync(maxabs_bits, 0, sizeof(uint32_t), st);
     maxabs_kernel<<<148 * 4, 256, 0, st>>>(rep, n_rep_elems, maxabs_bits);
+    // column sums of the item rows in a fixed order (deterministic); the mean is sum * (1 / n_items)
+    if (int rc = igcn_colsum_masked(rep, item_row0, item_row0 + n_items, D, nullptr, center_scratch, center_sum, stream)) return rc;
+    const float inv_n = n_items > 0 ? 1.f / (float)n_items : 0.f;
     if (n_eval > 0)
-        tc_pack_kernel<<<(unsigned)((n_eval + 15) / 16), 256, 0, st>>>(rep, user_ids, 0, n_eval, D, TC_BM, kc, 1, maxabs_bits, a_img);
+        tc_pack_kernel<<<(unsigned)((n_eval + 15) / 16), 256, 0, st>>>(rep, user_ids, 0, n_eval, D, TC_BM, kc, 1, maxabs_bits, center_sum,
+                                                                       inv_n, a_img);
     if (n_items > 0)
-        tc_pack_kernel<<<(unsigned)((n_items + 15) / 16), 256, 0, st>>>(rep, nullptr, item_row0, n_items, D, TC_BN, kc, 0, maxabs_bits, b_img);
+        tc_pack_kernel<<<(unsigned)((n_items + 15) / 16), 256, 0, st>>>(rep, nullptr, item_row0, n_items, D, TC_BN, kc, 0, maxabs_bits,
+                                                                        center_sum, inv_n, b_img);
     IGCN_CHECK_LAUNCH();
     return 0;
 }
@@ -615,9 +643,11 @@ extern "C" int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, in
 
 extern "C" int igcn_tc_finalize(const float *rep, const int64_t *user_ids, int64_t n_eval, int64_t item_row0, int32_t D,
                                 int32_t n_splits, const int32_t *cand_items, const int32_t *cand_cnt, const float *cand_thr,
-                                const uint32_t *maxabs_bits, int32_t k, int32_t *out_items, float *out_scores,
-                                int32_t *fb_count, int64_t *fb_users, int32_t *fb_rows, void *stream) {
-    IGCN_CHECK_ARG(rep && user_ids && cand_items && cand_cnt && cand_thr && maxabs_bits && out_items && out_scores, "null pointer");
+                                const uint32_t *maxabs_bits, const float *center_sum, int64_t n_items, int32_t k,
+                                int32_t *out_items, float *out_scores, int32_t *fb_count, int64_t *fb_users, int32_t *fb_rows,
+                                void *stream) {
+    IGCN_CHECK_ARG(rep && user_ids && cand_items && cand_cnt && cand_thr && maxabs_bits && center_sum && out_items && out_scores,
+                   "null pointer");
     IGCN_CHECK_ARG(fb_count && fb_users && fb_rows, "null fallback buffers");
     IGCN_CHECK_ARG(k > 0 && k <= TC_KEEP - 8, "tensor-core path supports k <= 24");
     if (n_eval <= 0) return 0;
@@ -626,9 +656,10 @@ extern "C" int igcn_tc_finalize(const float *rep, const int64_t *user_ids, int64
     const size_t smem = (size_t)8 * n_splits * TC_CAP * sizeof(uint64_t);
     cudaError_t e = cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("igcn_tc_finalize: %s", cudaGetErrorString(e)); return (int)e; }
+    const float inv_n = n_items > 0 ? 1.f / (float)n_items : 0.f;
     tc_finalize_kernel<<<(unsigned)((n_eval + 7) / 8), 256, smem, st>>>(rep, user_ids, n_eval, item_row0, D, n_splits, cand_items,
-                                                                         cand_cnt, cand_thr, maxabs_bits, k, out_items, out_scores,
-                                                                         fb_count, fb_users, fb_rows);
+                                                                         cand_cnt, cand_thr, maxabs_bits, center_sum, inv_n, k,
+                                                                         out_items, out_scores, fb_count, fb_users, fb_rows);
     IGCN_CHECK_LAUNCH();
     return 0;
 }

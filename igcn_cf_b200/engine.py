@@ -556,7 +556,8 @@ class TcScorer:
             ws = {'a_img': z(a_b.value, torch.uint8), 'b_img': z(b_b.value, torch.uint8),
                   'cand_items': z(slots.value, torch.int32), 'cand_cnt': z(n_eval * n_splits, torch.int32),
                   'cand_thr': z(n_eval * n_splits, torch.float32), 'maxabs': z(1, torch.int32),
-                  'fb_count': z(1, torch.int32), 'fb_users': z(n_eval, torch.int64), 'fb_rows': z(n_eval, torch.int32)}
+                  'fb_count': z(1, torch.int32), 'fb_users': z(n_eval, torch.int64), 'fb_rows': z(n_eval, torch.int32),
+                  'center': z(D, torch.float32), 'center_scratch': z(((n_items + 255) // 256 + 1) * D, torch.float32)}
             self._ws = {key: ws}
         return ws
 
@@ -569,7 +570,7 @@ class TcScorer:
         ws = self._workspace(n_eval, n_items, D, n_splits, k, rep.device)
         st = stream_ptr
         call('igcn_tc_pack', ptr(rep), rep.numel(), ptr(user_ids), n_eval, n_users, n_items, D, ptr(ws['maxabs']),
-             ptr(ws['a_img']), ptr(ws['b_img']), st())
+             ptr(ws['a_img']), ptr(ws['b_img']), ptr(ws['center']), ptr(ws['center_scratch']), st())
         tile_ptr, entries = (None, None)
         if mask is not None:
             tile_ptr, entries = mask.tiles(n_items, users_host)
@@ -583,7 +584,7 @@ class TcScorer:
         out_i = torch.empty((n_eval, k), dtype=torch.int32, device=rep.device)
         out_s = torch.empty((n_eval, k), dtype=torch.float32, device=rep.device)
         call('igcn_tc_finalize', ptr(rep), ptr(user_ids), n_eval, n_users, D, n_splits, ptr(ws['cand_items']),
-             ptr(ws['cand_cnt']), ptr(ws['cand_thr']), ptr(ws['maxabs']), int(k), ptr(out_i), ptr(out_s),
+             ptr(ws['cand_cnt']), ptr(ws['cand_thr']), ptr(ws['maxabs']), ptr(ws['center']), n_items, int(k), ptr(out_i), ptr(out_s),
              ptr(ws['fb_count']), ptr(ws['fb_users']), ptr(ws['fb_rows']), st())
         # users whose bound did not verify: exact kernel on the device-side list (no host sync)
         score_topk_exact(rep, ws['fb_users'], n_users, n_items, k, mask, item_lo, item_hi, banned_bits,

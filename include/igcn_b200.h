@@ -240,6 +240,9 @@ int igcn_score_topk_exact(const float *rep, const int64_t *user_ids, int64_t n_e
  *   igcn_tc_finalize    exact fp32 re-scoring (same FMA order as the exact kernel), top-k, and the
  *                       proof check; users that fail it are appended to (fb_users, fb_rows, fb_count)
  *                       for igcn_score_topk_exact.
+ * Item rows are packed relative to the mean item row (center_sum[D] = column sums of the item rows, written
+ * by igcn_tc_pack through center_scratch [ceil(n_items/256)+1, D]; igcn_tc_finalize reads it back): a per-user
+ * constant does not change the ranking, and the bound then scales with |i - mean| instead of |i|.
  * a_img / b_img must be zero-initialised by the caller (padding rows); sizes from igcn_tc_workspace.
  * mask_tile_ptr [ceil(n_eval/128), ceil(n_items/256)+1] + mask_entries ((row<<8)|col, uint16) is the
  * seen-item CSR bucketed by (user tile, item tile); dump (tests only) receives every s_hat. */
@@ -247,7 +250,8 @@ int igcn_tc_workspace(int64_t n_eval, int64_t n_items, int32_t D, int32_t n_spli
                       int64_t *a_img_bytes, int64_t *b_img_bytes, int64_t *cand_slots);
 int igcn_tc_pack(const float *rep, int64_t n_rep_elems, const int64_t *user_ids, int64_t n_eval,
                  int64_t item_row0, int64_t n_items, int32_t D, uint32_t *maxabs_bits,
-                 uint8_t *a_img, uint8_t *b_img, void *stream);
+                 uint8_t *a_img, uint8_t *b_img, float *center_sum, float *center_scratch,
+                 void *stream);
 int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, int64_t n_eval, int64_t n_items,
                        int32_t D, int32_t n_splits, int64_t item_lo, int64_t item_hi,
                        const uint32_t *banned_bits, const int32_t *mask_tile_ptr,
@@ -256,6 +260,7 @@ int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, int64_t n_eva
 int igcn_tc_finalize(const float *rep, const int64_t *user_ids, int64_t n_eval, int64_t item_row0,
                      int32_t D, int32_t n_splits, const int32_t *cand_items,
                      const int32_t *cand_cnt, const float *cand_thr, const uint32_t *maxabs_bits,
+                     const float *center_sum, int64_t n_items,
                      int32_t k, int32_t *out_items, float *out_scores, int32_t *fb_count,
                      int64_t *fb_users, int32_t *fb_rows, void *stream);
 

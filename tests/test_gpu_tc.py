@@ -47,10 +47,14 @@ def test_tensor_core_scores_are_upper_bounds():
     maxabs = ws['maxabs'].view(torch.float32).item()
     assert maxabs == rep.abs().max().item()
     scale = 2.0 ** (9 - int(np.floor(np.log2(maxabs))))
-    exact = (rep[:n_users].double() @ rep[n_users:].double().t()).cpu().numpy()
+    items = rep[n_users:].double()
+    mean = torch.from_numpy(ws['center'].cpu().numpy().astype(np.float64) * np.float64(np.float32(1.0) / np.float32(n_items))).to(DEV)
+    assert torch.allclose(mean, items.mean(dim=0), atol=1e-7)
+    centered = items - mean                                    # the tensor core scores u . (i - mean item)
+    exact = (rep[:n_users].double() @ centered.t()).cpu().numpy()
     s_hat = dump[:n_users, :n_items].double().cpu().numpy() / scale ** 2
     nu = rep[:n_users].double().norm(dim=1).cpu().numpy()[:, None]
-    ni = rep[n_users:].double().norm(dim=1).cpu().numpy()[None, :]
+    ni = centered.norm(dim=1).cpu().numpy()[None, :]
     slack = s_hat - exact
     assert slack.min() >= 0.0, slack.min()                      # never below the exact score
     assert (slack <= 2.2e-3 * nu * ni + 1e-6).all()             # and not wastefully loose (c = 1e-3)
