@@ -77,8 +77,10 @@ struct RowVec {
 template <int LPR, int V, bool EXACT, int MODE, int DROP>
 __device__ __forceinline__ void gather_range(const PropArgs &a, RowVec<LPR, V, EXACT> &acc, int64_t beg, int64_t end,
                                              int64_t grow, int lane, uint32_t gmask, uint64_t seed) {
-    const int32_t *__restrict__ col = a.g.col;
-    const float *__restrict__ val = a.g.val;
+    // 32-bit offsets relative to the first non-zero of the range keep the loop state in few registers
+    const int32_t *__restrict__ colp = a.g.col + beg;
+    const float *__restrict__ valp = (MODE == MODE_SPMM && a.g.val) ? a.g.val + beg : nullptr;
+    const int len = (int)(end - beg);
     const int D = a.D;
     const float *__restrict__ Tl = a.X + lane * 4;
     constexpr bool COLS = (MODE == MODE_SPMM && DROP == 2);
@@ -87,23 +89,22 @@ __device__ __forceinline__ void gather_range(const PropArgs &a, RowVec<LPR, V, E
 
     int c_next = 0;
     float v_next = 1.f;
-    if (beg + lane < end) {
-        c_next = __ldg(col + beg + lane);
-        if (MODE == MODE_SPMM && val) v_next = __ldg(val + beg + lane);
+    if (lane < len) {
+        c_next = __ldg(colp + lane);
+        if (valp) v_next = __ldg(valp + lane);
     }
-    for (int64_t e0 = beg; e0 < end; e0 += LPR) {
-        const int n = (int)min((int64_t)LPR, end - e0);
+    for (int o = 0; o < len; o += LPR) {
+        const int n = min(LPR, len - o);
         int c = c_next;
         float w = v_next;
         {   // prefetch the next batch
-            const int64_t e = e0 + LPR + lane;
-            if (e < end) {
-                c_next = __ldg(col + e);
-                if (MODE == MODE_SPMM && val) v_next = __ldg(val + e);
+            const int e = o + LPR + lane;
+            if (e < len) {
+                c_next = __ldg(colp + e);
+                if (valp) v_next = __ldg(valp + e);
             }
         }
         if (lane < n) {
-            const int64_t e = e0 + lane;
             if (MODE == MODE_SPMM) {
                 if (COLS && !((__ldg(a.col_bits + (c >> 5)) >> (c & 31)) & 1u)) w = 0.f;   // X[c] is an exact zero row
             } else {
@@ -113,6 +114,7 @@ __device__ __forceinline__ void gather_range(const PropArgs &a, RowVec<LPR, V, E
                                                                : edge_hash(seed, (uint32_t)c, (uint32_t)grow);
                     keep = h >= a.thresh;
                 } else if (DROP == 2) {
+                    const int64_t e = beg + o + lane;
                     const int64_t b = (MODE == MODE_INMO_FWD) ? e : __ldg(a.drop.tperm + e);
                     keep = (__ldg(a.drop.edge_keep + (b >> 5)) >> (b & 31)) & 1u;
                 }

@@ -43,7 +43,7 @@ def main():
     rp, colh, valh = full.rowptr_full, full.col_full, full.val_full
     for (r0, r1) in ((0, n), (0, 9470), (75173, 80959)):
         lo, hi = int(rp[r0]), int(rp[r1])
-        for thr, ch in ((256, 128), (128, 64), (64, 32), (32, 16), (16, 8)):
+        for thr, ch in ((256, 128), (128, 64)):
             csr = graph.CsrDevice(rp[r0:r1 + 1] - lo, colh[lo:hi], valh[lo:hi], n, dev, threshold=thr, chunk=ch)
             off = r0 * D * 4
             fn = lambda: call('igcn_spmm', csr.struct(D), ptr(x), ptr(y) + off, D, none, 0, None, 1.0, None, 0, stream_ptr())
