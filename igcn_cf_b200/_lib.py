@@ -78,6 +78,7 @@ _SIGNATURES = {
     'igcn_peer_close': [c_void_p],
     'igcn_peer_free': [c_void_p],
     'igcn_peer_barrier': [C.POINTER(c_void_p), c_int32, c_int32, c_void_p, c_void_p, c_void_p],
+    'igcn_peer_push': [C.POINTER(c_void_p), c_int32, c_int32, c_int64, c_int64, c_void_p],
 }
 EXPORTS = ['igcn_abi_version', 'igcn_last_error'] + sorted(_SIGNATURES)
 

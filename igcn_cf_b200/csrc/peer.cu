@@ -52,6 +52,24 @@ __global__ void peer_barrier_kernel(const __grid_constant__ BarrierArgs a) {
     if (threadIdx.x == 0) *a.epoch = e;
 }
 
+struct PushArgs {
+    float *peer[IGCN_MAX_PEERS];
+    int n_peers, rank;
+    int64_t off, n4;                   // element offset of the block, number of float4 in it
+};
+
+// Bulk form of the all-gather: this rank's freshly written row block streams out to every other rank's copy
+// in long coalesced bursts (one 512-byte store per warp instruction and peer).
+__global__ void __launch_bounds__(256) peer_push_kernel(const __grid_constant__ PushArgs a) {
+    const float4 *__restrict__ src = reinterpret_cast<const float4 *>(a.peer[a.rank] + a.off);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n4; i += stride) {
+        const float4 v = __ldcg(src + i);
+        for (int p = 0; p < a.n_peers; ++p)
+            if (p != a.rank) __stcg(reinterpret_cast<float4 *>(a.peer[p] + a.off) + i, v);
+    }
+}
+
 }  // namespace igcn
 
 using namespace igcn;
@@ -115,6 +133,22 @@ extern "C" int igcn_peer_barrier(uint32_t *const *flags_host, int32_t n_peers, i
     a.n_peers = n_peers; a.rank = rank; a.epoch = epoch_dev; a.status = status_dev;
     a.timeout_cycles = 4000000000LL;    // ~2 s at 1.9 GHz
     peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(a);
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_peer_push(float *const *peer_host, int32_t n_peers, int32_t rank, int64_t elem_offset, int64_t n_elems,
+                              void *stream) {
+    IGCN_CHECK_ARG(peer_host, "null pointer");
+    IGCN_CHECK_ARG(n_peers >= 1 && n_peers <= IGCN_MAX_PEERS && rank >= 0 && rank < n_peers, "bad rank / peer count");
+    IGCN_CHECK_ARG(elem_offset >= 0 && n_elems >= 0 && !(elem_offset & 3) && !(n_elems & 3), "block must be float4 aligned");
+    if (n_elems == 0 || n_peers == 1) return 0;
+    PushArgs a{};
+    for (int p = 0; p < n_peers; ++p) a.peer[p] = peer_host[p];
+    a.n_peers = n_peers; a.rank = rank; a.off = elem_offset; a.n4 = n_elems / 4;
+    int64_t blocks = (a.n4 + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    peer_push_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(a);
     IGCN_CHECK_LAUNCH();
     return 0;
 }

@@ -5,6 +5,7 @@ igcn_cf_b200._lib; PyTorch only owns the buffers, the stream and (optionally) th
 Reference call sites are cited on each method.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -31,9 +32,22 @@ class Shard:
     kernels may store into.  Which rows this rank computes is a property of the graph objects
     (`adj.blocks`).  `None` stands for the single-GPU case."""
 
+    # row blocks of at least this many bytes leave through igcn_peer_push (bulk, after the kernel) instead of
+    # the kernel epilogue's peer stores: measured on the 2.8 GB layers of the scale-out graph the scattered
+    # in-kernel stores reach ~100 GB/s, the bulk push the link rate
+    PUSH_BYTES = int(os.environ.get('IGCN_PEER_PUSH_BYTES', 32 << 20))
+
     def __init__(self, ctx):
         self.ctx = ctx
         self._bufs = {}
+
+    def bulk(self, n_rows, dim):
+        return n_rows * dim * 4 >= self.PUSH_BYTES
+
+    def push(self, t, row0, n_rows, dim):
+        """Stream rows [row0, +n_rows) of symmetric buffer `t` to every other rank."""
+        arr, world = self.peers(t, 0)
+        call('igcn_peer_push', arr, world, self.ctx.rank, row0 * dim, n_rows * dim, stream_ptr())
 
     def new_buffer(self, rows, dim):
         buf = self.ctx.alloc((rows, dim), torch.float32)
@@ -104,10 +118,16 @@ class Propagator:
         """One layer.  rows = (row_list int64, n_list int32[1], max_list): compute the listed rows only
         (igcn_spmm_rows); cols = bitmap of the columns whose X row is non-zero (igcn_spmm_cols)."""
         sh = self.shard
+        pushes = []
         for blk in adj.blocks:
             row0 = blk.row0
             off = row0 * self.dim * 4
-            peers, n_peers = _peer_args(sh, y, off)
+            if sh is not None and sh.bulk(blk.csr.n_rows, self.dim) and rows is None:
+                sh.peers(y, off)                                   # must be a symmetric buffer all the same
+                peers, n_peers = None, 0
+                pushes.append((row0, blk.csr.n_rows))
+            else:
+                peers, n_peers = _peer_args(sh, y, off)
             head = (blk.csr.struct(self.dim), ptr(x), ptr(y) + off, self.dim, self._adds(adds, off), len(adds),
                     None if rowscale is None else ptr(rowscale) + row0 * 4, float(alpha))
             if rows is not None:
@@ -116,6 +136,8 @@ class Propagator:
                 call('igcn_spmm_cols', *head, ptr(cols), peers, n_peers, stream_ptr())
             else:
                 call('igcn_spmm', *head, peers, n_peers, stream_ptr())
+        for row0, n_rows in pushes:
+            sh.push(y, row0, n_rows, self.dim)
         if sh is not None:
             sh.ctx.barrier()
 
@@ -161,12 +183,20 @@ class Propagator:
 
 def inmo_forward(feat, emb, x0, drop, dim, shard=None):
     """X0 = F~ E with dropout fused (model.py:423-432 after model.py:435)."""
+    pushes = []
     for blk in feat.blocks:
         row0 = blk.row0
         off = row0 * dim * 4
-        peers, n_peers = _peer_args(shard, x0, off)
+        if shard is not None and shard.bulk(blk.csr.n_rows, dim):
+            shard.peers(x0, off)
+            peers, n_peers = None, 0
+            pushes.append((row0, blk.csr.n_rows))
+        else:
+            peers, n_peers = _peer_args(shard, x0, off)
         call('igcn_inmo_fwd', blk.csr.struct(dim), ptr(feat.tmpl), ptr(feat.rowscale) + row0 * 4, _drop_struct(drop),
              ptr(emb), ptr(x0) + off, dim, row0, feat.n_users, feat.glob_user, feat.glob_item, peers, n_peers, stream_ptr())
+    for row0, n_rows in pushes:
+        shard.push(x0, row0, n_rows, dim)
     if shard is not None:
         shard.ctx.barrier()
 

@@ -283,6 +283,12 @@ int igcn_peer_close(void *ptr);
 int igcn_peer_free(void *ptr);
 int igcn_peer_barrier(uint32_t *const *flags_host, int32_t n_peers, int32_t rank,
                       uint32_t *epoch_dev, uint32_t *status_dev, void *stream);
+/* Bulk alternative to the in-kernel peer stores for LARGE row blocks (hundreds of MB per layer, where
+ * scattered 128-byte NVLink writes from the SpMM epilogue run far below link speed): after the layer kernel
+ * has written this rank's rows into its own copy, stream elements [elem_offset, +n_elems) of that buffer
+ * (fp32, multiples of 4) to the same place in every other rank's copy.  peer_host as in igcn_spmm. */
+int igcn_peer_push(float *const *peer_host, int32_t n_peers, int32_t rank, int64_t elem_offset,
+                   int64_t n_elems, void *stream);
 
 /* hit[u][j] = 1 if rec[u][j] is in eval_items[eval_ptr[u] .. eval_ptr[u+1]) (sorted), else 0:
  * the membership double loop of BasicTrainer.calculate_metrics (trainer.py:111-115). */
