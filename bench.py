@@ -44,6 +44,7 @@ SCALEOUT = {
     'scaleout-mid': (1_000_000, 200_000, 50_000_000),
     'scaleout-small': (100_000, 50_000, 5_000_000),
 }
+DROPUI = {'dropui-gowalla': 'gowalla', 'dropui-amazon': 'amazon', 'dropui-small': 'small'}   # BASELINE.json configs[3]
 BATCH = 2048
 METRIC = 'ms/epoch (propagate+BPR)'
 
@@ -142,8 +143,10 @@ def build_dataset(shape, device):
 
 
 def build_model(ds, kind, dropout, l2_reg, device, use_graph=True):
+    import torch
     from igcn_cf_b200.model import get_model
     from igcn_cf_b200.trainer import get_trainer
+    torch.manual_seed(2021)                     # reference launchers: set_seed(2021) (run/run.py:12)
     mcfg = {'name': kind, 'embedding_size': 64, 'n_layers': 3, 'device': device}
     tcfg = {'optimizer': 'Adam', 'lr': 1e-3, 'l2_reg': l2_reg, 'device': device, 'n_epochs': 1, 'batch_size': BATCH,
             'dataloader_num_workers': 0, 'test_batch_size': 512, 'topks': [20], 'cuda_graph': use_graph, 'seed': 2021}
@@ -354,12 +357,102 @@ def run_scaleout(args):
         dist.destroy_process_group()
 
 
+def run_dropui(args):
+    """BASELINE.json configs[3]: IGCN trained on the reduced split (first 80 % of users, items < 0.8 I),
+    then the inductive sequence of run/dropui/igcn_dropui.py:26-35 on the full split WITHOUT retraining:
+    generate_graph, generate_feat(is_updating=True), update_feat_mat, inductive_eval (six full-ranking
+    passes).  The reference's only published number for this path is 3.4 s (run/plot.py:199-207, hardware
+    not stated), so vs_baseline = 3.4 s / this time."""
+    import contextlib
+    import io
+    import torch
+    import torch.distributed as dist
+    from igcn_cf_b200 import dist as idist
+    from igcn_cf_b200 import synth
+    from igcn_cf_b200.dataset import get_dataset
+    from igcn_cf_b200.model import get_model
+    from igcn_cf_b200.trainer import get_trainer
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    peers = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+        peers = idist.init_peers()
+    steps = 3 if args.steps is None else args.steps
+    warmup = 1 if args.warmup is None else args.warmup
+    full = synth.gen_named(DROPUI[args.workload], seed=2021)
+    ds_small = get_dataset({'name': 'SyntheticDataset', 'split': full, 'variant': 'dropui', 'device': dev})
+    ds_full = get_dataset({'name': 'SyntheticDataset', 'split': full, 'device': dev})
+    mcfg = {'name': 'IGCN', 'embedding_size': 64, 'n_layers': 3, 'device': dev, 'dropout': 0.3, 'feature_ratio': 1.}
+    tcfg = {'name': 'IGCNTrainer', 'optimizer': 'Adam', 'lr': 1e-3, 'l2_reg': 0., 'aux_reg': 0.01, 'device': dev,
+            'n_epochs': 1, 'batch_size': BATCH, 'dataloader_num_workers': 0, 'test_batch_size': 512, 'topks': [20],
+            'seed': 2021}
+    torch.manual_seed(2021)
+    model = get_model(mcfg, ds_small)
+    trainer = get_trainer(tcfg, ds_small, model)
+    model.train()
+    for _ in range(50):                               # a short stretch of training on the reduced graph
+        trainer.step.run()
+    model.feat_mat_anneal()
+    old = (model.norm_adj, model.feat_mat, model.row_sum)
+
+    def inductive():
+        model.config['dataset'] = ds_full
+        model.n_users, model.n_items = ds_full.n_users, ds_full.n_items
+        model.norm_adj = model.generate_graph(ds_full)
+        model.feat_mat, _, _, model.row_sum = model.generate_feat(ds_full, is_updating=True)
+        model.update_feat_mat()
+        tr = get_trainer(tcfg, ds_full, model)
+        tr.inductive_eval(ds_small.n_users, ds_small.n_items)
+        torch.cuda.synchronize()
+
+    def reset():
+        model.config['dataset'] = ds_small
+        model.n_users, model.n_items = ds_small.n_users, ds_small.n_items
+        model.norm_adj, model.feat_mat, model.row_sum = old
+        model._bump()
+
+    times = []
+    out = io.StringIO()
+    for i in range(warmup + steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(out):
+            inductive()
+        if world > 1:
+            dist.barrier()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+        reset()
+    sec = sum(times) / len(times)
+    if rank == 0:
+        line = {'metric': 'inductive inference time (re-aggregate + 6 full-ranking passes, no retraining)', 'value': sec,
+                'unit': 's', 'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3,
+                'higher_is_better': False, 'scaling': 'strong', 'vs_baseline': 3.4 / sec, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': args.workload, 'model': 'IGCN', 'n_users': ds_full.n_users, 'n_items': ds_full.n_items,
+                           'n_old_users': ds_small.n_users, 'n_old_items': ds_small.n_items,
+                           'baseline': 'INMO-LGCN inductive inference 3.4 s, reference run/plot.py:199-207 (hardware not stated)',
+                           'timed': 'wall clock, host graph/template rebuild included'},
+                'e2e': {'value': sec, 'unit': 's', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 6 * ds_full.n_users * 20 * 4},
+                'last_result_lines': out.getvalue().strip().splitlines()[-6:]}
+        print(json.dumps(line))
+    if world > 1:
+        peers.check()
+        idist.shutdown()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=None)
     ap.add_argument('--warmup', type=int, default=None)
-    ap.add_argument('--workload', default='yelp-lightgcn', choices=sorted(WORKLOADS) + sorted(SCALEOUT))
+    ap.add_argument('--workload', default='yelp-lightgcn', choices=sorted(WORKLOADS) + sorted(SCALEOUT) + sorted(DROPUI))
     ap.add_argument('--eval-users', type=int, default=None, help='scale-out: users scored per rank (default: all of its share)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -367,6 +460,8 @@ def main():
     args = ap.parse_args()
     if args.workload in SCALEOUT:
         return run_scaleout(args)
+    if args.workload in DROPUI:
+        return run_dropui(args)
     shape, kind, l2_reg, dropout = WORKLOADS[args.workload]
     if args.impl == 'reference':
         args.steps = 5 if args.steps is None else args.steps

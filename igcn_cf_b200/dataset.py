@@ -77,6 +77,19 @@ class BasicDataset(Dataset):
         for which in ('train', 'val', 'test'):
             output_data(os.path.join(path, which + '.txt'), getattr(self, which + '_data'))
 
+    def csr(self, which):
+        """(ptr int64 [U+1], items int64) numpy arrays of the 'train' | 'val' | 'test' lists, list order kept.
+        Built once per list object (the trainers use it instead of re-walking the Python lists on every
+        evaluation); replacing `self.<which>_data` by another list object invalidates the entry."""
+        lists = getattr(self, which + '_data')
+        cache = self.__dict__.setdefault('_csr_cache', {})
+        hit = cache.get(which)
+        if hit is None or hit[0] is not lists or hit[1] != len(lists):
+            from .engine import lists_to_arrays
+            hit = (lists, len(lists), lists_to_arrays(lists))
+            cache[which] = hit
+        return hit[2]
+
     def _finish(self):
         """train_array / train_pairs from train_data (dataset.py:150-152)."""
         lens = np.fromiter((len(x) for x in self.train_data), dtype=np.int64, count=len(self.train_data))

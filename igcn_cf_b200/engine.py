@@ -500,12 +500,20 @@ class ListCSR:
     """Per-user item lists as a sorted CSR on the device (+ host copies for the tile bucketing)."""
 
     def __init__(self, lists, device, sort=True):
-        lens = np.fromiter((len(x) for x in lists), dtype=np.int64, count=len(lists))
-        ptr_ = np.zeros(len(lists) + 1, dtype=np.int64)
-        np.cumsum(lens, out=ptr_[1:])
-        flat = np.fromiter((i for x in lists for i in x), dtype=np.int64, count=int(ptr_[-1]))
+        ptr_, flat = lists_to_arrays(lists)
+        self._init_arrays(ptr_, flat, device, sort)
+
+    @classmethod
+    def from_arrays(cls, ptr_, items, device, sort=True):
+        """Same object from numpy CSR arrays (ptr int64 [n+1], items [nnz]) -- no Python-level iteration."""
+        self = object.__new__(cls)
+        self._init_arrays(np.ascontiguousarray(ptr_, dtype=np.int64), np.asarray(items, dtype=np.int64), device, sort)
+        return self
+
+    def _init_arrays(self, ptr_, flat, device, sort):
+        lens = np.diff(ptr_)
         if sort and len(flat):
-            rows = np.repeat(np.arange(len(lists), dtype=np.int64), lens)
+            rows = np.repeat(np.arange(len(lens), dtype=np.int64), lens)
             flat = flat[np.lexsort((flat, rows))]
         self.lens = lens
         self.ptr_host, self.items_host = ptr_, flat.astype(np.int32)
@@ -548,6 +556,39 @@ class ListCSR:
                    torch.from_numpy(ent.view(np.int16).copy()).to(self.device))
             self._tiles = {key: hit}
         return hit
+
+
+def lists_to_arrays(lists):
+    """list-of-lists -> (ptr int64 [n+1], items int64 [nnz]) numpy arrays (order inside a list kept)."""
+    lens = np.fromiter(map(len, lists), dtype=np.int64, count=len(lists))
+    ptr_ = np.zeros(len(lists) + 1, dtype=np.int64)
+    np.cumsum(lens, out=ptr_[1:])
+    flat = np.fromiter((i for x in lists for i in x), dtype=np.int64, count=int(ptr_[-1]))
+    return ptr_, flat
+
+
+def merge_csr(a, b):
+    """Row-wise concatenation of two CSR array pairs with the same number of rows."""
+    (pa, ia), (pb, ib) = a, b
+    la, lb = np.diff(pa), np.diff(pb)
+    ptr_ = np.zeros(len(pa), dtype=np.int64)
+    np.cumsum(la + lb, out=ptr_[1:])
+    out = np.empty(int(ptr_[-1]), dtype=np.int64)
+    ra = np.repeat(ptr_[:-1], la) + (np.arange(len(ia), dtype=np.int64) - np.repeat(pa[:-1], la))
+    rb = np.repeat(ptr_[:-1] + la, lb) + (np.arange(len(ib), dtype=np.int64) - np.repeat(pb[:-1], lb))
+    out[ra], out[rb] = ia, ib
+    return ptr_, out
+
+
+def restrict_csr(csr, user_lo, user_hi, item_lo, item_hi):
+    """Rows outside [user_lo, user_hi) emptied, items outside [item_lo, item_hi) dropped (the list surgery of
+    BasicTrainer.inductive_eval, trainer.py:185-217, on arrays)."""
+    ptr_, items = csr
+    rows = np.repeat(np.arange(len(ptr_) - 1, dtype=np.int64), np.diff(ptr_))
+    keep = (rows >= user_lo) & (rows < user_hi) & (items >= item_lo) & (items < item_hi)
+    new_ptr = np.zeros(len(ptr_), dtype=np.int64)
+    np.cumsum(np.bincount(rows[keep], minlength=len(ptr_) - 1), out=new_ptr[1:])
+    return new_ptr, items[keep]
 
 
 def lists_to_csr(lists, device, sort=True):

@@ -174,13 +174,23 @@ class BasicTrainer:
     # ---- metrics (trainer.py:109-138)
     def _eval_csr(self, eval_data):
         """Sorted CSR of an eval list-of-lists; rebuilt when any inner list object or length changed
-        (inductive_eval swaps inner lists in place, trainer.py:185-217)."""
+        (the reference's inductive_eval swaps inner lists in place, trainer.py:185-217).  An engine.ListCSR is
+        passed through (our inductive_eval restricts on arrays)."""
+        if isinstance(eval_data, engine.ListCSR):
+            return eval_data
         sig = (tuple(map(id, eval_data)), tuple(map(len, eval_data)))
         hit = self._eval_cache.get(id(eval_data))
         if hit is None or hit[0] != sig:
             hit = (sig, engine.lists_to_csr(eval_data, self.device))
-            self._eval_cache = {id(eval_data): hit}
+            self._eval_cache[id(eval_data)] = hit
         return hit[1]
+
+    def _dataset_csr(self, which):
+        """numpy CSR of dataset.<which>_data: the dataset's cached arrays when it offers them."""
+        get = getattr(self.dataset, 'csr', None)
+        if callable(get):
+            return get(which)
+        return engine.lists_to_arrays(getattr(self.dataset, which + '_data'))
 
     def calculate_metrics(self, eval_data, rec_items):
         """Precision / Recall / NDCG @k with the reference's dtypes: fp32 hit matrix and log2 table,
@@ -219,11 +229,10 @@ class BasicTrainer:
         key = (val_or_test, id(ds.train_data), id(ds.val_data), len(ds.train_data))
         hit = self._mask_cache.get(val_or_test)
         if hit is None or hit[0] != key:
+            arrays = self._dataset_csr('train')
             if val_or_test == 'test':
-                lists = [a + b for a, b in zip(ds.train_data, ds.val_data)]
-            else:
-                lists = ds.train_data
-            hit = (key, engine.lists_to_csr(lists, self.device))
+                arrays = engine.merge_csr(arrays, self._dataset_csr('val'))
+            hit = (key, engine.ListCSR.from_arrays(arrays[0], arrays[1], self.device))
             self._mask_cache[val_or_test] = hit
         return hit[1]
 
@@ -268,8 +277,20 @@ class BasicTrainer:
         return self.recommend(val_or_test, banned_items, users=self.test_users[lo:hi],
                               users_host=np.arange(lo, hi, dtype=np.int64))[0]
 
-    def eval(self, val_or_test, banned_items=None):
-        eval_data = getattr(self.dataset, val_or_test + '_data')
+    def eval(self, val_or_test, banned_items=None, eval_data=None):
+        """trainer.py:140-177.  eval_data (extension): score against this engine.ListCSR / list-of-lists instead
+        of dataset.<val_or_test>_data (masking still follows val_or_test)."""
+        if eval_data is None:
+            eval_data = getattr(self.dataset, val_or_test + '_data')
+            if callable(getattr(self.dataset, 'csr', None)):
+                # the dataset keeps numpy CSR arrays per list OBJECT (replacing dataset.<x>_data, as the
+                # reference's inductive_eval does, is noticed; editing the inner lists in place is not)
+                arrays = self.dataset.csr(val_or_test)
+                hit = self._eval_cache.get(val_or_test)
+                if hit is None or hit[0] is not arrays:
+                    hit = (arrays, engine.ListCSR.from_arrays(arrays[0], arrays[1], self.device))
+                    self._eval_cache[val_or_test] = hit
+                eval_data = hit[1]
         peers = getattr(self.model, '_peers', None)
         rec_dev = self.recommend_local(val_or_test, banned_items)
         if peers is not None:
@@ -291,36 +312,24 @@ class BasicTrainer:
         return results, metrics
 
     def inductive_eval(self, n_old_users, n_old_items):
-        """Six test passes over user/item subsets (trainer.py:179-219)."""
+        """Six test passes over user/item subsets (trainer.py:179-219).  The reference edits copies of
+        dataset.test_data list by list; the same restrictions are applied here to the CSR arrays of the test
+        lists and handed to eval() directly -- dataset.test_data itself is never touched."""
         ds = self.dataset
-        full = ds.test_data.copy()
         n_u, n_i = ds.n_users, ds.n_items
-
-        def restrict(users, keep):
-            ds.test_data = full.copy()
-            for user in range(n_u):
-                if user not in users:
-                    ds.test_data[user] = []
-                elif keep is not None:
-                    items = np.array(ds.test_data[user])
-                    ds.test_data[user] = items[keep(items)].tolist()
-
-        all_users, old_users = range(n_u), range(n_old_users)
-        new_users = range(n_old_users, n_u)
-        old_items = lambda it: it < n_old_items
-        new_items = lambda it: it >= n_old_items
+        full = self._dataset_csr('test')
         ban_new, ban_old = np.arange(n_old_items, n_i), np.arange(n_old_items)
-        plan = [('All users and all items', all_users, None, None),
-                ('Old users and all items', old_users, None, None),
-                ('New users and all items', new_users, None, None),
-                ('All users and old items', all_users, old_items, ban_new),
-                ('All users and new items', all_users, new_items, ban_old),
-                ('Old users and old items', old_users, old_items, ban_new)]
-        for title, users, keep, banned in plan:
-            restrict(users, keep)
-            results, _ = self.eval('test', banned_items=banned)
+        plan = [('All users and all items', (0, n_u), (0, n_i), None),
+                ('Old users and all items', (0, n_old_users), (0, n_i), None),
+                ('New users and all items', (n_old_users, n_u), (0, n_i), None),
+                ('All users and old items', (0, n_u), (0, n_old_items), ban_new),
+                ('All users and new items', (0, n_u), (n_old_items, n_i), ban_old),
+                ('Old users and old items', (0, n_old_users), (0, n_old_items), ban_new)]
+        for title, users, items, banned in plan:
+            ptr_, flat = engine.restrict_csr(full, users[0], users[1], items[0], items[1])
+            results, _ = self.eval('test', banned_items=banned,
+                                   eval_data=engine.ListCSR.from_arrays(ptr_, flat, self.device))
             print('{:s} result. {:s}'.format(title, results))
-        ds.test_data = full.copy()
 
 
 class _FusedBPRMixin:
