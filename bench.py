@@ -609,8 +609,10 @@ def main():
                            'n_items': ds.n_items, 'train_interactions': len(ds), 'nnz_adj': nnz, 'dim': D, 'layers': 3,
                            'batch': BATCH, 'steps_per_epoch': steps_per_epoch, 'sampler': 'device', 'cuda_graph': True,
                            'parallelism': 'single GPU' if world == 1 else
-                           'propagation rows sharded over %d GPUs (fused NVLink peer-store all-gather per layer), '
-                           'BPR step + Adam replicated, eval users sharded' % world,
+                           ('propagation rows sharded over %d GPUs (fused NVLink peer-store all-gather per layer), '
+                            'BPR step + Adam replicated, eval users sharded' % world) if model._rows_sharded() else
+                           ('training step replicated on %d GPUs (graph too small for the per-layer exchange to pay '
+                            'off, DESIGN.md 7), eval users sharded' % world),
                            'l2': 'no explicit flush: a step touches ~%d MB of distinct buffers (> 126 MB L2)'
                                  % ((8 * n * D * 4 + nnz * 8) // 2 ** 20)},
                 'e2e': {'value': e2e_ms_step * steps_per_epoch, 'unit': 'ms', 'ms_per_step': e2e_ms_step,

@@ -12,6 +12,7 @@ generate_* call; `get_rep` is a single autograd node backed by libigcn_b200.so; 
 representation is cached until a parameter or graph changes (the reference recomputes the full
 propagation for every 512-user batch, model.py:119); there is no CPU path.
 """
+import os
 import sys
 
 import numpy as np
@@ -51,8 +52,16 @@ class BasicModel(nn.Module):
         self.n_users = model_config['dataset'].n_users
         self.n_items = model_config['dataset'].n_items
         self.trainable = True
-        # row-sharded multi-GPU mode: on when igcn_cf_b200.dist.init_peers() was called (world > 1)
-        self._peers = dist.current() if model_config.get('shard', True) else None
+        # multi-GPU (igcn_cf_b200.dist.init_peers() was called, world > 1).  model_config['shard']:
+        #   False   single-GPU behaviour on every rank
+        #   True    propagation rows sharded over the ranks (fused NVLink all-gather), eval users sharded
+        #   'auto'  (default) eval users always sharded; rows sharded only when the graph is large enough for
+        #           the per-layer exchange (N*D*4 bytes into every rank) to pay off -- on the paper-sized graphs
+        #           it does not, so training runs as replicas there
+        mode = model_config.get('shard', 'auto')
+        self._peers = dist.current() if mode else None
+        self._shard_rows = mode is True
+        self._shard_auto = mode == 'auto'
 
     def predict(self, users):
         raise NotImplementedError
@@ -77,15 +86,27 @@ class _GraphModel(BasicModel):
     def graph_version(self):
         return (id(self.norm_adj), id(getattr(self, 'feat_mat', None)), self.n_users, self.n_items)
 
-    def _shard_arg(self):
-        return None if self._peers is None else (self._peers.rank, self._peers.world)
+    SHARD_MIN_NNZ = int(os.environ.get('IGCN_SHARD_MIN_NNZ', 4_000_000))
+
+    def _rows_sharded(self, dataset=None):
+        if self._peers is None:
+            return False
+        if self._shard_auto and dataset is not None:
+            dg = getattr(dataset, 'device_graph', None)
+            nnz = 2 * (dg.n_interactions if dg is not None else len(graph.train_pairs_of(dataset)))
+            self._shard_rows = nnz >= self.SHARD_MIN_NNZ
+            self._shard_auto = False                     # decided once per model: all graphs of a model agree
+        return self._shard_rows
+
+    def _shard_arg(self, dataset=None):
+        return (self._peers.rank, self._peers.world) if self._rows_sharded(dataset) else None
 
     def _propagator(self):
         n = self.n_users + self.n_items
         block = self.norm_adj.block_key()
         p = self._prop
         if p is None or (p.n, p.dim, p.n_layers, p.block) != (n, self.embedding_size, self.n_layers, block):
-            shard = None if self._peers is None else engine.Shard(self._peers)
+            shard = engine.Shard(self._peers) if self._rows_sharded() else None
             p = engine.Propagator(n, self.embedding_size, self.n_layers, self.device, shard)
             p.block = block
             self._prop = p
@@ -147,9 +168,9 @@ class LightGCN(_GraphModel):
         """D^-1/2 A D^-1/2 as a device CSR (model.py:85-94)."""
         dg = getattr(dataset, 'device_graph', None)
         if dg is not None:
-            return graph.NormAdj.from_device(dg, shard=self._shard_arg())
+            return graph.NormAdj.from_device(dg, shard=self._shard_arg(dataset))
         return graph.NormAdj(dataset.n_users, dataset.n_items, graph.train_pairs_of(dataset), self.device,
-                             shard=self._shard_arg())
+                             shard=self._shard_arg(dataset))
 
     def get_rep(self):
         self._check_graph()
@@ -263,7 +284,7 @@ class IGCN(_GraphModel):
             if is_updating or self.feature_ratio < 1.:
                 raise RuntimeError('device-resident graphs support feature_ratio == 1 without template updates')
             adj = self.norm_adj if self.norm_adj.shape[0] == dg.n_users + dg.n_items else None
-            feat = graph.TemplateFeat.from_device(dg, adj=adj, shard=self._shard_arg())
+            feat = graph.TemplateFeat.from_device(dg, adj=adj, shard=self._shard_arg(dataset))
             self._aux = None
             return feat, IdentityMap(dg.n_users), IdentityMap(dg.n_items), feat.row_sum
         if not is_updating:
@@ -280,7 +301,7 @@ class IGCN(_GraphModel):
             user_map, item_map = self.user_map, self.item_map
         ut, it = self._maps_to_arrays(user_map, item_map)
         feat = graph.TemplateFeat(self.n_users, self.n_items, graph.train_pairs_of(dataset), ut, it,
-                                  len(user_map), len(item_map), self.device, shard=self._shard_arg())
+                                  len(user_map), len(item_map), self.device, shard=self._shard_arg(dataset))
         self._aux = None
         return feat, user_map, item_map, feat.row_sum
 
@@ -321,7 +342,7 @@ class IGCN(_GraphModel):
             return None                                  # model.py:264-265
         feat = self.feat_mat
         if self.injected_keep is not None:
-            if self._peers is not None:
+            if self._rows_sharded():
                 raise RuntimeError('replaying an explicit dropout mask is a single-GPU test facility')
             ek, sk = feat.keep_bits(self.injected_keep)
             self.injected_keep = None
