@@ -212,6 +212,31 @@ class IdentityMap:
         return ((k, k) for k in range(self.n))
 
 
+class Popularity(BasicModel):
+    """Item-popularity ranker (model.py:338-351; run/dropui/igcn_dropui.py:43-48 evaluates it next to IGCN).
+    Expressed as a 4-wide representation -- user rows (1, 0, 0, 0), item rows (degree, 0, 0, 0) -- so that the
+    fused score + mask + top-k kernels rank it like any other model: score(u, i) = degree(i)."""
+
+    def __init__(self, model_config):
+        super().__init__(model_config)
+        self.item_degree = self.calculate_degree(model_config['dataset'])
+        self.trainable = False
+
+    def calculate_degree(self, dataset):
+        pairs = graph.train_pairs_of(dataset)
+        deg = np.bincount(pairs[:, 1], minlength=self.n_items).astype(np.float32)
+        return torch.tensor(deg, dtype=torch.float32, device=self.device)
+
+    def get_rep(self):
+        rep = torch.zeros((self.n_users + self.n_items, 4), dtype=torch.float32, device=self.device)
+        rep[:self.n_users, 0] = 1.
+        rep[self.n_users:, 0] = self.item_degree
+        return rep
+
+    def predict(self, users):
+        return self.item_degree[None, :].repeat(users.shape[0], 1)
+
+
 def graph_rank_nodes(dataset, ranking_metric):
     """Template ("core") node ranking for feature_ratio < 1 (utils.py:94-123).  Host-side, one-off."""
     adj = graph.build_adjacency(dataset.n_users, dataset.n_items, graph.train_pairs_of(dataset))
@@ -396,3 +421,12 @@ class IGCN(_GraphModel):
         self.feat_mat, _, _, self.row_sum = self.generate_feat(self.config['dataset'], is_updating=True)
         self.update_feat_mat()
         self._bump()
+
+
+class IMF(IGCN):
+    """INMO-MF (model.py:536-543): the template layer alone, no propagation -- IGCN with zero layers, whatever
+    n_layers the config carries (config.py:44 passes 0).  Runs on the same fused step and ranking kernels."""
+
+    def __init__(self, model_config):
+        super().__init__(model_config)
+        self.n_layers = 0

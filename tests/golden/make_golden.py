@@ -17,6 +17,7 @@ Outputs (tests/golden/):
   tiny_igcn.npz            IGCN: feat, rep (eval + train w/ recorded dropout), fwd/bwd, epoch, anneal, evals
   tiny_igcn_dropui.npz     train on the dropui split, re-aggregate on the full graph, inductive_eval
   tiny_igcn_ratio.npz      feature_ratio 0.5 ('sort' ranking): maps, feat, rep
+  tiny_siblings.npz        IMF (one epoch, evals) and Popularity (evals)
 """
 import os
 import sys
@@ -338,6 +339,46 @@ def golden_ratio(ds, out_path):
     print('wrote', out_path, len(out), 'arrays')
 
 
+def golden_siblings(ds, out_path):
+    """Sibling models that run on the same operators: IMF (= IGCN without propagation layers,
+    model.py:536-543, config.py:44-48) and Popularity (model.py:338-351, used by run/dropui/igcn_dropui.py:43-48)."""
+    out = {}
+    mcfg = {'name': 'IMF', 'embedding_size': 64, 'n_layers': 0, 'device': DEV, 'dropout': 0.1, 'feature_ratio': 1.}
+    tcfg = {'name': 'IGCNTrainer', 'optimizer': 'Adam', 'lr': 1.e-3, 'l2_reg': 1.e-5, 'aux_reg': 0.1, 'device': DEV,
+            'n_epochs': 1, 'batch_size': 2048, 'dataloader_num_workers': 0, 'test_batch_size': 512, 'topks': [5, 20]}
+    R_utils.set_seed(SEED)
+    model = R_model.get_model(mcfg, ds)
+    trainer = R_trainer.get_trainer(tcfg, ds, model)
+    out['imf_emb0'] = model.embedding.weight.detach().numpy().copy()
+    model.eval()
+    with torch.no_grad():
+        out['imf_rep0_eval'] = model.get_rep().numpy().copy()
+    model.train()
+    R_utils.set_seed(SEED + 1)
+    with Recorder() as rec:
+        out['imf_epoch_loss'] = np.float64(trainer.train_one_epoch())
+    out['imf_epoch_triples'] = np.stack(rec.main)
+    out['imf_epoch_aux_triples'] = np.stack(rec.aux)
+    for s, r in enumerate(rec.rands):
+        out['imf_epoch_rand_%d' % s] = r
+    out['imf_epoch_n_steps'] = np.int64(len(rec.rands))
+    out['imf_emb1'] = model.embedding.weight.detach().numpy().copy()
+    out['imf_w1'] = model.w.detach().numpy().copy()
+    model.eval()
+    with torch.no_grad():
+        out['imf_rep1_eval'] = model.get_rep().numpy().copy()
+    eval_all(trainer, out, 'imf_e1')
+
+    pm = R_model.get_model({'name': 'Popularity', 'device': DEV}, ds)
+    pt = R_trainer.get_trainer({'name': 'BasicTrainer', 'device': DEV, 'n_epochs': 0, 'topks': [5, 20],
+                                'test_batch_size': 512}, ds, pm)
+    out['pop_item_degree'] = pm.item_degree.numpy().copy()
+    out['pop_train_return'] = np.float64(pt.train(verbose=False))
+    eval_all(pt, out, 'pop')
+    np.savez_compressed(out_path, **out)
+    print('wrote', out_path, len(out), 'arrays')
+
+
 def main():
     split = synth.gen_named('tiny', seed=SEED)
     with tempfile.TemporaryDirectory() as tmp:
@@ -350,6 +391,7 @@ def main():
         golden_igcn(ds, os.path.join(HERE, 'tiny_igcn.npz'))
         golden_dropui(split, tmp, os.path.join(HERE, 'tiny_igcn_dropui.npz'))
         golden_ratio(ds, os.path.join(HERE, 'tiny_igcn_ratio.npz'))
+        golden_siblings(ds, os.path.join(HERE, 'tiny_siblings.npz'))
 
 
 if __name__ == '__main__':

@@ -137,3 +137,24 @@ def test_metrics_edge_cases():
     assert res['Precision'][1] == np.float32(0.5)
     assert abs(res['Recall'][3] - 0.75) < 1e-12
     assert res['NDCG'][3].dtype == np.float32
+
+
+def test_imf_is_igcn_without_layers(tiny):
+    """IMF (model.py:536-543) = the oracle's IGCN with n_layers = 0: rep, one recorded epoch, evals."""
+    g = load_golden('tiny_siblings')
+    m = R.OracleIGCN(tiny['n_users'], tiny['n_items'], tiny['pairs'], 0, g['imf_emb0'], 0.1, l2_reg=1e-5, aux_reg=0.1)
+    assert rel_err(m.get_rep(train=False).detach().numpy(), g['imf_rep0_eval']) < TOL
+    tri, atri = g['imf_epoch_triples'], g['imf_epoch_aux_triples']
+    tot, cnt = 0., 0
+    for s, lo in enumerate(range(0, len(tri), 2048)):
+        b, a = _t(tri[lo:lo + 2048]), _t(atri[lo:lo + 2048])
+        tot += m.train_step(b[:, 0], b[:, 1], b[:, 2], a[:, 0], a[:, 1], a[:, 2],
+                            rand=_t(g['imf_epoch_rand_%d' % s])) * len(b)
+        cnt += len(b)
+    m.anneal()
+    assert abs(tot / cnt - float(g['imf_epoch_loss'])) < 1e-6
+    assert rel_err(m.emb.detach().numpy(), g['imf_emb1']) < 1e-5
+    assert rel_err(m.get_rep().detach().numpy(), g['imf_rep1_eval']) < 1e-5
+    for which in ('train', 'val', 'test'):
+        metrics, rec = R.evaluate(m, which, tiny['train'], tiny['val'], tiny[which], [5, 20])
+        assert np.array_equal(rec, g['imf_e1_%s_rec' % which])
