@@ -55,9 +55,10 @@ class BasicModel(nn.Module):
         # multi-GPU (igcn_cf_b200.dist.init_peers() was called, world > 1).  model_config['shard']:
         #   False   single-GPU behaviour on every rank
         #   True    propagation rows sharded over the ranks (fused NVLink all-gather), eval users sharded
-        #   'auto'  (default) eval users always sharded; rows sharded only when the graph is large enough for
-        #           the per-layer exchange (N*D*4 bytes into every rank) to pay off -- on the paper-sized graphs
-        #           it does not, so training runs as replicas there
+        #   'auto'  (default) eval users always sharded; rows sharded only when every rank keeps at least
+        #           SHARD_MIN_NNZ_PER_RANK non-zeros, i.e. when the per-layer exchange (N*D*4 bytes into every rank)
+        #           pays off -- measured: Amazon-shaped on 2 GPUs yes (1.23x), on 8 no; Yelp/Gowalla-shaped never
+        #           (DESIGN.md 7), so training runs as replicas there
         mode = model_config.get('shard', 'auto')
         self._peers = dist.current() if mode else None
         self._shard_rows = mode is True
@@ -86,7 +87,7 @@ class _GraphModel(BasicModel):
     def graph_version(self):
         return (id(self.norm_adj), id(getattr(self, 'feat_mat', None)), self.n_users, self.n_items)
 
-    SHARD_MIN_NNZ = int(os.environ.get('IGCN_SHARD_MIN_NNZ', 4_000_000))
+    SHARD_MIN_NNZ_PER_RANK = int(os.environ.get('IGCN_SHARD_MIN_NNZ_PER_RANK', 2_000_000))
 
     def _rows_sharded(self, dataset=None):
         if self._peers is None:
@@ -94,7 +95,7 @@ class _GraphModel(BasicModel):
         if self._shard_auto and dataset is not None:
             dg = getattr(dataset, 'device_graph', None)
             nnz = 2 * (dg.n_interactions if dg is not None else len(graph.train_pairs_of(dataset)))
-            self._shard_rows = nnz >= self.SHARD_MIN_NNZ
+            self._shard_rows = nnz >= self.SHARD_MIN_NNZ_PER_RANK * self._peers.world
             self._shard_auto = False                     # decided once per model: all graphs of a model agree
         return self._shard_rows
 
