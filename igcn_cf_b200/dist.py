@@ -3,12 +3,14 @@
 The reference is single-process / single-GPU, so nothing here mirrors a reference
 interface.  What shards, and how:
 
-* propagation -- contiguous blocks of node rows, balanced by non-zeros (`shard_bounds`); every rank
-  keeps a full replica of each layer's input and computes its own row block; the kernel epilogue
-  stores the finished rows into EVERY rank's copy through peer-mapped memory (the all-gather is
-  fused into the SpMM), and `PeerContext.barrier()` -- a device-side flag barrier on the launch
-  stream -- separates the layers.  The result is bit-identical to one GPU: a row is reduced by one
-  rank in the same order whatever the rank count.
+* propagation -- every rank owns one slice of the user rows and one of the item rows, each balanced by
+  non-zeros (`shard_bounds`, applied per half by graph._row_ranges); every rank keeps a full replica of
+  each layer's input and computes its own rows; the kernel epilogue stores the finished rows into EVERY
+  rank's copy through peer-mapped memory (the all-gather is fused into the SpMM; large blocks go out
+  through igcn_peer_push instead), and `PeerContext.barrier()` -- a device-side flag barrier on the
+  launch stream -- separates the layers.  The result is bit-identical to one GPU: a row is reduced by
+  one rank in the same order whatever the rank count.  Whether rows are sharded at all is the model's
+  decision (model_config['shard'], 'auto' = only when the exchange pays off).
 * BPR step / Adam -- replicated on the gathered representation (6,144 rows; cheaper than talking).
 * evaluation -- users split evenly (`split_range`), no communication until the top-k lists are
   gathered for the metrics (`gather_rows`).

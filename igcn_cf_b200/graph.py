@@ -3,8 +3,9 @@
 `NormAdj` is what `LightGCN.generate_graph` returns here and `TemplateFeat` what
 `IGCN.generate_feat` returns.  Both keep the reference's observable surface (`shape`,
 `indices()`, `values()`, `_nnz()`, `to_sparse_coo()`; reference model.py:85-94, 386-421) but store
-one CSR on the GPU (int64 rowptr, int32 col, fp32 val) plus the long-row chunk plan the kernels
-use (include/igcn_b200.h, `igcn_csr`).  They are built ONCE per generate_* call, not once per
+one CSR per owned row range on the GPU (int64 rowptr, int32 col, fp32 val; one range on a single GPU,
+a user slice + an item slice per rank when rows are sharded) plus the row-class / long-row chunk plan
+the kernels use (include/igcn_b200.h, `igcn_csr`).  They are built ONCE per generate_* call, not once per
 `get_rep` as the reference's `dgl.graph(...)` is (model.py:99-100, 439-440).
 
 HBM layout: rowptr[N+1] int64 | col[nnz] int32 | val[nnz] fp32 | chunk plan (5 small int arrays)
