@@ -236,15 +236,34 @@ def cpu_step_time(ds, kind, dropout, l2_reg, steps, warmup=1):
     return sum(times) / len(times), m
 
 
+def cpu_eval_users_per_s(ds, oracle_model, n_batches=2, batch=512):
+    """Full-ranking users/s of the CPU port on a bounded sample: the reference's eval loop body (predict -- which
+    re-propagates the whole graph for every 512-user batch, model.py:118-123 -- mask, topk; trainer.py:145-164)."""
+    import torch
+    from oracle import restate as R
+    t0 = time.perf_counter()
+    done = 0
+    for b in range(n_batches):
+        users = list(range(b * batch, min(ds.n_users, (b + 1) * batch)))
+        if not users:
+            break
+        with torch.no_grad():
+            scores = oracle_model.predict(torch.tensor(users, dtype=torch.int64))
+        R.masked_topk(scores, users, 20, ds.train_data)
+        done += len(users)
+    return done / (time.perf_counter() - t0), '%d batches of %d users (eval(\'val\') loop body)' % (n_batches, batch)
+
+
 def run_reference(args, shape, kind, l2_reg, dropout):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     ds = build_dataset(shape, 'cpu')
     steps_per_epoch = math.ceil(len(ds) / BATCH)
-    sec, _ = cpu_step_time(ds, kind, dropout if dropout is not None else 0., l2_reg, args.steps, args.warmup)
+    sec, orc = cpu_step_time(ds, kind, dropout if dropout is not None else 0., l2_reg, args.steps, args.warmup)
     value = sec * 1e3 * steps_per_epoch
     cores = os.cpu_count() or 1
+    eval_ups, eval_sample = cpu_eval_users_per_s(ds, orc)
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'ms', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': False, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -252,7 +271,8 @@ def run_reference(args, shape, kind, l2_reg, dropout):
                        'train_interactions': len(ds), 'batch': BATCH, 'steps_per_epoch': steps_per_epoch},
             'cpu_baseline': {'value': value, 'unit': 'ms', 'cores': cores, 'kind': 'port',
                              'sample': '%d full train steps of %d per epoch, extrapolated' % (args.steps, steps_per_epoch)},
-            'e2e': {'value': value, 'unit': 'ms', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+            'e2e': {'value': value, 'unit': 'ms', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0,
+            'eval': {'users_per_s': eval_ups, 'sample': eval_sample}}
     print(json.dumps(line))
 
 
@@ -596,10 +616,11 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sec, _ = cpu_step_time(build_dataset(shape, 'cpu') if False else ds, kind, dropout if dropout is not None else 0.,
-                               l2_reg, args.cpu_steps, 1)
+        sec, orc = cpu_step_time(ds, kind, dropout if dropout is not None else 0., l2_reg, args.cpu_steps, 1)
+        eval_ups, eval_sample = cpu_eval_users_per_s(ds, orc)
         cpu = {'value': sec * 1e3 * steps_per_epoch, 'unit': 'ms', 'cores': os.cpu_count() or 1, 'kind': 'port',
-               'sample': '%d full train steps of %d per epoch (oracle/restate.py), extrapolated' % (args.cpu_steps, steps_per_epoch)}
+               'sample': '%d full train steps of %d per epoch (oracle/restate.py), extrapolated' % (args.cpu_steps, steps_per_epoch),
+               'eval_users_per_s': eval_ups, 'eval_sample': eval_sample}
 
     if rank == 0:
         line = {'metric': METRIC, 'value': ms_per_step * steps_per_epoch, 'unit': 'ms', 'n_gpus': world, 'steps': args.steps,
