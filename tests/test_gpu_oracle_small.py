@@ -85,3 +85,49 @@ def test_igcn_step_with_zero_dropout(small):
         assert abs(loss - ref_loss.item()) < TOL
     assert rel_err(model.embedding.weight.detach().cpu().numpy(), orc.emb.detach().numpy()) < TOL
     assert rel_err(model.w.detach().cpu().numpy(), orc.w.detach().numpy()) < TOL
+
+
+def test_igcn_partial_templates_training_and_device_sampler(small):
+    """feature_ratio 0.5 (model.py:386-421 with core users/items only): the fused step works in template-id
+    space for the auxiliary loss, template rows without a node get no gradient, and the device sampler of the
+    auxiliary stream only draws template users / template items of their train lists (dataset.py:258-273)."""
+    from igcn_cf_b200.model import get_model
+    from igcn_cf_b200.trainer import get_trainer
+    from oracle import restate as R
+    ds = small
+    torch.manual_seed(2)
+    model = get_model({'name': 'IGCN', 'embedding_size': 64, 'n_layers': 3, 'device': DEV, 'dropout': 0.0,
+                       'feature_ratio': 0.5, 'ranking_metric': 'degree'}, ds)
+    t_u, t_i = len(model.user_map), len(model.item_map)
+    assert (t_u, t_i) == (ds.n_users // 2, ds.n_items // 2) and model.embedding.weight.shape[0] == t_u + t_i + 2
+    trainer = get_trainer({'name': 'IGCNTrainer', 'optimizer': 'Adam', 'lr': 1e-3, 'l2_reg': 1e-4, 'aux_reg': 0.05,
+                           'device': DEV, 'n_epochs': 1, 'batch_size': 2048, 'dataloader_num_workers': 0,
+                           'test_batch_size': 512, 'topks': [20], 'cuda_graph': False, 'seed': 9}, ds, model)
+    emb0 = model.embedding.weight.detach().cpu().numpy()
+    orc = R.OracleIGCN(ds.n_users, ds.n_items, ds.train_pairs, 3, emb0, 0.0, l2_reg=1e-4, aux_reg=0.05,
+                       user_map=dict(model.user_map), item_map=dict(model.item_map))
+    model.eval()
+    with torch.no_grad():
+        assert rel_err(model.get_rep().cpu().numpy(), orc.get_rep().detach().numpy()) < TOL
+    model.train()
+    rng = np.random.default_rng(5)
+    for s in range(2):
+        t = torch.from_numpy(_rand_triples(ds, 2048, 10 + s))
+        a = torch.from_numpy(np.stack([rng.integers(t_u, size=2048), rng.integers(t_i, size=2048),
+                                       rng.integers(t_i, size=2048)], axis=1).astype(np.int64))
+        ref_loss = orc.loss(t[:, 0], t[:, 1], t[:, 2], a[:, 0], a[:, 1], a[:, 2], train=False)
+        orc.opt.zero_grad()
+        ref_loss.backward()
+        orc.opt.step()
+        loss = trainer.step.run(t.to(DEV), a.to(DEV)).item()
+        assert abs(loss - ref_loss.item()) < TOL
+    assert rel_err(model.embedding.weight.detach().cpu().numpy(), orc.emb.detach().numpy()) < TOL
+    assert rel_err(model.w.detach().cpu().numpy(), orc.w.detach().numpy()) < TOL
+    # device sampler in template space: valid ids, positives from the user's template items, negatives outside
+    inv_u = {v: k for k, v in model.user_map.items()}
+    trainer.step.run()
+    aux = trainer.step.a_triples.cpu().numpy()
+    assert aux[:, 0].max() < t_u and aux[:, 1:].max() < t_i and aux.min() >= 0
+    for u, p, n in aux[:300]:
+        tmpl_items = {model.item_map[i] for i in ds.train_data[inv_u[int(u)]] if i in model.item_map}
+        assert int(p) in tmpl_items and int(n) not in tmpl_items
