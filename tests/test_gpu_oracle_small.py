@@ -131,3 +131,45 @@ def test_igcn_partial_templates_training_and_device_sampler(small):
     for u, p, n in aux[:300]:
         tmpl_items = {model.item_map[i] for i in ds.train_data[inv_u[int(u)]] if i in model.item_map}
         assert int(p) in tmpl_items and int(n) not in tmpl_items
+
+
+def test_duplicate_interactions_and_empty_users():
+    """Collisions and holes the reference tolerates: a (user, item) pair listed twice becomes an adjacency value
+    of 2 (utils.py:46-48 sums duplicates, degrees count it twice), users / items without any train interaction
+    keep degree clamp 1 (model.py:87-88) and are skipped by the sampler (dataset.py:120-122)."""
+    from igcn_cf_b200.dataset import get_dataset
+    from igcn_cf_b200.model import get_model
+    from igcn_cf_b200.trainer import get_trainer
+    from oracle import restate as R
+    rng = np.random.default_rng(3)
+    n_users, n_items = 90, 120
+    train = [sorted(rng.choice(n_items - 5, size=int(rng.integers(3, 15)), replace=False).tolist()) for _ in range(n_users)]
+    train[7] = []                                   # user without train items
+    train[20] = train[20] + train[20][:2]           # duplicated interactions
+    train[33] = [5, 5, 5, 9]
+    empty = [[] for _ in range(n_users)]
+    test = [[int(rng.integers(n_items))] for _ in range(n_users)]
+    ds = get_dataset({'name': 'ListDataset', 'train': train, 'val': empty, 'test': test, 'n_items': n_items, 'device': DEV})
+    for kind in ('LightGCN', 'IGCN'):
+        torch.manual_seed(4)
+        cfg = {'name': kind, 'embedding_size': 64, 'n_layers': 2, 'device': DEV}
+        if kind == 'IGCN':
+            cfg.update(dropout=0.0, feature_ratio=1.)
+        model = get_model(cfg, ds)
+        emb0 = model.embedding.weight.detach().cpu().numpy()
+        orc = (R.OracleLightGCN(n_users, n_items, ds.train_pairs, 2, emb0) if kind == 'LightGCN'
+               else R.OracleIGCN(n_users, n_items, ds.train_pairs, 2, emb0, 0.0))
+        model.eval()
+        with torch.no_grad():
+            assert rel_err(model.get_rep().cpu().numpy(), orc.get_rep().detach().numpy()) < TOL, kind
+    trainer = get_trainer({'name': 'IGCNTrainer', 'optimizer': 'Adam', 'lr': 1e-3, 'l2_reg': 0., 'aux_reg': 0.01,
+                           'device': DEV, 'n_epochs': 1, 'batch_size': 512, 'dataloader_num_workers': 0,
+                           'test_batch_size': 512, 'topks': [5], 'cuda_graph': False, 'seed': 1}, ds, model)
+    model.train()
+    trainer.step.run()
+    tri = trainer.step.triples[:512].cpu().numpy()
+    assert 7 not in set(tri[:, 0].tolist())          # the empty user is never drawn
+    seen = [set(x) for x in train]
+    assert all(p in seen[u] and n not in seen[u] for u, p, n in tri)
+    _, metrics = trainer.eval('test')                # items 115..119 have no interaction at all: still rankable
+    assert 0.0 <= metrics['Recall'][5] <= 1.0
