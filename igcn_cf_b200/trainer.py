@@ -209,10 +209,13 @@ class BasicTrainer:
             with np.errstate(invalid='ignore', divide='ignore'):
                 recalls = hit_num / eval_data_len
             max_hit_num = np.minimum(eval_data_len, k)
-            max_hit_matrix = (np.arange(k)[None, :] < max_hit_num[:, None]).astype(np.float32)
             denominator = np.log2(np.arange(2, k + 2, dtype=np.float32))[None, :]
             dcgs = np.sum(hit_matrix[:, :k] / denominator, axis=1)
-            idcgs = np.sum(max_hit_matrix / denominator, axis=1)
+            # the ideal DCG of a user only depends on min(len, k): evaluate the reference's expression
+            # (trainer.py:126-130) once per possible value -- same numpy row reduction, so the same bits -- and
+            # look it up instead of building a second [U, k] matrix
+            ideal_rows = (np.arange(k)[None, :] < np.arange(k + 1)[:, None]).astype(np.float32)
+            idcgs = np.sum(ideal_rows / denominator, axis=1)[max_hit_num]
             with np.errstate(invalid='ignore', divide='ignore'):
                 ndcgs = dcgs / idcgs
             user_masks = (max_hit_num > 0)
