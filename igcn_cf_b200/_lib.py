@@ -63,7 +63,8 @@ _SIGNATURES = {
                   c_int64, c_void_p, c_void_p],
     'igcn_step_tick': [c_void_p, c_float, c_float, c_float, c_void_p],
     'igcn_score_topk_exact': [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p,
-                              c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+                              c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_int32, c_void_p, c_int64, c_void_p],
     'igcn_tc_workspace': [c_int64, c_int64, c_int32, c_int32, C.POINTER(c_int64), C.POINTER(c_int64),
                           C.POINTER(c_int64)],
     'igcn_tc_pack': [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
@@ -118,7 +119,7 @@ def ptr(t):
 
 
 # kernels launched per entry point (igcn_bpr_bwd launches 2 more when dw is requested)
-KERNELS_PER_CALL = {'igcn_colsum_masked': 2, 'igcn_tc_pack': 5, 'igcn_tc_workspace': 0, 'igcn_peer_alloc': 0,
+KERNELS_PER_CALL = {'igcn_colsum_masked': 2, 'igcn_score_topk_exact': 1, 'igcn_tc_pack': 5, 'igcn_tc_workspace': 0, 'igcn_peer_alloc': 0,
                     'igcn_peer_open': 0, 'igcn_peer_close': 0, 'igcn_peer_free': 0}
 launch_count = 0          # running total of kernel launches issued through this binding
 profile_hook = None       # optional callable(name, phase, args) used by bench.py to time launches

@@ -77,6 +77,11 @@ struct ExactArgs {
     float *out_scores;
     const int32_t *out_rows;     // optional: output row of entry b (default b)
     const int32_t *n_eval_dev;   // optional: device-side entry count (<= n_eval)
+    // item-range splitting for SHORT user lists (the tensor-core path's fallback is typically a handful of users:
+    // one CTA scanning the whole catalogue for them would be a multi-millisecond serial tail)
+    int n_item_splits;           // blockIdx.y range; used only while the entry count is <= split_cap
+    int64_t split_cap;
+    uint64_t *split_keys;        // [split_cap, n_item_splits, k] partial top-k keys, merged by exact_merge_kernel
 };
 
 // smem: Us[BM][D+4] | Is[BN][min(D,64)+4] | keys[BM][CAP] (u64) | cnt[BM] | thr[BM]
@@ -96,6 +101,9 @@ __global__ void __launch_bounds__(EX_THREADS, 1) score_topk_exact_kernel(const _
     const int d4 = D >> 2;
     const int64_t n_eval = a.n_eval_dev ? min(a.n_eval, (int64_t)*a.n_eval_dev) : a.n_eval;
     if (ubase >= n_eval) return;
+    const int n_splits = (a.n_item_splits > 1 && n_eval <= a.split_cap) ? a.n_item_splits : 1;
+    const int split = blockIdx.y;
+    if (split >= n_splits) return;
 
     for (int idx = tid; idx < BM * d4; idx += EX_THREADS) {
         const int r = idx / d4, c = idx % d4;
@@ -107,10 +115,12 @@ __global__ void __launch_bounds__(EX_THREADS, 1) score_topk_exact_kernel(const _
     if (tid == 0) need_compact = 0;
     __syncthreads();
 
-    const int64_t j_begin = max((int64_t)0, a.item_lo) / BN * BN;
+    const int64_t j_first = max((int64_t)0, a.item_lo) / BN * BN;
     const int64_t j_end = min(a.n_items, a.item_hi);
+    const int64_t n_tiles = (max(j_end, j_first) - j_first + BN - 1) / BN, per = (n_tiles + n_splits - 1) / n_splits;
+    const int64_t j_begin = j_first + split * per * BN, j_stop = min(j_end, j_begin + per * BN);
     const int KC = min(D, 64), KCP = KC + 4;      // item tile holds at most 64 dims at a time
-    for (int64_t j0 = j_begin; j0 < j_end; j0 += BN) {
+    for (int64_t j0 = j_begin; j0 < j_stop; j0 += BN) {
         float acc[4][8];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -187,6 +197,11 @@ __global__ void __launch_bounds__(EX_THREADS, 1) score_topk_exact_kernel(const _
         const int n = cnt[r];
         const int64_t orow = a.out_rows ? (int64_t)__ldg(a.out_rows + urow) : urow;
         warp_sort_desc(keys + r * CAP, n, lane);
+        if (n_splits > 1) {       // partial result of this item range; exact_merge_kernel picks the final top-k
+            for (int q = lane; q < a.k; q += 32)
+                a.split_keys[((size_t)urow * n_splits + split) * a.k + q] = q < n ? keys[r * CAP + q] : 0ULL;
+            continue;
+        }
         for (int q = lane; q < a.k; q += 32) {
             int32_t item = -1;
             float sc = -INFINITY;
@@ -198,6 +213,30 @@ __global__ void __launch_bounds__(EX_THREADS, 1) score_topk_exact_kernel(const _
             a.out_items[orow * a.k + q] = item;
             a.out_scores[orow * a.k + q] = sc;
         }
+    }
+}
+
+// One warp per entry: merge the per-split top-k lists (keys are totally ordered: score, then lower item id).
+__global__ void __launch_bounds__(256) exact_merge_kernel(const __grid_constant__ ExactArgs a) {
+    extern __shared__ uint64_t merge_keys[];             // [8 warps][pow2 >= n_item_splits * k]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t n_eval = a.n_eval_dev ? min(a.n_eval, (int64_t)*a.n_eval_dev) : a.n_eval;
+    if (n_eval > a.split_cap) return;                     // the scoring kernel ran unsplit and wrote the final lists
+    const int64_t b = (int64_t)blockIdx.x * 8 + wid;
+    if (b >= n_eval) return;
+    const int n = a.n_item_splits * a.k;
+    int n_pad = 32;
+    while (n_pad < n) n_pad <<= 1;
+    uint64_t *keys = merge_keys + (size_t)wid * n_pad;
+    for (int e = lane; e < n; e += 32) keys[e] = a.split_keys[(size_t)b * n + e];
+    __syncwarp();
+    warp_sort_desc(keys, n, lane);
+    const int64_t orow = a.out_rows ? (int64_t)__ldg(a.out_rows + b) : b;
+    for (int q = lane; q < a.k; q += 32) {
+        const uint64_t key = keys[q];
+        const bool ok = key != 0ULL;
+        a.out_items[orow * a.k + q] = ok ? 0x7fffffff - (int32_t)(key & 0xffffffffu) : -1;
+        a.out_scores[orow * a.k + q] = ok ? order_float((uint32_t)(key >> 32)) : -INFINITY;
     }
 }
 
@@ -224,20 +263,32 @@ extern "C" int igcn_score_topk_exact(const float *rep, const int64_t *user_ids, 
                                      int64_t n_items, int32_t D, const int64_t *mask_ptr, const int32_t *mask_items,
                                      int64_t item_lo, int64_t item_hi, const uint32_t *banned_bits, int32_t k,
                                      int32_t *out_items, float *out_scores, const int32_t *out_rows,
-                                     const int32_t *n_eval_dev, void *stream) {
+                                     const int32_t *n_eval_dev, int32_t n_item_splits, uint64_t *split_keys,
+                                     int64_t split_cap, void *stream) {
     IGCN_CHECK_ARG(rep && user_ids && out_items && out_scores, "null pointer");
     IGCN_CHECK_ARG(D > 0 && D <= 128 && !(D & 3), "embedding size unsupported (need D % 4 == 0, D <= 128)");
     IGCN_CHECK_ARG(k > 0 && k <= CAP - BN, "k must be in [1, 128]");
     IGCN_CHECK_ARG(!mask_ptr || mask_items, "mask_ptr without mask_items");
     IGCN_CHECK_ARG(n_items > 0 && n_items < 0x7fffffff, "n_items out of range");
     if (n_eval <= 0) return 0;
+    IGCN_CHECK_ARG(n_item_splits >= 1 && n_item_splits <= 64, "n_item_splits must be in [1, 64]");
+    IGCN_CHECK_ARG(n_item_splits == 1 || (split_keys && split_cap > 0), "item splitting needs the split_keys scratch");
     ExactArgs a{rep, user_ids, n_eval, item_row0, n_items, D, mask_ptr, mask_items, item_lo, item_hi, banned_bits, k,
-                out_items, out_scores, out_rows, n_eval_dev};
+                out_items, out_scores, out_rows, n_eval_dev, n_item_splits, split_cap, split_keys};
     const size_t smem = ((size_t)BM * (D + 4) + (size_t)BN * ((D < 64 ? D : 64) + 4)) * sizeof(float) + (size_t)BM * CAP * sizeof(uint64_t) + BM * 8;
     cudaError_t e = cudaFuncSetAttribute(score_topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("igcn_score_topk_exact: %s", cudaGetErrorString(e)); return (int)e; }
     const int64_t blocks = (n_eval + BM - 1) / BM;
-    score_topk_exact_kernel<<<(unsigned)blocks, EX_THREADS, smem, as_stream(stream)>>>(a);
+    score_topk_exact_kernel<<<dim3((unsigned)blocks, (unsigned)n_item_splits), EX_THREADS, smem, as_stream(stream)>>>(a);
+    if (n_item_splits > 1) {
+        int n_pad = 32;
+        while (n_pad < n_item_splits * k) n_pad <<= 1;
+        const size_t msmem = (size_t)8 * n_pad * sizeof(uint64_t);
+        e = cudaFuncSetAttribute(exact_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+        if (e != cudaSuccess) { set_error("igcn_score_topk_exact: %s", cudaGetErrorString(e)); return (int)e; }
+        const int64_t mblocks = (min(n_eval, split_cap) + 7) / 8;
+        exact_merge_kernel<<<(unsigned)mblocks, 256, msmem, as_stream(stream)>>>(a);
+    }
     IGCN_CHECK_LAUNCH();
     return 0;
 }

@@ -596,9 +596,13 @@ def lists_to_csr(lists, device, sort=True):
     return ListCSR(lists, device, sort)
 
 
+FALLBACK_SPLITS, FALLBACK_SPLIT_CAP = 64, 2048      # item ranges / max users for the split form of the exact kernel
+
+
 def score_topk_exact(rep, user_ids, n_users, n_items, k, mask=None, item_lo=0, item_hi=None, banned_bits=None,
-                     out=None, out_rows=None, n_eval_dev=None):
-    """Exact CUDA-core kernel (also the tensor-core path's fallback)."""
+                     out=None, out_rows=None, n_eval_dev=None, split_keys=None):
+    """Exact CUDA-core kernel (also the tensor-core path's fallback; `split_keys` = scratch of
+    FALLBACK_SPLIT_CAP * FALLBACK_SPLITS * k uint64 enables the item-split form for short user lists)."""
     n = int(user_ids.shape[0])
     if out is None:
         out = (torch.empty((n, k), dtype=torch.int32, device=rep.device),
@@ -606,7 +610,8 @@ def score_topk_exact(rep, user_ids, n_users, n_items, k, mask=None, item_lo=0, i
     mptr, mitems = (None, None) if mask is None else (mask[0], mask[1])
     call('igcn_score_topk_exact', ptr(rep), ptr(user_ids), n, n_users, n_items, rep.shape[1], ptr(mptr), ptr(mitems),
          int(item_lo), int(n_items if item_hi is None else item_hi), ptr(banned_bits), int(k), ptr(out[0]), ptr(out[1]),
-         ptr(out_rows), ptr(n_eval_dev), stream_ptr())
+         ptr(out_rows), ptr(n_eval_dev), 1 if split_keys is None else FALLBACK_SPLITS, ptr(split_keys),
+         0 if split_keys is None else FALLBACK_SPLIT_CAP, stream_ptr())
     return out
 
 
@@ -628,6 +633,7 @@ class TcScorer:
                   'cand_items': z(slots.value, torch.int32), 'cand_cnt': z(n_eval * n_splits, torch.int32),
                   'cand_thr': z(n_eval * n_splits, torch.float32), 'maxabs': z(1, torch.int32),
                   'fb_count': z(1, torch.int32), 'fb_users': z(n_eval, torch.int64), 'fb_rows': z(n_eval, torch.int32),
+                  'split_keys': z(FALLBACK_SPLIT_CAP * FALLBACK_SPLITS * k, torch.int64),
                   'center': z(D, torch.float32), 'center_scratch': z(((n_items + 255) // 256 + 1) * D, torch.float32)}
             self._ws = {key: ws}
         return ws
@@ -659,7 +665,7 @@ class TcScorer:
              ptr(ws['fb_count']), ptr(ws['fb_users']), ptr(ws['fb_rows']), st())
         # users whose bound did not verify: exact kernel on the device-side list (no host sync)
         score_topk_exact(rep, ws['fb_users'], n_users, n_items, k, mask, item_lo, item_hi, banned_bits,
-                         out=(out_i, out_s), out_rows=ws['fb_rows'], n_eval_dev=ws['fb_count'])
+                         out=(out_i, out_s), out_rows=ws['fb_rows'], n_eval_dev=ws['fb_count'], split_keys=ws['split_keys'])
         self.last_fallback = ws['fb_count']
         if dump:
             return out_i, out_s, dump_t, ws

@@ -223,13 +223,18 @@ int igcn_step_tick(igcn_step_state *state_dev, float lr, float beta1, float beta
  * Output per user: k item ids (int32, -1 when fewer than k candidates) and scores, sorted by
  * (score descending, item ascending).  This is the exact CUDA-core kernel; it is also the
  * fallback the tensor-core path uses for users whose candidate bound does not verify: out_rows
- * (may be NULL) gives the output row of entry b, n_eval_dev (may be NULL) a device-side count. */
+ * (may be NULL) gives the output row of entry b, n_eval_dev (may be NULL) a device-side count.
+ * n_item_splits > 1 (with split_keys [split_cap, n_item_splits, k] uint64 scratch): while the entry count is
+ * <= split_cap the catalogue is cut into n_item_splits ranges scanned by separate CTAs and merged by a second
+ * kernel -- a fallback list of a few users then costs a fraction of a millisecond instead of one CTA's serial
+ * pass over all items; larger counts run unsplit.  Pass 1 / NULL / 0 for the plain behaviour. */
 int igcn_score_topk_exact(const float *rep, const int64_t *user_ids, int64_t n_eval,
                           int64_t item_row0, int64_t n_items, int32_t D,
                           const int64_t *mask_ptr, const int32_t *mask_items,
                           int64_t item_lo, int64_t item_hi, const uint32_t *banned_bits,
                           int32_t k, int32_t *out_items, float *out_scores,
-                          const int32_t *out_rows, const int32_t *n_eval_dev, void *stream);
+                          const int32_t *out_rows, const int32_t *n_eval_dev,
+                          int32_t n_item_splits, uint64_t *split_keys, int64_t split_cap, void *stream);
 
 /* ---- tensor-core scoring (tcgen05 / TMEM / bulk TMA), D <= 64, k <= 24 ------------------------
  * Same contract as igcn_score_topk_exact, split in three launches the host chains on one stream:

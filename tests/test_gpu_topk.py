@@ -115,3 +115,27 @@ def test_hits_kernel():
     csr = engine.lists_to_csr([[9, 1], [], [9]], DEV)
     hit = engine.hit_matrix(rec, csr).cpu().numpy()
     assert hit.tolist() == [[1, 0, 0], [0, 0, 0], [0, 0, 1]] and hit.dtype == np.float32
+
+
+@pytest.mark.parametrize('n_list', [1, 9, 700, 2500])
+def test_exact_kernel_item_split_form_equals_plain(n_list):
+    """The fallback form (catalogue cut into ranges + merge, used while the user list is short) returns exactly
+    the plain kernel's lists; above the cap (2048 entries) it silently runs unsplit."""
+    from igcn_cf_b200 import engine
+    g = torch.Generator().manual_seed(n_list)
+    n_users, n_items, k = 3000, 5000, 20
+    rep = (torch.randn(n_users + n_items, 64, generator=g) * 0.1).to(DEV)
+    rep[n_users + 100:n_users + 140] = rep[n_users + 7]            # exact ties across range boundaries
+    rng = np.random.default_rng(n_list)
+    lists = [sorted(rng.choice(n_items, size=int(rng.integers(0, 30)), replace=False).tolist()) for _ in range(n_users)]
+    mask = engine.lists_to_csr(lists, DEV)
+    users = torch.from_numpy(rng.choice(n_users, size=n_list, replace=n_list > n_users)).to(DEV)
+    count = torch.tensor([n_list], dtype=torch.int32, device=DEV)
+    rows = torch.arange(n_list, dtype=torch.int32, device=DEV)
+    plain = engine.score_topk_exact(rep, users, n_users, n_items, k, mask, 50, 4900)
+    scratch = torch.zeros(engine.FALLBACK_SPLIT_CAP * engine.FALLBACK_SPLITS * k, dtype=torch.int64, device=DEV)
+    out = (torch.full((n_list, k), -7, dtype=torch.int32, device=DEV), torch.zeros((n_list, k), device=DEV))
+    engine.score_topk_exact(rep, users, n_users, n_items, k, mask, 50, 4900, out=out, out_rows=rows, n_eval_dev=count,
+                            split_keys=scratch)
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], plain[0]) and torch.equal(out[1], plain[1])
