@@ -130,13 +130,15 @@ __device__ __forceinline__ void gather_range(const PropArgs &a, RowVec<LPR, V, E
             c = 0;
         }
         if (COLS) {
-            // few columns survive the filter: visit only those, still in ascending order, 4 gathers in flight
+            // few columns survive the filter (about a quarter, often none): visit only those, still in ascending
+            // order, QC at a time -- padding every trip to 4 slots cost more instructions than it hid latency
+            constexpr int QC = 2;
             uint32_t km = (__ballot_sync(gmask, w != 0.f) >> gshift) & ((1u << LPR) - 1u);
             while (km) {
-                float4 x[Q][V];
-                float ww[Q];
+                float4 x[QC][V];
+                float ww[QC];
 #pragma unroll
-                for (int q = 0; q < Q; ++q) {
+                for (int q = 0; q < QC; ++q) {
                     const bool ok = km != 0u;
                     const int j = ok ? __ffs(km) - 1 : 0;
                     km &= km - 1u;
@@ -148,7 +150,7 @@ __device__ __forceinline__ void gather_range(const PropArgs &a, RowVec<LPR, V, E
                         x[q][i] = (ok && RowVec<LPR, V, EXACT>::on(i, lane, D)) ? ld4(p + i * LPR * 4) : f4zero();
                 }
 #pragma unroll
-                for (int q = 0; q < Q; ++q)
+                for (int q = 0; q < QC; ++q)
 #pragma unroll
                     for (int i = 0; i < V; ++i) fma4(acc.v[i], ww[q], x[q][i]);
             }
