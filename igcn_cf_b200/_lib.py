@@ -119,7 +119,7 @@ def ptr(t):
 
 
 # kernels launched per entry point (igcn_bpr_bwd launches 2 more when dw is requested)
-KERNELS_PER_CALL = {'igcn_colsum_masked': 2, 'igcn_score_topk_exact': 1, 'igcn_tc_pack': 5, 'igcn_tc_workspace': 0, 'igcn_peer_alloc': 0,
+KERNELS_PER_CALL = {'igcn_colsum_masked': 2, 'igcn_score_topk_exact': 3, 'igcn_tc_pack': 5, 'igcn_tc_workspace': 0, 'igcn_peer_alloc': 0,
                     'igcn_peer_open': 0, 'igcn_peer_close': 0, 'igcn_peer_free': 0}
 launch_count = 0          # running total of kernel launches issued through this binding
 profile_hook = None       # optional callable(name, phase, args) used by bench.py to time launches

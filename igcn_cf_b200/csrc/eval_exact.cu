@@ -101,9 +101,12 @@ __global__ void __launch_bounds__(EX_THREADS, 1) score_topk_exact_kernel(const _
     const int d4 = D >> 2;
     const int64_t n_eval = a.n_eval_dev ? min(a.n_eval, (int64_t)*a.n_eval_dev) : a.n_eval;
     if (ubase >= n_eval) return;
-    const int n_splits = (a.n_item_splits > 1 && n_eval <= a.split_cap) ? a.n_item_splits : 1;
+    // two launches share this kernel when item splitting is on: gridDim.y > 1 is the split pass (runs only while
+    // the entry count fits split_cap), gridDim.y == 1 the plain pass (runs only when it does not)
+    const bool split_on = a.n_item_splits > 1 && n_eval <= a.split_cap;
+    if (a.n_item_splits > 1 && split_on != (gridDim.y > 1)) return;
+    const int n_splits = split_on ? a.n_item_splits : 1;
     const int split = blockIdx.y;
-    if (split >= n_splits) return;
 
     for (int idx = tid; idx < BM * d4; idx += EX_THREADS) {
         const int r = idx / d4, c = idx % d4;
@@ -279,7 +282,13 @@ extern "C" int igcn_score_topk_exact(const float *rep, const int64_t *user_ids, 
     cudaError_t e = cudaFuncSetAttribute(score_topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("igcn_score_topk_exact: %s", cudaGetErrorString(e)); return (int)e; }
     const int64_t blocks = (n_eval + BM - 1) / BM;
-    score_topk_exact_kernel<<<dim3((unsigned)blocks, (unsigned)n_item_splits), EX_THREADS, smem, as_stream(stream)>>>(a);
+    if (n_item_splits > 1) {
+        // split pass over at most split_cap entries; both passes look at the device-side count and one of them exits
+        const int64_t sblocks = (min(n_eval, split_cap) + BM - 1) / BM;
+        score_topk_exact_kernel<<<dim3((unsigned)sblocks, (unsigned)n_item_splits), EX_THREADS, smem, as_stream(stream)>>>(a);
+    }
+    if (n_item_splits == 1 || n_eval > split_cap)
+        score_topk_exact_kernel<<<dim3((unsigned)blocks, 1u), EX_THREADS, smem, as_stream(stream)>>>(a);
     if (n_item_splits > 1) {
         int n_pad = 32;
         while (n_pad < n_item_splits * k) n_pad <<= 1;
