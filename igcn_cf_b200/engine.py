@@ -328,7 +328,8 @@ class TrainStep:
             self.w_m, self.w_v = opt.moments(model.w)
             self.colsum_scratch = colsum_scratch(n, D, dev)
         self._graphs = {}
-        self._side = torch.cuda.Stream(device=dev)
+        self._side = torch.cuda.Stream(device=dev)       # main scatter plan: joins before the last forward layer
+        self._side2 = torch.cuda.Stream(device=dev)      # auxiliary plan (IGCN): joins before the gradient kernels
 
     # -- pieces
     def _sample(self, B):
@@ -356,8 +357,13 @@ class TrainStep:
         with torch.cuda.stream(self._side):
             call('igcn_bpr_plan', ptr(self.triples), B, m.n_users, m.n_users + m.n_items, ptr(self.order),
                  ptr(self.seg_start), ptr(self.seg_row), ptr(self.n_seg), ptr(self.touched), st())
+        if self.is_igcn:
+            self._side2.wait_stream(main)
+            with torch.cuda.stream(self._side2):
+                call('igcn_bpr_plan', ptr(self.a_triples), B, m.feat_mat.t_users, m.embedding.weight.shape[0],
+                     ptr(self.a_order), ptr(self.a_seg_start), ptr(self.a_seg_row), ptr(self.a_n_seg), None, st())
         # forward: full layers 1..L-1, then the last layer + layer mean on the batch's rows only (the plan's
-        # sorted unique row list); the aux plan is only needed by the gradient kernels
+        # sorted unique row list)
         rows = (self.seg_row, self.n_seg, 3 * B)
         join = lambda: main.wait_stream(self._side)
         if self.is_igcn:
@@ -370,11 +376,6 @@ class TrainStep:
             l2_table = emb
         if L == 0:
             join()
-        if self.is_igcn:
-            self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
-                call('igcn_bpr_plan', ptr(self.a_triples), B, m.feat_mat.t_users, m.embedding.weight.shape[0],
-                     ptr(self.a_order), ptr(self.a_seg_start), ptr(self.a_seg_row), ptr(self.a_n_seg), None, st())
         call('igcn_bpr_fwd', ptr(rep), ptr(l2_table), None, ptr(self.triples), B, m.n_users, D, ptr(self.sp),
              ptr(self.sig), ptr(self.l2), st())
         if self.is_igcn:
@@ -388,6 +389,8 @@ class TrainStep:
                  ptr(self.acc), st())
         # backward
         main.wait_stream(self._side)
+        if self.is_igcn:
+            main.wait_stream(self._side2)
         self.gprime.zero_()
         if self.is_igcn and m.feat_mat.tmpl is not None:
             # template rows without a node in this graph get no gradient; zeroed here, one barrier or more
