@@ -329,7 +329,8 @@ class TrainStep:
             self.colsum_scratch = colsum_scratch(n, D, dev)
         self._graphs = {}
         self._side = torch.cuda.Stream(device=dev)       # main scatter plan: joins before the last forward layer
-        self._side2 = torch.cuda.Stream(device=dev)      # auxiliary plan (IGCN): joins before the gradient kernels
+        self._side2 = torch.cuda.Stream(device=dev)      # zeroed gradient buffers + auxiliary plan: joins before the gradient kernels
+        self._side3 = torch.cuda.Stream(device=dev)      # loss value + running meter: nothing downstream reads them; joins at the end
 
     # -- pieces
     def _sample(self, B):
@@ -357,9 +358,17 @@ class TrainStep:
         with torch.cuda.stream(self._side):
             call('igcn_bpr_plan', ptr(self.triples), B, m.n_users, m.n_users + m.n_items, ptr(self.order),
                  ptr(self.seg_start), ptr(self.seg_row), ptr(self.n_seg), ptr(self.touched), st())
-        if self.is_igcn:
-            self._side2.wait_stream(main)
-            with torch.cuda.stream(self._side2):
+        # second side stream: everything else the gradient kernels need that does not depend on the forward pass --
+        # the zeroed gradient buffers and (IGCN) the auxiliary scatter plan; joins before the gradient kernels
+        self._side2.wait_stream(main)
+        with torch.cuda.stream(self._side2):
+            self.gprime.zero_()
+            if self.is_igcn:
+                self.d_w.zero_()
+                if m.feat_mat.tmpl is not None:
+                    # template rows without a node in this graph get no gradient; zeroed long before any rank
+                    # stores template rows into this copy (several barriers later)
+                    self.d_emb.zero_()
                 call('igcn_bpr_plan', ptr(self.a_triples), B, m.feat_mat.t_users, m.embedding.weight.shape[0],
                      ptr(self.a_order), ptr(self.a_seg_start), ptr(self.a_seg_row), ptr(self.a_n_seg), None, st())
         # forward: full layers 1..L-1, then the last layer + layer mean on the batch's rows only (the plan's
@@ -382,20 +391,17 @@ class TrainStep:
             t_u = m.feat_mat.t_users
             call('igcn_bpr_fwd', ptr(emb), None, ptr(m.w.data), ptr(self.a_triples), B, t_u, D, ptr(self.a_sp),
                  ptr(self.a_sig), None, st())
-            call('igcn_loss_finalize', ptr(self.sp), ptr(self.l2), ptr(self.a_sp), B, B, self.l2_reg, self.aux_reg,
-                 ptr(self.loss), ptr(self.acc), st())
-        else:
-            call('igcn_loss_finalize', ptr(self.sp), ptr(self.l2), None, B, 0, self.l2_reg, 0.0, ptr(self.loss),
-                 ptr(self.acc), st())
+        self._side3.wait_stream(main)
+        with torch.cuda.stream(self._side3):
+            if self.is_igcn:
+                call('igcn_loss_finalize', ptr(self.sp), ptr(self.l2), ptr(self.a_sp), B, B, self.l2_reg, self.aux_reg,
+                     ptr(self.loss), ptr(self.acc), st())
+            else:
+                call('igcn_loss_finalize', ptr(self.sp), ptr(self.l2), None, B, 0, self.l2_reg, 0.0, ptr(self.loss),
+                     ptr(self.acc), st())
         # backward
         main.wait_stream(self._side)
-        if self.is_igcn:
-            main.wait_stream(self._side2)
-        self.gprime.zero_()
-        if self.is_igcn and m.feat_mat.tmpl is not None:
-            # template rows without a node in this graph get no gradient; zeroed here, one barrier or more
-            # before any rank stores template rows into this copy
-            self.d_emb.zero_()
+        main.wait_stream(self._side2)
         call('igcn_bpr_bwd', ptr(rep), None, ptr(self.triples), B, m.n_users, D, ptr(self.sig), 1.0 / (L + 1),
              self.l2_reg if self.is_igcn else 0.0, 1 if self.is_igcn else 0, ptr(self.order), ptr(self.seg_start),
              ptr(self.seg_row), ptr(self.n_seg), ptr(self.gprime), 0, None, None, st())
@@ -406,7 +412,6 @@ class TrainStep:
             prop.backward(m.norm_adj, self.gprime, g_scaled, rowscale=feat.rowscale, alpha=inv_keep,
                           gprime_rows=self.touched)
             inmo_backward(feat, g_scaled, self.d_emb, drop, D, self.colsum_scratch, self.shard)
-            self.d_w.zero_()
             call('igcn_bpr_bwd', ptr(emb), ptr(m.w.data), ptr(self.a_triples), B, feat.t_users, D, ptr(self.a_sig),
                  float(self.aux_reg), 0.0, 0, ptr(self.a_order), ptr(self.a_seg_start), ptr(self.a_seg_row),
                  ptr(self.a_n_seg), ptr(self.d_emb), 1, ptr(self.d_w), ptr(self.dw_scratch), st())
@@ -422,6 +427,7 @@ class TrainStep:
             w = m.w.data
             call('igcn_adam', ptr(w), ptr(self.d_w), ptr(self.w_m), ptr(self.w_v), w.numel(), self.lr, BETA1,
                  BETA2, ADAM_EPS, 0, ptr(self.state), st())
+        main.wait_stream(self._side3)
 
     def _production_drop(self):
         m = self.model
