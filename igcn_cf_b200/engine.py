@@ -631,6 +631,22 @@ class TcScorer:
         self._ws = {}
         self.last_fallback = None       # device int32[1]: users sent to the exact kernel by the last call
 
+    @staticmethod
+    def pick_splits(n_utiles, n_sm=148):
+        """Item-range splits per user tile: one CTA per SM at a time, so the grid (n_utiles x splits CTAs) should
+        fill whole waves of 148; few user tiles need more splits to occupy the chip at all.  More splits also mean
+        more candidate lists per user, hence the small penalty."""
+        n_utiles = max(1, int(n_utiles))
+        if n_utiles * 8 <= 2 * n_sm:
+            return int(min(8, max(1, -(-2 * n_sm // n_utiles))))
+        best, best_score = 1, -1.0
+        for s in (1, 2, 3, 4):
+            waves = n_utiles * s / n_sm
+            score = waves / -(-n_utiles * s // n_sm) - 0.02 * (s - 1)
+            if score > best_score:
+                best, best_score = s, score
+        return best
+
     def _workspace(self, n_eval, n_items, D, n_splits, k, device):
         key = (n_eval, n_items, D, n_splits, k, str(device))
         ws = self._ws.get(key)
@@ -652,7 +668,7 @@ class TcScorer:
         n_eval, D = int(user_ids.shape[0]), int(rep.shape[1])
         item_hi = n_items if item_hi is None else item_hi
         if n_splits is None:
-            n_splits = int(min(8, max(1, -(-296 // max(1, (n_eval + 127) // 128)))))
+            n_splits = self.pick_splits((n_eval + 127) // 128)
         ws = self._workspace(n_eval, n_items, D, n_splits, k, rep.device)
         st = stream_ptr
         call('igcn_tc_pack', ptr(rep), rep.numel(), ptr(user_ids), n_eval, n_users, n_items, D, ptr(ws['maxabs']),
