@@ -8,7 +8,7 @@ A "step" is one BPR training step (2,048 triples): sample -> propagate (L SpMM l
 ms_per_step x ceil(E_train / 2048) with everything resident in HBM (CUDA-graph replay, device
 sampler).  `e2e` is the same metric through the public trainer step with HOST triples in pinned
 memory copied H2D every step and the loss read back D2H every step (what the reference does,
-trainer.py:234/247).  `eval` is the second half of BASELINE.json's metric: full-ranking users/s.
+trainer.py:234/247; the read of step i's loss is overlapped with step i + 1).  `eval` is the second half of BASELINE.json's metric: full-ranking users/s.
 `roofline` describes the dominant kernel (the CSR SpMM) against the measured HBM peak; `cpu_baseline`
 times the CPU oracle port of the reference's step on this box's host cores (a reported baseline).
 
@@ -552,15 +552,31 @@ def main():
     tp = torch.from_numpy(pairs)
     host = torch.stack([tp[sel, 0], tp[sel, 1], torch.randint(ds.n_items, (pool, BATCH), generator=g)], dim=2).pin_memory()
     is_igcn = kind == 'IGCN'
-    for i in range(3):
-        b = host[i].to(dev, non_blocking=True)
-        step.run(b, b if is_igcn else None).item()
+    # every step: H2D of that step's triples from pinned memory, one public step call, D2H of that step's loss into
+    # pinned memory.  The loss of step i is READ on the host after step i + 1 has been enqueued (the way a training
+    # loop with a prefetching loader and asynchronous logging runs), so the device does not idle on a host round trip.
+    ploss = torch.zeros(2, dtype=torch.float32).pin_memory()
+    evs = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_loop(n):
+        total = 0.0
+        for i in range(n):
+            b = host[i % pool].to(dev, non_blocking=True)
+            loss_t = step.run(b, b if is_igcn else None)
+            ploss[i % 2:i % 2 + 1].copy_(loss_t, non_blocking=True)
+            evs[i % 2].record()
+            if i > 0:
+                evs[(i - 1) % 2].synchronize()
+                total += float(ploss[(i - 1) % 2])
+        evs[(n - 1) % 2].synchronize()
+        return total + float(ploss[(n - 1) % 2])
+
+    e2e_loop(3)
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        b = host[i % pool].to(dev, non_blocking=True)
-        step.run(b, b if is_igcn else None).item()
+    e2e_loss_sum = e2e_loop(args.steps)
     barrier()
+    assert math.isfinite(e2e_loss_sum)
     e2e_ms_step = (time.perf_counter() - t0) * 1e3 / args.steps
     h2d = BATCH * 3 * 8
     if world > 1:
