@@ -299,7 +299,7 @@ class BasicTrainer:
         if peers is not None:
             # the top-k lists are gathered so that every rank reports the same metrics
             rec_dev = dist.gather_rows(rec_dev, self.dataset.n_users, peers.group)
-        rec_items = rec_dev.cpu().numpy().astype(np.int64)
+        rec_items = rec_dev.cpu().numpy()          # int32 ids; the hit matrix is computed from the device copy
         self._last_rec = (rec_items, rec_dev)
         metrics = self.calculate_metrics(eval_data, rec_items)
         self._last_rec = None
