@@ -73,6 +73,7 @@ _SIGNATURES = {
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'igcn_tc_finalize': [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                          c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'igcn_predict_scores': [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p],
     'igcn_hits': [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p],
     'igcn_peer_alloc': [c_int64, C.POINTER(c_void_p), c_void_p],
     'igcn_peer_open': [c_void_p, C.POINTER(c_void_p)],

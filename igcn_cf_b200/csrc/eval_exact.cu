@@ -243,6 +243,27 @@ __global__ void __launch_bounds__(256) exact_merge_kernel(const __grid_constant_
     }
 }
 
+// Dense score block for the reference's predict() API (model.py:118-123): out[b][j] = <rep[user_ids[b]], rep[item_row0 + j]>
+// with the same fp32 FMA chain (ascending d) as the ranking kernels.  The evaluation path never materialises
+// this matrix; predict() exists for callers of the reference API that want raw scores.
+__global__ void __launch_bounds__(256) predict_scores_kernel(const float *__restrict__ rep, const int64_t *__restrict__ user_ids,
+                                                             int64_t item_row0, int64_t n_items, int D, float *__restrict__ out) {
+    extern __shared__ __align__(16) float urow[];
+    const int64_t b = blockIdx.y;
+    const float *u = rep + __ldg(user_ids + b) * D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) urow[d] = u[d];
+    __syncthreads();
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_items) return;
+    const float *it = rep + (item_row0 + j) * D;
+    float s = 0.f;
+    for (int d = 0; d < D; d += 4) {
+        const float4 x = ld4(urow + d), y = ld4(it + d);
+        s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+    }
+    out[b * n_items + j] = s;
+}
+
 __global__ void hits_kernel(const int32_t *__restrict__ rec, int64_t n, int k, const int64_t *__restrict__ ptr,
                             const int32_t *__restrict__ items, float *hit) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -298,6 +319,18 @@ extern "C" int igcn_score_topk_exact(const float *rep, const int64_t *user_ids, 
         const int64_t mblocks = (min(n_eval, split_cap) + 7) / 8;
         exact_merge_kernel<<<(unsigned)mblocks, 256, msmem, as_stream(stream)>>>(a);
     }
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_predict_scores(const float *rep, const int64_t *user_ids, int64_t n_eval, int64_t item_row0,
+                                   int64_t n_items, int32_t D, float *out, void *stream) {
+    IGCN_CHECK_ARG(rep && user_ids && out, "null pointer");
+    IGCN_CHECK_ARG(D > 0 && D <= 1024 && !(D & 3), "embedding size unsupported (need D % 4 == 0)");
+    IGCN_CHECK_ARG(n_eval <= 65535, "at most 65535 users per call");
+    if (n_eval <= 0 || n_items <= 0) return 0;
+    predict_scores_kernel<<<dim3((unsigned)((n_items + 255) / 256), (unsigned)n_eval), 256, (size_t)D * sizeof(float), as_stream(stream)>>>(
+        rep, user_ids, item_row0, n_items, D, out);
     IGCN_CHECK_LAUNCH();
     return 0;
 }

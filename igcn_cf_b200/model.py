@@ -145,12 +145,19 @@ class _GraphModel(BasicModel):
         self._bump()
 
     def predict(self, users):
-        """LightGCN.predict (model.py:118-123); the trainer's eval() does not come through here, it
-        uses the fused score + mask + top-k kernel on the cached representation."""
-        rep = self.get_rep()
-        users_r = rep[users, :]
-        all_items_r = rep[self.n_users:, :]
-        return torch.mm(users_r, all_items_r.t())
+        """LightGCN.predict (model.py:118-123): dense scores [len(users), n_items] from the igcn_predict_scores
+        kernel.  The trainer's eval() does not come through here, it uses the fused score + mask + top-k kernels
+        on the cached representation; gradients do not flow through predict (the reference only calls it under
+        eval)."""
+        from ._lib import call, ptr, stream_ptr
+        rep = self.get_rep().detach().contiguous()
+        users = torch.as_tensor(users, dtype=torch.int64, device=rep.device).contiguous()
+        out = torch.empty((users.shape[0], self.n_items), dtype=torch.float32, device=rep.device)
+        for lo in range(0, users.shape[0], 65535):
+            chunk = users[lo:lo + 65535]
+            call('igcn_predict_scores', ptr(rep), ptr(chunk), chunk.shape[0], self.n_users, self.n_items, rep.shape[1],
+                 ptr(out[lo:lo + 65535]), stream_ptr())
+        return out
 
 
 class LightGCN(_GraphModel):

@@ -295,6 +295,12 @@ int igcn_peer_barrier(uint32_t *const *flags_host, int32_t n_peers, int32_t rank
 int igcn_peer_push(float *const *peer_host, int32_t n_peers, int32_t rank, int64_t elem_offset,
                    int64_t n_elems, void *stream);
 
+/* out[b][j] = <rep[user_ids[b]], rep[item_row0 + j]> (fp32 FMA chain, ascending d): the dense score block of
+ * LightGCN.predict (model.py:118-123, torch.mm at :122) for callers that want raw scores; n_eval <= 65535 per
+ * call.  The evaluation path does not use it (scores never reach HBM there). */
+int igcn_predict_scores(const float *rep, const int64_t *user_ids, int64_t n_eval, int64_t item_row0,
+                        int64_t n_items, int32_t D, float *out, void *stream);
+
 /* hit[u][j] = 1 if rec[u][j] is in eval_items[eval_ptr[u] .. eval_ptr[u+1]) (sorted), else 0:
  * the membership double loop of BasicTrainer.calculate_metrics (trainer.py:111-115). */
 int igcn_hits(const int32_t *rec, int64_t n_users, int32_t k, const int64_t *eval_ptr,
