@@ -267,7 +267,7 @@ def run_reference(args, shape, kind, l2_reg, dropout):
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'ms', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': False, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': args.workload, 'shape': shape, 'model': kind, 'n_users': ds.n_users, 'n_items': ds.n_items,
+            'config': {'workload': args.workload, 'shape': shape, 'n_users': ds.n_users, 'n_items': ds.n_items,
                        'train_interactions': len(ds), 'batch': BATCH, 'steps_per_epoch': steps_per_epoch},
             'cpu_baseline': {'value': value, 'unit': 'ms', 'cores': cores, 'kind': 'port',
                              'sample': '%d full train steps of %d per epoch, extrapolated' % (args.steps, steps_per_epoch)},
@@ -357,7 +357,7 @@ def run_scaleout(args):
         line = {'metric': 'full-rank eval users/s (propagate + fused score/top-k)', 'value': total_scored / ((prop_ms + score_ms) * 1e-3),
                 'unit': 'users/s', 'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ms_per_step': prop_ms + score_ms,
                 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': args.workload, 'model': 'IGCN', 'n_users': ds.n_users, 'n_items': ds.n_items,
+                'config': {'workload': args.workload, 'n_users': ds.n_users, 'n_items': ds.n_items,
                            'interactions': len(ds), 'nnz_adj': nnz, 'dim': D, 'layers': L, 'users_scored': total_scored,
                            'generated_on_device_s': round(gen_s, 2),
                            'l2': 'inputs larger than L2 (layer table %d MB)' % (n * D * 4 // 2 ** 20),
@@ -454,7 +454,7 @@ def run_dropui(args):
         line = {'metric': 'inductive inference time (re-aggregate + 6 full-ranking passes, no retraining)', 'value': sec,
                 'unit': 's', 'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3,
                 'higher_is_better': False, 'scaling': 'strong', 'vs_baseline': 3.4 / sec, 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': args.workload, 'model': 'IGCN', 'n_users': ds_full.n_users, 'n_items': ds_full.n_items,
+                'config': {'workload': args.workload, 'n_users': ds_full.n_users, 'n_items': ds_full.n_items,
                            'n_old_users': ds_small.n_users, 'n_old_items': ds_small.n_items,
                            'baseline': 'INMO-LGCN inductive inference 3.4 s, reference run/plot.py:199-207 (hardware not stated)',
                            'timed': 'wall clock, host graph/template rebuild included'},
@@ -642,7 +642,7 @@ def main():
         line = {'metric': METRIC, 'value': ms_per_step * steps_per_epoch, 'unit': 'ms', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': False,
                 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': args.workload, 'shape': shape, 'model': kind, 'n_users': ds.n_users,
+                'config': {'workload': args.workload, 'shape': shape, 'n_users': ds.n_users,
                            'n_items': ds.n_items, 'train_interactions': len(ds), 'nnz_adj': nnz, 'dim': D, 'layers': 3,
                            'batch': BATCH, 'steps_per_epoch': steps_per_epoch, 'sampler': 'device', 'cuda_graph': True,
                            'parallelism': 'single GPU' if world == 1 else
