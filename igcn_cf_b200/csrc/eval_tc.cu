@@ -27,115 +27,19 @@
 //           row's candidate buffer in shared memory, warp-cooperative compaction when it fills.
 // Pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty double buffer (MMA <-> epilogue),
 // bitmap full (helper -> epilogue).
-#include <cuda_fp16.h>
 
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace igcn {
 
-constexpr int TC_BM = 128;        // users per CTA tile (UMMA M)
 constexpr int TC_BN = 256;        // items per tile     (UMMA N)
 constexpr int TC_CAP = 96;        // candidate slots per user row
 constexpr int TC_KEEP = 32;       // the threshold never rises above the TC_KEEP-th best upper bound
 constexpr int TC_STAGES = 2;      // item-tile smem stages
 constexpr int TC_THREADS = 7 * 32;
 constexpr int TC_STAGE_W = 36;    // words per row of the chunk staging area (16 B aligned, conflict-free)
-constexpr float TC_C = 1.0e-3f;           // relative bound constant (> 2^-10 + 2^-22 + 80 * 2^-23)
-constexpr float TC_EPS_U = 4.76837158e-7f;   // 2^-21, absolute slack in the user bound entry
-constexpr float TC_EPS_I = 4.8828125e-4f;    // 2^-11, absolute slack in the item bound entry
-
-// ------------------------------------------------------------------ small PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// Wait used by the helper warps (TMA producer, MMA issuer, mask builder): the suspend-time hint parks the
-// thread in hardware instead of spinning through issue slots the epilogue warps on the same scheduler need.
-__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "PARK_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
-        "@P1 bra PARK_DONE;\n\t"
-        "bra PARK_LOOP;\n\t"
-        "PARK_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// core matrix = 8 rows x 16 bytes, contiguous 128 B; LBO = byte distance between the two K-adjacent
-// core matrices of one MMA, SBO = byte distance between 8-row groups; version 1 (sm_100).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3fff);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, both operands K-major, M = 128, N = 256.
-__device__ __forceinline__ uint32_t umma_idesc_f16_m128_n256() {
-    return (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-}
-
-__device__ __forceinline__ uint32_t f_order(float f) {
-    const uint32_t u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float order_f(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
 
 // ------------------------------------------------------------------ operand packing
 __global__ void maxabs_kernel(const float *__restrict__ x, int64_t n, uint32_t *out) {
@@ -144,15 +48,6 @@ __global__ void maxabs_kernel(const float *__restrict__ x, int64_t n, uint32_t *
         m = max(m, __float_as_uint(fabsf(x[i])));
     m = __reduce_max_sync(0xffffffffu, m);
     if ((threadIdx.x & 31) == 0) atomicMax(out, m);   // max is order independent: deterministic
-}
-
-// scale = 2^(9 - floor(log2(maxabs))) so that the largest |element| lands in [512, 1024)
-__device__ __forceinline__ float tc_scale(const uint32_t *maxabs_bits) {
-    const float m = __uint_as_float(*maxabs_bits);
-    if (!(m > 0.f) || !isfinite(m)) return 1.f;
-    int e;
-    frexpf(m, &e);   // m = f * 2^e, f in [0.5, 1)  -> floor(log2 m) = e - 1
-    return ldexpf(1.f, 10 - e);
 }
 
 // One group of 16 lanes converts one row (D <= 64) into its tile image: kcores core matrices of
@@ -205,7 +100,7 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ 
 struct TcArgs {
     const uint8_t *a_img;
     const uint8_t *b_img;
-    int n_utiles, n_itiles, n_splits, kcores;
+    int n_utiles, n_itiles, n_splits, n_head, kcores;      // the first n_head user tiles are not split
     int64_t n_eval, n_items, item_lo, item_hi;
     const uint32_t *banned;
     const int32_t *mask_tile_ptr;     // [n_utiles, n_itiles + 1] or NULL
@@ -236,7 +131,6 @@ __device__ __forceinline__ uint32_t warp_sort_desc(uint32_t x, int lane) {
 
 // Candidate buffer entry: low word = raw fp32 score bits, high word = item id (what the predicated
 // epilogue store writes).
-__device__ __forceinline__ float entry_score(uint64_t e) { return __uint_as_float((uint32_t)e); }
 
 // Lane-parallel compaction: every lane shrinks ITS OWN row's buffer, no cross-lane traffic except
 // the common loop bound.  A float bisection between the current threshold and the row maximum finds
@@ -291,18 +185,6 @@ __device__ __forceinline__ void compact_lanes(uint64_t *mybuf, int &cnt, float &
     }
 }
 
-// hit |= (score > thr) << bit   -- two instructions (FSETP + predicated LOP3), no branch
-__device__ __forceinline__ void hit_if_gt(uint32_t vbits, float thr, uint32_t &hits, uint32_t bit) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.gt.f32 p, %1, %2;\n\t"
-        "@p or.b32 %0, %0, %3;\n\t"
-        "}"
-        : "+r"(hits)
-        : "f"(__uint_as_float(vbits)), "f"(thr), "r"(bit));
-}
-
 // VARIANT: 0 production, 1 = also dump every s_hat (tests), 2 / 3 = timing experiments selected with the
 // IGCN_TC_EXPERIMENT environment variable (results are NOT valid): 2 reads the accumulators but does not filter
 // (TMA + MMA + TMEM-read floor), 3 filters against thr = +inf (full filter cost, no hits, no compaction).
@@ -319,13 +201,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
     TcSmem *sm = reinterpret_cast<TcSmem *>(stage + TC_BM * TC_STAGE_W);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ut = blockIdx.x / a.n_splits, sp = blockIdx.x % a.n_splits;
+    // CTA -> (user tile, item split): head tiles scan every item tile in one CTA, the others are split n_splits ways
+    const bool head = (int)blockIdx.x < a.n_head;
+    const int rest = (int)blockIdx.x - a.n_head;
+    const int ut = head ? (int)blockIdx.x : a.n_head + rest / a.n_splits;
+    const int sp = head ? 0 : rest % a.n_splits;
+    const int ns = head ? 1 : a.n_splits;
     // item tiles intersecting [item_lo, item_hi), divided evenly over the splits
     const int64_t hi_eff = min(a.item_hi, a.n_items);
     const int t_first = (int)(max((int64_t)0, a.item_lo) / TC_BN);
     const int t_last = (int)((hi_eff + TC_BN - 1) / TC_BN);                 // exclusive
     const int n_t = max(0, t_last - t_first);
-    const int per = (n_t + a.n_splits - 1) / a.n_splits;
+    const int per = (n_t + ns - 1) / ns;
     const int t0 = t_first + sp * per, t1 = min(t_last, t0 + per);
     const int n_it = max(0, t1 - t0);
 
@@ -361,7 +248,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
     } else if (warp == 1) {
         // ===== MMA issuer (one thread)
         if (lane == 0 && n_it > 0) {
-            const uint32_t idesc = umma_idesc_f16_m128_n256();
+            const uint32_t idesc = umma_idesc_f16_m128(TC_BN);
             const uint32_t sbo = (uint32_t)a.kcores * 128, lbo = 128;
             const int ksteps = a.kcores / 2;
             mbar_wait_parked(&sm->a_full, 0);
@@ -500,6 +387,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 a.cand_cnt[b * a.n_splits + sp] = n;
                 a.cand_thr[b * a.n_splits + sp] = th;
             }
+            if (head && lane > 0 && lane < a.n_splits) {          // the list slots an unsplit tile does not use
+                a.cand_cnt[b * a.n_splits + lane] = 0;
+                a.cand_thr[b * a.n_splits + lane] = -INFINITY;
+            }
         }
     }
     tc_fence_before();
@@ -515,7 +406,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
 // eval_exact.cu), rank by (score desc, item asc), emit top-k, and verify that the k-th exact score
 // is strictly above every dropped item's upper bound.  Unverified users are appended to a list.
 __global__ void __launch_bounds__(256) tc_finalize_kernel(const float *__restrict__ rep, const int64_t *__restrict__ user_ids,
-                                                          int64_t n_eval, int64_t item_row0, int D, int n_splits,
+                                                          int64_t n_eval, int64_t item_row0, int D, int n_splits, int list_cap,
                                                           const int32_t *__restrict__ cand_items, const int32_t *__restrict__ cand_cnt,
                                                           const float *__restrict__ cand_thr, const uint32_t *__restrict__ maxabs_bits,
                                                           const float *__restrict__ center_sum, float inv_n,
@@ -525,7 +416,7 @@ __global__ void __launch_bounds__(256) tc_finalize_kernel(const float *__restric
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t b = (int64_t)blockIdx.x * 8 + wid;
     if (b >= n_eval) return;
-    const int cap = n_splits * TC_CAP;
+    const int cap = n_splits * list_cap;
     uint64_t *keys = fin_keys + (size_t)wid * cap;
     const int64_t u = user_ids[b];
     const float *urow = rep + u * D;
@@ -534,7 +425,7 @@ __global__ void __launch_bounds__(256) tc_finalize_kernel(const float *__restric
     for (int sp = 0; sp < n_splits; ++sp) {
         const int c = cand_cnt[b * n_splits + sp];
         thr_max = fmaxf(thr_max, cand_thr[b * n_splits + sp]);
-        const int32_t *src = cand_items + ((size_t)b * n_splits + sp) * TC_CAP;
+        const int32_t *src = cand_items + ((size_t)b * n_splits + sp) * list_cap;
         for (int e = lane; e < c; e += 32) {
             const int32_t item = src[e];
             const float *irow = rep + (item_row0 + item) * D;
@@ -589,24 +480,33 @@ __global__ void __launch_bounds__(256) tc_finalize_kernel(const float *__restric
 
 }  // namespace igcn
 
+#include "eval_tc_pair.cuh"
+
 using namespace igcn;
 
 static int tc_kcores(int D) { return ((D + 15) / 16) * 2 + 2; }
+// user_tiles = 1: score_tc_kernel (N = 256 item tiles, 96-slot lists); 2: score_tc3_kernel (N = 128, 56-slot lists)
+static int tc_item_tile(int user_tiles) { return user_tiles == 2 ? T3_BN : TC_BN; }
+static int tc_list_cap(int user_tiles) { return user_tiles == 2 ? T3_CAP : TC_CAP; }
+static int tc_max_k(int user_tiles) { return (user_tiles == 2 ? T3_KEEP : TC_KEEP) - 8; }
 
-extern "C" int igcn_tc_workspace(int64_t n_eval, int64_t n_items, int32_t D, int32_t n_splits, int64_t *a_img_bytes,
-                                 int64_t *b_img_bytes, int64_t *cand_slots) {
+extern "C" int igcn_tc_workspace(int64_t n_eval, int64_t n_items, int32_t D, int32_t n_splits, int32_t user_tiles,
+                                 int64_t *a_img_bytes, int64_t *b_img_bytes, int64_t *cand_slots) {
+    IGCN_CHECK_ARG(user_tiles == 1 || user_tiles == 2, "user_tiles must be 1 or 2");
     IGCN_CHECK_ARG(D > 0 && D <= 64 && !(D & 3), "tensor-core scoring supports D % 4 == 0, D <= 64");
     IGCN_CHECK_ARG(n_splits >= 1 && n_splits <= 8, "n_splits must be in [1, 8]");
     const int64_t kc = tc_kcores(D);
     *a_img_bytes = (n_eval + TC_BM - 1) / TC_BM * (TC_BM / 8) * kc * 128;
-    *b_img_bytes = (n_items + TC_BN - 1) / TC_BN * (TC_BN / 8) * kc * 128;
-    *cand_slots = n_eval * n_splits * TC_CAP;
+    const int64_t bn = tc_item_tile(user_tiles);
+    *b_img_bytes = (n_items + bn - 1) / bn * (bn / 8) * kc * 128;
+    *cand_slots = n_eval * n_splits * tc_list_cap(user_tiles);
     return 0;
 }
 
 extern "C" int igcn_tc_pack(const float *rep, int64_t n_rep_elems, const int64_t *user_ids, int64_t n_eval, int64_t item_row0,
-                            int64_t n_items, int32_t D, uint32_t *maxabs_bits, uint8_t *a_img, uint8_t *b_img, float *center_sum,
-                            float *center_scratch, void *stream) {
+                            int64_t n_items, int32_t D, int32_t user_tiles, uint32_t *maxabs_bits, uint8_t *a_img, uint8_t *b_img,
+                            float *center_sum, float *center_scratch, void *stream) {
+    IGCN_CHECK_ARG(user_tiles == 1 || user_tiles == 2, "user_tiles must be 1 or 2");
     IGCN_CHECK_ARG(rep && user_ids && maxabs_bits && a_img && b_img && center_sum && center_scratch, "null pointer");
     IGCN_CHECK_ARG(D > 0 && D <= 64 && !(D & 3), "tensor-core scoring supports D % 4 == 0, D <= 64");
     cudaStream_t st = as_stream(stream);
@@ -620,26 +520,48 @@ extern "C" int igcn_tc_pack(const float *rep, int64_t n_rep_elems, const int64_t
         tc_pack_kernel<<<(unsigned)((n_eval + 15) / 16), 256, 0, st>>>(rep, user_ids, 0, n_eval, D, TC_BM, kc, 1, maxabs_bits, center_sum,
                                                                        inv_n, a_img);
     if (n_items > 0)
-        tc_pack_kernel<<<(unsigned)((n_items + 15) / 16), 256, 0, st>>>(rep, nullptr, item_row0, n_items, D, TC_BN, kc, 0, maxabs_bits,
-                                                                        center_sum, inv_n, b_img);
+        tc_pack_kernel<<<(unsigned)((n_items + 15) / 16), 256, 0, st>>>(rep, nullptr, item_row0, n_items, D, tc_item_tile(user_tiles), kc, 0,
+                                                                        maxabs_bits, center_sum, inv_n, b_img);
     IGCN_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, int64_t n_eval, int64_t n_items, int32_t D,
-                                  int32_t n_splits, int64_t item_lo, int64_t item_hi, const uint32_t *banned_bits,
+                                  int32_t n_splits, int32_t n_head, int32_t user_tiles, int64_t item_lo, int64_t item_hi, const uint32_t *banned_bits,
                                   const int32_t *mask_tile_ptr, const uint16_t *mask_entries, int32_t *cand_items,
                                   int32_t *cand_cnt, float *cand_thr, float *dump, void *stream) {
     IGCN_CHECK_ARG(a_img && b_img && cand_items && cand_cnt && cand_thr, "null pointer");
     IGCN_CHECK_ARG(D > 0 && D <= 64 && !(D & 3), "tensor-core scoring supports D % 4 == 0, D <= 64");
     IGCN_CHECK_ARG(n_splits >= 1 && n_splits <= 8, "n_splits must be in [1, 8]");
     IGCN_CHECK_ARG(!mask_tile_ptr || mask_entries, "mask_tile_ptr without mask_entries");
+    IGCN_CHECK_ARG(user_tiles == 1 || (user_tiles == 2 && !dump), "user_tiles must be 1 or 2 (no dump with 2)");
     if (n_eval <= 0) return 0;
+    const int n_utiles_all = (int)((n_eval + TC_BM - 1) / TC_BM);
+    const int n_groups = (n_utiles_all + user_tiles - 1) / user_tiles;       // CTA groups: user tiles or pairs of them
+    IGCN_CHECK_ARG(n_head >= 0 && n_head <= n_groups, "n_head must be in [0, number of user-tile groups]");
+    const unsigned n_ctas = (unsigned)(n_head + (n_groups - n_head) * n_splits);
+    if (user_tiles == 2) {
+        Tc3Args p{};
+        p.a_img = a_img; p.b_img = b_img;
+        p.n_utiles = (int)((n_eval + TC_BM - 1) / TC_BM);
+        p.n_buckets = (int)((n_items + 255) / 256);
+        p.n_splits = n_splits; p.n_head = n_head; p.kcores = tc_kcores(D);
+        p.n_eval = n_eval; p.n_items = n_items; p.item_lo = item_lo; p.item_hi = item_hi;
+        p.banned = banned_bits; p.mask_tile_ptr = mask_tile_ptr; p.mask_entries = mask_entries;
+        p.cand_items = cand_items; p.cand_cnt = cand_cnt; p.cand_thr = cand_thr;
+        const size_t smem3 = (size_t)(2 * (TC_BM / 8) + T3_STAGES * (T3_BN / 8)) * p.kcores * 128 + (size_t)2 * TC_BM * (T3_CAP + 1) * 8 +
+                             (size_t)T3_ACC * TC_BM * 4 * 4 + (size_t)8 * 32 * T3_STAGE_W * 4 + sizeof(Tc3Smem) + 64;
+        cudaError_t e3 = cudaFuncSetAttribute(score_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+        if (e3 != cudaSuccess) { set_error("igcn_tc_candidates: %s", cudaGetErrorString(e3)); return (int)e3; }
+        score_tc3_kernel<<<n_ctas, T3_THREADS, smem3, as_stream(stream)>>>(p);
+        IGCN_CHECK_LAUNCH();
+        return 0;
+    }
     TcArgs a{};
     a.a_img = a_img; a.b_img = b_img;
     a.n_utiles = (int)((n_eval + TC_BM - 1) / TC_BM);
     a.n_itiles = (int)((n_items + TC_BN - 1) / TC_BN);
-    a.n_splits = n_splits; a.kcores = tc_kcores(D);
+    a.n_splits = n_splits; a.n_head = n_head; a.kcores = tc_kcores(D);
     a.n_eval = n_eval; a.n_items = n_items; a.item_lo = item_lo; a.item_hi = item_hi;
     a.banned = banned_bits; a.mask_tile_ptr = mask_tile_ptr; a.mask_entries = mask_entries;
     a.cand_items = cand_items; a.cand_cnt = cand_cnt; a.cand_thr = cand_thr; a.dump = dump;
@@ -649,29 +571,31 @@ extern "C" int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, in
     auto kern = dump ? score_tc_kernel<1> : experiment == 2 ? score_tc_kernel<2> : experiment == 3 ? score_tc_kernel<3> : score_tc_kernel<0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("igcn_tc_candidates: %s", cudaGetErrorString(e)); return (int)e; }
-    kern<<<(unsigned)(a.n_utiles * n_splits), TC_THREADS, smem, as_stream(stream)>>>(a);
+    kern<<<n_ctas, TC_THREADS, smem, as_stream(stream)>>>(a);
     IGCN_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int igcn_tc_finalize(const float *rep, const int64_t *user_ids, int64_t n_eval, int64_t item_row0, int32_t D,
-                                int32_t n_splits, const int32_t *cand_items, const int32_t *cand_cnt, const float *cand_thr,
-                                const uint32_t *maxabs_bits, const float *center_sum, int64_t n_items, int32_t k,
+                                int32_t n_splits, int32_t user_tiles, const int32_t *cand_items, const int32_t *cand_cnt,
+                                const float *cand_thr, const uint32_t *maxabs_bits, const float *center_sum, int64_t n_items, int32_t k,
                                 int32_t *out_items, float *out_scores, int32_t *fb_count, int64_t *fb_users, int32_t *fb_rows,
                                 void *stream) {
     IGCN_CHECK_ARG(rep && user_ids && cand_items && cand_cnt && cand_thr && maxabs_bits && center_sum && out_items && out_scores,
                    "null pointer");
     IGCN_CHECK_ARG(fb_count && fb_users && fb_rows, "null fallback buffers");
-    IGCN_CHECK_ARG(k > 0 && k <= TC_KEEP - 8, "tensor-core path supports k <= 24");
+    IGCN_CHECK_ARG(user_tiles == 1 || user_tiles == 2, "user_tiles must be 1 or 2");
+    IGCN_CHECK_ARG(k > 0 && k <= tc_max_k(user_tiles), "tensor-core path supports k <= 24 (k <= 20 with two user tiles per CTA)");
     if (n_eval <= 0) return 0;
     cudaStream_t st = as_stream(stream);
     cudaMemsetAsync(fb_count, 0, sizeof(int32_t), st);
-    const size_t smem = (size_t)8 * n_splits * TC_CAP * sizeof(uint64_t);
+    const int list_cap = tc_list_cap(user_tiles);
+    const size_t smem = (size_t)8 * n_splits * list_cap * sizeof(uint64_t);
     cudaError_t e = cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("igcn_tc_finalize: %s", cudaGetErrorString(e)); return (int)e; }
     const float inv_n = n_items > 0 ? 1.f / (float)n_items : 0.f;
-    tc_finalize_kernel<<<(unsigned)((n_eval + 7) / 8), 256, smem, st>>>(rep, user_ids, n_eval, item_row0, D, n_splits, cand_items,
-                                                                         cand_cnt, cand_thr, maxabs_bits, center_sum, inv_n, k,
+    tc_finalize_kernel<<<(unsigned)((n_eval + 7) / 8), 256, smem, st>>>(rep, user_ids, n_eval, item_row0, D, n_splits, list_cap,
+                                                                         cand_items, cand_cnt, cand_thr, maxabs_bits, center_sum, inv_n, k,
                                                                          out_items, out_scores, fb_count, fb_users, fb_rows);
     IGCN_CHECK_LAUNCH();
     return 0;

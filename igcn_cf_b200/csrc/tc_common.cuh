@@ -1,0 +1,129 @@
+// Device helpers shared by the tensor-core scoring kernels (eval_tc.cu, eval_tc3.cu): mbarrier / bulk-TMA /
+// tcgen05 PTX wrappers, UMMA descriptors, order-preserving float keys.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace igcn {
+
+constexpr int TC_BM = 128;        // users per UMMA tile (M)
+constexpr float TC_C = 1.0e-3f;           // relative bound constant (> 2^-10 + 2^-22 + 80 * 2^-23)
+constexpr float TC_EPS_U = 4.76837158e-7f;   // 2^-21, absolute slack in the user bound entry
+constexpr float TC_EPS_I = 4.8828125e-4f;    // 2^-11, absolute slack in the item bound entry
+
+// ------------------------------------------------------------------ small PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// Wait used by the helper warps (TMA producer, MMA issuer, mask builder): the suspend-time hint parks the
+// thread in hardware instead of spinning through issue slots the epilogue warps on the same scheduler need.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "PARK_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "@P1 bra PARK_DONE;\n\t"
+        "bra PARK_LOOP;\n\t"
+        "PARK_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// core matrix = 8 rows x 16 bytes, contiguous 128 B; LBO = byte distance between the two K-adjacent
+// core matrices of one MMA, SBO = byte distance between 8-row groups; version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, both operands K-major, M = 128, N = n.
+__device__ __forceinline__ uint32_t umma_idesc_f16_m128(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t f_order(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float order_f(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
+
+// scale = 2^(9 - floor(log2(maxabs))) so that the largest |element| lands in [512, 1024)
+__device__ __forceinline__ float tc_scale(const uint32_t *maxabs_bits) {
+    const float m = __uint_as_float(*maxabs_bits);
+    if (!(m > 0.f) || !isfinite(m)) return 1.f;
+    int e;
+    frexpf(m, &e);   // m = f * 2^e, f in [0.5, 1)  -> floor(log2 m) = e - 1
+    return ldexpf(1.f, 10 - e);
+}
+
+// hit |= (score > thr) << bit   -- two instructions (FSETP + predicated LOP3), no branch
+__device__ __forceinline__ void hit_if_gt(uint32_t vbits, float thr, uint32_t &hits, uint32_t bit) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.gt.f32 p, %1, %2;\n\t"
+        "@p or.b32 %0, %0, %3;\n\t"
+        "}"
+        : "+r"(hits)
+        : "f"(__uint_as_float(vbits)), "f"(thr), "r"(bit));
+}
+
+__device__ __forceinline__ float entry_score(uint64_t e) { return __uint_as_float((uint32_t)e); }
+
+}  // namespace igcn
