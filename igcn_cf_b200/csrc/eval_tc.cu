@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
 // eval_exact.cu), rank by (score desc, item asc), emit top-k, and verify that the k-th exact score
 // is strictly above every dropped item's upper bound.  Unverified users are appended to a list.
 __global__ void __launch_bounds__(256) tc_finalize_kernel(const float *__restrict__ rep, const int64_t *__restrict__ user_ids,
-                                                          int64_t n_eval, int64_t item_row0, int D, int n_splits, int list_cap,
+                                                          int64_t n_eval, int64_t item_row0, int D, int n_splits,
                                                           const int32_t *__restrict__ cand_items, const int32_t *__restrict__ cand_cnt,
                                                           const float *__restrict__ cand_thr, const uint32_t *__restrict__ maxabs_bits,
                                                           const float *__restrict__ center_sum, float inv_n,
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(256) tc_finalize_kernel(const float *__restric
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t b = (int64_t)blockIdx.x * 8 + wid;
     if (b >= n_eval) return;
-    const int cap = n_splits * list_cap;
+    const int cap = n_splits * TC_CAP;
     uint64_t *keys = fin_keys + (size_t)wid * cap;
     const int64_t u = user_ids[b];
     const float *urow = rep + u * D;
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(256) tc_finalize_kernel(const float *__restric
     for (int sp = 0; sp < n_splits; ++sp) {
         const int c = cand_cnt[b * n_splits + sp];
         thr_max = fmaxf(thr_max, cand_thr[b * n_splits + sp]);
-        const int32_t *src = cand_items + ((size_t)b * n_splits + sp) * list_cap;
+        const int32_t *src = cand_items + ((size_t)b * n_splits + sp) * TC_CAP;
         for (int e = lane; e < c; e += 32) {
             const int32_t item = src[e];
             const float *irow = rep + (item_row0 + item) * D;
@@ -480,33 +480,24 @@ __global__ void __launch_bounds__(256) tc_finalize_kernel(const float *__restric
 
 }  // namespace igcn
 
-#include "eval_tc_pair.cuh"
-
 using namespace igcn;
 
 static int tc_kcores(int D) { return ((D + 15) / 16) * 2 + 2; }
-// user_tiles = 1: score_tc_kernel (N = 256 item tiles, 96-slot lists); 2: score_tc3_kernel (N = 128, 56-slot lists)
-static int tc_item_tile(int user_tiles) { return user_tiles == 2 ? T3_BN : TC_BN; }
-static int tc_list_cap(int user_tiles) { return user_tiles == 2 ? T3_CAP : TC_CAP; }
-static int tc_max_k(int user_tiles) { return (user_tiles == 2 ? T3_KEEP : TC_KEEP) - 8; }
 
-extern "C" int igcn_tc_workspace(int64_t n_eval, int64_t n_items, int32_t D, int32_t n_splits, int32_t user_tiles,
-                                 int64_t *a_img_bytes, int64_t *b_img_bytes, int64_t *cand_slots) {
-    IGCN_CHECK_ARG(user_tiles == 1 || user_tiles == 2, "user_tiles must be 1 or 2");
+extern "C" int igcn_tc_workspace(int64_t n_eval, int64_t n_items, int32_t D, int32_t n_splits, int64_t *a_img_bytes,
+                                 int64_t *b_img_bytes, int64_t *cand_slots) {
     IGCN_CHECK_ARG(D > 0 && D <= 64 && !(D & 3), "tensor-core scoring supports D % 4 == 0, D <= 64");
     IGCN_CHECK_ARG(n_splits >= 1 && n_splits <= 8, "n_splits must be in [1, 8]");
     const int64_t kc = tc_kcores(D);
     *a_img_bytes = (n_eval + TC_BM - 1) / TC_BM * (TC_BM / 8) * kc * 128;
-    const int64_t bn = tc_item_tile(user_tiles);
-    *b_img_bytes = (n_items + bn - 1) / bn * (bn / 8) * kc * 128;
-    *cand_slots = n_eval * n_splits * tc_list_cap(user_tiles);
+    *b_img_bytes = (n_items + TC_BN - 1) / TC_BN * (TC_BN / 8) * kc * 128;
+    *cand_slots = n_eval * n_splits * TC_CAP;
     return 0;
 }
 
 extern "C" int igcn_tc_pack(const float *rep, int64_t n_rep_elems, const int64_t *user_ids, int64_t n_eval, int64_t item_row0,
-                            int64_t n_items, int32_t D, int32_t user_tiles, uint32_t *maxabs_bits, uint8_t *a_img, uint8_t *b_img,
-                            float *center_sum, float *center_scratch, void *stream) {
-    IGCN_CHECK_ARG(user_tiles == 1 || user_tiles == 2, "user_tiles must be 1 or 2");
+                            int64_t n_items, int32_t D, uint32_t *maxabs_bits, uint8_t *a_img, uint8_t *b_img, float *center_sum,
+                            float *center_scratch, void *stream) {
     IGCN_CHECK_ARG(rep && user_ids && maxabs_bits && a_img && b_img && center_sum && center_scratch, "null pointer");
     IGCN_CHECK_ARG(D > 0 && D <= 64 && !(D & 3), "tensor-core scoring supports D % 4 == 0, D <= 64");
     cudaStream_t st = as_stream(stream);
@@ -520,46 +511,27 @@ extern "C" int igcn_tc_pack(const float *rep, int64_t n_rep_elems, const int64_t
         tc_pack_kernel<<<(unsigned)((n_eval + 15) / 16), 256, 0, st>>>(rep, user_ids, 0, n_eval, D, TC_BM, kc, 1, maxabs_bits, center_sum,
                                                                        inv_n, a_img);
     if (n_items > 0)
-        tc_pack_kernel<<<(unsigned)((n_items + 15) / 16), 256, 0, st>>>(rep, nullptr, item_row0, n_items, D, tc_item_tile(user_tiles), kc, 0,
-                                                                        maxabs_bits, center_sum, inv_n, b_img);
+        tc_pack_kernel<<<(unsigned)((n_items + 15) / 16), 256, 0, st>>>(rep, nullptr, item_row0, n_items, D, TC_BN, kc, 0, maxabs_bits,
+                                                                        center_sum, inv_n, b_img);
     IGCN_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, int64_t n_eval, int64_t n_items, int32_t D,
-                                  int32_t n_splits, int32_t n_head, int32_t user_tiles, int64_t item_lo, int64_t item_hi, const uint32_t *banned_bits,
+                                  int32_t n_splits, int32_t n_head, int64_t item_lo, int64_t item_hi, const uint32_t *banned_bits,
                                   const int32_t *mask_tile_ptr, const uint16_t *mask_entries, int32_t *cand_items,
                                   int32_t *cand_cnt, float *cand_thr, float *dump, void *stream) {
     IGCN_CHECK_ARG(a_img && b_img && cand_items && cand_cnt && cand_thr, "null pointer");
     IGCN_CHECK_ARG(D > 0 && D <= 64 && !(D & 3), "tensor-core scoring supports D % 4 == 0, D <= 64");
     IGCN_CHECK_ARG(n_splits >= 1 && n_splits <= 8, "n_splits must be in [1, 8]");
     IGCN_CHECK_ARG(!mask_tile_ptr || mask_entries, "mask_tile_ptr without mask_entries");
-    IGCN_CHECK_ARG(user_tiles == 1 || (user_tiles == 2 && !dump), "user_tiles must be 1 or 2 (no dump with 2)");
     if (n_eval <= 0) return 0;
-    const int n_utiles_all = (int)((n_eval + TC_BM - 1) / TC_BM);
-    const int n_groups = (n_utiles_all + user_tiles - 1) / user_tiles;       // CTA groups: user tiles or pairs of them
-    IGCN_CHECK_ARG(n_head >= 0 && n_head <= n_groups, "n_head must be in [0, number of user-tile groups]");
-    const unsigned n_ctas = (unsigned)(n_head + (n_groups - n_head) * n_splits);
-    if (user_tiles == 2) {
-        Tc3Args p{};
-        p.a_img = a_img; p.b_img = b_img;
-        p.n_utiles = (int)((n_eval + TC_BM - 1) / TC_BM);
-        p.n_buckets = (int)((n_items + 255) / 256);
-        p.n_splits = n_splits; p.n_head = n_head; p.kcores = tc_kcores(D);
-        p.n_eval = n_eval; p.n_items = n_items; p.item_lo = item_lo; p.item_hi = item_hi;
-        p.banned = banned_bits; p.mask_tile_ptr = mask_tile_ptr; p.mask_entries = mask_entries;
-        p.cand_items = cand_items; p.cand_cnt = cand_cnt; p.cand_thr = cand_thr;
-        const size_t smem3 = (size_t)(2 * (TC_BM / 8) + T3_STAGES * (T3_BN / 8)) * p.kcores * 128 + (size_t)2 * TC_BM * (T3_CAP + 1) * 8 +
-                             (size_t)T3_ACC * TC_BM * 4 * 4 + (size_t)8 * 32 * T3_STAGE_W * 4 + sizeof(Tc3Smem) + 64;
-        cudaError_t e3 = cudaFuncSetAttribute(score_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-        if (e3 != cudaSuccess) { set_error("igcn_tc_candidates: %s", cudaGetErrorString(e3)); return (int)e3; }
-        score_tc3_kernel<<<n_ctas, T3_THREADS, smem3, as_stream(stream)>>>(p);
-        IGCN_CHECK_LAUNCH();
-        return 0;
-    }
+    const int n_utiles = (int)((n_eval + TC_BM - 1) / TC_BM);
+    IGCN_CHECK_ARG(n_head >= 0 && n_head <= n_utiles, "n_head must be in [0, number of user tiles]");
+    const unsigned n_ctas = (unsigned)(n_head + (n_utiles - n_head) * n_splits);
     TcArgs a{};
     a.a_img = a_img; a.b_img = b_img;
-    a.n_utiles = (int)((n_eval + TC_BM - 1) / TC_BM);
+    a.n_utiles = n_utiles;
     a.n_itiles = (int)((n_items + TC_BN - 1) / TC_BN);
     a.n_splits = n_splits; a.n_head = n_head; a.kcores = tc_kcores(D);
     a.n_eval = n_eval; a.n_items = n_items; a.item_lo = item_lo; a.item_hi = item_hi;
@@ -577,25 +549,23 @@ extern "C" int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, in
 }
 
 extern "C" int igcn_tc_finalize(const float *rep, const int64_t *user_ids, int64_t n_eval, int64_t item_row0, int32_t D,
-                                int32_t n_splits, int32_t user_tiles, const int32_t *cand_items, const int32_t *cand_cnt,
-                                const float *cand_thr, const uint32_t *maxabs_bits, const float *center_sum, int64_t n_items, int32_t k,
+                                int32_t n_splits, const int32_t *cand_items, const int32_t *cand_cnt, const float *cand_thr,
+                                const uint32_t *maxabs_bits, const float *center_sum, int64_t n_items, int32_t k,
                                 int32_t *out_items, float *out_scores, int32_t *fb_count, int64_t *fb_users, int32_t *fb_rows,
                                 void *stream) {
     IGCN_CHECK_ARG(rep && user_ids && cand_items && cand_cnt && cand_thr && maxabs_bits && center_sum && out_items && out_scores,
                    "null pointer");
     IGCN_CHECK_ARG(fb_count && fb_users && fb_rows, "null fallback buffers");
-    IGCN_CHECK_ARG(user_tiles == 1 || user_tiles == 2, "user_tiles must be 1 or 2");
-    IGCN_CHECK_ARG(k > 0 && k <= tc_max_k(user_tiles), "tensor-core path supports k <= 24 (k <= 20 with two user tiles per CTA)");
+    IGCN_CHECK_ARG(k > 0 && k <= TC_KEEP - 8, "tensor-core path supports k <= 24");
     if (n_eval <= 0) return 0;
     cudaStream_t st = as_stream(stream);
     cudaMemsetAsync(fb_count, 0, sizeof(int32_t), st);
-    const int list_cap = tc_list_cap(user_tiles);
-    const size_t smem = (size_t)8 * n_splits * list_cap * sizeof(uint64_t);
+    const size_t smem = (size_t)8 * n_splits * TC_CAP * sizeof(uint64_t);
     cudaError_t e = cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("igcn_tc_finalize: %s", cudaGetErrorString(e)); return (int)e; }
     const float inv_n = n_items > 0 ? 1.f / (float)n_items : 0.f;
-    tc_finalize_kernel<<<(unsigned)((n_eval + 7) / 8), 256, smem, st>>>(rep, user_ids, n_eval, item_row0, D, n_splits, list_cap,
-                                                                         cand_items, cand_cnt, cand_thr, maxabs_bits, center_sum, inv_n, k,
+    tc_finalize_kernel<<<(unsigned)((n_eval + 7) / 8), 256, smem, st>>>(rep, user_ids, n_eval, item_row0, D, n_splits, cand_items,
+                                                                         cand_cnt, cand_thr, maxabs_bits, center_sum, inv_n, k,
                                                                          out_items, out_scores, fb_count, fb_users, fb_rows);
     IGCN_CHECK_LAUNCH();
     return 0;

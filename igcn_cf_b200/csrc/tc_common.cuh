@@ -1,4 +1,4 @@
-// Device helpers shared by the tensor-core scoring kernels (eval_tc.cu, eval_tc3.cu): mbarrier / bulk-TMA /
+// Device helpers shared by the tensor-core scoring kernels (eval_tc.cu): mbarrier / bulk-TMA /
 // tcgen05 PTX wrappers, UMMA descriptors, order-preserving float keys.
 #pragma once
 #include <cuda_fp16.h>

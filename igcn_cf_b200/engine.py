@@ -633,8 +633,8 @@ class TcScorer:
 
     @staticmethod
     def pick_splits(n_groups, n_sm=148):
-        """Uniform item-range splits per CTA group (user tile or pair of them): enough CTAs (one per SM at a
-        time) for two waves when there are few groups, one split otherwise.  (Choosing uniform splits to fill
+        """Uniform item-range splits per user tile: enough CTAs (one per SM at a
+        time) for two waves when there are few user tiles, one split otherwise.  (Choosing uniform splits to fill
         whole waves of 148 was tried: a third candidate list per user cost more in the epilogue and in
         igcn_tc_finalize than the fuller last wave gained -- Gowalla-shaped 0.71 vs 0.68 ms.)"""
         return int(min(8, max(1, -(-2 * n_sm // max(1, int(n_groups))))))
@@ -642,9 +642,9 @@ class TcScorer:
     @classmethod
     def plan_ctas(cls, n_groups, n_sm=148):
         """(n_head, n_splits) of igcn_tc_candidates.  Every extra list costs a threshold warm-up in the epilogue, so
-        with at least one wave of groups only the TAIL (the groups left over after whole waves of n_sm CTAs) is
-        split, just enough to fill the last wave: 297 groups -> 296 unsplit + 1 group in 8 splits = 2 1/8 waves
-        instead of 3.  Fewer groups than SMs: uniform splits (pick_splits)."""
+        with at least one wave of user tiles only the TAIL (the tiles left over after whole waves of n_sm CTAs) is
+        split, just enough to fill the last wave: 297 tiles -> 296 unsplit + 1 tile in 8 splits = 2 1/8 waves
+        instead of 3.  Fewer user tiles than SMs: uniform splits (pick_splits)."""
         forced = int(os.environ.get('IGCN_TC_SPLITS', 0))
         if forced:
             return 0, forced
@@ -654,23 +654,12 @@ class TcScorer:
         splits = 1 if tail == 0 else int(min(8, n_sm // tail))
         return (n_groups, 1) if splits == 1 else (n_groups - tail, splits)
 
-    @staticmethod
-    def pick_user_tiles(n_utiles, k, dump=False):
-        """1 or 2 user tiles (128 users each) per CTA.  Two tiles share every item tile (half the item-image
-        traffic) but keep shorter lists (k <= 20); with few user tiles one per CTA fills the SMs better."""
-        if k > 20 or dump:
-            return 1
-        forced = os.environ.get('IGCN_TC_USER_TILES')
-        if forced:
-            return int(forced)
-        return 2 if n_utiles >= 296 else 1
-
-    def _workspace(self, n_eval, n_items, D, n_splits, user_tiles, k, device):
-        key = (n_eval, n_items, D, n_splits, user_tiles, k, str(device))
+    def _workspace(self, n_eval, n_items, D, n_splits, k, device):
+        key = (n_eval, n_items, D, n_splits, k, str(device))
         ws = self._ws.get(key)
         if ws is None:
             a_b, b_b, slots = C.c_int64(), C.c_int64(), C.c_int64()
-            call('igcn_tc_workspace', n_eval, n_items, D, n_splits, user_tiles, C.byref(a_b), C.byref(b_b), C.byref(slots))
+            call('igcn_tc_workspace', n_eval, n_items, D, n_splits, C.byref(a_b), C.byref(b_b), C.byref(slots))
             z = lambda n, dt: torch.zeros(n, dtype=dt, device=device)
             ws = {'a_img': z(a_b.value, torch.uint8), 'b_img': z(b_b.value, torch.uint8),
                   'cand_items': z(slots.value, torch.int32), 'cand_cnt': z(n_eval * n_splits, torch.int32),
@@ -682,18 +671,15 @@ class TcScorer:
         return ws
 
     def topk(self, rep, user_ids, n_users, n_items, k, mask=None, item_lo=0, item_hi=None, banned_bits=None,
-             users_host=None, n_splits=None, dump=False, user_tiles=None):
+             users_host=None, n_splits=None, dump=False):
         n_eval, D = int(user_ids.shape[0]), int(rep.shape[1])
         item_hi = n_items if item_hi is None else item_hi
-        n_utiles = (n_eval + 127) // 128
-        if user_tiles is None:
-            user_tiles = self.pick_user_tiles(n_utiles, k, dump)
         n_head = 0
         if n_splits is None:
-            n_head, n_splits = self.plan_ctas(-(-n_utiles // user_tiles))
-        ws = self._workspace(n_eval, n_items, D, n_splits, user_tiles, k, rep.device)
+            n_head, n_splits = self.plan_ctas((n_eval + 127) // 128)
+        ws = self._workspace(n_eval, n_items, D, n_splits, k, rep.device)
         st = stream_ptr
-        call('igcn_tc_pack', ptr(rep), rep.numel(), ptr(user_ids), n_eval, n_users, n_items, D, user_tiles, ptr(ws['maxabs']),
+        call('igcn_tc_pack', ptr(rep), rep.numel(), ptr(user_ids), n_eval, n_users, n_items, D, ptr(ws['maxabs']),
              ptr(ws['a_img']), ptr(ws['b_img']), ptr(ws['center']), ptr(ws['center_scratch']), st())
         tile_ptr, entries = (None, None)
         if mask is not None:
@@ -702,12 +688,12 @@ class TcScorer:
         if dump:
             dump_t = torch.zeros(((n_eval + 127) // 128 * 128, (n_items + 255) // 256 * 256), dtype=torch.float32,
                                  device=rep.device)
-        call('igcn_tc_candidates', ptr(ws['a_img']), ptr(ws['b_img']), n_eval, n_items, D, n_splits, n_head, user_tiles,
+        call('igcn_tc_candidates', ptr(ws['a_img']), ptr(ws['b_img']), n_eval, n_items, D, n_splits, n_head,
              int(item_lo), int(item_hi), ptr(banned_bits), ptr(tile_ptr), ptr(entries), ptr(ws['cand_items']), ptr(ws['cand_cnt']),
              ptr(ws['cand_thr']), ptr(dump_t), st())
         out_i = torch.empty((n_eval, k), dtype=torch.int32, device=rep.device)
         out_s = torch.empty((n_eval, k), dtype=torch.float32, device=rep.device)
-        call('igcn_tc_finalize', ptr(rep), ptr(user_ids), n_eval, n_users, D, n_splits, user_tiles, ptr(ws['cand_items']),
+        call('igcn_tc_finalize', ptr(rep), ptr(user_ids), n_eval, n_users, D, n_splits, ptr(ws['cand_items']),
              ptr(ws['cand_cnt']), ptr(ws['cand_thr']), ptr(ws['maxabs']), ptr(ws['center']), n_items, int(k), ptr(out_i), ptr(out_s),
              ptr(ws['fb_count']), ptr(ws['fb_users']), ptr(ws['fb_rows']), st())
         # users whose bound did not verify: exact kernel on the device-side list (no host sync)

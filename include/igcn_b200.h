@@ -251,27 +251,23 @@ int igcn_score_topk_exact(const float *rep, const int64_t *user_ids, int64_t n_e
  * a_img / b_img must be zero-initialised by the caller (padding rows); sizes from igcn_tc_workspace.
  * mask_tile_ptr [ceil(n_eval/128), ceil(n_items/256)+1] + mask_entries ((row<<8)|col, uint16) is the
  * seen-item CSR bucketed by (user tile, item tile); dump (tests only) receives every s_hat.
- * n_head: the first n_head CTA groups (user tiles, or pairs of them) scan all item tiles in one CTA and use
- * only list slot 0; the remaining groups are split n_splits ways -- the host sizes the split tail so that it
- * fills the last wave of SMs (0 = every group is split).
- * user_tiles (the same value in all four calls) picks the candidate kernel: 1 = one 128-user tile per CTA,
- * N256 item tiles, 96-slot lists, k <= 24; 2 = two user tiles per CTA sharing each N128 item tile (half the
- * item-image traffic), eight epilogue warps, 56-slot lists, k <= 20, no dump. */
+ * n_head: the first n_head user tiles scan all item tiles in one CTA and use only list slot 0; the remaining
+ * tiles are split n_splits ways -- the host sizes the split tail so that it fills the last wave of SMs
+ * (0 = every user tile is split). */
 int igcn_tc_workspace(int64_t n_eval, int64_t n_items, int32_t D, int32_t n_splits,
-                      int32_t user_tiles, int64_t *a_img_bytes, int64_t *b_img_bytes, int64_t *cand_slots);
+                      int64_t *a_img_bytes, int64_t *b_img_bytes, int64_t *cand_slots);
 int igcn_tc_pack(const float *rep, int64_t n_rep_elems, const int64_t *user_ids, int64_t n_eval,
-                 int64_t item_row0, int64_t n_items, int32_t D, int32_t user_tiles,
-                 uint32_t *maxabs_bits,
+                 int64_t item_row0, int64_t n_items, int32_t D, uint32_t *maxabs_bits,
                  uint8_t *a_img, uint8_t *b_img, float *center_sum, float *center_scratch,
                  void *stream);
 int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, int64_t n_eval, int64_t n_items,
-                       int32_t D, int32_t n_splits, int32_t n_head, int32_t user_tiles, int64_t item_lo,
+                       int32_t D, int32_t n_splits, int32_t n_head, int64_t item_lo,
                        int64_t item_hi,
                        const uint32_t *banned_bits, const int32_t *mask_tile_ptr,
                        const uint16_t *mask_entries, int32_t *cand_items, int32_t *cand_cnt,
                        float *cand_thr, float *dump, void *stream);
 int igcn_tc_finalize(const float *rep, const int64_t *user_ids, int64_t n_eval, int64_t item_row0,
-                     int32_t D, int32_t n_splits, int32_t user_tiles, const int32_t *cand_items,
+                     int32_t D, int32_t n_splits, const int32_t *cand_items,
                      const int32_t *cand_cnt, const float *cand_thr, const uint32_t *maxabs_bits,
                      const float *center_sum, int64_t n_items,
                      int32_t k, int32_t *out_items, float *out_scores, int32_t *fb_count,

@@ -113,19 +113,18 @@ def test_tc_large_dynamic_range():
     assert torch.equal(ex[0], tc[0]) and torch.equal(ex[1], tc[1])
 
 
-@pytest.mark.parametrize('user_tiles', [1, 2])
-def test_tc_split_tail_plan(user_tiles):
-    """More CTA groups than SMs: whole waves are left unsplit (list slot 0 only) and the tail is split to fill
-    the last wave -- both candidate kernels, same answer as the exact kernel."""
+@pytest.mark.parametrize('n_tiles', [150, 300])
+def test_tc_split_tail_plan(n_tiles):
+    """More user tiles than SMs: whole waves are left unsplit (list slot 0 only) and the tail is split to fill
+    the last wave; same answer as the exact kernel."""
     from igcn_cf_b200 import engine
-    n_users, n_items, D, k = 299 * 128 + 3, 700, 32, 20
+    n_users, n_items, D, k = (n_tiles - 1) * 128 + 3, 700, 32, 20
     rep, lists = _case(n_users, n_items, D, seed=11, mask_deg=3)
-    n_groups = -(-300 // user_tiles)
-    n_head, n_splits = engine.TcScorer.plan_ctas(n_groups)
-    assert 0 < n_head < n_groups and n_splits > 1 and n_head % 148 == 0
+    n_head, n_splits = engine.TcScorer.plan_ctas(n_tiles)
+    assert 0 < n_head < n_tiles and n_splits > 1 and n_head % 148 == 0
     mask = engine.lists_to_csr(lists, DEV)
     u = torch.arange(n_users, device=DEV)
     ex = engine.score_topk(rep, u, n_users, n_items, k, mask, impl='exact')
-    tc = engine.TcScorer().topk(rep, u, n_users, n_items, k, mask, user_tiles=user_tiles)
+    tc = engine.score_topk(rep, u, n_users, n_items, k, mask, impl='tc')
     torch.cuda.synchronize()
     assert torch.equal(ex[0], tc[0]) and torch.equal(ex[1], tc[1])

@@ -1,5 +1,5 @@
-"""Times the evaluation pass of a bench workload under several (user tiles per CTA, item splits) settings of the
-tensor-core scoring path:   python tools/time_eval.py [workload] [ut:splits ...]      (splits 0 = engine default)
+"""Times the evaluation pass of a bench workload under several item-split settings of the tensor-core scoring
+path:   python tools/time_eval.py [workload] [splits ...]      (0 = engine default plan, s > 0 = s uniform splits)
 Prints one line per setting: device ms per recommend pass (CUDA events), users sent to the exact kernel."""
 import os
 import sys
@@ -12,7 +12,7 @@ import bench  # noqa: E402
 
 def main():
     workload = sys.argv[1] if len(sys.argv) > 1 else 'yelp-lightgcn'
-    settings = sys.argv[2:] or ['1:0', '2:0']
+    settings = sys.argv[2:] or ['0', '1', '2']
     shape, kind, l2_reg, dropout = bench.WORKLOADS[workload]
     dev = torch.device('cuda:0')
     ds = bench.build_dataset(shape, dev)
@@ -20,9 +20,7 @@ def main():
     from igcn_cf_b200 import engine
     ref = None
     for s in settings:
-        ut, sp = s.split(':')
-        os.environ['IGCN_TC_USER_TILES'] = ut
-        os.environ['IGCN_TC_SPLITS'] = sp
+        os.environ['IGCN_TC_SPLITS'] = s
         for _ in range(3):
             model._bump()
             rec = trainer.recommend_local('val')
@@ -36,8 +34,8 @@ def main():
         torch.cuda.synchronize()
         same = True if ref is None else bool(torch.equal(ref, rec))
         ref = rec if ref is None else ref
-        print('%s user_tiles=%s splits=%s: %.3f ms/pass, fallback users %d, same lists as first setting: %s'
-              % (workload, ut, sp, e0.elapsed_time(e1) / reps, int(engine._tc_scorer.last_fallback.item()), same), flush=True)
+        print('%s splits=%s: %.3f ms/pass, fallback users %d, same lists as first setting: %s'
+              % (workload, s, e0.elapsed_time(e1) / reps, int(engine._tc_scorer.last_fallback.item()), same), flush=True)
 
 
 if __name__ == '__main__':
