@@ -109,7 +109,14 @@ struct TcArgs {
     int32_t *cand_cnt;                // [n_eval, n_splits]
     float *cand_thr;                  // [n_eval, n_splits]   (scaled units; -inf = nothing was dropped)
     float *dump;                      // optional [n_utiles*128, n_itiles*256] of s_hat (tests)
+    int dbg;                          // timing experiments (IGCN_TC_DEBUG): 1 producer/MMA threads spin instead of parking,
+                                      // 2 mask builder spins, 4 mask builder builds nothing (invalid results)
 };
+
+__device__ __forceinline__ void mbar_wait_helper(uint64_t *bar, uint32_t parity, bool spin) {
+    if (spin) mbar_wait(bar, parity);
+    else mbar_wait_parked(bar, parity);
+}
 
 struct TcSmem {
     uint64_t full[TC_STAGES], empty[TC_STAGES], a_full, tmem_full[2], tmem_empty[2], mask_full[2];
@@ -187,7 +194,9 @@ __device__ __forceinline__ void compact_lanes(uint64_t *mybuf, int &cnt, float &
 
 // VARIANT: 0 production, 1 = also dump every s_hat (tests), 2 / 3 = timing experiments selected with the
 // IGCN_TC_EXPERIMENT environment variable (results are NOT valid): 2 reads the accumulators but does not filter
-// (TMA + MMA + TMEM-read floor), 3 filters against thr = +inf (full filter cost, no hits, no compaction).
+// (TMA + MMA + TMEM-read floor), 3 filters against thr = +inf (full filter cost, no hits, no compaction),
+// 4 = as 2 but only the first TC_STAGES item tiles are fetched (no item-image stream), 5 = as 2 but the epilogue
+// does not read TMEM at all, 6 = 4 and 5 together (MMA issue + the mbarrier hand-offs only).
 template <int VARIANT>
 __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -240,7 +249,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             for (int it = 0; it < n_it; ++it) {
                 const int s = it % TC_STAGES;
                 const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
-                mbar_wait_parked(&sm->empty[s], ph ^ 1u);
+                mbar_wait_helper(&sm->empty[s], ph ^ 1u, a.dbg & 1);
+                if ((VARIANT == 4 || VARIANT == 6) && it >= TC_STAGES) {
+                    mbar_arrive(&sm->full[s]);
+                    continue;
+                }
                 mbar_arrive_expect_tx(&sm->full[s], b_bytes);
                 bulk_g2s(sB + (size_t)s * b_bytes, a.b_img + (size_t)(t0 + it) * b_bytes, b_bytes, &sm->full[s]);
             }
@@ -251,11 +264,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             const uint32_t idesc = umma_idesc_f16_m128(TC_BN);
             const uint32_t sbo = (uint32_t)a.kcores * 128, lbo = 128;
             const int ksteps = a.kcores / 2;
-            mbar_wait_parked(&sm->a_full, 0);
+            mbar_wait_helper(&sm->a_full, 0, a.dbg & 1);
             for (int it = 0; it < n_it; ++it) {
                 const int s = it % TC_STAGES, acc = it & 1;
-                mbar_wait_parked(&sm->tmem_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
-                mbar_wait_parked(&sm->full[s], (uint32_t)(it / TC_STAGES) & 1u);
+                mbar_wait_helper(&sm->tmem_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u, a.dbg & 1);
+                mbar_wait_helper(&sm->full[s], (uint32_t)(it / TC_STAGES) & 1u, a.dbg & 1);
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + (size_t)s * b_bytes);
                 for (int ks = 0; ks < ksteps; ++ks)
@@ -269,7 +282,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         // ===== mask helper: seen-item bucket + banned bitmap + item range -> bitmap[acc][8 words][128 rows]
         for (int it = 0; it < n_it; ++it) {
             const int acc = it & 1, t = t0 + it;
-            mbar_wait_parked(&sm->tmem_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+            mbar_wait_helper(&sm->tmem_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u, a.dbg & 2);
+            if (a.dbg & 4) {
+                if (lane == 0) mbar_arrive(&sm->mask_full[acc]);
+                continue;
+            }
             uint32_t *bm = bitmap + (size_t)acc * TC_BM * 8;
             uint32_t common = 0;
             if (lane < 8) {
@@ -314,6 +331,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             mbar_wait(&sm->tmem_full[acc], ph);
             mbar_wait(&sm->mask_full[acc], ph);
             tc_fence_after();
+            if (VARIANT == 5 || VARIANT == 6) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm->tmem_empty[acc]);
+                continue;
+            }
             uint32_t *bm = bitmap + (size_t)acc * TC_BM * 8 + row;          // word w of this row at bm[w * 128]
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_BN;
             uint32_t va[32], vb[32];
@@ -324,7 +347,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 const uint32_t m = bm[ch * TC_BM];
                 bm[ch * TC_BM] = 0u;
                 const uint32_t item0 = (uint32_t)(t * TC_BN + ch * 32);
-                if (VARIANT == 2) {
+                if (VARIANT == 2 || VARIANT == 4) {
                     uint32_t x = 0;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) x ^= v[c];
@@ -539,8 +562,13 @@ extern "C" int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, in
     a.cand_items = cand_items; a.cand_cnt = cand_cnt; a.cand_thr = cand_thr; a.dump = dump;
     const size_t smem = (size_t)(TC_BM / 8 + TC_STAGES * (TC_BN / 8)) * a.kcores * 128 + (size_t)TC_BM * (TC_CAP + 1) * 8 +
                         2 * TC_BM * 8 * 4 + (size_t)TC_BM * TC_STAGE_W * 4 + sizeof(TcSmem) + 64;
-    static const int experiment = getenv("IGCN_TC_EXPERIMENT") ? atoi(getenv("IGCN_TC_EXPERIMENT")) : 0;
-    auto kern = dump ? score_tc_kernel<1> : experiment == 2 ? score_tc_kernel<2> : experiment == 3 ? score_tc_kernel<3> : score_tc_kernel<0>;
+    const char *dbg_env = getenv("IGCN_TC_DEBUG");
+    a.dbg = dbg_env ? atoi(dbg_env) : 0;
+    const char *exp_env = getenv("IGCN_TC_EXPERIMENT");      // read per call: tools/tc_floor.py sweeps it in one process
+    const int experiment = exp_env ? atoi(exp_env) : 0;
+    auto kern = dump ? score_tc_kernel<1>
+                : experiment == 2 ? score_tc_kernel<2> : experiment == 3 ? score_tc_kernel<3> : experiment == 4 ? score_tc_kernel<4>
+                : experiment == 5 ? score_tc_kernel<5> : experiment == 6 ? score_tc_kernel<6> : score_tc_kernel<0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("igcn_tc_candidates: %s", cudaGetErrorString(e)); return (int)e; }
     kern<<<n_ctas, TC_THREADS, smem, as_stream(stream)>>>(a);
