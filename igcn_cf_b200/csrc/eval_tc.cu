@@ -144,7 +144,6 @@ __device__ __forceinline__ uint32_t warp_sort_desc(uint32_t x, int lane) {
 // lo with count(score >= lo) >= TC_KEEP (8 halvings: within a few entries of TC_KEEP); entries below
 // lo are dropped and lo becomes the row's threshold.  A row that cannot be shrunk (ties) gives up:
 // thr = +inf makes the finalize kernel route that user to the exact kernel.
-template <int GIVE_UP>
 __device__ __forceinline__ void compact_lanes(uint64_t *mybuf, int &cnt, float &thr) {
     const bool act = cnt > TC_KEEP + 8;
     const int n = act ? cnt : 0;
@@ -188,7 +187,7 @@ __device__ __forceinline__ void compact_lanes(uint64_t *mybuf, int &cnt, float &
             if (j + u < n && entry_score(e[u]) >= lo) mybuf[w++] = e[u];
     }
     if (act) {
-        if (w > GIVE_UP) { cnt = 0; thr = INFINITY; }       // flat scores: hand the user to the exact kernel
+        if (w > TC_CAP - 32) { cnt = 0; thr = INFINITY; }   // flat scores: hand the user to the exact kernel
         else { cnt = w; thr = lo; }
     }
 }
@@ -344,7 +343,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             tc_ld32(taddr, va);
             // two chunks per iteration so the next TMEM load is always in flight behind the filter
             auto filter = [&](uint32_t (&v)[32], int ch) {
-                if (__any_sync(0xffffffffu, cnt > TC_CAP - 32)) compact_lanes<TC_CAP - 32>(mybuf, cnt, thr);
+                if (__any_sync(0xffffffffu, cnt > TC_CAP - 32)) compact_lanes(mybuf, cnt, thr);
                 const uint32_t m = bm[ch * TC_BM];
                 bm[ch * TC_BM] = 0u;
                 const uint32_t item0 = (uint32_t)(t * TC_BN + ch * 32);
@@ -414,253 +413,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             if (head && lane > 0 && lane < a.n_splits) {          // the list slots an unsplit tile does not use
                 a.cand_cnt[b * a.n_splits + lane] = 0;
                 a.cand_thr[b * a.n_splits + lane] = -INFINITY;
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
-    }
-}
-
-
-// ------------------------------------------------------------------ candidate kernel, eight epilogue warps
-// score_tc_kernel is bound by its four epilogue warps (one per scheduler: every TMEM, shared-memory and
-// dependent-issue latency is exposed, tools/tc_floor.py).  Here TWO threads serve each user row -- warp 4 + q
-// filters columns 0..127 of every tile, warp 8 + q columns 128..255 -- and share ONE candidate list and ONE
-// threshold in shared memory: hits (about 1 % of the scores) are appended with a shared-memory atomic counter,
-// the threshold is read once per tile.  The pair meets once per tile through two named barriers used
-// asymmetrically (bar.arrive / bar.sync): the second thread announces that its appends are done, the first one
-// shrinks the list if fewer than 32 slots are free (same lane-parallel bisection as above) and releases the
-// second one with the new threshold.  The first T8_WARM tiles of a CTA, where almost every score is a hit, are
-// filtered by the first thread alone with the room check before every 32-column step.  A row whose list
-// overflows inside one tile (> 32 hits in 256 columns after the warm-up: structured input) is handed to the
-// exact kernel like a row of ties.  Lists hold 80 entries in shared memory (the staging area doubles); the
-// global list layout, the operand images and igcn_tc_finalize are unchanged.
-constexpr int T8_CAP = 80;
-constexpr int T8_LIMIT = T8_CAP - 32;
-constexpr int T8_WARM = 4;
-constexpr int T8_THREADS = 12 * 32;
-
-__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-__global__ void __launch_bounds__(T8_THREADS, 1) score_tc8_kernel(const __grid_constant__ TcArgs a) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const uint32_t a_bytes = (uint32_t)(TC_BM / 8) * a.kcores * 128;
-    const uint32_t b_bytes = (uint32_t)(TC_BN / 8) * a.kcores * 128;
-    uint8_t *sA = smem_raw;
-    uint8_t *sB = sA + a_bytes;
-    uint64_t *cand = reinterpret_cast<uint64_t *>(sB + (size_t)TC_STAGES * b_bytes);          // [128 rows][T8_CAP + 1]
-    uint32_t *bitmap = reinterpret_cast<uint32_t *>(cand + (size_t)TC_BM * (T8_CAP + 1));       // [2 acc][8 words][128 rows]
-    uint32_t *stage = bitmap + 2 * TC_BM * 8;                                                   // [256 threads][TC_STAGE_W]
-    int *row_cnt = reinterpret_cast<int *>(stage + 2 * TC_BM * TC_STAGE_W);                     // [128]
-    float *row_thr = reinterpret_cast<float *>(row_cnt + TC_BM);                                // [128]
-    TcSmem *sm = reinterpret_cast<TcSmem *>(row_thr + TC_BM);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool head = (int)blockIdx.x < a.n_head;
-    const int rest = (int)blockIdx.x - a.n_head;
-    const int ut = head ? (int)blockIdx.x : a.n_head + rest / a.n_splits;
-    const int sp = head ? 0 : rest % a.n_splits;
-    const int ns = head ? 1 : a.n_splits;
-    const int64_t hi_eff = min(a.item_hi, a.n_items);
-    const int t_first = (int)(max((int64_t)0, a.item_lo) / TC_BN);
-    const int t_last = (int)((hi_eff + TC_BN - 1) / TC_BN);                 // exclusive
-    const int n_t = max(0, t_last - t_first);
-    const int per = (n_t + ns - 1) / ns;
-    const int t0 = t_first + sp * per, t1 = min(t_last, t0 + per);
-    const int n_it = max(0, t1 - t0);
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
-        mbar_init(&sm->a_full, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm->tmem_full[i], 1); mbar_init(&sm->tmem_empty[i], 8); mbar_init(&sm->mask_full[i], 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = threadIdx.x; i < 2 * TC_BM * 8; i += T8_THREADS) bitmap[i] = 0u;
-    if (threadIdx.x < TC_BM) { row_cnt[threadIdx.x] = 0; row_thr[threadIdx.x] = -INFINITY; }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "n"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = sm->tmem_base;
-
-    if (warp == 0) {
-        // ===== bulk-TMA producer
-        if (lane == 0 && n_it > 0) {
-            mbar_arrive_expect_tx(&sm->a_full, a_bytes);
-            bulk_g2s(sA, a.a_img + (size_t)ut * a_bytes, a_bytes, &sm->a_full);
-            for (int it = 0; it < n_it; ++it) {
-                const int s = it % TC_STAGES;
-                mbar_wait_parked(&sm->empty[s], ((uint32_t)(it / TC_STAGES) & 1u) ^ 1u);
-                mbar_arrive_expect_tx(&sm->full[s], b_bytes);
-                bulk_g2s(sB + (size_t)s * b_bytes, a.b_img + (size_t)(t0 + it) * b_bytes, b_bytes, &sm->full[s]);
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer (one thread)
-        if (lane == 0 && n_it > 0) {
-            const uint32_t idesc = umma_idesc_f16_m128(TC_BN);
-            const uint32_t sbo = (uint32_t)a.kcores * 128, lbo = 128;
-            const int ksteps = a.kcores / 2;
-            mbar_wait_parked(&sm->a_full, 0);
-            for (int it = 0; it < n_it; ++it) {
-                const int s = it % TC_STAGES, acc = it & 1;
-                mbar_wait_parked(&sm->tmem_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
-                mbar_wait_parked(&sm->full[s], (uint32_t)(it / TC_STAGES) & 1u);
-                tc_fence_after();
-                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + (size_t)s * b_bytes);
-                for (int ks = 0; ks < ksteps; ++ks)
-                    tc_mma_f16(tmem_base + (uint32_t)acc * TC_BN, umma_desc(a0 + ks * 256, lbo, sbo), umma_desc(b0 + ks * 256, lbo, sbo),
-                               idesc, ks > 0 ? 1u : 0u);
-                tc_commit(&sm->empty[s]);
-                tc_commit(&sm->tmem_full[acc]);
-            }
-        }
-    } else if (warp == 2) {
-        // ===== mask builder (as in score_tc_kernel)
-        for (int it = 0; it < n_it; ++it) {
-            const int acc = it & 1, t = t0 + it;
-            mbar_wait_parked(&sm->tmem_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
-            uint32_t *bm = bitmap + (size_t)acc * TC_BM * 8;
-            uint32_t common = 0;
-            if (lane < 8) {
-                const int64_t c0 = (int64_t)t * TC_BN + lane * 32;
-                if (c0 < a.item_lo) common |= (a.item_lo - c0 >= 32) ? 0xffffffffu : ((1u << (a.item_lo - c0)) - 1u);
-                if (c0 + 32 > hi_eff) common |= (c0 >= hi_eff) ? 0xffffffffu : ~((1u << (hi_eff - c0)) - 1u);
-                if (a.banned && c0 < a.n_items) common |= __ldg(a.banned + (c0 >> 5));
-            }
-            if (__any_sync(0xffffffffu, common != 0u)) {
-                for (int w = 0; w < 8; ++w) {
-                    const uint32_t cw = __shfl_sync(0xffffffffu, common, w);
-                    if (cw)
-                        for (int r = lane; r < TC_BM; r += 32) bm[w * TC_BM + r] |= cw;
-                }
-                __syncwarp();
-            }
-            if (a.mask_tile_ptr) {
-                const int32_t *p = a.mask_tile_ptr + (size_t)ut * (a.n_itiles + 1) + t;
-                const int e0 = __ldg(p), e1 = __ldg(p + 1);
-                for (int e = e0 + lane; e < e1; e += 32) {
-                    const uint32_t ent = a.mask_entries[e];
-                    atomicOr(bm + ((ent & 255u) >> 5) * TC_BM + (ent >> 8), 1u << (ent & 31u));
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm->mask_full[acc]);
-        }
-    } else if (warp >= 4) {
-        // ===== epilogue: two threads per user row (TMEM lane), column halves g = 0 / 1
-        const int g = (warp - 4) >> 2, q = warp & 3;
-        const int row = q * 32 + lane;
-        uint64_t *mybuf = cand + (size_t)row * (T8_CAP + 1);
-        uint32_t *mystage = stage + ((size_t)(warp - 4) * 32 + lane) * TC_STAGE_W;
-        volatile int *cntp = row_cnt + row;
-        volatile float *thrp = row_thr + row;
-        const uint32_t bar_done = 1 + q, bar_go = 5 + q;      // named barriers of this pair of warps (64 threads)
-        auto shrink = [&]() {                                   // warp-collective; only ever called by the g == 0 warp
-            int cnt = *cntp;
-            float th = *thrp;
-            if (cnt > T8_CAP) { cnt = 0; th = INFINITY; }      // entries were lost: exact kernel
-            compact_lanes<T8_LIMIT>(mybuf, cnt, th);
-            *cntp = cnt;
-            *thrp = th;
-        };
-        for (int it = 0; it < n_it; ++it) {
-            const int acc = it & 1, t = t0 + it;
-            const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-            mbar_wait(&sm->tmem_full[acc], ph);
-            mbar_wait(&sm->mask_full[acc], ph);
-            tc_fence_after();
-            const bool warm = it < T8_WARM;
-            const int c_lo = warm ? 0 : g * 4, c_hi = warm ? (g == 0 ? 8 : 0) : g * 4 + 4;
-            uint32_t *bm = bitmap + (size_t)acc * TC_BM * 8 + row;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_BN;
-            float thr = *thrp;
-            uint32_t va[32], vb[32];
-            auto filter = [&](uint32_t (&v)[32], int ch) {
-                if (warm && __any_sync(0xffffffffu, *cntp > T8_LIMIT)) {
-                    shrink();
-                    thr = *thrp;
-                }
-                const uint32_t m = bm[ch * TC_BM];
-                bm[ch * TC_BM] = 0u;
-                const uint32_t item0 = (uint32_t)(t * TC_BN + ch * 32);
-#pragma unroll
-                for (int c = 0; c < 32; c += 4)
-                    *reinterpret_cast<uint4 *>(mystage + c) = make_uint4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-                uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    hit_if_gt(v[c], thr, h0, 1u << c);
-                    hit_if_gt(v[c + 8], thr, h1, 1u << (c + 8));
-                    hit_if_gt(v[c + 16], thr, h2, 1u << (c + 16));
-                    hit_if_gt(v[c + 24], thr, h3, 1u << (c + 24));
-                }
-                uint32_t hits = (h0 | h1 | h2 | h3) & ~m;
-                while (hits) {
-                    const int c0 = __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    const bool two = hits != 0u;
-                    const int c1 = two ? __ffs(hits) - 1 : c0;
-                    hits &= hits - 1;
-                    const uint32_t s0 = mystage[c0], s1 = mystage[c1];
-                    const int slot = atomicAdd(row_cnt + row, two ? 2 : 1);
-                    if (slot < T8_CAP) mybuf[slot] = ((uint64_t)(item0 + c0) << 32) | s0;
-                    if (two && slot + 1 < T8_CAP) mybuf[slot + 1] = ((uint64_t)(item0 + c1) << 32) | s1;
-                }
-            };
-            if (c_lo < c_hi) {
-                tc_ld32(taddr + c_lo * 32, va);
-#pragma unroll 1
-                for (int ch = c_lo; ch < c_hi; ch += 2) {
-                    tc_wait_ld();
-                    tc_ld32(taddr + (ch + 1) * 32, vb);
-                    filter(va, ch);
-                    tc_wait_ld();
-                    if (ch + 2 < c_hi) tc_ld32(taddr + (ch + 2) * 32, va);
-                    filter(vb, ch + 1);
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm->tmem_empty[acc]);
-            // pair hand-off: g = 1 announces its appends, g = 0 makes room and releases it with the new threshold
-            if (g == 1) {
-                __threadfence_block();
-                named_bar_arrive(bar_done, 64);
-                named_bar_sync(bar_go, 64);
-            } else {
-                named_bar_sync(bar_done, 64);
-                if (__any_sync(0xffffffffu, *cntp > T8_LIMIT)) shrink();
-                __threadfence_block();
-                named_bar_arrive(bar_go, 64);
-            }
-        }
-        if (g == 0) {
-            __syncwarp();
-            for (int r = 0; r < 32; ++r) {
-                const int64_t b = (int64_t)ut * TC_BM + q * 32 + r;
-                if (b >= a.n_eval) break;
-                const int n = row_cnt[q * 32 + r];
-                const float th = row_thr[q * 32 + r];
-                const uint64_t *src = cand + (size_t)(q * 32 + r) * (T8_CAP + 1);
-                int32_t *dst = a.cand_items + ((size_t)b * a.n_splits + sp) * TC_CAP;
-                for (int e = lane; e < n; e += 32) dst[e] = (int32_t)(uint32_t)(src[e] >> 32);
-                if (lane == 0) {
-                    a.cand_cnt[b * a.n_splits + sp] = n;
-                    a.cand_thr[b * a.n_splits + sp] = th;
-                }
-                if (head && lane > 0 && lane < a.n_splits) {
-                    a.cand_cnt[b * a.n_splits + lane] = 0;
-                    a.cand_thr[b * a.n_splits + lane] = -INFINITY;
-                }
             }
         }
     }
@@ -819,16 +571,6 @@ extern "C" int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, in
                 : experiment == 5 ? score_tc_kernel<5> : experiment == 6 ? score_tc_kernel<6> : score_tc_kernel<0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("igcn_tc_candidates: %s", cudaGetErrorString(e)); return (int)e; }
-    const char *epi_env = getenv("IGCN_TC_EPILOGUE");
-    if (!dump && experiment == 0 && epi_env && atoi(epi_env) == 8) {
-        const size_t smem8 = (size_t)(TC_BM / 8 + TC_STAGES * (TC_BN / 8)) * a.kcores * 128 + (size_t)TC_BM * (T8_CAP + 1) * 8 +
-                             2 * TC_BM * 8 * 4 + (size_t)2 * TC_BM * TC_STAGE_W * 4 + (size_t)TC_BM * 8 + sizeof(TcSmem);
-        cudaError_t e8 = cudaFuncSetAttribute(score_tc8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
-        if (e8 != cudaSuccess) { set_error("igcn_tc_candidates: %s (%zu bytes of shared memory)", cudaGetErrorString(e8), smem8); return (int)e8; }
-        score_tc8_kernel<<<n_ctas, T8_THREADS, smem8, as_stream(stream)>>>(a);
-        IGCN_CHECK_LAUNCH();
-        return 0;
-    }
     kern<<<n_ctas, TC_THREADS, smem, as_stream(stream)>>>(a);
     IGCN_CHECK_LAUNCH();
     return 0;

@@ -2,7 +2,7 @@
 variant (eval_tc.cu: 0 production, 2 no filter, 3 filter without hits, 4 no item-image stream, 5 no TMEM reads,
 6 neither) and prints the CUDA-event time of the candidates launch alone.  Variants other than 0 produce invalid
 lists, so only igcn_tc_pack + igcn_tc_candidates are called here.
-IGCN_TC_DEBUG flags (TcArgs.dbg) and IGCN_TC_EPILOGUE (8 = score_tc8_kernel) can be appended: variant:flags:8.
+IGCN_TC_DEBUG flags (TcArgs.dbg) can be appended as variant:flags.
     python tools/tc_floor.py [workload] [variant[:flags] ...]"""
 import os
 import sys
@@ -33,8 +33,7 @@ def main():
          ptr(ws['a_img']), ptr(ws['b_img']), ptr(ws['center']), ptr(ws['center_scratch']), stream_ptr())
     tile_ptr, entries = mask.tiles(n_items, None)
     for v in variants:
-        f = v.split(':') + ['0', '0']          # variant[:debug flags[:epilogue warps]]
-        os.environ['IGCN_TC_EXPERIMENT'], os.environ['IGCN_TC_DEBUG'], os.environ['IGCN_TC_EPILOGUE'] = f[:3]
+        os.environ['IGCN_TC_EXPERIMENT'], os.environ['IGCN_TC_DEBUG'] = (v.split(':') + ['0'])[:2]
         def launch():
             call('igcn_tc_candidates', ptr(ws['a_img']), ptr(ws['b_img']), n_users, n_items, D, n_splits, n_head, 0, n_items,
                  None, ptr(tile_ptr), ptr(entries), ptr(ws['cand_items']), ptr(ws['cand_cnt']), ptr(ws['cand_thr']), None,
