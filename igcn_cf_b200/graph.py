@@ -76,12 +76,12 @@ class CsrDevice:
         self.rowptr_host = np.ascontiguousarray(rowptr, dtype=np.int64)
         self.rowptr = torch.from_numpy(self.rowptr_host).to(self.device)
         if torch.is_tensor(col):
-            self.col_host = None
+            self._col_host = None
             self.col = col.to(device=self.device, dtype=torch.int32).contiguous()
             self.val = None if val is None else val.to(device=self.device, dtype=torch.float32).contiguous()
         else:
-            self.col_host = np.ascontiguousarray(col, dtype=np.int32)
-            self.col = torch.from_numpy(self.col_host).to(self.device)
+            self._col_host = np.ascontiguousarray(col, dtype=np.int32)
+            self.col = torch.from_numpy(self._col_host).to(self.device)
             self.val = None if val is None else torch.from_numpy(np.ascontiguousarray(val, dtype=np.float32)).to(self.device)
         self.threshold = int(threshold)
         plan = chunk_plan(self.rowptr_host, threshold, chunk)
@@ -95,6 +95,13 @@ class CsrDevice:
         self.n_medium = max(0, int((deg > MEDIUM_NNZ).sum()) - self.n_long)
         self._partial = {}
         self._structs = {}
+
+    @property
+    def col_host(self):
+        """Host copy of the column indices (fetched once from the device for CSRs that were built there)."""
+        if self._col_host is None:
+            self._col_host = self.col.cpu().numpy()
+        return self._col_host
 
     def with_values(self, val):
         """Same pattern/plan, different (or no) value array; shares index memory."""
@@ -199,11 +206,55 @@ class DeviceGraph:
     first.  Produced by igcn_cf_b200.synth.gen_device for graphs too large to pass through Python lists
     (BASELINE.json config 5: 10 M users, 1 M items, 500 M interactions)."""
 
-    def __init__(self, n_users, n_items, rowptr, col):
+    def __init__(self, n_users, n_items, rowptr, col, mult=None):
         self.n_users, self.n_items = int(n_users), int(n_items)
         self.rowptr, self.col = rowptr, col
+        self.mult = mult                      # fp32 [nnz] multiplicity of duplicated interactions, None = all 1
         self.rowptr_host = rowptr.cpu().numpy()
         self.device = col.device
+        self._rows = None
+
+    @classmethod
+    def from_pairs(cls, n_users, n_items, pairs, device):
+        """Edge list -> symmetric CSR on the device (replaces the scipy build of
+        utils.py:41-49 / model.py:85-94 on the inductive-update path): [E, 2] (user, item) pairs, duplicates
+        counted like scipy's sum_duplicates.  Two sorts, two histograms and one scan; the only host traffic is
+        the upload of the pairs and the read-back of rowptr for the row plan."""
+        n_users, n_items = int(n_users), int(n_items)
+        p = torch.as_tensor(np.ascontiguousarray(pairs, dtype=np.int64) if not torch.is_tensor(pairs) else pairs)
+        p = p.to(device=device, dtype=torch.int64).reshape(-1, 2)
+        key = torch.sort(p[:, 0] * n_items + p[:, 1])[0]                 # (user, item) order = user rows of the CSR
+        key, cnt = torch.unique_consecutive(key, return_counts=True)
+        u = torch.div(key, n_items, rounding_mode='floor')
+        i = key - u * n_items
+        key2, perm = torch.sort(i * n_users + u)                         # (item, user) order = item rows
+        i2 = torch.div(key2, n_users, rounding_mode='floor')
+        u2 = key2 - i2 * n_users
+        n = n_users + n_items
+        rowptr = torch.zeros(n + 1, dtype=torch.int64, device=p.device)
+        torch.cumsum(torch.cat([torch.bincount(u, minlength=n_users), torch.bincount(i2, minlength=n_items)]), 0, out=rowptr[1:])
+        col = torch.cat([i + n_users, u2]).to(torch.int32)
+        mult = None
+        if key.shape[0] != p.shape[0]:                                   # some pair occurs more than once
+            mult = torch.cat([cnt, cnt[perm]]).to(torch.float32)
+        return cls(n_users, n_items, rowptr, col, mult)
+
+    def rows(self):
+        """Row id of every non-zero (int64 [nnz], cached)."""
+        if self._rows is None:
+            n = self.n_users + self.n_items
+            self._rows = torch.repeat_interleave(torch.arange(n, device=self.device), self.rowptr[1:] - self.rowptr[:-1])
+        return self._rows
+
+    def degrees_host(self):
+        """fp32 row sums of the adjacency (duplicates counted) as a host array: np.diff(rowptr) without
+        duplicates.  d^-1/2 is taken on the host with numpy like the reference does (utils.py:44-46) so that
+        the values are bit-identical to the host-built graph whatever the GPU's pow rounds to."""
+        if self.mult is None:
+            return np.diff(self.rowptr_host).astype(np.float32)
+        n = self.n_users + self.n_items
+        deg = torch.zeros(n, dtype=torch.float64, device=self.device).index_add_(0, self.rows(), self.mult.double())
+        return deg.cpu().numpy().astype(np.float32)
 
     @property
     def n_interactions(self):
@@ -228,20 +279,46 @@ class NormAdj(_SparseView, _Blocked):
         self.rowptr_full = dg.rowptr_host
         self.col_full = self.val_full = self.multiplicity_host = None
         self.nnz = int(self.rowptr_full[-1])
-        deg = (dg.rowptr[1:] - dg.rowptr[:-1]).clamp_(min=1).to(torch.float32)
-        d_inv = torch.pow(deg, -0.5)
+        self._dg = dg
+        deg = np.maximum(np.float32(1.), dg.degrees_host())
+        d_inv = torch.from_numpy(np.power(deg, np.float32(-0.5)).astype(np.float32)).to(dg.device)
         blocks = []
         for row0, row1 in _row_ranges(self.rowptr_full, dg.n_users, shard):
             rp, col, lo, hi = dg.block(row0, row1)
             rows = torch.repeat_interleave(torch.arange(row0, row1, device=dg.device),
                                            dg.rowptr[row0 + 1:row1 + 1] - dg.rowptr[row0:row1])
-            val = d_inv[rows] * d_inv[col.long()]
-            del rows
+            # same rounding sequence as d_mat.dot(adj).dot(d_mat) in fp32: (d_r * a) * d_c
+            left = d_inv[rows] if dg.mult is None else d_inv[rows] * dg.mult[lo:hi]
+            val = left * d_inv[col.long()]
+            del rows, left
             blocks.append(RowBlock(row0, row1, CsrDevice(rp, col, val, n, dg.device)))
         self._set_blocks(blocks)
         self._coo_cache = None
         self._sampler = (dg.rowptr[:dg.n_users + 1], dg.col[:dg.n_interactions])
         return self
+
+    # host copies of a device-built graph, fetched on first use (compat views, tools)
+    @property
+    def col_full(self):
+        if self._col_full is None and getattr(self, '_dg', None) is not None:
+            self._col_full = self._dg.col.cpu().numpy()
+        return self._col_full
+
+    @col_full.setter
+    def col_full(self, v):
+        self._col_full = v
+
+    @property
+    def val_full(self):
+        if self._val_full is None and getattr(self, '_dg', None) is not None:
+            if len(self.blocks) != 1:
+                raise RuntimeError('val_full of a row-sharded device-built graph is not available')
+            self._val_full = self.csr.val.cpu().numpy()
+        return self._val_full
+
+    @val_full.setter
+    def val_full(self, v):
+        self._val_full = v
 
     def __init__(self, n_users, n_items, pairs, device, shard=None):
         adj = build_adjacency(n_users, n_items, pairs)
@@ -292,16 +369,26 @@ class TemplateFeat(_SparseView, _Blocked):
     row_sum[N], rowscale[N]."""
 
     @classmethod
-    def from_device(cls, dg, adj=None, shard=None):
-        """feature_ratio == 1 template structure of a DeviceGraph (identity template map); shares the index
-        arrays of `adj` (a NormAdj built from the same graph and shard) when given."""
+    def from_device(cls, dg, adj=None, shard=None, user_tmpl=None, item_tmpl=None, t_users=None, t_items=None):
+        """Template structure of a DeviceGraph; shares the index arrays of `adj` (a NormAdj built from the same
+        graph and shard) when given.  user_tmpl / item_tmpl: host int arrays, template id of every user / item
+        or -1 (model.py:392-412 as arrays); None = every node is its own template (feature_ratio == 1).  The
+        membership count behind row_sum (model.py:419) is one gather + one segmented integer sum on the device."""
         self = object.__new__(cls)
         n = dg.n_users + dg.n_items
         self.n_users, self.n_items = dg.n_users, dg.n_items
+        self._dg = dg
+        self.rowptr_full, self.col_full = dg.rowptr_host, None
+        if user_tmpl is not None:
+            self.t_users, self.t_items = int(t_users), int(t_items)
+            tmpl = np.concatenate([user_tmpl, np.where(item_tmpl >= 0, item_tmpl + self.t_users, -1)]).astype(np.int32)
+            identity = (self.t_users == dg.n_users and self.t_items == dg.n_items
+                        and np.array_equal(tmpl, np.arange(n, dtype=np.int32)))
+            if not identity:
+                return self._finish_partial(dg, tmpl, shard, adj)
         self.t_users, self.t_items = dg.n_users, dg.n_items
         self.shape = torch.Size([n, n + 2])
-        self.tmpl_host = None
-        self.rowptr_full, self.col_full = dg.rowptr_host, None
+        self.tmpl_host = None if user_tmpl is None else tmpl
         ranges = _row_ranges(self.rowptr_full, dg.n_users, shard)
         if adj is not None and list(adj.block_key()) == ranges:
             blocks = [RowBlock(b.row0, b.row1, b.csr.with_values(None)) for b in adj.blocks]
@@ -310,11 +397,56 @@ class TemplateFeat(_SparseView, _Blocked):
                       for r0, r1 in ranges]
         self._set_blocks(blocks)
         self.tmpl = None
-        self.row_sum = (dg.rowptr[1:] - dg.rowptr[:-1]).to(torch.float32) + 1.0
+        self.row_sum = torch.from_numpy(dg.degrees_host() + np.float32(1.)).to(self.device)
         self.rowscale = torch.ones(n, dtype=torch.float32, device=self.device)
         self.glob_user, self.glob_item = n, n + 1
         self._order = self._tperm = None
         return self
+
+    def _finish_partial(self, dg, tmpl, shard, adj):
+        """from_device when some node is not a template: keep the whole adjacency pattern, tmpl[] filters."""
+        n = dg.n_users + dg.n_items
+        self.shape = torch.Size([n, self.t_users + self.t_items + 2])
+        self.tmpl_host = tmpl
+        ranges = _row_ranges(self.rowptr_full, dg.n_users, shard)
+        if adj is not None and list(adj.block_key()) == ranges:
+            blocks = [RowBlock(b.row0, b.row1, b.csr.with_values(None)) for b in adj.blocks]
+        else:
+            blocks = [RowBlock(r0, r1, CsrDevice(dg.block(r0, r1)[0], dg.block(r0, r1)[1], None, n, dg.device))
+                      for r0, r1 in ranges]
+        self._set_blocks(blocks)
+        self.tmpl = torch.from_numpy(tmpl).to(self.device)
+        member = (self.tmpl[dg.col.long()] >= 0).to(torch.float64)
+        if dg.mult is not None:
+            member = member * dg.mult.double()
+        row_sum = torch.zeros(n, dtype=torch.float64, device=self.device).index_add_(0, dg.rows(), member)
+        self.row_sum = row_sum.to(torch.float32) + 1.0
+        self.rowscale = torch.ones(n, dtype=torch.float32, device=self.device)
+        self.glob_user = self.t_users + self.t_items
+        self.glob_item = self.t_users + self.t_items + 1
+        self._order = self._tperm = None
+        return self
+
+    @property
+    def col_full(self):
+        if self._col_full is None and getattr(self, '_dg', None) is not None:
+            self._col_full = self._dg.col.cpu().numpy()
+        return self._col_full
+
+    @col_full.setter
+    def col_full(self, v):
+        self._col_full = v
+
+    @property
+    def tmpl_host(self):
+        """Template id of every node on the host (the identity when every node is a template)."""
+        if self._tmpl_host is None:
+            self._tmpl_host = np.arange(self.n_users + self.n_items, dtype=np.int32)
+        return self._tmpl_host
+
+    @tmpl_host.setter
+    def tmpl_host(self, v):
+        self._tmpl_host = v
 
     def __init__(self, n_users, n_items, pairs, user_tmpl, item_tmpl, t_users, t_items, device, shard=None):
         adj = build_adjacency(n_users, n_items, pairs)

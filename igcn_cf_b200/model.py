@@ -102,6 +102,25 @@ class _GraphModel(BasicModel):
     def _shard_arg(self, dataset=None):
         return (self._peers.rank, self._peers.world) if self._rows_sharded(dataset) else None
 
+    _dg_cache = None
+
+    def _device_graph_of(self, dataset):
+        """The train graph of `dataset` as a graph.DeviceGraph: the dataset's own (scale-out datasets), or the CSR
+        built ON THE DEVICE from its train pairs (graph.DeviceGraph.from_pairs; SURVEY.md 8f rank 1 -- the
+        inductive update of run/dropui rebuilds graph and templates in milliseconds instead of a scipy pass
+        each).  generate_graph and generate_feat of the same dataset share one build.  model_config
+        'graph_builder': 'host' selects the numpy/scipy constructors instead (bit-identical structures)."""
+        dg = getattr(dataset, 'device_graph', None)
+        if dg is not None:
+            return dg
+        if self.config.get('graph_builder', 'device') == 'host':
+            return None
+        pairs = graph.train_pairs_of(dataset)
+        key = (id(dataset), id(pairs), len(pairs), dataset.n_users, dataset.n_items)
+        if self._dg_cache is None or self._dg_cache[0] != key:
+            self._dg_cache = (key, graph.DeviceGraph.from_pairs(dataset.n_users, dataset.n_items, pairs, self.device))
+        return self._dg_cache[1]
+
     def _propagator(self):
         n = self.n_users + self.n_items
         block = self.norm_adj.block_key()
@@ -174,7 +193,7 @@ class LightGCN(_GraphModel):
 
     def generate_graph(self, dataset):
         """D^-1/2 A D^-1/2 as a device CSR (model.py:85-94)."""
-        dg = getattr(dataset, 'device_graph', None)
+        dg = self._device_graph_of(dataset)
         if dg is not None:
             return graph.NormAdj.from_device(dg, shard=self._shard_arg(dataset))
         return graph.NormAdj(dataset.n_users, dataset.n_items, graph.train_pairs_of(dataset), self.device,
@@ -320,6 +339,7 @@ class IGCN(_GraphModel):
             feat = graph.TemplateFeat.from_device(dg, adj=adj, shard=self._shard_arg(dataset))
             self._aux = None
             return feat, IdentityMap(dg.n_users), IdentityMap(dg.n_items), feat.row_sum
+        dg = self._device_graph_of(dataset)
         if not is_updating:
             if self.feature_ratio < 1.:
                 ranked_users, ranked_items = graph_rank_nodes(dataset, ranking_metric)
@@ -333,8 +353,15 @@ class IGCN(_GraphModel):
         else:
             user_map, item_map = self.user_map, self.item_map
         ut, it = self._maps_to_arrays(user_map, item_map)
-        feat = graph.TemplateFeat(self.n_users, self.n_items, graph.train_pairs_of(dataset), ut, it,
-                                  len(user_map), len(item_map), self.device, shard=self._shard_arg(dataset))
+        if dg is not None:
+            adj = getattr(self, 'norm_adj', None)
+            if adj is None or getattr(adj, '_dg', None) is not dg:
+                adj = None                         # only a NormAdj of the same build shares its index arrays
+            feat = graph.TemplateFeat.from_device(dg, adj=adj, shard=self._shard_arg(dataset), user_tmpl=ut, item_tmpl=it,
+                                                  t_users=len(user_map), t_items=len(item_map))
+        else:
+            feat = graph.TemplateFeat(self.n_users, self.n_items, graph.train_pairs_of(dataset), ut, it,
+                                      len(user_map), len(item_map), self.device, shard=self._shard_arg(dataset))
         self._aux = None
         return feat, user_map, item_map, feat.row_sum
 

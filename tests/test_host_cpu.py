@@ -132,3 +132,45 @@ def test_chunk_plan_covers_long_rows():
     assert length.tolist() == [256, 256, 256, 232, 256, 256, 78]
     assert first.tolist() == [0, 0, 0, 0, 4, 4, 4] and count.tolist() == [4, 4, 4, 4, 3, 3, 3]
     assert graph.chunk_plan(np.array([0, 5, 9], dtype=np.int64))[0].size == 0
+
+
+@pytest.mark.parametrize('dups', [False, True])
+def test_device_graph_builder_matches_scipy_builder(dups):
+    """the edge list -> CSR / values / template row sums built with device ops
+    (DeviceGraph.from_pairs + from_device; torch ops, so they also run on the CPU here) are bit-identical to
+    the numpy/scipy constructors that restate utils.py:41-49 and model.py:386-421 -- including duplicated
+    interactions, isolated nodes and partial template sets."""
+    rng = np.random.default_rng(7)
+    n_users, n_items = 90, 70
+    pairs = np.stack([rng.integers(0, n_users - 5, 900), rng.integers(3, n_items, 900)], axis=1).astype(np.int64)
+    if not dups:
+        pairs = np.unique(pairs, axis=0)
+        pairs = pairs[rng.permutation(len(pairs))]
+    dev = torch.device('cpu')
+    dg = graph.DeviceGraph.from_pairs(n_users, n_items, pairs, dev)
+    assert (dg.mult is not None) == dups
+    host = graph.NormAdj(n_users, n_items, pairs, dev)
+    devb = graph.NormAdj.from_device(dg)
+    assert np.array_equal(host.rowptr_full, devb.rowptr_full)
+    assert np.array_equal(host.col_full, devb.col_full) and np.array_equal(host.csr.col_host, devb.csr.col_host)
+    assert np.array_equal(host.val_full, devb.val_full)                    # bit-identical, not allclose
+    assert torch.equal(host.indices(), devb.indices()) and torch.equal(host.values(), devb.values())
+    sr, sc = devb.sampler_csr()
+    assert np.array_equal(sr.numpy(), host.rowptr_full[:n_users + 1]) and np.array_equal(sc.numpy(), host.col_full[:sr[-1]])
+    # templates: identity, and a partial set (every third user / the first 50 items)
+    ut = np.where(np.arange(n_users) % 3 == 0, np.arange(n_users) // 3, -1)
+    it = np.where(np.arange(n_items) < 50, np.arange(n_items), -1)
+    cases = [(np.arange(n_users), np.arange(n_items), n_users, n_items), (ut, it, int((ut >= 0).sum()), 50)]
+    for u_t, i_t, tu, ti in cases:
+        fh = graph.TemplateFeat(n_users, n_items, pairs, u_t, i_t, tu, ti, dev)
+        fd = graph.TemplateFeat.from_device(dg, adj=devb, user_tmpl=u_t, item_tmpl=i_t, t_users=tu, t_items=ti)
+        assert fh.shape == fd.shape and (fh.tmpl is None) == (fd.tmpl is None)
+        assert fh.tmpl is None or torch.equal(fh.tmpl, fd.tmpl)
+        assert torch.equal(fh.row_sum, fd.row_sum)
+        assert (fh.glob_user, fh.glob_item) == (fd.glob_user, fd.glob_item)
+        fh.set_alpha(0.7)
+        fd.set_alpha(0.7)
+        assert torch.equal(fh.indices(), fd.indices()) and torch.equal(fh.values(), fd.values())
+        assert torch.equal(fh.tperm(), fd.tperm())
+    fi = graph.TemplateFeat.from_device(dg, adj=devb)                      # feature_ratio == 1 shortcut
+    assert fi.tmpl is None and torch.equal(fi.row_sum, graph.TemplateFeat(n_users, n_items, pairs, *cases[0], dev).row_sum)
