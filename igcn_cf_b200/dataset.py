@@ -49,12 +49,26 @@ class BasicDataset(Dataset):
         self.train_data = None
         self.val_data = None
         self.test_data = None
-        self.train_array = None
+        self._train_array = None
         self.train_pairs = None
         print('init dataset ' + dataset_config['name'])
 
+    @property
+    def train_array(self):
+        """[[user, item], ...] (dataset.py:150-152).  Nothing in this package reads it (the kernels take
+        `train_pairs`), so the E two-element Python lists are only materialised when a caller asks for them."""
+        if self._train_array is None and self.train_pairs is not None:
+            self._train_array = self.train_pairs.tolist()
+        return self._train_array
+
+    @train_array.setter
+    def train_array(self, value):
+        self._train_array = value
+        if value is not None:
+            self.train_pairs = None            # an array assigned from outside wins (graph.train_pairs_of re-derives)
+
     def __len__(self):
-        return len(self.train_array)
+        return len(self.train_pairs) if self.train_pairs is not None else len(self.train_array)
 
     def __getitem__(self, index):
         """Host triple sampler, same draw sequence as dataset.py:119-131 (the index is ignored).
@@ -85,18 +99,22 @@ class BasicDataset(Dataset):
         cache = self.__dict__.setdefault('_csr_cache', {})
         hit = cache.get(which)
         if hit is None or hit[0] is not lists or hit[1] != len(lists):
-            from .engine import lists_to_arrays
-            hit = (lists, len(lists), lists_to_arrays(lists))
+            parsed = self.__dict__.get('_parsed', {}).get(id(lists))
+            if parsed is not None and parsed[0] is lists and sum(map(len, lists)) == len(parsed[2]):
+                arrays = (parsed[1], parsed[2])                    # what the file parser already produced
+            else:
+                from .engine import lists_to_arrays
+                arrays = lists_to_arrays(lists)
+            hit = (lists, len(lists), arrays)
             cache[which] = hit
         return hit[2]
 
     def _finish(self):
         """train_array / train_pairs from train_data (dataset.py:150-152)."""
-        lens = np.fromiter((len(x) for x in self.train_data), dtype=np.int64, count=len(self.train_data))
-        users = np.repeat(np.arange(len(self.train_data), dtype=np.int64), lens)
-        items = np.fromiter((i for x in self.train_data for i in x), dtype=np.int64, count=int(lens.sum()))
+        ptr, items = self.csr('train')
+        users = np.repeat(np.arange(len(self.train_data), dtype=np.int64), np.diff(ptr))
+        self._train_array = None
         self.train_pairs = np.stack([users, items], axis=1) if len(users) else np.zeros((0, 2), dtype=np.int64)
-        self.train_array = self.train_pairs.tolist()
 
 
 class ProcessedDataset(BasicDataset):
@@ -113,14 +131,37 @@ class ProcessedDataset(BasicDataset):
         self._finish()
 
     def read_data(self, file_path):
-        data = []
-        with open(file_path, 'r') as f:
-            lines = f.read().strip().split('\n')
-        for line in lines:
-            items = [int(tok) for tok in line.split(' ')[1:]]
-            if items:
-                self.n_items = max(self.n_items, max(items) + 1)
-            data.append(items)
+        """One line per user, "<user> <item> <item> ..." (dataset.py:154-164).  The whole file is tokenised by
+        numpy in one call and cut into rows with the per-line token counts; the CSR arrays
+        are kept for `csr()` so the trainers never walk the lists again.  Files that are not plain
+        single-space separated integers go through the reference's per-token Python loop."""
+        with open(file_path, 'rb') as f:
+            raw = f.read().strip()
+        lines = raw.split(b'\n') if raw else []
+        try:
+            counts = np.fromiter((ln.count(b' ') for ln in lines), dtype=np.int64, count=len(lines))
+            tokens = np.fromstring(raw.decode('ascii'), dtype=np.int64, sep=' ') if raw else np.zeros(0, dtype=np.int64)
+            if tokens.size != int(counts.sum()) + len(lines):
+                raise ValueError('irregular separators')
+        except (ValueError, UnicodeDecodeError, DeprecationWarning):
+            data = []
+            for line in raw.decode().split('\n') if raw else []:
+                items = [int(tok) for tok in line.split(' ')[1:]]
+                if items:
+                    self.n_items = max(self.n_items, max(items) + 1)
+                data.append(items)
+            return data
+        ptr = np.zeros(len(lines) + 1, dtype=np.int64)
+        np.cumsum(counts, out=ptr[1:])
+        keep = np.ones(tokens.size, dtype=bool)
+        keep[ptr[:-1] + np.arange(len(lines))] = False            # the leading user id of every line
+        items = tokens[keep]
+        if items.size:
+            self.n_items = max(self.n_items, int(items.max()) + 1)
+        flat = items.tolist()
+        bounds = ptr.tolist()
+        data = [flat[bounds[u]:bounds[u + 1]] for u in range(len(lines))]
+        self.__dict__.setdefault('_parsed', {})[id(data)] = (data, ptr, items)
         return data
 
 

@@ -174,3 +174,37 @@ def test_device_graph_builder_matches_scipy_builder(dups):
         assert torch.equal(fh.tperm(), fd.tperm())
     fi = graph.TemplateFeat.from_device(dg, adj=devb)                      # feature_ratio == 1 shortcut
     assert fi.tmpl is None and torch.equal(fi.row_sum, graph.TemplateFeat(n_users, n_items, pairs, *cases[0], dev).row_sum)
+
+
+def test_processed_dataset_fast_parser(tmp_path):
+    """ProcessedDataset.read_data (dataset.py:154-164): the numpy tokeniser gives the lists, n_items, train
+    pairs and CSR arrays of the reference's per-token loop, keeps users without items, and falls back to that
+    loop for files with irregular separators."""
+    import warnings
+    from igcn_cf_b200.dataset import ProcessedDataset, output_data
+    rng = np.random.default_rng(3)
+    lists = {w: [sorted(rng.choice(60, size=int(rng.integers(0, 6)), replace=False).tolist()) for _ in range(40)]
+             for w in ('train', 'val', 'test')}
+    lists['train'][7] = []
+    lists['test'][39] = []
+    for w in lists:
+        output_data(str(tmp_path / (w + '.txt')), lists[w])
+    with warnings.catch_warnings():
+        warnings.simplefilter('error')                      # the tokeniser must not lean on deprecated numpy paths
+        ds = ProcessedDataset({'name': 'ProcessedDataset', 'path': str(tmp_path), 'device': torch.device('cpu')})
+    assert ds.train_data == lists['train'] and ds.val_data == lists['val'] and ds.test_data == lists['test']
+    assert ds.n_users == 40 and ds.n_items == 1 + max(max(x) for w in lists for x in lists[w] if x)
+    assert ds.train_array == [[u, i] for u, x in enumerate(lists['train']) for i in x]
+    for w in lists:
+        ptr, items = ds.csr(w)
+        assert ptr.tolist() == np.cumsum([0] + [len(x) for x in lists[w]]).tolist()
+        assert items.tolist() == [i for x in lists[w] for i in x]
+    assert '_parsed' in ds.__dict__                          # the arrays came from the parser, not from a list walk
+    # irregular separators (double space): same result through the reference's loop
+    with open(tmp_path / 'val.txt', 'w') as f:
+        for u, x in enumerate(lists['val']):
+            f.write(' '.join([str(u)] + [str(i) for i in x]) + '\n')
+    raw = open(tmp_path / 'train.txt').read().replace('\n', ' \n', 1)
+    open(tmp_path / 'train.txt', 'w').write(raw)
+    with pytest.raises(ValueError):
+        ProcessedDataset({'name': 'ProcessedDataset', 'path': str(tmp_path), 'device': torch.device('cpu')})
