@@ -124,18 +124,6 @@ struct TcSmem {
     uint32_t pad;
 };
 
-__device__ __forceinline__ uint32_t warp_sort_desc(uint32_t x, int lane) {
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1)
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
-            const bool dir = (lane & k) == 0, lower = (lane & j) == 0;
-            x = (lower == dir) ? max(x, y) : min(x, y);
-        }
-    return x;
-}
-
 // Candidate buffer entry: low word = raw fp32 score bits, high word = item id (what the predicated
 // epilogue store writes).
 
