@@ -208,3 +208,24 @@ def test_processed_dataset_fast_parser(tmp_path):
     open(tmp_path / 'train.txt', 'w').write(raw)
     with pytest.raises(ValueError):
         ProcessedDataset({'name': 'ProcessedDataset', 'path': str(tmp_path), 'device': torch.device('cpu')})
+
+
+def test_scoring_cta_plan(monkeypatch):
+    """TcScorer.plan_ctas: whole waves of user tiles stay unsplit, only the tail that would run as a partial
+    last wave is split (at most 8 ways, never more CTAs than one wave); fewer tiles than SMs: uniform splits."""
+    from igcn_cf_b200.engine import TcScorer
+    monkeypatch.delenv('IGCN_TC_SPLITS', raising=False)
+    for n in list(range(1, 700)) + [1175, 5000, 78125]:
+        n_head, n_splits = TcScorer.plan_ctas(n)
+        assert 0 <= n_head <= n and 1 <= n_splits <= 8
+        if n < 148:
+            assert n_head == 0 and n_splits == TcScorer.pick_splits(n)
+            continue
+        tail = n - n_head
+        assert n_head % 148 == 0 or tail == 0                      # the unsplit part is whole waves (or everything)
+        assert tail * n_splits <= 148 or n_splits == 1             # the split tail fits one wave
+        if tail and n_splits > 1:
+            assert tail * (n_splits + 1) > 148 or n_splits == 8    # and uses as much of it as 8 splits allow
+    assert TcScorer.plan_ctas(588) == (588, 1) and TcScorer.plan_ctas(297) == (296, 8) and TcScorer.plan_ctas(234) == (234, 1)
+    monkeypatch.setenv('IGCN_TC_SPLITS', '3')
+    assert TcScorer.plan_ctas(588) == (0, 3)
