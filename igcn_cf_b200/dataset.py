@@ -33,6 +33,8 @@ def output_data(file_path, data):
 
 class BasicDataset(Dataset):
     """dataset.py:47-65, 116-137."""
+    _train_array = None          # class-level defaults: subclasses that skip __init__ still answer train_array
+    train_pairs = None
 
     def __init__(self, dataset_config):
         print(dataset_config)
