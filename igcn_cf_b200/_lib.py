@@ -65,6 +65,8 @@ _SIGNATURES = {
     'igcn_score_topk_exact': [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p,
                               c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int32, c_void_p, c_int64, c_void_p],
+    'igcn_spmm_hot': [C.POINTER(CsrStruct), c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, C.POINTER(c_void_p), c_int32,
+                      c_void_p, c_float, c_void_p],
     'igcn_tc_workspace': [c_int64, c_int64, c_int32, c_int32, C.POINTER(c_int64), C.POINTER(c_int64),
                           C.POINTER(c_int64)],
     'igcn_tc_pack': [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p,

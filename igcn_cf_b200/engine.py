@@ -66,6 +66,9 @@ def _peer_args(shard, t, byte_offset):
     return (None, 0) if shard is None else shard.peers(t, byte_offset)
 
 
+HOT_ROWS = int(os.environ.get('IGCN_SPMM_HOT', 0))      # experimental igcn_spmm_hot: rows of X staged per SM (0 = off)
+
+
 class Propagator:
     """L-layer propagation with the layer mean fused into the last SpMM, and its backward.
 
@@ -134,6 +137,10 @@ class Propagator:
                 call('igcn_spmm_rows', *head, ptr(rows[0]), ptr(rows[1]), int(rows[2]), row0, peers, n_peers, stream_ptr())
             elif cols is not None:
                 call('igcn_spmm_cols', *head, ptr(cols), peers, n_peers, stream_ptr())
+            elif HOT_ROWS and sh is None and self.dim == 64 and blk.csr.row_order is not None:
+                # experimental: hottest rows of x staged in shared memory (csrc/spmm_hot.cu), bit-identical output
+                col_enc, hot_ids, _ = blk.csr.hot_plan(HOT_ROWS)
+                call('igcn_spmm_hot', head[0], ptr(col_enc), ptr(hot_ids), int(hot_ids.shape[0]), *head[1:], stream_ptr())
             else:
                 call('igcn_spmm', *head, peers, n_peers, stream_ptr())
         for row0, n_rows in pushes:

@@ -236,6 +236,14 @@ int igcn_score_topk_exact(const float *rep, const int64_t *user_ids, int64_t n_e
                           const int32_t *out_rows, const int32_t *n_eval_dev,
                           int32_t n_item_splits, uint64_t *split_keys, int64_t split_cap, void *stream);
 
+/* ---- EXPERIMENTAL: igcn_spmm (no peers) with the n_hot highest-degree rows of X staged in shared memory by one
+ * persistent 1,024-thread CTA per SM (csrc/spmm_hot.cu).  col_enc = g->col with every hot column replaced by
+ * -(slot + 1), hot_ids[slot] = that column; both built by the host (graph.CsrDevice.hot_plan).  D == 64 only,
+ * n_hot <= 800.  Results are bit-identical to igcn_spmm.  Selected by the host with IGCN_SPMM_HOT=<n_hot>. */
+int igcn_spmm_hot(const igcn_csr *g, const int32_t *col_enc, const int32_t *hot_ids, int32_t n_hot,
+                  const float *X, float *Y, int32_t D, const float *const *add_host, int32_t n_add,
+                  const float *rowscale, float alpha, void *stream);
+
 /* ---- tensor-core scoring (tcgen05 / TMEM / bulk TMA), D <= 64, k <= 24 ------------------------
  * Same contract as igcn_score_topk_exact, split in three launches the host chains on one stream:
  *   igcn_tc_pack        fp32 rep rows -> fp16 operand images in the UMMA core-matrix layout, with one
