@@ -40,6 +40,7 @@ constexpr int TC_KEEP = 32;       // the threshold never rises above the TC_KEEP
 constexpr int TC_STAGES = 2;      // item-tile smem stages
 constexpr int TC_THREADS = 7 * 32;
 constexpr int TC_STAGE_W = 36;    // words per row of the chunk staging area (16 B aligned, conflict-free)
+constexpr float TC_THR_SCALE = 1024.f;   // experimental variant 7: thresholds enter the MMA as fp16(-thr / 1024) x 1024
 
 // ------------------------------------------------------------------ operand packing
 __global__ void maxabs_kernel(const float *__restrict__ x, int64_t n, uint32_t *out) {
@@ -52,6 +53,9 @@ __global__ void maxabs_kernel(const float *__restrict__ x, int64_t n, uint32_t *
 
 // One group of 16 lanes converts one row (D <= 64) into its tile image: kcores core matrices of
 // 8 fp16 (16 B) per row; the last K block holds the bound entry in its first element.
+// THR (experimental, IGCN_TC_EXPERIMENT=7): item rows also get TC_THR_SCALE in bound-block column 1 + (tile & 1), the
+// column the candidate kernel uses to let the tensor core subtract each user's threshold (see score_tc_kernel<7>).
+template <bool THR>
 __global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ rep, const int64_t *__restrict__ row_ids,
                                                       int64_t row0, int64_t n_rows, int D, int tile_rows, int kcores, int is_user,
                                                       const uint32_t *__restrict__ maxabs_bits, const float *__restrict__ center_sum,
@@ -91,6 +95,10 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ 
         const float b = is_user ? (TC_C * norm + TC_EPS_U) : (norm + TC_EPS_I);
         uint4 z = make_uint4(0u, 0u, 0u, 0u);
         z.x = (uint32_t)__half_as_ushort(__float2half_ru(b));
+        if (THR && !is_user) {
+            const uint32_t one = (uint32_t)__half_as_ushort(__float2half_rn(TC_THR_SCALE));      // a power of two: exact
+            if (tile & 1) z.y = one; else z.x |= one << 16;
+        }
         *reinterpret_cast<uint4 *>(base + (size_t)dcores * 128) = z;
         *reinterpret_cast<uint4 *>(base + (size_t)(dcores + 1) * 128) = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -185,6 +193,16 @@ __device__ __forceinline__ void compact_lanes(uint64_t *mybuf, int &cnt, float &
 // (TMA + MMA + TMEM-read floor), 3 filters against thr = +inf (full filter cost, no hits, no compaction),
 // 4 = as 2 but only the first TC_STAGES item tiles are fetched (no item-image stream), 5 = as 2 but the epilogue
 // does not read TMEM at all, 6 = 4 and 5 together (MMA issue + the mbarrier hand-offs only).
+// 7 = EXPERIMENTAL, valid results, not yet run on a GPU: the tensor core subtracts the row's threshold.  The bound
+// K block has unused columns: item tile t carries TC_THR_SCALE in column 1 + (t & 1) (tc_pack_kernel<true>) and
+// the user row carries a = fp16_up(-thr / TC_THR_SCALE) there, so the accumulator is s_hat - thr' with thr' =
+// -a * TC_THR_SCALE <= thr, and the filter is ONE funnel shift per score that collects sign bits instead of FSETP
+// + predicated add.  A row may rewrite its a for parity p only between tmem_full(t) and its own tmem_empty(t)
+// arrive (t & 1 == p): the next MMA that reads that column with a non-zero multiplier is tile t + 2, issued
+// after all four warps arrived; tile t + 1 multiplies it by zero.  The rare path adds thr' back (rounded up, plus
+// 2^-17 |thr'| for the extra fp32 accumulation error the large term causes) and re-checks s_hat > thr; the
+// recorded threshold is inflated by the same amount because the sign test itself carries that error.  Rows
+// start with thr = 0 instead of -inf (a = 0: items with a negative upper bound are dropped at once).
 template <int VARIANT>
 __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -311,8 +329,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         const int row = q * 32 + lane;
         uint64_t *mybuf = cand + (size_t)row * (TC_CAP + 1);
         uint32_t *mystage = stage + (size_t)row * TC_STAGE_W;
-        float thr = VARIANT == 3 ? INFINITY : -INFINITY;
+        float thr = VARIANT == 3 ? INFINITY : VARIANT == 7 ? 0.f : -INFINITY;
         int cnt = 0;
+        float ta0 = 0.f, ta1 = 0.f;                     // variant 7: threshold currently in the A tile, per tile parity
+        // this row's bound-block entry in the A image: 8-row group, first bound core, row within the group
+        uint8_t *my_a = sA + (size_t)(row >> 3) * a.kcores * 128 + (size_t)(a.kcores - 2) * 128 + (size_t)(row & 7) * 16;
         for (int it = 0; it < n_it; ++it) {
             const int acc = it & 1, t = t0 + it;
             const uint32_t ph = (uint32_t)(it >> 1) & 1u;
@@ -351,14 +372,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 for (int c = 0; c < 32; c += 4)
                     *reinterpret_cast<uint4 *>(mystage + c) = make_uint4(v[c], v[c + 1], v[c + 2], v[c + 3]);
                 uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+                if (VARIANT == 7) {
+                    // sign bits of the 32 accumulators (s_hat - thr'), four independent chains, highest column first so
+                    // that column c ends up in bit c; a clear sign bit is a hit
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    hit_if_gt(v[c], thr, h0, 1u << c);
-                    hit_if_gt(v[c + 8], thr, h1, 1u << (c + 8));
-                    hit_if_gt(v[c + 16], thr, h2, 1u << (c + 16));
-                    hit_if_gt(v[c + 24], thr, h3, 1u << (c + 24));
+                    for (int c = 7; c >= 0; --c) {
+                        h0 = __funnelshift_l(v[c], h0, 1);
+                        h1 = __funnelshift_l(v[c + 8], h1, 1);
+                        h2 = __funnelshift_l(v[c + 16], h2, 1);
+                        h3 = __funnelshift_l(v[c + 24], h3, 1);
+                    }
+                    h0 = ~(h0 | (h1 << 8) | (h2 << 16) | (h3 << 24));
+                    h1 = h2 = h3 = 0u;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        hit_if_gt(v[c], thr, h0, 1u << c);
+                        hit_if_gt(v[c + 8], thr, h1, 1u << (c + 8));
+                        hit_if_gt(v[c + 16], thr, h2, 1u << (c + 16));
+                        hit_if_gt(v[c + 24], thr, h3, 1u << (c + 24));
+                    }
                 }
                 uint32_t hits = (h0 | h1 | h2 | h3) & ~m;        // seen / banned / out-of-range columns never pass
+                if (VARIANT == 7) {
+                    const float ta = (t & 1) ? ta1 : ta0;
+                    const float pad = fabsf(ta) * 7.62939453125e-6f;              // 2^-17 |thr'|
+                    while (hits) {                               // one hit per trip: each is re-checked against thr
+                        const int c0 = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        const float s_up = __fadd_ru(__fadd_ru(__uint_as_float(mystage[c0]), ta), pad);
+                        if (s_up > thr) {
+                            mybuf[cnt] = ((uint64_t)(item0 + c0) << 32) | __float_as_uint(s_up);
+                            ++cnt;
+                        }
+                    }
+                }
                 while (hits) {                                   // rare: ~1 % of the elements; two per trip so that
                     const int c0 = __ffs(hits) - 1;              // both staged scores are in flight together
                     hits &= hits - 1;
@@ -380,6 +428,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 if (ch + 2 < 8) tc_ld32(taddr + (ch + 2) * 32, va);
                 filter(vb, ch + 1);
             }
+            if (VARIANT == 7) {
+                // put the current threshold into this parity's column of the A tile (only ever raises it)
+                const float ta = (t & 1) ? ta1 : ta0;
+                const float want = -thr * (1.f / TC_THR_SCALE);
+                if (thr > ta && want <= 65504.f) {
+                    const __half ah = __float2half_ru(want);                      // a >= -thr / S  =>  thr' = -a S <= thr
+                    *reinterpret_cast<__half *>(my_a + ((t & 1) ? 4 : 2)) = ah;
+                    const float nt = -__half2float(ah) * TC_THR_SCALE;
+                    if (t & 1) ta1 = nt; else ta0 = nt;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy store -> async-proxy (MMA) reads
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm->tmem_empty[acc]);
@@ -396,7 +456,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             for (int e = lane; e < n; e += 32) dst[e] = (int32_t)(uint32_t)(src[e] >> 32);
             if (lane == 0) {
                 a.cand_cnt[b * a.n_splits + sp] = n;
-                a.cand_thr[b * a.n_splits + sp] = th;
+                // variant 7: the sign test carries the accumulation error of the subtracted term (see above)
+                a.cand_thr[b * a.n_splits + sp] = (VARIANT == 7 && th < INFINITY) ? __fadd_ru(th, fabsf(th) * 7.62939453125e-6f) : th;
             }
             if (head && lane > 0 && lane < a.n_splits) {          // the list slots an unsplit tile does not use
                 a.cand_cnt[b * a.n_splits + lane] = 0;
@@ -519,11 +580,13 @@ extern "C" int igcn_tc_pack(const float *rep, int64_t n_rep_elems, const int64_t
     if (int rc = igcn_colsum_masked(rep, item_row0, item_row0 + n_items, D, nullptr, center_scratch, center_sum, stream)) return rc;
     const float inv_n = n_items > 0 ? 1.f / (float)n_items : 0.f;
     if (n_eval > 0)
-        tc_pack_kernel<<<(unsigned)((n_eval + 15) / 16), 256, 0, st>>>(rep, user_ids, 0, n_eval, D, TC_BM, kc, 1, maxabs_bits, center_sum,
+        tc_pack_kernel<false><<<(unsigned)((n_eval + 15) / 16), 256, 0, st>>>(rep, user_ids, 0, n_eval, D, TC_BM, kc, 1, maxabs_bits, center_sum,
                                                                        inv_n, a_img);
+    const char *exp_env = getenv("IGCN_TC_EXPERIMENT");       // 7: item tiles carry the threshold multiplier (score_tc_kernel<7>)
+    auto pack_items = (exp_env && atoi(exp_env) == 7) ? tc_pack_kernel<true> : tc_pack_kernel<false>;
     if (n_items > 0)
-        tc_pack_kernel<<<(unsigned)((n_items + 15) / 16), 256, 0, st>>>(rep, nullptr, item_row0, n_items, D, TC_BN, kc, 0, maxabs_bits,
-                                                                        center_sum, inv_n, b_img);
+        pack_items<<<(unsigned)((n_items + 15) / 16), 256, 0, st>>>(rep, nullptr, item_row0, n_items, D, TC_BN, kc, 0, maxabs_bits,
+                                                                    center_sum, inv_n, b_img);
     IGCN_CHECK_LAUNCH();
     return 0;
 }
@@ -556,7 +619,8 @@ extern "C" int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, in
     const int experiment = exp_env ? atoi(exp_env) : 0;
     auto kern = dump ? score_tc_kernel<1>
                 : experiment == 2 ? score_tc_kernel<2> : experiment == 3 ? score_tc_kernel<3> : experiment == 4 ? score_tc_kernel<4>
-                : experiment == 5 ? score_tc_kernel<5> : experiment == 6 ? score_tc_kernel<6> : score_tc_kernel<0>;
+                : experiment == 5 ? score_tc_kernel<5> : experiment == 6 ? score_tc_kernel<6>
+                : experiment == 7 ? score_tc_kernel<7> : score_tc_kernel<0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("igcn_tc_candidates: %s", cudaGetErrorString(e)); return (int)e; }
     kern<<<n_ctas, TC_THREADS, smem, as_stream(stream)>>>(a);

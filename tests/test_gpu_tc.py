@@ -128,3 +128,16 @@ def test_tc_split_tail_plan(n_tiles):
     tc = engine.score_topk(rep, u, n_users, n_items, k, mask, impl='tc')
     torch.cuda.synchronize()
     assert torch.equal(ex[0], tc[0]) and torch.equal(ex[1], tc[1])
+
+
+@pytest.mark.skipif(not __import__('os').environ.get('IGCN_EXPERIMENTAL'), reason='experimental kernel: set IGCN_EXPERIMENTAL=1')
+@pytest.mark.parametrize('n_users,n_items,D,k', [(300, 1000, 64, 20), (129, 257, 64, 5), (1000, 5000, 64, 20), (700, 20000, 32, 20)])
+def test_tc_threshold_in_mma_variant(monkeypatch, n_users, n_items, D, k):
+    """score_tc_kernel<7> (IGCN_TC_EXPERIMENT=7: the tensor core subtracts each row's threshold, the filter collects
+    sign bits): same lists and scores as the exact kernel; users whose top-k reaches into negative centred scores
+    go through the exact kernel, so only the answer is asserted, not the fallback count."""
+    monkeypatch.setenv('IGCN_TC_EXPERIMENT', '7')
+    rep, lists = _case(n_users, n_items, D, seed=n_items + 7)
+    ex, tc, fb = _both(rep, n_users, k, lists)
+    assert torch.equal(ex[0], tc[0]) and torch.equal(ex[1], tc[1])
+    assert fb < n_users                                     # the tensor-core path decided at least some users

@@ -1,6 +1,6 @@
 """Time decomposition of igcn_tc_candidates: runs the scoring of a bench workload once per IGCN_TC_EXPERIMENT
 variant (eval_tc.cu: 0 production, 2 no filter, 3 filter without hits, 4 no item-image stream, 5 no TMEM reads,
-6 neither) and prints the CUDA-event time of the candidates launch alone.  Variants other than 0 produce invalid
+6 neither, 7 = experimental threshold-in-MMA filter with valid results) and prints the CUDA-event time of the candidates launch alone.  Variants other than 0 produce invalid
 lists, so only igcn_tc_pack + igcn_tc_candidates are called here.
 IGCN_TC_DEBUG flags (TcArgs.dbg) can be appended as variant:flags.
     python tools/tc_floor.py [workload] [variant[:flags] ...]"""
