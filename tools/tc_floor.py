@@ -29,11 +29,12 @@ def main():
     scorer = engine.TcScorer()
     n_head, n_splits = scorer.plan_ctas((n_users + 127) // 128)
     ws = scorer._workspace(n_users, n_items, D, n_splits, k, dev)
-    call('igcn_tc_pack', ptr(rep), rep.numel(), ptr(users), n_users, n_users, n_items, D, ptr(ws['maxabs']),
-         ptr(ws['a_img']), ptr(ws['b_img']), ptr(ws['center']), ptr(ws['center_scratch']), stream_ptr())
     tile_ptr, entries = mask.tiles(n_items, None)
     for v in variants:
         os.environ['IGCN_TC_EXPERIMENT'], os.environ['IGCN_TC_DEBUG'] = (v.split(':') + ['0'])[:2]
+        # packed per variant: variant 7 needs the threshold multiplier in the item image
+        call('igcn_tc_pack', ptr(rep), rep.numel(), ptr(users), n_users, n_users, n_items, D, ptr(ws['maxabs']),
+             ptr(ws['a_img']), ptr(ws['b_img']), ptr(ws['center']), ptr(ws['center_scratch']), stream_ptr())
         def launch():
             call('igcn_tc_candidates', ptr(ws['a_img']), ptr(ws['b_img']), n_users, n_items, D, n_splits, n_head, 0, n_items,
                  None, ptr(tile_ptr), ptr(entries), ptr(ws['cand_items']), ptr(ws['cand_cnt']), ptr(ws['cand_thr']), None,
