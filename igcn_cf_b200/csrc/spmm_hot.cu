@@ -207,12 +207,22 @@ extern "C" int igcn_spmm_hot(const igcn_csr *g, const int32_t *col_enc, const in
     for (int j = 0; j < n_add; ++j) a.add[j] = add_host[j];
     const int64_t n_long = g->n_long_rows, n_med = g->n_medium_rows;
     a.total_units = g->n_chunks + n_med + (g->n_rows - n_long - n_med + kSUB - 1) / kSUB;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // one process drives one GPU: the SM count and the shared-memory opt-in are set up on the first call (which the
+    // callers make eagerly, before any CUDA-graph capture) and reused
+    static int sms = 0;
+    static size_t smem_ok = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
     const size_t smem = (size_t)n_hot * kD * 4;
-    cudaError_t e = cudaFuncSetAttribute(prop_hot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("igcn_spmm_hot: %s", cudaGetErrorString(e)); return (int)e; }
+    if (smem > smem_ok) {
+        cudaError_t e = cudaFuncSetAttribute(prop_hot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("igcn_spmm_hot: %s", cudaGetErrorString(e)); return (int)e; }
+        smem_ok = smem;
+    }
     const int64_t ctas = min((int64_t)sms, (a.total_units + kHotThreads / 32 - 1) / (kHotThreads / 32));
     prop_hot_kernel<<<(unsigned)ctas, kHotThreads, smem, as_stream(stream)>>>(a);
     IGCN_CHECK_LAUNCH();
