@@ -251,3 +251,25 @@ def test_hot_plan_encodes_the_most_gathered_columns():
     assert abs(coverage - counts[hot_ids].sum() / len(col)) < 1e-12
     assert (enc < 0).sum() == counts[hot_ids].sum()
     assert csr.hot_plan(H)[0] is csr.hot_plan(H)[0]                        # cached
+
+
+def test_device_graph_builder_row_sharded_blocks_match():
+    """Row-sharded construction (one user slice + one item slice per rank): the device builder cuts the same
+    blocks with the same values as the scipy builder, for every rank of a 3-rank world."""
+    rng = np.random.default_rng(9)
+    n_users, n_items = 120, 80
+    pairs = np.unique(np.stack([rng.integers(0, n_users, 1500), rng.integers(0, n_items, 1500)], axis=1), axis=0).astype(np.int64)
+    dev = torch.device('cpu')
+    dg = graph.DeviceGraph.from_pairs(n_users, n_items, pairs, dev)
+    for rank in range(3):
+        host = graph.NormAdj(n_users, n_items, pairs, dev, shard=(rank, 3))
+        devb = graph.NormAdj.from_device(dg, shard=(rank, 3))
+        assert host.block_key() == devb.block_key() and len(devb.blocks) == 2
+        for bh, bd in zip(host.blocks, devb.blocks):
+            assert np.array_equal(bh.csr.rowptr_host, bd.csr.rowptr_host)
+            assert torch.equal(bh.csr.col, bd.csr.col) and torch.equal(bh.csr.val, bd.csr.val)
+        fh = graph.TemplateFeat(n_users, n_items, pairs, np.arange(n_users), np.arange(n_items), n_users, n_items, dev, shard=(rank, 3))
+        fd = graph.TemplateFeat.from_device(dg, adj=devb, shard=(rank, 3))
+        assert fh.block_key() == fd.block_key() and torch.equal(fh.row_sum, fd.row_sum)
+        for bh, bd in zip(fh.blocks, fd.blocks):
+            assert torch.equal(bh.csr.col, bd.csr.col) and bd.csr.val is None
