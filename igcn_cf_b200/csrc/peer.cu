@@ -7,7 +7,9 @@
 // igcn_peer_barrier is the only synchronisation between layers: a one-CTA kernel that publishes this
 // rank's epoch in every rank's flag array (st.release.sys) and waits until every rank has published
 // the same epoch (ld.acquire.sys).  It lives on the launch stream, so it can be captured in the
-// step's CUDA graph; a bounded spin turns a lost peer into an error flag instead of a hung GPU.
+// step's CUDA graph; a bounded spin turns a lost peer into a trap (the context dies, every
+// later CUDA call of the process fails loudly) instead of a hung GPU or a silently wrong layer.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -44,7 +46,13 @@ __global__ void peer_barrier_kernel(const __grid_constant__ BarrierArgs a) {
         const uint32_t *mine = a.flags[a.rank] + p;
         const long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
-            if (clock64() - t0 > a.timeout_cycles) { *a.status = 1u; break; }
+            if (clock64() - t0 > a.timeout_cycles) {
+                // a lost peer is fatal: record it where the host can read it (mapped status word) and kill the
+                // context -- the layers behind this barrier would otherwise read rows that never arrived
+                *a.status = 1u;
+                __threadfence_system();
+                __trap();
+            }
             __nanosleep(64);
         }
     }
@@ -131,7 +139,16 @@ extern "C" int igcn_peer_barrier(uint32_t *const *flags_host, int32_t n_peers, i
     BarrierArgs a{};
     for (int p = 0; p < n_peers; ++p) a.flags[p] = flags_host[p];
     a.n_peers = n_peers; a.rank = rank; a.epoch = epoch_dev; a.status = status_dev;
-    a.timeout_cycles = 4000000000LL;    // ~2 s at 1.9 GHz
+    // host-side skew of seconds between ranks is normal (checkpoint I/O, a CUDA-graph capture on one rank), so the
+    // default is generous; IGCN_PEER_TIMEOUT_S overrides it
+    static long long timeout_cycles = 0;
+    if (!timeout_cycles) {
+        const char *env = getenv("IGCN_PEER_TIMEOUT_S");
+        double sec = env ? atof(env) : 120.0;
+        if (!(sec > 0.0)) sec = 120.0;
+        timeout_cycles = (long long)(sec * 1.9e9);
+    }
+    a.timeout_cycles = timeout_cycles;
     peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(a);
     IGCN_CHECK_LAUNCH();
     return 0;

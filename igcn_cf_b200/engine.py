@@ -456,6 +456,9 @@ class TrainStep:
             self.triples[:B].copy_(triples)
             if self.is_igcn:
                 self.a_triples[:B].copy_(aux_triples)
+        # the learning rate is a launch argument of igcn_step_tick / igcn_adam: follow the optimizer's param group
+        # (schedulers, manual decay) like Adam.step() does; a new value re-captures the CUDA graph
+        self.lr = float(self.opt.param_groups[0]['lr'])
         d = self._production_drop() if isinstance(drop, str) else drop
         if d is not None and d.get('mode', 0) == 2 and d.get('tperm') is None:
             d = dict(d, tperm=self.model.feat_mat.tperm())
@@ -463,9 +466,12 @@ class TrainStep:
         if not graphable:
             self._body(B, sample, d)
         else:
-            key = (B, sample, None if d is None else (d['mode'], d['p'], d['seed']), self.model.graph_version())
+            gv = self.model.graph_version()
+            key = (B, sample, None if d is None else (d['mode'], d['p'], d['seed']), gv, self.lr)
             g = self._graphs.get(key)
             if g is None:
+                # captured graphs of a replaced norm_adj / feat_mat hold pointers into buffers that may be freed
+                self._graphs = {k: v for k, v in self._graphs.items() if k[3] == gv}
                 if len(self._graphs) >= 8:
                     self._graphs.clear()
                 g = self._capture(B, sample, d)

@@ -14,6 +14,7 @@ pattern is the adjacency pattern filtered by template membership, SURVEY.md appe
 tmpl[N] int32 (only when some node is not a template) and rowscale[N] fp32.
 """
 import ctypes as C
+import itertools
 
 import numpy as np
 import scipy.sparse as sp
@@ -196,11 +197,18 @@ def _block_csr(rowptr, col, val, row0, row1, n_cols, device):
     return CsrDevice(rowptr[row0:row1 + 1] - lo, col[lo:hi], None if val is None else val[lo:hi], n_cols, device)
 
 
+_UID = itertools.count(1)
+
+
 class _Blocked:
     """Mixin: `blocks` (list of RowBlock) + single-block compatibility attributes."""
     blocks = ()
+    uid = 0
 
     def _set_blocks(self, blocks):
+        # a process-wide serial number identifies the graph object in cache keys (id() values are reused by CPython
+        # once an object is freed; a captured CUDA graph keyed on one would replay dangling pointers)
+        self.uid = next(_UID)
         self.blocks = blocks
         self.csr = blocks[0].csr                     # single-GPU view (tests, sampler, chunk statistics)
         self.row0, self.row1 = blocks[0].row0, blocks[0].row1

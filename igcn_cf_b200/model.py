@@ -29,7 +29,10 @@ def get_model(config, dataset):
     """Name-dispatched factory (model.py:16-21)."""
     config = config.copy()
     config['dataset'] = dataset
-    cls = getattr(sys.modules[__name__], config['name'])
+    cls = getattr(sys.modules[__name__], config['name'], None)
+    if cls is None or config.get('out_of_scope'):
+        raise NotImplementedError('model %r is a baseline outside the B200 hot path (SURVEY.md 2.1); implemented: '
+                                  'LightGCN, IGCN, IMF, MF, Popularity' % config['name'])
     return cls(config)
 
 
@@ -85,7 +88,11 @@ class _GraphModel(BasicModel):
         self._param_epoch += 1
 
     def graph_version(self):
-        return (id(self.norm_adj), id(getattr(self, 'feat_mat', None)), self.n_users, self.n_items)
+        """Identity of the graph objects the kernels read: their construction serial numbers (graph._Blocked.uid),
+        never id() -- CPython reuses ids of freed objects."""
+        feat = getattr(self, 'feat_mat', None)
+        return (getattr(self.norm_adj, 'uid', None), None if feat is None else getattr(feat, 'uid', None),
+                self.n_users, self.n_items)
 
     SHARD_MIN_NNZ_PER_RANK = int(os.environ.get('IGCN_SHARD_MIN_NNZ_PER_RANK', 2_000_000))
 
@@ -116,10 +123,13 @@ class _GraphModel(BasicModel):
         if self.config.get('graph_builder', 'device') == 'host':
             return None
         pairs = graph.train_pairs_of(dataset)
-        key = (id(dataset), id(pairs), len(pairs), dataset.n_users, dataset.n_items)
-        if self._dg_cache is None or self._dg_cache[0] != key:
-            self._dg_cache = (key, graph.DeviceGraph.from_pairs(dataset.n_users, dataset.n_items, pairs, self.device))
-        return self._dg_cache[1]
+        # the cache holds references to the dataset and its pair array, so their ids cannot be recycled while the
+        # entry is alive; `is` comparisons instead of id() keys
+        c = self._dg_cache
+        if c is None or c[0] is not dataset or c[1] is not pairs or c[2] != (len(pairs), dataset.n_users, dataset.n_items):
+            dg = graph.DeviceGraph.from_pairs(dataset.n_users, dataset.n_items, pairs, self.device)
+            self._dg_cache = c = (dataset, pairs, (len(pairs), dataset.n_users, dataset.n_items), dg)
+        return c[3]
 
     def _propagator(self):
         n = self.n_users + self.n_items

@@ -49,6 +49,7 @@ class Adam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=(engine.BETA1, engine.BETA2), eps=engine.ADAM_EPS))
         self.t = 0
         self.step_state = None      # igcn_step_state on the device, created lazily
+        self.on_step = None         # called after every update (the trainer hooks the model's eval-cache invalidation)
 
     def moments(self, p):
         st = self.state[p]
@@ -76,9 +77,66 @@ class Adam(torch.optim.Optimizer):
                      self.t, None, stream_ptr())
         if self.step_state is not None:
             self._sync_device_step()
+        if self.on_step is not None:
+            # igcn_adam wrote through raw device pointers: autograd's tensor versions did not move, so whoever
+            # caches values derived from the parameters (the eval-mode representation) has to be told
+            self.on_step()
 
     def _sync_device_step(self):
         self.step_state[:8].copy_(torch.tensor([self.t], dtype=torch.int64).view(torch.uint8))
+
+
+class BestCheckpoint:
+    """Best-validation checkpoint + patience policy of the reference's epoch loop (trainer.py:66, 90-106): a better
+    NDCG replaces the previous best file `checkpoints/<model>_<trainer>_<dataset>_<ndcg*100:.3f>.pth`, anything
+    else costs `val_interval` epochs of patience.
+
+    With one process per GPU every rank sees the same gathered metrics (replicas are bit-identical), so only rank 0
+    touches the file system -- through a temporary file and os.replace, so a reader never sees a torn file -- and
+    all ranks meet at a barrier before anyone reloads the best file."""
+
+    def __init__(self, trainer, directory):
+        self.tr, self.dir = trainer, directory
+        self.patience = trainer.max_patience
+        self.writer_rank = self._rank() == 0
+        if self.writer_rank:
+            os.makedirs(directory, exist_ok=True)
+
+    @staticmethod
+    def _rank():
+        import torch.distributed as td
+        return td.get_rank() if td.is_available() and td.is_initialized() else 0
+
+    @staticmethod
+    def _barrier():
+        import torch.distributed as td
+        if td.is_available() and td.is_initialized() and td.get_world_size() > 1:
+            td.barrier()
+
+    def offer(self, ndcg):
+        """Record one validation result; False = patience exhausted."""
+        tr = self.tr
+        if ndcg > tr.best_ndcg:
+            old = tr.save_path
+            tr.save_path = os.path.join(self.dir, '{:s}_{:s}_{:s}_{:.3f}.pth'.format(
+                tr.model.name, tr.name, tr.dataset.name, ndcg * 100))
+            tr.best_ndcg = ndcg
+            if self.writer_rank:
+                tmp = tr.save_path + '.tmp'
+                tr.model.save(tmp)
+                os.replace(tmp, tr.save_path)
+                if old and old != tr.save_path and os.path.exists(old):
+                    os.remove(old)
+            self.patience = tr.max_patience
+            print('Best NDCG, save model to {:s}'.format(tr.save_path))
+            return True
+        self.patience -= tr.val_interval
+        return self.patience > 0
+
+    def restore(self):
+        self._barrier()                 # the writer has finished before anyone reads
+        self.tr.model.load(self.tr.save_path)
+        self._barrier()                 # nobody removes / rewrites the file while another rank still reads it
 
 
 class BasicTrainer:
@@ -110,65 +168,66 @@ class BasicTrainer:
         if name != 'Adam':
             raise NotImplementedError('the B200 hot path implements Adam (every shipped config uses it); got ' + name)
         self.opt = Adam(self.model.parameters(), lr=self.config['lr'])
+        bump = getattr(self.model, '_bump', None)
+        if callable(bump):
+            self.opt.on_step = bump
 
     def train_one_epoch(self):
         raise NotImplementedError
 
     def record(self, writer, stage, metrics):
-        for metric in metrics:
+        """tensorboard scalars, tag layout of trainer.py:50-55."""
+        prefix = '{:s}_{:s}/{:s}'.format(self.model.name, self.name, stage)
+        for metric, per_k in metrics.items():
             for k in self.topks:
-                writer.add_scalar('{:s}_{:s}/{:s}_{:s}@{:d}'.format(self.model.name, self.name, stage, metric, k),
-                                  metrics[metric][k], self.epoch)
+                writer.add_scalar('{:s}_{:s}@{:d}'.format(prefix, metric, k), per_k[k], self.epoch)
+
+    def _timed(self, fn):
+        t0 = time.time()
+        out = fn()
+        return out, time.time() - t0
+
+    def _check_peers(self):
+        """Row-sharded runs: a device barrier that timed out must stop the run, not be trained through."""
+        peers = getattr(self.model, '_peers', None)
+        if peers is not None:
+            peers.check()
 
     def train(self, verbose=True, writer=None):
-        """Epoch loop, validation, best-NDCG checkpoint, patience (trainer.py:57-107)."""
+        """Epoch loop of trainer.py:57-107: one training epoch, eval('train') every epoch, eval('val') every
+        `val_interval` epochs, keep the checkpoint of the best validation NDCG@topks[0], stop after `max_patience`
+        epochs without improvement, reload the best checkpoint.  The printed lines, the tensorboard tags and the
+        checkpoint file names are the reference's (they are what downstream scripts parse); the policy lives in
+        BestCheckpoint, which is also what makes the loop safe with one process per GPU."""
+        say = print if verbose else (lambda *a, **k: None)
         if not self.model.trainable:
             results, metrics = self.eval('val')
-            if verbose:
-                print('Validation result. {:s}'.format(results))
+            say('Validation result. {:s}'.format(results))
             return metrics['NDCG'][self.topks[0]]
 
-        if not os.path.exists('checkpoints'):
-            os.mkdir('checkpoints')
-        patience = self.max_patience
+        keeper = BestCheckpoint(self, 'checkpoints')
+        tag = '{:s}_{:s}'.format(self.model.name, self.name)
         for self.epoch in range(self.n_epochs):
-            start_time = time.time()
-            self.model.train()
-            loss = self.train_one_epoch()
-            _, metrics = self.eval('train')
-            consumed_time = time.time() - start_time
-            if verbose:
-                print('Epoch {:d}/{:d}, Loss: {:.6f}, Time: {:.3f}s'.format(self.epoch, self.n_epochs, loss, consumed_time))
+            def one_epoch():
+                self.model.train()
+                loss = self.train_one_epoch()
+                return loss, self.eval('train')[1]
+            (loss, metrics), seconds = self._timed(one_epoch)
+            self._check_peers()
+            say('Epoch {:d}/{:d}, Loss: {:.6f}, Time: {:.3f}s'.format(self.epoch, self.n_epochs, loss, seconds))
             if writer:
-                writer.add_scalar('{:s}_{:s}/train_loss'.format(self.model.name, self.name), loss, self.epoch)
+                writer.add_scalar(tag + '/train_loss', loss, self.epoch)
                 self.record(writer, 'train', metrics)
-            if (self.epoch + 1) % self.val_interval != 0:
+            if (self.epoch + 1) % self.val_interval:
                 continue
-
-            start_time = time.time()
-            results, metrics = self.eval('val')
-            consumed_time = time.time() - start_time
-            if verbose:
-                print('Validation result. {:s}Time: {:.3f}s'.format(results, consumed_time))
+            (results, metrics), seconds = self._timed(lambda: self.eval('val'))
+            say('Validation result. {:s}Time: {:.3f}s'.format(results, seconds))
             if writer:
                 self.record(writer, 'validation', metrics)
-
-            ndcg = metrics['NDCG'][self.topks[0]]
-            if ndcg > self.best_ndcg:
-                if self.save_path:
-                    os.remove(self.save_path)
-                self.save_path = os.path.join('checkpoints', '{:s}_{:s}_{:s}_{:.3f}.pth'.format(
-                    self.model.name, self.name, self.dataset.name, ndcg * 100))
-                self.best_ndcg = ndcg
-                self.model.save(self.save_path)
-                patience = self.max_patience
-                print('Best NDCG, save model to {:s}'.format(self.save_path))
-            else:
-                patience -= self.val_interval
-                if patience <= 0:
-                    print('Early stopping!')
-                    break
-        self.model.load(self.save_path)
+            if not keeper.offer(metrics['NDCG'][self.topks[0]]):
+                print('Early stopping!')
+                break
+        keeper.restore()
         return self.best_ndcg
 
     # ---- metrics (trainer.py:109-138)
@@ -304,15 +363,13 @@ class BasicTrainer:
         metrics = self.calculate_metrics(eval_data, rec_items)
         self._last_rec = None
 
-        precison = ''
-        recall = ''
-        ndcg = ''
-        for k in self.topks:
-            precison += '{:.3f}%@{:d}, '.format(metrics['Precision'][k] * 100., k)
-            recall += '{:.3f}%@{:d}, '.format(metrics['Recall'][k] * 100., k)
-            ndcg += '{:.3f}%@{:d}, '.format(metrics['NDCG'][k] * 100., k)
-        results = 'Precision: {:s}Recall: {:s}NDCG: {:s}'.format(precison, recall, ndcg)
-        return results, metrics
+        return self.format_results(metrics), metrics
+
+    def format_results(self, metrics):
+        """'Precision: ..%@k, Recall: ..%@k, NDCG: ..%@k, ' -- the result line of trainer.py:169-176 (launchers and
+        log parsers read it; the field order and the '{:.3f}%@{:d}, ' cells are the interface)."""
+        cells = lambda name: ''.join('{:.3f}%@{:d}, '.format(metrics[name][k] * 100., k) for k in self.topks)
+        return 'Precision: {:s}Recall: {:s}NDCG: {:s}'.format(cells('Precision'), cells('Recall'), cells('NDCG'))
 
     def inductive_eval(self, n_old_users, n_old_items):
         """Six test passes over user/item subsets (trainer.py:179-219).  The reference edits copies of

@@ -290,7 +290,9 @@ int igcn_tc_finalize(const float *rep, const int64_t *user_ids, int64_t n_eval, 
  *   igcn_peer_barrier  device-side barrier on `stream` across n_peers ranks: flags_host[p] is rank p's
  *                      flag array (uint32 [IGCN_MAX_PEERS], peer-mapped, zero-initialised), epoch_dev a
  *                      local counter, status_dev a local word set to 1 if a peer did not arrive within
- *                      ~2 s (the kernel then returns instead of hanging the GPU).  CUDA-graph capturable.
+ *                      the timeout (120 s, IGCN_PEER_TIMEOUT_S overrides) -- the kernel then TRAPS: the context
+ *                      dies and every later CUDA call of the process fails, instead of a hung GPU or layers that
+ *                      silently read rows which never arrived.  CUDA-graph capturable.
  * Buffers from igcn_peer_alloc are owned by the library until igcn_peer_free; everything else in this
  * header operates on caller-owned memory. */
 #define IGCN_PEER_HANDLE_BYTES 64
