@@ -1,19 +1,30 @@
 #!/usr/bin/env python
-"""Benchmark of the INMO / IGCN hot path on B200 (contract: see the task statement and DESIGN.md).
+"""Benchmark of the INMO / IGCN hot path on B200 (contract: see the task statement and DESIGN.md 5).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload yelp-lightgcn] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload amazon-igcn] [--sub gowalla-igcn,yelp-lightgcn]
+                    [--impl reference]
 
-A "step" is one BPR training step (2,048 triples): sample -> propagate (L SpMM layers + fused mean)
--> fused BPR loss -> deterministic gradient -> backward propagation -> Adam.  `value` is ms/epoch =
-ms_per_step x ceil(E_train / 2048) with everything resident in HBM (CUDA-graph replay, device
-sampler).  `e2e` is the same metric through the public trainer step with HOST triples in pinned
-memory copied H2D every step and the loss read back D2H every step (what the reference does,
-trainer.py:234/247; the read of step i's loss is overlapped with step i + 1).  `eval` is the second half of BASELINE.json's metric: full-ranking users/s.
-`roofline` describes the dominant kernel (the CSR SpMM) against the measured HBM peak; `cpu_baseline`
-times the CPU oracle port of the reference's step on this box's host cores (a reported baseline).
+A "step" is one BPR training step (2,048 triples): sample -> propagate (INMO layer + L SpMM layers + fused mean)
+-> fused BPR (+ auxiliary) loss -> deterministic gradient -> backward propagation -> Adam.  `value` is ms/epoch =
+ms_per_step x ceil(E_train / 2048) with everything resident in HBM (CUDA-graph replay, device sampler); ms_per_step is
+the MEDIAN of --repeats timed regions of exactly K steps each (barrier + synchronize on both sides of every region,
+CUDA events, max over ranks).  `e2e` is the same metric through the public trainer step with HOST triples in pinned
+memory copied H2D every step and the loss read back D2H every step (trainer.py:234/247).  `eval` is the second half of
+BASELINE.json's metric: full-ranking users/s (also at the top level as eval_users_per_s / eval_e2e_users_per_s).
 
---impl reference times that CPU port only (the reference is pure Python/PyTorch; /root/reference is
-not present on the GPU box, so the pinned restatement in oracle/restate.py is what runs).
+The default workload is the largest single-GPU configuration of BASELINE.json (configs[2], IGCN on the Amazon-book
+shape); configs[0] (Gowalla-shaped IGCN, the north-star target) and configs[1] (Yelp-shaped LightGCN) are measured in
+the same run and reported as sub-blocks under `configs`, each with its own ms_per_step, rooflines, eval and CPU sample.
+At N > 1 every workload's step is timed BOTH replicated and with the propagation rows sharded over the ranks
+(ms_per_step_replicated / ms_per_step_row_sharded; `value` is the better one, `step_mode` says which) and the sharded
+path is checked bit for bit against the replicated one (`shard_parity`).
+
+`roofline` describes the dominant kernel (the CSR SpMM) against the measured HBM peak, `eval.roofline` the tcgen05
+scoring kernel against the measured tensor peak (algorithmic flops 2 U I 64); `cpu_baseline` times the CPU oracle port of
+the reference's step on this box's host cores (a reported baseline).
+
+--impl reference times that CPU port only (the reference is pure Python/PyTorch; /root/reference is not present on
+the GPU box, so the pinned restatement in oracle/restate.py is what runs), with the same `config` objects.
 """
 import argparse
 import json
@@ -142,12 +153,12 @@ def build_dataset(shape, device):
     return get_dataset({'name': 'SyntheticDataset', 'shape': shape, 'seed': 2021, 'device': device})
 
 
-def build_model(ds, kind, dropout, l2_reg, device, use_graph=True):
+def build_model(ds, kind, dropout, l2_reg, device, use_graph=True, shard='auto'):
     import torch
     from igcn_cf_b200.model import get_model
     from igcn_cf_b200.trainer import get_trainer
     torch.manual_seed(2021)                     # reference launchers: set_seed(2021) (run/run.py:12)
-    mcfg = {'name': kind, 'embedding_size': 64, 'n_layers': 3, 'device': device}
+    mcfg = {'name': kind, 'embedding_size': 64, 'n_layers': 3, 'device': device, 'shard': shard}
     tcfg = {'optimizer': 'Adam', 'lr': 1e-3, 'l2_reg': l2_reg, 'device': device, 'n_epochs': 1, 'batch_size': BATCH,
             'dataloader_num_workers': 0, 'test_batch_size': 512, 'topks': [20], 'cuda_graph': use_graph, 'seed': 2021}
     if kind == 'IGCN':
@@ -254,25 +265,49 @@ def cpu_eval_users_per_s(ds, oracle_model, n_batches=2, batch=512):
     return done / (time.perf_counter() - t0), '%d batches of %d users (eval(\'val\') loop body)' % (n_batches, batch)
 
 
-def run_reference(args, shape, kind, l2_reg, dropout):
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
-        return
-    ds = build_dataset(shape, 'cpu')
+def workload_config(name, ds):
+    """The `config` object of the JSON line: what the workload IS (identical in both arms; how an arm runs it is
+    in `impl_config`)."""
+    shape, kind, l2_reg, dropout = WORKLOADS[name]
+    n, e = ds.n_users + ds.n_items, len(ds)
+    return {'workload': name, 'shape': shape, 'n_users': ds.n_users, 'n_items': ds.n_items, 'train_interactions': e,
+            'nnz_adj': 2 * e, 'dim': 64, 'layers': 3, 'batch': BATCH, 'steps_per_epoch': math.ceil(e / BATCH),
+            'l2': ('no explicit flush: a step touches ~%d MB of distinct buffers (> 126 MB L2)' if (8 * n * 64 * 4 + 2 * e * 8) > 126 << 20
+                   else 'L2-RESIDENT test workload (~%d MB): not a valid bench configuration') % ((8 * n * 64 * 4 + 2 * e * 8) // 2 ** 20)}
+
+
+def cpu_block(ds, name, steps, warmup=1, eval_batches=2):
+    """cpu_baseline object of one workload: the oracle port on this box's host cores (bounded sample)."""
+    shape, kind, l2_reg, dropout = WORKLOADS[name]
     steps_per_epoch = math.ceil(len(ds) / BATCH)
-    sec, orc = cpu_step_time(ds, kind, dropout if dropout is not None else 0., l2_reg, args.steps, args.warmup)
-    value = sec * 1e3 * steps_per_epoch
-    cores = os.cpu_count() or 1
-    eval_ups, eval_sample = cpu_eval_users_per_s(ds, orc)
-    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'ms', 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': False, 'scaling': 'strong',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': args.workload, 'shape': shape, 'n_users': ds.n_users, 'n_items': ds.n_items,
-                       'train_interactions': len(ds), 'batch': BATCH, 'steps_per_epoch': steps_per_epoch},
-            'cpu_baseline': {'value': value, 'unit': 'ms', 'cores': cores, 'kind': 'port',
-                             'sample': '%d full train steps of %d per epoch, extrapolated' % (args.steps, steps_per_epoch)},
-            'e2e': {'value': value, 'unit': 'ms', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0,
-            'eval': {'users_per_s': eval_ups, 'sample': eval_sample}}
+    sec, orc = cpu_step_time(ds, kind, dropout if dropout is not None else 0., l2_reg, steps, warmup)
+    eval_ups, eval_sample = cpu_eval_users_per_s(ds, orc, n_batches=eval_batches)
+    return {'value': sec * 1e3 * steps_per_epoch, 'unit': 'ms', 'cores': os.cpu_count() or 1, 'kind': 'port',
+            'sample': '%d full train steps of %d per epoch (oracle/restate.py), extrapolated' % (steps, steps_per_epoch),
+            'ms_per_step': sec * 1e3, 'eval_users_per_s': eval_ups, 'eval_sample': eval_sample}
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference's step (oracle/restate.py, the same torch CPU ops the
+    reference reaches) on this box's host cores, same `config` as the B200 arm; rank 0 alone runs it."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    blocks = {}
+    for name in [args.workload] + [w for w in args.sub if w != args.workload]:
+        ds = build_dataset(WORKLOADS[name][0], 'cpu')
+        cpu = cpu_block(ds, name, args.steps if name == args.workload else max(1, min(args.steps, 2)), args.warmup)
+        blocks[name] = (workload_config(name, ds), cpu)
+    cfg, cpu = blocks[args.workload]
+    line = {'impl': 'reference', 'metric': METRIC, 'value': cpu['value'], 'unit': 'ms', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': cpu['ms_per_step'], 'higher_is_better': False, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
+            'impl_config': {'what': 'oracle/restate.py CPU port, torch CPU ops, %d threads' % cpu['cores']},
+            'cpu_baseline': cpu, 'e2e': {'value': cpu['value'], 'unit': 'ms', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0, 'eval_users_per_s': cpu['eval_users_per_s'], 'eval_e2e_users_per_s': cpu['eval_users_per_s'],
+            'eval': {'users_per_s': cpu['eval_users_per_s'], 'sample': cpu['eval_sample']},
+            'configs': {k: {'config': c, 'value': b['value'], 'ms_per_step': b['ms_per_step'], 'cpu_baseline': b,
+                            'eval_users_per_s': b['eval_users_per_s']}
+                        for k, (c, b) in blocks.items() if k != args.workload}}
     print(json.dumps(line))
 
 
@@ -352,7 +387,7 @@ def run_scaleout(args):
     alg = b_feat + L * b_adj + L * n_local * D * 4
     n_scored = int(users.shape[0])
     total_scored = n_scored * world if args.eval_users else ds.n_users
-    flops = 2.0 * n_scored * ds.n_items * 80
+    flops = 2.0 * n_scored * ds.n_items * D               # algorithmic 2 U I D
     if rank == 0:
         line = {'metric': 'full-rank eval users/s (propagate + fused score/top-k)', 'value': total_scored / ((prop_ms + score_ms) * 1e-3),
                 'unit': 'users/s', 'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ms_per_step': prop_ms + score_ms,
@@ -467,101 +502,92 @@ def run_dropui(args):
         dist.destroy_process_group()
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=None)
-    ap.add_argument('--warmup', type=int, default=None)
-    ap.add_argument('--workload', default='yelp-lightgcn', choices=sorted(WORKLOADS) + sorted(SCALEOUT) + sorted(DROPUI))
-    ap.add_argument('--eval-users', type=int, default=None, help='scale-out: users scored per rank (default: all of its share)')
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--cpu-steps', type=int, default=4)
-    args = ap.parse_args()
-    if args.workload in SCALEOUT:
-        return run_scaleout(args)
-    if args.workload in DROPUI:
-        return run_dropui(args)
-    shape, kind, l2_reg, dropout = WORKLOADS[args.workload]
-    if args.impl == 'reference':
-        args.steps = 5 if args.steps is None else args.steps
-        args.warmup = 1 if args.warmup is None else args.warmup
-        return run_reference(args, shape, kind, l2_reg, dropout)
-    args.steps = 1000 if args.steps is None else args.steps
-    args.warmup = 20 if args.warmup is None else max(3, args.warmup)
+class Env:
+    """Process-wide bench state: rank / world, device, peer context, reductions over ranks."""
 
-    import torch
-    import torch.distributed as dist
-    from igcn_cf_b200 import _lib
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    peers = None
-    if world > 1:
-        from igcn_cf_b200 import dist as idist
-        dist.init_process_group('nccl', device_id=dev)
-        peers = idist.init_peers()        # rows of the propagation sharded over the ranks, fused peer-store all-gather
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device('cuda', self.local)
+        self.peers = None
+        if self.world > 1:
+            from igcn_cf_b200 import dist as idist
+            dist.init_process_group('nccl', device_id=self.dev)
+            self.peers = idist.init_peers()
 
-    ds = build_dataset(shape, dev)
-    model, trainer = build_model(ds, kind, dropout, l2_reg, dev)
-    n, nnz, D = model.n_users + model.n_items, model.norm_adj.nnz, 64
-    n_local, nnz_local = model.norm_adj.local_rows, model.norm_adj.local_nnz
-    steps_per_epoch = math.ceil(len(ds) / BATCH)
-    step = trainer.step
-    model.train()
-
-    def barrier():
-        if world > 1:
+    def barrier(self):
+        import torch
+        if self.world > 1:
+            import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- launches per step (eager), then warm-up (captures the CUDA graph)
-    step.use_graph = False
-    before = _lib.launch_count
-    step.run()
-    launches_per_step = _lib.launch_count - before
-    step.use_graph = True
-    for _ in range(args.warmup):
-        step.run()
-
-    # ---- timed region: K steps, resident in HBM, device sampler, graph replay
-    sampler = ClockSampler(local)
-    sampler.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step.run()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([float(x)], device=self.dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
-    ms_per_step = ms / args.steps
+        return float(t.item())
 
-    # ---- e2e: host triples (pinned) -> H2D every step, loss D2H every step, public step API
+    def all_true(self, flag):
+        return self.max_over_ranks(0.0 if flag else 1.0) == 0.0
+
+    def close(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            from igcn_cf_b200 import dist as idist
+            self.peers.check()
+            idist.shutdown()
+            dist.destroy_process_group()
+
+
+def median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2]
+
+
+def time_steps(env, step, steps, repeats):
+    """`repeats` timed regions of EXACTLY `steps` graph-replayed steps each: barrier + synchronize on both sides, CUDA
+    events on the launch stream, max over ranks per region; returns (median ms/step, all regions)."""
+    import torch
+    out = []
+    for _ in range(repeats):
+        env.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step.run()
+        e1.record()
+        env.barrier()
+        out.append(env.max_over_ranks(e0.elapsed_time(e1)) / steps)
+    return median(out), out
+
+
+def time_e2e(env, ds, step, is_igcn, steps, repeats):
+    """Public step API fed HOST triples: every step copies that step's triples H2D from pinned memory and reads that
+    step's loss back D2H (what trainer.py:234/247 do).  The loss of step i is READ on the host after step i + 1 has
+    been enqueued (a training loop with a prefetching loader and asynchronous logging), so the device does not idle
+    on a host round trip.  Wall clock around `steps` steps, median of `repeats` regions, max over ranks."""
+    import torch
     pairs = ds.train_pairs
     g = torch.Generator().manual_seed(0)
     pool = 64
     sel = torch.randint(len(pairs), (pool, BATCH), generator=g)
     tp = torch.from_numpy(pairs)
     host = torch.stack([tp[sel, 0], tp[sel, 1], torch.randint(ds.n_items, (pool, BATCH), generator=g)], dim=2).pin_memory()
-    is_igcn = kind == 'IGCN'
-    # every step: H2D of that step's triples from pinned memory, one public step call, D2H of that step's loss into
-    # pinned memory.  The loss of step i is READ on the host after step i + 1 has been enqueued (the way a training
-    # loop with a prefetching loader and asynchronous logging runs), so the device does not idle on a host round trip.
     ploss = torch.zeros(2, dtype=torch.float32).pin_memory()
     evs = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_loop(n):
+    def loop(n):
         total = 0.0
         for i in range(n):
-            b = host[i % pool].to(dev, non_blocking=True)
+            b = host[i % pool].to(env.dev, non_blocking=True)
             loss_t = step.run(b, b if is_igcn else None)
             ploss[i % 2:i % 2 + 1].copy_(loss_t, non_blocking=True)
             evs[i % 2].record()
@@ -571,120 +597,223 @@ def main():
         evs[(n - 1) % 2].synchronize()
         return total + float(ploss[(n - 1) % 2])
 
-    e2e_loop(3)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_loss_sum = e2e_loop(args.steps)
-    barrier()
-    assert math.isfinite(e2e_loss_sum)
-    e2e_ms_step = (time.perf_counter() - t0) * 1e3 / args.steps
-    h2d = BATCH * 3 * 8
-    if world > 1:
-        t = torch.tensor([e2e_ms_step], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms_step = t.item()
+    loop(3)
+    out = []
+    for _ in range(repeats):
+        env.barrier()
+        t0 = time.perf_counter()
+        total = loop(steps)
+        env.barrier()
+        assert math.isfinite(total)
+        out.append(env.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps))
+    return median(out), BATCH * 3 * 8 * (2 if is_igcn else 1)
 
-    # ---- full-ranking evaluation (second half of the metric)
+
+def time_eval(env, model, trainer, reps=7):
+    """Second half of the metric: one full-ranking evaluation = propagate once + fused score / mask / top-20 over this
+    rank's users (device time, CUDA events, max over ranks, median of `reps`); e2e = trainer.eval('val') wall clock
+    (adds the gather of the lists, their D2H copy and the metrics)."""
+    import torch
     for _ in range(3):                         # warm: allocator blocks, mask tiles, workspaces
         model._bump()
         trainer.eval('val')
-    barrier()
-    reps = 5
-    e0.record()
-    walls = []
+    dev_ms, e2e_ms = [], []
     for _ in range(reps):
-        tw = time.perf_counter()
+        env.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         model._bump()                          # force the propagation to be recomputed, as after training
-        rec = trainer.recommend_local('val')
-        if os.environ.get('IGCN_BENCH_DEBUG'):
-            torch.cuda.synchronize()
-            walls.append(round((time.perf_counter() - tw) * 1e3, 3))
-    e1.record()
-    barrier()
-    eval_ms = e0.elapsed_time(e1) / reps
-    if world > 1:
-        t = torch.tensor([eval_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        eval_ms = t.item()
-    if walls:
-        from igcn_cf_b200 import engine as _e
-        sys.stderr.write('eval walls %s fallback users %d\n' % (walls, int(_e._tc_scorer.last_fallback.item())))
-    t0 = time.perf_counter()
-    model._bump()
-    trainer.eval('val')
-    torch.cuda.synchronize()
-    eval_e2e_ms = (time.perf_counter() - t0) * 1e3
-    if world > 1:
-        t = torch.tensor([eval_e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        eval_e2e_ms = t.item()
+        trainer.recommend_local('val')
+        e1.record()
+        env.barrier()
+        dev_ms.append(env.max_over_ranks(e0.elapsed_time(e1)))
+    for _ in range(reps):
+        env.barrier()
+        t0 = time.perf_counter()
+        model._bump()
+        trainer.eval('val')
+        torch.cuda.synchronize()
+        e2e_ms.append(env.max_over_ranks((time.perf_counter() - t0) * 1e3))
+    return median(dev_ms), median(e2e_ms)
 
-    # ---- per-kernel profile + roofline of the dominant kernel
+
+def measure(env, name, args, main):
+    """One workload on this process group -> the block of numbers the JSON line carries for it."""
+    import torch
+    from igcn_cf_b200 import _lib
+    from igcn_cf_b200 import dist as idist
+    shape, kind, l2_reg, dropout = WORKLOADS[name]
+    is_igcn = kind == 'IGCN'
+    ds = build_dataset(shape, env.dev)
+    cfg = workload_config(name, ds)
+    steps_per_epoch = cfg['steps_per_epoch']
+    repeats = args.repeats if main else max(3, args.repeats // 2)
+    D = 64
+    # at N > 1 the step is timed BOTH ways: replicated on every rank (no exchange on the training path) and with the
+    # propagation rows sharded (fused NVLink all-gather per layer); evaluation users are sharded in both
+    modes = [('single', False)] if env.world == 1 else [('replicated', 'users'), ('row_sharded', True)]
+    built = {}
+    for mode, shard in modes:
+        model, trainer = build_model(ds, kind, dropout, l2_reg, env.dev, shard=shard)
+        model.train()
+        built[mode] = (model, trainer)
+
+    # ---- N > 1: the row-sharded path must reproduce the replicated one bit for bit (rep before training, weights
+    # after one identical step); this is tests/dist_worker.py folded into the bench so every driver run proves it
+    parity = None
+    if env.world > 1:
+        (m_a, t_a), (m_b, t_b) = built['replicated'], built['row_sharded']
+        assert m_b._rows_sharded() and not m_a._rows_sharded()
+        ok = True
+        for m in (m_a, m_b):
+            m.eval()
+        with torch.no_grad():
+            ok &= torch.equal(m_a.get_rep(), m_b.get_rep())
+        for m, t in ((m_a, t_a), (m_b, t_b)):
+            m.train()
+            t.step.use_graph = False
+            t.step.run()
+            t.step.use_graph = True
+        ok &= torch.equal(m_a.embedding.weight.data, m_b.embedding.weight.data)
+        ok &= torch.equal(t_a.step.loss, t_b.step.loss)
+        parity = 'bit-identical' if env.all_true(bool(ok)) else 'MISMATCH'
+
+    res = {}
+    for mode, (model, trainer) in built.items():
+        step = trainer.step
+        step.use_graph = False
+        before = _lib.launch_count
+        step.run()
+        launches = _lib.launch_count - before
+        step.use_graph = True
+        for _ in range(args.warmup):
+            step.run()
+        ms, regions = time_steps(env, step, args.steps, repeats)
+        res[mode] = {'ms_per_step': ms, 'regions': [round(x, 5) for x in regions], 'launches_per_step': launches}
+    best = min(res, key=lambda k: res[k]['ms_per_step'])
+    model, trainer = built[best]
+    step = trainer.step
+    ms_per_step = res[best]['ms_per_step']
+
+    e2e_ms_step, h2d = time_e2e(env, ds, step, is_igcn, args.steps, max(3, repeats // 2))
+
+    # ---- evaluation: every mode (the row-sharded model also shards the one propagation of an evaluation)
+    ev = {}
+    for mode, (m, t) in built.items():
+        ev[mode] = time_eval(env, m, t)
+    ev_best = min(ev, key=lambda k: ev[k][0])
+    eval_ms, eval_e2e_ms = ev[ev_best]
+    m_ev, t_ev = built[ev_best]
+
+    # ---- per-kernel profile + rooflines of the dominant kernels (this rank's share of the work)
+    n, nnz = model.n_users + model.n_items, model.norm_adj.nnz
+    n_local, nnz_local = model.norm_adj.local_rows, model.norm_adj.local_nnz
     summary, spmm_gbs, spmm_avg_ms, spmm_avg_bytes = profile_kernels(trainer, n_local, nnz_local, D, 10, n)
     peak, tc_peak, peak_src = measured_peaks()
-    traffic = measured_traffic(args.workload) if world == 1 else {}
-    ev_ms = profile_eval(trainer)
+    traffic = measured_traffic(name) if env.world == 1 else {}
+    ev_ms = profile_eval(t_ev)
     tc_ms = ev_ms.get('igcn_tc_candidates')
-    n_eval_local = ds.n_users if peers is None else (lambda r: r[1] - r[0])(idist.split_range(ds.n_users, rank, world))
-    tc_flops = 2.0 * n_eval_local * ds.n_items * 80     # K = 64 dims + the 16-wide error-bound block (this rank's users)
+    n_eval_local = ds.n_users if env.world == 1 else (lambda r: r[1] - r[0])(idist.split_range(ds.n_users, env.rank, env.world))
+    tc_flops = 2.0 * n_eval_local * ds.n_items * D           # algorithmic: 2 U I D (SURVEY.md 8d); the bound block is overhead
     total = sum(v['ms_per_step'] for v in summary.values())
     shares = {k: round(v['ms_per_step'] / total, 4) for k, v in sorted(summary.items(), key=lambda kv: -kv[1]['ms_per_step'])}
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sec, orc = cpu_step_time(ds, kind, dropout if dropout is not None else 0., l2_reg, args.cpu_steps, 1)
-        eval_ups, eval_sample = cpu_eval_users_per_s(ds, orc)
-        cpu = {'value': sec * 1e3 * steps_per_epoch, 'unit': 'ms', 'cores': os.cpu_count() or 1, 'kind': 'port',
-               'sample': '%d full train steps of %d per epoch (oracle/restate.py), extrapolated' % (args.cpu_steps, steps_per_epoch),
-               'eval_users_per_s': eval_ups, 'eval_sample': eval_sample}
+    block = {'config': cfg, 'value': ms_per_step * steps_per_epoch, 'ms_per_step': ms_per_step, 'step_mode': best,
+             'repeats': repeats, 'ms_per_step_regions': res[best]['regions'],
+             'e2e': {'value': e2e_ms_step * steps_per_epoch, 'unit': 'ms', 'ms_per_step': e2e_ms_step,
+                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
+             'launches_per_step': res[best]['launches_per_step'],
+             'eval': {'users_per_s': ds.n_users / (eval_ms * 1e-3), 'ms': eval_ms,
+                      'e2e_users_per_s': ds.n_users / (eval_e2e_ms * 1e-3), 'e2e_ms': eval_e2e_ms, 'mode': ev_best,
+                      'what': 'propagate once + fused score/mask/top-20 over all %d users x %d items; e2e adds the gather / D2H of the lists and the metrics'
+                              % (ds.n_users, ds.n_items),
+                      'kernel_ms': {k: round(v, 4) for k, v in sorted(ev_ms.items(), key=lambda kv: -kv[1])},
+                      'roofline': None if not tc_ms else {
+                          'kernel': 'score_tc_kernel (igcn_tc_candidates, tcgen05 kind::f16)', 'bound': 'tensor',
+                          'achieved': tc_flops / (tc_ms * 1e-3) / 1e12, 'peak': tc_peak, 'unit': 'TFLOP/s',
+                          'frac': tc_flops / (tc_ms * 1e-3) / 1e12 / tc_peak, 'traffic': traffic.get('igcn_tc_candidates'),
+                          'flops_counted': '2*U*I*64 (algorithmic; the 16-wide error-bound K block is not counted)'}},
+             'roofline': {'kernel': 'prop_kernel<8,2,SPMM> (igcn_spmm, full layers)', 'bound': 'hbm', 'achieved': spmm_gbs, 'peak': peak,
+                          'unit': 'GB/s', 'frac': spmm_gbs / peak, 'traffic': traffic.get('igcn_spmm'), 'peak_source': peak_src,
+                          'avg_launch_ms': spmm_avg_ms, 'algorithmic_bytes_per_launch': spmm_avg_bytes},
+             'kernel_shares': shares, 'kernel_ms_per_step_eager': round(total, 4)}
+    if env.world > 1:
+        block['ms_per_step_replicated'] = res['replicated']['ms_per_step']
+        block['ms_per_step_row_sharded'] = res['row_sharded']['ms_per_step']
+        block['shard_parity'] = parity
+        block['eval']['ms_by_mode'] = {k: round(v[0], 4) for k, v in ev.items()}
+    block['_l2_inputs'] = (nnz_local, spmm_avg_ms)
+    if env.rank == 0 and env.world == 1 and not args.no_cpu_baseline:
+        block['cpu_baseline'] = cpu_block(ds, name, args.cpu_steps if main else 2, 1)
+    del built
+    torch.cuda.empty_cache()
+    return block
 
-    if rank == 0:
-        line = {'metric': METRIC, 'value': ms_per_step * steps_per_epoch, 'unit': 'ms', 'n_gpus': world, 'steps': args.steps,
-                'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': False,
-                'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': args.workload, 'shape': shape, 'n_users': ds.n_users,
-                           'n_items': ds.n_items, 'train_interactions': len(ds), 'nnz_adj': nnz, 'dim': D, 'layers': 3,
-                           'batch': BATCH, 'steps_per_epoch': steps_per_epoch, 'sampler': 'device', 'cuda_graph': True,
-                           'parallelism': 'single GPU' if world == 1 else
-                           ('propagation rows sharded over %d GPUs (fused NVLink peer-store all-gather per layer), '
-                            'BPR step + Adam replicated, eval users sharded' % world) if model._rows_sharded() else
-                           ('training step replicated on %d GPUs (graph too small for the per-layer exchange to pay '
-                            'off, DESIGN.md 7), eval users sharded' % world),
-                           'l2': 'no explicit flush: a step touches ~%d MB of distinct buffers (> 126 MB L2)'
-                                 % ((8 * n * D * 4 + nnz * 8) // 2 ** 20)},
-                'e2e': {'value': e2e_ms_step * steps_per_epoch, 'unit': 'ms', 'ms_per_step': e2e_ms_step,
-                        'h2d_bytes_per_step': h2d * (2 if is_igcn else 1), 'd2h_bytes_per_step': 4},
-                'gpu_launches': launches_per_step * args.steps,
-                'eval': {'users_per_s': ds.n_users / (eval_ms * 1e-3), 'ms': eval_ms,
-                         'e2e_users_per_s': ds.n_users / (eval_e2e_ms * 1e-3), 'e2e_ms': eval_e2e_ms,
-                         'what': 'propagate once + fused score/mask/top-20 over all %d users x %d items; e2e adds D2H of the lists and host metrics'
-                                 % (ds.n_users, ds.n_items),
-                         'kernel_ms': {k: round(v, 4) for k, v in sorted(ev_ms.items(), key=lambda kv: -kv[1])},
-                         'roofline': None if not tc_ms else {
-                             'kernel': 'score_tc_kernel (igcn_tc_candidates, tcgen05 kind::f16)', 'bound': 'tensor',
-                             'achieved': tc_flops / (tc_ms * 1e-3) / 1e12, 'peak': tc_peak, 'unit': 'TFLOP/s',
-                             'frac': tc_flops / (tc_ms * 1e-3) / 1e12 / tc_peak,
-                             'traffic': traffic.get('igcn_tc_candidates'),
-                             'flops_counted': '2*U*I*80 (64 dims + 16-wide bound block)'}},
-                'roofline': {'kernel': 'prop_kernel<8,2,SPMM> (igcn_spmm, full layers)', 'bound': 'hbm', 'achieved': spmm_gbs, 'peak': peak,
-                             'unit': 'GB/s', 'frac': spmm_gbs / peak, 'traffic': traffic.get('igcn_spmm'), 'peak_source': peak_src,
-                             'avg_launch_ms': spmm_avg_ms, 'algorithmic_bytes_per_launch': spmm_avg_bytes},
-                'kernel_shares': shares, 'kernel_ms_per_step_eager': round(total, 4), 'clocks': clocks}
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=None)
+    ap.add_argument('--warmup', type=int, default=None)
+    ap.add_argument('--workload', default='amazon-igcn', choices=sorted(WORKLOADS) + sorted(SCALEOUT) + sorted(DROPUI))
+    ap.add_argument('--sub', default='gowalla-igcn,yelp-lightgcn',
+                    help='comma-separated workloads reported as sub-blocks `configs` of the same JSON line ("" = none)')
+    ap.add_argument('--repeats', type=int, default=10, help='timed regions of K steps each; the median is reported')
+    ap.add_argument('--eval-users', type=int, default=None, help='scale-out: users scored per rank (default: all of its share)')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-steps', type=int, default=4)
+    args = ap.parse_args()
+    args.sub = [w for w in args.sub.split(',') if w]
+    if args.workload in SCALEOUT:
+        return run_scaleout(args)
+    if args.workload in DROPUI:
+        return run_dropui(args)
+    if args.impl == 'reference':
+        args.steps = 4 if args.steps is None else min(args.steps, 6)      # bounded sample: ~1.7 s per Amazon-shaped CPU step
+        args.warmup = 1 if args.warmup is None else min(args.warmup, 1)
+        return run_reference(args)
+    args.steps = 200 if args.steps is None else args.steps
+    args.warmup = 20 if args.warmup is None else max(3, args.warmup)
+
+    env = Env()
+    sampler = ClockSampler(env.local)
+    sampler.start()
+    main_block = measure(env, args.workload, args, True)
+    clocks = sampler.stop()
+    subs = {w: measure(env, w, args, False) for w in args.sub if w != args.workload}
+
+    if env.rank == 0:
+        world = env.world
+        b = main_block
+        line = {'metric': METRIC, 'value': b['value'], 'unit': 'ms', 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': b['ms_per_step'], 'higher_is_better': False,
+                'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': b['config'],
+                'impl_config': {'sampler': 'device', 'cuda_graph': True, 'timing': 'median of %d regions of %d steps' % (b['repeats'], args.steps),
+                                'parallelism': 'single GPU' if world == 1 else
+                                ('propagation rows sharded over %d GPUs (fused NVLink peer-store all-gather per layer), BPR step + Adam '
+                                 'replicated, eval users sharded' % world) if b['step_mode'] == 'row_sharded' else
+                                ('training step replicated on %d GPUs (faster than the row-sharded step on this graph, both timed), '
+                                 'eval users sharded' % world)},
+                'e2e': b['e2e'], 'gpu_launches': b['launches_per_step'] * args.steps,
+                'eval_users_per_s': b['eval']['users_per_s'], 'eval_e2e_users_per_s': b['eval']['e2e_users_per_s']}
+        for k in ('step_mode', 'ms_per_step_replicated', 'ms_per_step_row_sharded', 'shard_parity', 'ms_per_step_regions',
+                  'eval', 'roofline', 'kernel_shares', 'kernel_ms_per_step_eager', 'cpu_baseline'):
+            if k in b:
+                line[k] = b[k]
+        line['clocks'] = clocks
         # secondary diagnostic (DESIGN.md 6): the layer table is L2-resident on these graphs, so what the gather kernel
         # actually saturates is the L2->SM fabric (~6.3 kB/cycle full chip, B300_MICROARCH.md "LTS throughput cap")
         sm_mhz = clocks.get('sm_mhz') or clocks.get('sm_max_mhz') or 1965
         l2_peak = 6300.0 * sm_mhz * 1e6 / 1e9
-        l2_ach = nnz_local * D * 4 / (spmm_avg_ms * 1e-3) / 1e9
-        line['roofline']['l2_gather'] = {'bound': 'l2->sm fabric', 'achieved': l2_ach, 'peak': l2_peak, 'unit': 'GB/s',
-                                         'frac': l2_ach / l2_peak, 'bytes_counted': 'nnz * D * 4 per launch (gathered rows only)'}
-        if cpu:
-            line['cpu_baseline'] = cpu
+        for blk in [b] + list(subs.values()):
+            nnz_local, spmm_avg_ms = blk.pop('_l2_inputs')
+            l2_ach = nnz_local * 64 * 4 / (spmm_avg_ms * 1e-3) / 1e9
+            blk['roofline']['l2_gather'] = {'bound': 'l2->sm fabric', 'achieved': l2_ach, 'peak': l2_peak, 'unit': 'GB/s',
+                                            'frac': l2_ach / l2_peak, 'bytes_counted': 'nnz * D * 4 per launch (gathered rows only)'}
+        line['configs'] = subs
         print(json.dumps(line))
-    if world > 1:
-        peers.check()
-        from igcn_cf_b200 import dist as idist
-        idist.shutdown()
-        dist.destroy_process_group()
+    env.close()
 
 
 if __name__ == '__main__':

@@ -11,7 +11,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'libigcn_b200.so')
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_ADD = 8
 MAX_PEERS = 8
 
@@ -65,16 +65,14 @@ _SIGNATURES = {
     'igcn_score_topk_exact': [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p,
                               c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int32, c_void_p, c_int64, c_void_p],
-    'igcn_spmm_hot': [C.POINTER(CsrStruct), c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, C.POINTER(c_void_p), c_int32,
-                      c_void_p, c_float, c_void_p],
     'igcn_tc_workspace': [c_int64, c_int64, c_int32, c_int32, C.POINTER(c_int64), C.POINTER(c_int64),
                           C.POINTER(c_int64)],
-    'igcn_tc_pack': [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
+    'igcn_tc_pack': [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                      c_void_p, c_void_p, c_void_p],
     'igcn_tc_candidates': [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_int64, c_int64, c_void_p,
-                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'igcn_tc_finalize': [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
-                         c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+                         c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'igcn_predict_scores': [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p],
     'igcn_hits': [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p],
     'igcn_peer_alloc': [c_int64, C.POINTER(c_void_p), c_void_p],

@@ -22,9 +22,17 @@
 //           core-matrix layout written by tc_pack_kernel, so a tile is one contiguous copy)
 //   warp 1  TMEM allocator + single-thread tcgen05.mma issuer (M128 x N256 x K16, 5 per tile)
 //   warp 2  mask helper: turns the (user tile, item tile) bucket of seen items, the banned bitmap
-//           and the item range into a 128 x 256 bitmap in shared memory
-//   warp 3-6 epilogue: tcgen05.ld 32x32b (thread = user row), threshold + mask filter, append to the
-//           row's candidate buffer in shared memory, warp-cooperative compaction when it fills.
+//           and the item range into a 128 x 256 bitmap in shared memory (and clears what it set two
+//           tiles earlier: the epilogue never writes the bitmap)
+//   warp 3-6 epilogue: tcgen05.ld 32x32b (thread = user row).  The filter is built around the ALU pipe
+//           (16 lanes/clk per scheduler: one warp instruction every 2 cycles): a compare + predicated OR
+//           per score costs 4 cycles per column and warp, 1,024 cycles per 256-column tile against 640
+//           cycles of MMA, whatever the number of epilogue warps.  So the common case does no compare
+//           at all: the 32 scores of a chunk are max-reduced with 3-input FMNMX (0.5 instruction per
+//           score), ONE vote asks whether any row of the warp beats its threshold, and only then the
+//           8-column groups that contain a hit are compared, masked and appended.  Items are scanned in
+//           a caller-supplied order (most popular first): thresholds tighten within the first tiles and
+//           most later chunks take the compare-free path.
 // Pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty double buffer (MMA <-> epilogue),
 // bitmap full (helper -> epilogue).
 
@@ -39,8 +47,7 @@ constexpr int TC_CAP = 96;        // candidate slots per user row
 constexpr int TC_KEEP = 32;       // the threshold never rises above the TC_KEEP-th best upper bound
 constexpr int TC_STAGES = 2;      // item-tile smem stages
 constexpr int TC_THREADS = 7 * 32;
-constexpr int TC_STAGE_W = 36;    // words per row of the chunk staging area (16 B aligned, conflict-free)
-constexpr float TC_THR_SCALE = 1024.f;   // experimental variant 7: thresholds enter the MMA as fp16(-thr / 1024) x 1024
+constexpr int TC_STAGE_W = 12;    // words per row of the 8-score staging area (16 B aligned; 128-bit stores of 8 lanes hit 8 bank groups)
 
 // ------------------------------------------------------------------ operand packing
 __global__ void maxabs_kernel(const float *__restrict__ x, int64_t n, uint32_t *out) {
@@ -53,11 +60,10 @@ __global__ void maxabs_kernel(const float *__restrict__ x, int64_t n, uint32_t *
 
 // One group of 16 lanes converts one row (D <= 64) into its tile image: kcores core matrices of
 // 8 fp16 (16 B) per row; the last K block holds the bound entry in its first element.
-// THR (experimental, IGCN_TC_EXPERIMENT=7): item rows also get TC_THR_SCALE in bound-block column 1 + (tile & 1), the
-// column the candidate kernel uses to let the tensor core subtract each user's threshold (see score_tc_kernel<7>).
-template <bool THR>
+// Row r of the image is rep row row_ids[r] (users), row0 + perm[r] (items in scan order) or row0 + r.
 __global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ rep, const int64_t *__restrict__ row_ids,
-                                                      int64_t row0, int64_t n_rows, int D, int tile_rows, int kcores, int is_user,
+                                                      const int32_t *__restrict__ perm, int64_t row0, int64_t n_rows, int D,
+                                                      int tile_rows, int kcores, int is_user,
                                                       const uint32_t *__restrict__ maxabs_bits, const float *__restrict__ center_sum,
                                                       float inv_n, uint8_t *__restrict__ img) {
     const int lane = threadIdx.x & 15;
@@ -65,7 +71,7 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ 
     if (r >= n_rows) return;
     const uint32_t gmask = 0xffffu << ((threadIdx.x & 31) & 16);
     const float scale = tc_scale(maxabs_bits);
-    const int64_t src = row_ids ? row_ids[r] : row0 + r;
+    const int64_t src = row_ids ? row_ids[r] : row0 + (perm ? (int64_t)perm[r] : r);
     float4 v = f4zero();
     if (lane * 4 < D) {
         v = ld4(rep + src * D + lane * 4);
@@ -95,10 +101,6 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ 
         const float b = is_user ? (TC_C * norm + TC_EPS_U) : (norm + TC_EPS_I);
         uint4 z = make_uint4(0u, 0u, 0u, 0u);
         z.x = (uint32_t)__half_as_ushort(__float2half_ru(b));
-        if (THR && !is_user) {
-            const uint32_t one = (uint32_t)__half_as_ushort(__float2half_rn(TC_THR_SCALE));      // a power of two: exact
-            if (tile & 1) z.y = one; else z.x |= one << 16;
-        }
         *reinterpret_cast<uint4 *>(base + (size_t)dcores * 128) = z;
         *reinterpret_cast<uint4 *>(base + (size_t)(dcores + 1) * 128) = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -117,6 +119,7 @@ struct TcArgs {
     int32_t *cand_cnt;                // [n_eval, n_splits]
     float *cand_thr;                  // [n_eval, n_splits]   (scaled units; -inf = nothing was dropped)
     float *dump;                      // optional [n_utiles*128, n_itiles*256] of s_hat (tests)
+    unsigned long long *stats;        // optional [5] filter statistics (igcn_tc_candidates_stats)
     int dbg;                          // timing experiments (IGCN_TC_DEBUG): 1 producer/MMA threads spin instead of parking,
                                       // 2 mask builder spins, 4 mask builder builds nothing (invalid results)
 };
@@ -188,21 +191,12 @@ __device__ __forceinline__ void compact_lanes(uint64_t *mybuf, int &cnt, float &
     }
 }
 
-// VARIANT: 0 production, 1 = also dump every s_hat (tests), 2 / 3 = timing experiments selected with the
-// IGCN_TC_EXPERIMENT environment variable (results are NOT valid): 2 reads the accumulators but does not filter
-// (TMA + MMA + TMEM-read floor), 3 filters against thr = +inf (full filter cost, no hits, no compaction),
-// 4 = as 2 but only the first TC_STAGES item tiles are fetched (no item-image stream), 5 = as 2 but the epilogue
-// does not read TMEM at all, 6 = 4 and 5 together (MMA issue + the mbarrier hand-offs only).
-// 7 = EXPERIMENTAL, valid results, not yet run on a GPU: the tensor core subtracts the row's threshold.  The bound
-// K block has unused columns: item tile t carries TC_THR_SCALE in column 1 + (t & 1) (tc_pack_kernel<true>) and
-// the user row carries a = fp16_up(-thr / TC_THR_SCALE) there, so the accumulator is s_hat - thr' with thr' =
-// -a * TC_THR_SCALE <= thr, and the filter is ONE funnel shift per score that collects sign bits instead of FSETP
-// + predicated add.  A row may rewrite its a for parity p only between tmem_full(t) and its own tmem_empty(t)
-// arrive (t & 1 == p): the next MMA that reads that column with a non-zero multiplier is tile t + 2, issued
-// after all four warps arrived; tile t + 1 multiplies it by zero.  The rare path adds thr' back (rounded up, plus
-// 2^-17 |thr'| for the extra fp32 accumulation error the large term causes) and re-checks s_hat > thr; the
-// recorded threshold is inflated by the same amount because the sign test itself carries that error.  Rows
-// start with thr = 0 instead of -inf (a = 0: items with a negative upper bound are dropped at once).
+// VARIANT: 0 production, 1 = also dump every s_hat (tests), 4 = production + filter statistics (TcArgs.stats:
+// chunks seen / chunks that left the compare-free path / 8-column groups compared / candidates appended /
+// compactions); 2, 3, 5 = timing experiments selected with the IGCN_TC_EXPERIMENT environment variable (results
+// are NOT valid): 2 reads the accumulators but does not filter (TMA + MMA + TMEM-read floor), 3 filters against
+// thr = +inf (the compare-free path on every chunk, no hits, no compaction), 5 does not read TMEM at all (MMA
+// issue + the mbarrier hand-offs only).
 template <int VARIANT>
 __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -212,7 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
     uint8_t *sB = sA + a_bytes;
     uint64_t *cand = reinterpret_cast<uint64_t *>(sB + (size_t)TC_STAGES * b_bytes);
     uint32_t *bitmap = reinterpret_cast<uint32_t *>(cand + (size_t)TC_BM * (TC_CAP + 1));
-    uint32_t *stage = bitmap + 2 * TC_BM * 8;                       // [128 rows][TC_STAGE_W] chunk staging
+    uint32_t *stage = bitmap + 2 * TC_BM * 8;                       // [128 rows][TC_STAGE_W]: one 8-score group per row
     TcSmem *sm = reinterpret_cast<TcSmem *>(stage + TC_BM * TC_STAGE_W);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -256,10 +250,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 const int s = it % TC_STAGES;
                 const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
                 mbar_wait_helper(&sm->empty[s], ph ^ 1u, a.dbg & 1);
-                if ((VARIANT == 4 || VARIANT == 6) && it >= TC_STAGES) {
-                    mbar_arrive(&sm->full[s]);
-                    continue;
-                }
                 mbar_arrive_expect_tx(&sm->full[s], b_bytes);
                 bulk_g2s(sB + (size_t)s * b_bytes, a.b_img + (size_t)(t0 + it) * b_bytes, b_bytes, &sm->full[s]);
             }
@@ -285,15 +275,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             }
         }
     } else if (warp == 2) {
-        // ===== mask helper: seen-item bucket + banned bitmap + item range -> bitmap[acc][8 words][128 rows]
-        for (int it = 0; it < n_it; ++it) {
-            const int acc = it & 1, t = t0 + it;
-            mbar_wait_helper(&sm->tmem_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u, a.dbg & 2);
-            if (a.dbg & 4) {
-                if (lane == 0) mbar_arrive(&sm->mask_full[acc]);
-                continue;
-            }
-            uint32_t *bm = bitmap + (size_t)acc * TC_BM * 8;
+        // ===== mask helper: seen-item bucket + banned bitmap + item range -> bitmap[acc][8 words][128 rows].
+        // The epilogue only reads the bitmap, so before building tile `it` the helper un-sets what it set for
+        // tile `it - 2` (same buffer): apply(t, false) stores zero words exactly where apply(t, true) OR-ed bits.
+        auto apply = [&](int t, bool set, uint32_t *bm) {
             uint32_t common = 0;
             if (lane < 8) {
                 const int64_t c0 = (int64_t)t * TC_BN + lane * 32;
@@ -305,7 +290,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 for (int w = 0; w < 8; ++w) {
                     const uint32_t cw = __shfl_sync(0xffffffffu, common, w);
                     if (cw)
-                        for (int r = lane; r < TC_BM; r += 32) bm[w * TC_BM + r] |= cw;
+                        for (int r = lane; r < TC_BM; r += 32) {
+                            if (set) bm[w * TC_BM + r] |= cw; else bm[w * TC_BM + r] = 0u;
+                        }
                 }
                 __syncwarp();
             }
@@ -314,49 +301,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 const int e0 = __ldg(p), e1 = __ldg(p + 1);
                 for (int e = e0 + lane; e < e1; e += 32) {
                     const uint32_t ent = a.mask_entries[e];
-                    atomicOr(bm + ((ent & 255u) >> 5) * TC_BM + (ent >> 8), 1u << (ent & 31u));
+                    uint32_t *w = bm + ((ent & 255u) >> 5) * TC_BM + (ent >> 8);
+                    if (set) atomicOr(w, 1u << (ent & 31u)); else *w = 0u;
                 }
             }
             __syncwarp();
+        };
+        for (int it = 0; it < n_it; ++it) {
+            const int acc = it & 1, t = t0 + it;
+            mbar_wait_helper(&sm->tmem_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u, a.dbg & 2);
+            if (a.dbg & 4) {
+                if (lane == 0) mbar_arrive(&sm->mask_full[acc]);
+                continue;
+            }
+            uint32_t *bm = bitmap + (size_t)acc * TC_BM * 8;
+            if (it >= 2) apply(t - 2, false, bm);
+            apply(t, true, bm);
+            __threadfence_block();
             if (lane == 0) mbar_arrive(&sm->mask_full[acc]);
         }
     } else {
-        // ===== epilogue: thread = user row (TMEM lane).  Per 32-column chunk: tcgen05.ld -> stage the
-        // 32 scores in shared memory (8 x STS.128) -> build a hit mask with FSETP + predicated OR (no
-        // branches, 4 independent chains) -> clear masked columns with one AND -> rare slow path
-        // appends the hits from the staged copy.
+        // ===== epilogue: thread = user row (TMEM lane)
         const int q = warp & 3;                         // warps 3,4,5,6 -> TMEM lane quarters 3,0,1,2
         const int row = q * 32 + lane;
         uint64_t *mybuf = cand + (size_t)row * (TC_CAP + 1);
         uint32_t *mystage = stage + (size_t)row * TC_STAGE_W;
-        float thr = VARIANT == 3 ? INFINITY : VARIANT == 7 ? 0.f : -INFINITY;
+        float thr = VARIANT == 3 ? INFINITY : -INFINITY;
         int cnt = 0;
-        float ta0 = 0.f, ta1 = 0.f;                     // variant 7: threshold currently in the A tile, per tile parity
-        // this row's bound-block entry in the A image: 8-row group, first bound core, row within the group
-        uint8_t *my_a = sA + (size_t)(row >> 3) * a.kcores * 128 + (size_t)(a.kcores - 2) * 128 + (size_t)(row & 7) * 16;
+        uint32_t st_chunks = 0, st_slow = 0, st_groups = 0, st_hits = 0, st_compact = 0;     // VARIANT 4 only
         for (int it = 0; it < n_it; ++it) {
             const int acc = it & 1, t = t0 + it;
             const uint32_t ph = (uint32_t)(it >> 1) & 1u;
             mbar_wait(&sm->tmem_full[acc], ph);
             mbar_wait(&sm->mask_full[acc], ph);
             tc_fence_after();
-            if (VARIANT == 5 || VARIANT == 6) {
+            if (VARIANT == 5) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm->tmem_empty[acc]);
                 continue;
             }
-            uint32_t *bm = bitmap + (size_t)acc * TC_BM * 8 + row;          // word w of this row at bm[w * 128]
+            const uint32_t *bm = bitmap + (size_t)acc * TC_BM * 8 + row;    // word w of this row at bm[w * 128]
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_BN;
             uint32_t va[32], vb[32];
             tc_ld32(taddr, va);
             // two chunks per iteration so the next TMEM load is always in flight behind the filter
             auto filter = [&](uint32_t (&v)[32], int ch) {
-                if (__any_sync(0xffffffffu, cnt > TC_CAP - 32)) compact_lanes(mybuf, cnt, thr);
-                const uint32_t m = bm[ch * TC_BM];
-                bm[ch * TC_BM] = 0u;
                 const uint32_t item0 = (uint32_t)(t * TC_BN + ch * 32);
-                if (VARIANT == 2 || VARIANT == 4) {
+                if (VARIANT == 2) {
                     uint32_t x = 0;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) x ^= v[c];
@@ -368,55 +360,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
 #pragma unroll
                     for (int c = 0; c < 32; ++c) d[c] = __uint_as_float(v[c]);
                 }
+                // ---- compare-free path: maxima of the four 8-column groups (3-input FMNMX), one vote per chunk
+                float gm[4];
 #pragma unroll
-                for (int c = 0; c < 32; c += 4)
-                    *reinterpret_cast<uint4 *>(mystage + c) = make_uint4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-                uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-                if (VARIANT == 7) {
-                    // sign bits of the 32 accumulators (s_hat - thr'), four independent chains, highest column first so
-                    // that column c ends up in bit c; a clear sign bit is a hit
-#pragma unroll
-                    for (int c = 7; c >= 0; --c) {
-                        h0 = __funnelshift_l(v[c], h0, 1);
-                        h1 = __funnelshift_l(v[c + 8], h1, 1);
-                        h2 = __funnelshift_l(v[c + 16], h2, 1);
-                        h3 = __funnelshift_l(v[c + 24], h3, 1);
-                    }
-                    h0 = ~(h0 | (h1 << 8) | (h2 << 16) | (h3 << 24));
-                    h1 = h2 = h3 = 0u;
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        hit_if_gt(v[c], thr, h0, 1u << c);
-                        hit_if_gt(v[c + 8], thr, h1, 1u << (c + 8));
-                        hit_if_gt(v[c + 16], thr, h2, 1u << (c + 16));
-                        hit_if_gt(v[c + 24], thr, h3, 1u << (c + 24));
-                    }
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t *f = &v[g * 8];
+                    gm[g] = fmaxf(fmax3(f[0], f[1], f[2]), fmax3(f[3], f[4], fmax3(f[5], f[6], f[7])));
                 }
-                uint32_t hits = (h0 | h1 | h2 | h3) & ~m;        // seen / banned / out-of-range columns never pass
-                if (VARIANT == 7) {
-                    const float ta = (t & 1) ? ta1 : ta0;
-                    const float pad = fabsf(ta) * 7.62939453125e-6f;              // 2^-17 |thr'|
-                    while (hits) {                               // one hit per trip: each is re-checked against thr
-                        const int c0 = __ffs(hits) - 1;
-                        hits &= hits - 1;
-                        const float s_up = __fadd_ru(__fadd_ru(__uint_as_float(mystage[c0]), ta), pad);
-                        if (s_up > thr) {
-                            mybuf[cnt] = ((uint64_t)(item0 + c0) << 32) | __float_as_uint(s_up);
-                            ++cnt;
+                const float m = fmaxf(fmax3(gm[0], gm[1], gm[2]), gm[3]);
+                if (VARIANT == 4) ++st_chunks;
+                if (!__any_sync(0xffffffffu, m > thr)) return;
+                // ---- some row of the warp has a score above its threshold in this chunk
+                if (VARIANT == 4) ++st_slow;
+                if (__any_sync(0xffffffffu, cnt > TC_CAP - 32)) {
+                    compact_lanes(mybuf, cnt, thr);
+                    if (VARIANT == 4) ++st_compact;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (!__any_sync(0xffffffffu, gm[g] > thr)) continue;
+                    if (VARIANT == 4) ++st_groups;
+                    uint32_t h = 0;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) hit_if_gt(v[g * 8 + c], thr, h, 1u << c);
+                    if (h) {
+                        // rare per row (about one row in twenty of a compared group): stage the 8 scores so that the
+                        // hit columns can be addressed, drop seen / banned / out-of-range columns, append
+                        *reinterpret_cast<uint4 *>(mystage) = make_uint4(v[g * 8], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
+                        *reinterpret_cast<uint4 *>(mystage + 4) = make_uint4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
+                        h &= ~(bm[ch * TC_BM] >> (g * 8));
+                        while (h) {
+                            const int c0 = __ffs(h) - 1;
+                            h &= h - 1;
+                            mybuf[cnt++] = ((uint64_t)(item0 + g * 8 + c0) << 32) | mystage[c0];
+                            if (VARIANT == 4) ++st_hits;
                         }
                     }
-                }
-                while (hits) {                                   // rare: ~1 % of the elements; two per trip so that
-                    const int c0 = __ffs(hits) - 1;              // both staged scores are in flight together
-                    hits &= hits - 1;
-                    const bool two = hits != 0u;
-                    const int c1 = two ? __ffs(hits) - 1 : c0;
-                    hits &= hits - 1;
-                    const uint32_t s0 = mystage[c0], s1 = mystage[c1];
-                    mybuf[cnt] = ((uint64_t)(item0 + c0) << 32) | s0;
-                    if (two) mybuf[cnt + 1] = ((uint64_t)(item0 + c1) << 32) | s1;
-                    cnt += two ? 2 : 1;
                 }
             };
 #pragma unroll 1
@@ -427,18 +406,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 tc_wait_ld();
                 if (ch + 2 < 8) tc_ld32(taddr + (ch + 2) * 32, va);
                 filter(vb, ch + 1);
-            }
-            if (VARIANT == 7) {
-                // put the current threshold into this parity's column of the A tile (only ever raises it)
-                const float ta = (t & 1) ? ta1 : ta0;
-                const float want = -thr * (1.f / TC_THR_SCALE);
-                if (thr > ta && want <= 65504.f) {
-                    const __half ah = __float2half_ru(want);                      // a >= -thr / S  =>  thr' = -a S <= thr
-                    *reinterpret_cast<__half *>(my_a + ((t & 1) ? 4 : 2)) = ah;
-                    const float nt = -__half2float(ah) * TC_THR_SCALE;
-                    if (t & 1) ta1 = nt; else ta0 = nt;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy store -> async-proxy (MMA) reads
             }
             tc_fence_before();
             __syncwarp();
@@ -456,12 +423,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             for (int e = lane; e < n; e += 32) dst[e] = (int32_t)(uint32_t)(src[e] >> 32);
             if (lane == 0) {
                 a.cand_cnt[b * a.n_splits + sp] = n;
-                // variant 7: the sign test carries the accumulation error of the subtracted term (see above)
-                a.cand_thr[b * a.n_splits + sp] = (VARIANT == 7 && th < INFINITY) ? __fadd_ru(th, fabsf(th) * 7.62939453125e-6f) : th;
+                a.cand_thr[b * a.n_splits + sp] = th;
             }
             if (head && lane > 0 && lane < a.n_splits) {          // the list slots an unsplit tile does not use
                 a.cand_cnt[b * a.n_splits + lane] = 0;
                 a.cand_thr[b * a.n_splits + lane] = -INFINITY;
+            }
+        }
+        if (VARIANT == 4 && a.stats) {
+            // chunk / group counters are per warp (lane 0 speaks), appended candidates per row (summed)
+            const uint32_t hits = __reduce_add_sync(0xffffffffu, st_hits);
+            if (lane == 0) {
+                atomicAdd(a.stats + 0, (unsigned long long)st_chunks);
+                atomicAdd(a.stats + 1, (unsigned long long)st_slow);
+                atomicAdd(a.stats + 2, (unsigned long long)st_groups);
+                atomicAdd(a.stats + 3, (unsigned long long)hits);
+                atomicAdd(a.stats + 4, (unsigned long long)st_compact);
             }
         }
     }
@@ -482,6 +459,7 @@ __global__ void __launch_bounds__(256) tc_finalize_kernel(const float *__restric
                                                           const int32_t *__restrict__ cand_items, const int32_t *__restrict__ cand_cnt,
                                                           const float *__restrict__ cand_thr, const uint32_t *__restrict__ maxabs_bits,
                                                           const float *__restrict__ center_sum, float inv_n,
+                                                          const int32_t *__restrict__ item_perm,
                                                           int k, int32_t *out_items, float *out_scores, int32_t *fb_count,
                                                           int64_t *fb_users, int32_t *fb_rows) {
     extern __shared__ uint64_t fin_keys[];               // [8 warps][n_splits * TC_CAP]
@@ -499,7 +477,7 @@ __global__ void __launch_bounds__(256) tc_finalize_kernel(const float *__restric
         thr_max = fmaxf(thr_max, cand_thr[b * n_splits + sp]);
         const int32_t *src = cand_items + ((size_t)b * n_splits + sp) * TC_CAP;
         for (int e = lane; e < c; e += 32) {
-            const int32_t item = src[e];
+            const int32_t item = item_perm ? __ldg(item_perm + src[e]) : src[e];     // scan position -> item id
             const float *irow = rep + (item_row0 + item) * D;
             float s = 0.f;
             for (int d = 0; d < D; d += 4) {
@@ -568,8 +546,8 @@ extern "C" int igcn_tc_workspace(int64_t n_eval, int64_t n_items, int32_t D, int
 }
 
 extern "C" int igcn_tc_pack(const float *rep, int64_t n_rep_elems, const int64_t *user_ids, int64_t n_eval, int64_t item_row0,
-                            int64_t n_items, int32_t D, uint32_t *maxabs_bits, uint8_t *a_img, uint8_t *b_img, float *center_sum,
-                            float *center_scratch, void *stream) {
+                            int64_t n_items, int32_t D, const int32_t *item_perm, uint32_t *maxabs_bits, uint8_t *a_img,
+                            uint8_t *b_img, float *center_sum, float *center_scratch, void *stream) {
     IGCN_CHECK_ARG(rep && user_ids && maxabs_bits && a_img && b_img && center_sum && center_scratch, "null pointer");
     IGCN_CHECK_ARG(D > 0 && D <= 64 && !(D & 3), "tensor-core scoring supports D % 4 == 0, D <= 64");
     cudaStream_t st = as_stream(stream);
@@ -580,13 +558,11 @@ extern "C" int igcn_tc_pack(const float *rep, int64_t n_rep_elems, const int64_t
     if (int rc = igcn_colsum_masked(rep, item_row0, item_row0 + n_items, D, nullptr, center_scratch, center_sum, stream)) return rc;
     const float inv_n = n_items > 0 ? 1.f / (float)n_items : 0.f;
     if (n_eval > 0)
-        tc_pack_kernel<false><<<(unsigned)((n_eval + 15) / 16), 256, 0, st>>>(rep, user_ids, 0, n_eval, D, TC_BM, kc, 1, maxabs_bits, center_sum,
-                                                                       inv_n, a_img);
-    const char *exp_env = getenv("IGCN_TC_EXPERIMENT");       // 7: item tiles carry the threshold multiplier (score_tc_kernel<7>)
-    auto pack_items = (exp_env && atoi(exp_env) == 7) ? tc_pack_kernel<true> : tc_pack_kernel<false>;
+        tc_pack_kernel<<<(unsigned)((n_eval + 15) / 16), 256, 0, st>>>(rep, user_ids, nullptr, 0, n_eval, D, TC_BM, kc, 1, maxabs_bits,
+                                                                        center_sum, inv_n, a_img);
     if (n_items > 0)
-        pack_items<<<(unsigned)((n_items + 15) / 16), 256, 0, st>>>(rep, nullptr, item_row0, n_items, D, TC_BN, kc, 0, maxabs_bits,
-                                                                    center_sum, inv_n, b_img);
+        tc_pack_kernel<<<(unsigned)((n_items + 15) / 16), 256, 0, st>>>(rep, nullptr, item_perm, item_row0, n_items, D, TC_BN, kc, 0,
+                                                                         maxabs_bits, center_sum, inv_n, b_img);
     IGCN_CHECK_LAUNCH();
     return 0;
 }
@@ -594,7 +570,7 @@ extern "C" int igcn_tc_pack(const float *rep, int64_t n_rep_elems, const int64_t
 extern "C" int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, int64_t n_eval, int64_t n_items, int32_t D,
                                   int32_t n_splits, int32_t n_head, int64_t item_lo, int64_t item_hi, const uint32_t *banned_bits,
                                   const int32_t *mask_tile_ptr, const uint16_t *mask_entries, int32_t *cand_items,
-                                  int32_t *cand_cnt, float *cand_thr, float *dump, void *stream) {
+                                  int32_t *cand_cnt, float *cand_thr, float *dump, unsigned long long *stats, void *stream) {
     IGCN_CHECK_ARG(a_img && b_img && cand_items && cand_cnt && cand_thr, "null pointer");
     IGCN_CHECK_ARG(D > 0 && D <= 64 && !(D & 3), "tensor-core scoring supports D % 4 == 0, D <= 64");
     IGCN_CHECK_ARG(n_splits >= 1 && n_splits <= 8, "n_splits must be in [1, 8]");
@@ -610,17 +586,16 @@ extern "C" int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, in
     a.n_splits = n_splits; a.n_head = n_head; a.kcores = tc_kcores(D);
     a.n_eval = n_eval; a.n_items = n_items; a.item_lo = item_lo; a.item_hi = item_hi;
     a.banned = banned_bits; a.mask_tile_ptr = mask_tile_ptr; a.mask_entries = mask_entries;
-    a.cand_items = cand_items; a.cand_cnt = cand_cnt; a.cand_thr = cand_thr; a.dump = dump;
+    a.cand_items = cand_items; a.cand_cnt = cand_cnt; a.cand_thr = cand_thr; a.dump = dump; a.stats = stats;
     const size_t smem = (size_t)(TC_BM / 8 + TC_STAGES * (TC_BN / 8)) * a.kcores * 128 + (size_t)TC_BM * (TC_CAP + 1) * 8 +
                         2 * TC_BM * 8 * 4 + (size_t)TC_BM * TC_STAGE_W * 4 + sizeof(TcSmem) + 64;
     const char *dbg_env = getenv("IGCN_TC_DEBUG");
     a.dbg = dbg_env ? atoi(dbg_env) : 0;
     const char *exp_env = getenv("IGCN_TC_EXPERIMENT");      // read per call: tools/tc_floor.py sweeps it in one process
     const int experiment = exp_env ? atoi(exp_env) : 0;
-    auto kern = dump ? score_tc_kernel<1>
-                : experiment == 2 ? score_tc_kernel<2> : experiment == 3 ? score_tc_kernel<3> : experiment == 4 ? score_tc_kernel<4>
-                : experiment == 5 ? score_tc_kernel<5> : experiment == 6 ? score_tc_kernel<6>
-                : experiment == 7 ? score_tc_kernel<7> : score_tc_kernel<0>;
+    auto kern = dump ? score_tc_kernel<1> : stats ? score_tc_kernel<4>
+                : experiment == 2 ? score_tc_kernel<2> : experiment == 3 ? score_tc_kernel<3>
+                : experiment == 5 ? score_tc_kernel<5> : score_tc_kernel<0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("igcn_tc_candidates: %s", cudaGetErrorString(e)); return (int)e; }
     kern<<<n_ctas, TC_THREADS, smem, as_stream(stream)>>>(a);
@@ -630,9 +605,9 @@ extern "C" int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, in
 
 extern "C" int igcn_tc_finalize(const float *rep, const int64_t *user_ids, int64_t n_eval, int64_t item_row0, int32_t D,
                                 int32_t n_splits, const int32_t *cand_items, const int32_t *cand_cnt, const float *cand_thr,
-                                const uint32_t *maxabs_bits, const float *center_sum, int64_t n_items, int32_t k,
-                                int32_t *out_items, float *out_scores, int32_t *fb_count, int64_t *fb_users, int32_t *fb_rows,
-                                void *stream) {
+                                const uint32_t *maxabs_bits, const float *center_sum, int64_t n_items, const int32_t *item_perm,
+                                int32_t k, int32_t *out_items, float *out_scores, int32_t *fb_count, int64_t *fb_users,
+                                int32_t *fb_rows, void *stream) {
     IGCN_CHECK_ARG(rep && user_ids && cand_items && cand_cnt && cand_thr && maxabs_bits && center_sum && out_items && out_scores,
                    "null pointer");
     IGCN_CHECK_ARG(fb_count && fb_users && fb_rows, "null fallback buffers");
@@ -645,7 +620,7 @@ extern "C" int igcn_tc_finalize(const float *rep, const int64_t *user_ids, int64
     if (e != cudaSuccess) { set_error("igcn_tc_finalize: %s", cudaGetErrorString(e)); return (int)e; }
     const float inv_n = n_items > 0 ? 1.f / (float)n_items : 0.f;
     tc_finalize_kernel<<<(unsigned)((n_eval + 7) / 8), 256, smem, st>>>(rep, user_ids, n_eval, item_row0, D, n_splits, cand_items,
-                                                                         cand_cnt, cand_thr, maxabs_bits, center_sum, inv_n, k,
+                                                                         cand_cnt, cand_thr, maxabs_bits, center_sum, inv_n, item_perm, k,
                                                                          out_items, out_scores, fb_count, fb_users, fb_rows);
     IGCN_CHECK_LAUNCH();
     return 0;

@@ -124,6 +124,19 @@ __device__ __forceinline__ void hit_if_gt(uint32_t vbits, float thr, uint32_t &h
         : "f"(__uint_as_float(vbits)), "f"(thr), "r"(bit));
 }
 
+// 3-input maximum (FMNMX3 on sm_100): two reductions per ALU-pipe slot
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float fmax3(uint32_t a, uint32_t b, uint32_t c) {
+    return fmax3(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c));
+}
+__device__ __forceinline__ float fmax3(uint32_t a, uint32_t b, float c) {
+    return fmax3(__uint_as_float(a), __uint_as_float(b), c);
+}
+
 __device__ __forceinline__ float entry_score(uint64_t e) { return __uint_as_float((uint32_t)e); }
 
 }  // namespace igcn

@@ -66,9 +66,6 @@ def _peer_args(shard, t, byte_offset):
     return (None, 0) if shard is None else shard.peers(t, byte_offset)
 
 
-HOT_ROWS = int(os.environ.get('IGCN_SPMM_HOT', 0))      # experimental igcn_spmm_hot: rows of X staged per SM (0 = off)
-
-
 class Propagator:
     """L-layer propagation with the layer mean fused into the last SpMM, and its backward.
 
@@ -137,10 +134,6 @@ class Propagator:
                 call('igcn_spmm_rows', *head, ptr(rows[0]), ptr(rows[1]), int(rows[2]), row0, peers, n_peers, stream_ptr())
             elif cols is not None:
                 call('igcn_spmm_cols', *head, ptr(cols), peers, n_peers, stream_ptr())
-            elif HOT_ROWS and sh is None and self.dim == 64 and blk.csr.row_order is not None:
-                # experimental: hottest rows of x staged in shared memory (csrc/spmm_hot.cu), bit-identical output
-                col_enc, hot_ids, _ = blk.csr.hot_plan(HOT_ROWS)
-                call('igcn_spmm_hot', head[0], ptr(col_enc), ptr(hot_ids), int(hot_ids.shape[0]), *head[1:], stream_ptr())
             else:
                 call('igcn_spmm', *head, peers, n_peers, stream_ptr())
         for row0, n_rows in pushes:
@@ -547,13 +540,16 @@ class ListCSR:
     def __getitem__(self, i):          # (ptr, items, lens) tuple view used by older call sites
         return (self.ptr, self.items, self.lens)[i]
 
-    def tiles(self, n_items, users_host=None):
+    def tiles(self, n_items, users_host=None, order=None):
         """Seen-item pairs bucketed by (128-user tile, 256-item tile) for the tensor-core kernel:
-        (tile_ptr int32 [n_utiles, n_itiles + 1], entries uint16 ((row << 8) | col))."""
-        key = (int(n_items), None if users_host is None else users_host.tobytes())
+        (tile_ptr int32 [n_utiles, n_itiles + 1], entries uint16 ((row << 8) | col)).  With an ItemOrder the item
+        coordinate is the item's POSITION in the scan order."""
+        key = (int(n_items), None if users_host is None else users_host.tobytes(), None if order is None else order.uid)
         hit = self._tiles.get(key)
         if hit is None:
             ptr_, items = self.ptr_host, self.items_host.astype(np.int64)
+            if order is not None:
+                items = order.pos_host[items]
             if users_host is None:
                 n_eval = len(ptr_) - 1
                 pos = np.repeat(np.arange(n_eval, dtype=np.int64), np.diff(ptr_))
@@ -616,6 +612,50 @@ def restrict_csr(csr, user_lo, user_hi, item_lo, item_hi):
 def lists_to_csr(lists, device, sort=True):
     """list-of-lists -> ListCSR (indexable as (ptr, items, lens))."""
     return ListCSR(lists, device, sort)
+
+
+class ItemOrder:
+    """Scan order of the items for the tensor-core scoring path: perm[p] = item at position p, pos[i] = position of
+    item i.  A static permutation (the trainers pass train popularity, most popular first): the result does not
+    depend on it, the cost does -- items that rank high for most users come first, the per-user thresholds tighten
+    within the first tiles and the filter's compare-free path takes almost every later chunk."""
+    _uids = iter(range(1, 1 << 62))
+
+    def __init__(self, perm_host, device):
+        perm_host = np.ascontiguousarray(perm_host, dtype=np.int64)
+        n = len(perm_host)
+        pos = np.empty(n, dtype=np.int64)
+        pos[perm_host] = np.arange(n, dtype=np.int64)
+        if not np.array_equal(np.sort(perm_host), np.arange(n, dtype=np.int64)):
+            raise ValueError('item order must be a permutation of range(n_items)')
+        self.uid = next(ItemOrder._uids)
+        self.perm_host, self.pos_host = perm_host, pos
+        self.perm = torch.from_numpy(perm_host.astype(np.int32)).to(device)
+        self._bits = {}
+
+    @classmethod
+    def by_score(cls, item_score, device):
+        """Descending `item_score` (e.g. train degree), ties by item id."""
+        item_score = np.asarray(item_score)
+        return cls(np.argsort(-item_score, kind='stable'), device)
+
+    def position_bits(self, n_items, item_lo, item_hi, banned_bits):
+        """Bitmap over POSITIONS of the items outside [item_lo, item_hi) or banned (None when nothing is excluded)."""
+        if item_lo <= 0 and item_hi >= n_items and banned_bits is None:
+            return None
+        key = (int(item_lo), int(item_hi), None if banned_bits is None else banned_bits.data_ptr())
+        hit = self._bits.get(key)
+        if hit is None or hit[0] is not banned_bits:
+            # host-side (tiny, cached): only the inductive evaluation passes restrict or ban items
+            ids = np.arange(n_items, dtype=np.int64)
+            bad = (ids < item_lo) | (ids >= item_hi)
+            if banned_bits is not None:
+                words = banned_bits.cpu().numpy().view(np.uint32)
+                bad |= ((words[ids >> 5] >> (ids & 31).astype(np.uint32)) & 1).astype(bool)
+            from .graph import _pack_bits
+            hit = (banned_bits, _pack_bits(bad[self.perm_host], self.perm.device))
+            self._bits = {key: hit}
+        return hit[1]
 
 
 FALLBACK_SPLITS, FALLBACK_SPLIT_CAP = 64, 2048      # item ranges / max users for the split form of the exact kernel
@@ -684,30 +724,40 @@ class TcScorer:
         return ws
 
     def topk(self, rep, user_ids, n_users, n_items, k, mask=None, item_lo=0, item_hi=None, banned_bits=None,
-             users_host=None, n_splits=None, dump=False):
+             users_host=None, n_splits=None, dump=False, order=None, stats=None):
+        """order: ItemOrder (scan order of the items) or None; stats: uint64 [5] device tensor (instrumented kernel)."""
         n_eval, D = int(user_ids.shape[0]), int(rep.shape[1])
         item_hi = n_items if item_hi is None else item_hi
+        # the candidate kernel works in position space: with a scan order, ranges / banned items become one bitmap
+        # over positions, and the exact fallback keeps the caller's item-id arguments
+        c_lo, c_hi, c_bits, perm = item_lo, item_hi, banned_bits, None
+        if order is not None:
+            if len(order.perm_host) != n_items:
+                raise RuntimeError('item order has %d entries, the catalogue %d' % (len(order.perm_host), n_items))
+            perm = order.perm
+            c_bits = order.position_bits(n_items, item_lo, item_hi, banned_bits)
+            c_lo, c_hi = 0, n_items
         n_head = 0
         if n_splits is None:
             n_head, n_splits = self.plan_ctas((n_eval + 127) // 128)
         ws = self._workspace(n_eval, n_items, D, n_splits, k, rep.device)
         st = stream_ptr
-        call('igcn_tc_pack', ptr(rep), rep.numel(), ptr(user_ids), n_eval, n_users, n_items, D, ptr(ws['maxabs']),
+        call('igcn_tc_pack', ptr(rep), rep.numel(), ptr(user_ids), n_eval, n_users, n_items, D, ptr(perm), ptr(ws['maxabs']),
              ptr(ws['a_img']), ptr(ws['b_img']), ptr(ws['center']), ptr(ws['center_scratch']), st())
         tile_ptr, entries = (None, None)
         if mask is not None:
-            tile_ptr, entries = mask.tiles(n_items, users_host)
+            tile_ptr, entries = mask.tiles(n_items, users_host, order)
         dump_t = None
         if dump:
             dump_t = torch.zeros(((n_eval + 127) // 128 * 128, (n_items + 255) // 256 * 256), dtype=torch.float32,
                                  device=rep.device)
         call('igcn_tc_candidates', ptr(ws['a_img']), ptr(ws['b_img']), n_eval, n_items, D, n_splits, n_head,
-             int(item_lo), int(item_hi), ptr(banned_bits), ptr(tile_ptr), ptr(entries), ptr(ws['cand_items']), ptr(ws['cand_cnt']),
-             ptr(ws['cand_thr']), ptr(dump_t), st())
+             int(c_lo), int(c_hi), ptr(c_bits), ptr(tile_ptr), ptr(entries), ptr(ws['cand_items']), ptr(ws['cand_cnt']),
+             ptr(ws['cand_thr']), ptr(dump_t), ptr(stats), st())
         out_i = torch.empty((n_eval, k), dtype=torch.int32, device=rep.device)
         out_s = torch.empty((n_eval, k), dtype=torch.float32, device=rep.device)
         call('igcn_tc_finalize', ptr(rep), ptr(user_ids), n_eval, n_users, D, n_splits, ptr(ws['cand_items']),
-             ptr(ws['cand_cnt']), ptr(ws['cand_thr']), ptr(ws['maxabs']), ptr(ws['center']), n_items, int(k), ptr(out_i), ptr(out_s),
+             ptr(ws['cand_cnt']), ptr(ws['cand_thr']), ptr(ws['maxabs']), ptr(ws['center']), n_items, ptr(perm), int(k), ptr(out_i), ptr(out_s),
              ptr(ws['fb_count']), ptr(ws['fb_users']), ptr(ws['fb_rows']), st())
         # users whose bound did not verify: exact kernel on the device-side list (no host sync)
         score_topk_exact(rep, ws['fb_users'], n_users, n_items, k, mask, item_lo, item_hi, banned_bits,
@@ -722,10 +772,11 @@ _tc_scorer = TcScorer()
 
 
 def score_topk(rep, user_ids, n_users, n_items, k, mask=None, item_lo=0, item_hi=None, banned_bits=None,
-               users_host=None, impl='auto'):
+               users_host=None, impl='auto', order=None):
     """Fused scoring + seen-item mask + top-k for `user_ids` (model.py:118-123 + trainer.py:149-164).
     Returns (items int32 [n, k], scores fp32 [n, k]), sorted by (score desc, item asc); slots without
-    a candidate hold -1 / -inf.  impl: 'tc' (tcgen05 path, D <= 64 and k <= 24), 'exact', or 'auto'."""
+    a candidate hold -1 / -inf.  impl: 'tc' (tcgen05 path, D <= 64 and k <= 24), 'exact', or 'auto'.  order: an
+    ItemOrder, the order in which the tensor-core path scans the catalogue (cost only, never the result)."""
     _lib.require_cuda(rep, torch.float32, 'rep')
     tc_ok = rep.shape[1] <= 64 and k <= 24 and (mask is None or isinstance(mask, ListCSR))
     if impl == 'tc' and not tc_ok:
@@ -738,7 +789,7 @@ def score_topk(rep, user_ids, n_users, n_items, k, mask=None, item_lo=0, item_hi
         n = int(user_ids.shape[0])
         if n != len(mask.ptr_host) - 1 or not bool((user_ids == torch.arange(n, device=user_ids.device)).all()):
             users_host = user_ids.cpu().numpy()
-    return _tc_scorer.topk(rep, user_ids, n_users, n_items, k, mask, item_lo, item_hi, banned_bits, users_host)
+    return _tc_scorer.topk(rep, user_ids, n_users, n_items, k, mask, item_lo, item_hi, banned_bits, users_host, order=order)
 
 
 def hit_matrix(rec, eval_csr):

@@ -104,24 +104,6 @@ class CsrDevice:
             self._col_host = self.col.cpu().numpy()
         return self._col_host
 
-    def hot_plan(self, n_hot):
-        """(col_enc int32 [nnz], hot_ids int32 [n_hot]) for igcn_spmm_hot: the n_hot most gathered columns get a
-        shared-memory slot, their occurrences in the column array are stored as -(slot + 1).  Device ops, cached."""
-        plans = self.__dict__.setdefault('_hot_plans', {})
-        plan = plans.get(n_hot)
-        if plan is None:
-            col = self.col.long()
-            counts = torch.bincount(col, minlength=self.n_cols)
-            n_hot = int(min(n_hot, self.n_cols))
-            hot_ids = torch.topk(counts, n_hot).indices
-            slot = torch.full((self.n_cols,), -1, dtype=torch.int64, device=self.device)
-            slot[hot_ids] = torch.arange(n_hot, device=self.device)
-            s = slot[col]
-            plan = (torch.where(s >= 0, -(s + 1), col).to(torch.int32).contiguous(), hot_ids.to(torch.int32).contiguous(),
-                    float((s >= 0).sum().item()) / max(1, self.nnz))
-            plans[n_hot] = plan
-        return plan
-
     def with_values(self, val):
         """Same pattern/plan, different (or no) value array; shares index memory."""
         other = object.__new__(CsrDevice)

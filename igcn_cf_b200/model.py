@@ -57,6 +57,7 @@ class BasicModel(nn.Module):
         self.trainable = True
         # multi-GPU (igcn_cf_b200.dist.init_peers() was called, world > 1).  model_config['shard']:
         #   False   single-GPU behaviour on every rank
+        #   'users' training step replicated, evaluation users sharded (no exchange anywhere on the training path)
         #   True    propagation rows sharded over the ranks (fused NVLink all-gather), eval users sharded
         #   'auto'  (default) eval users always sharded; rows sharded only when every rank keeps at least
         #           SHARD_MIN_NNZ_PER_RANK non-zeros, i.e. when the per-layer exchange (N*D*4 bytes into every rank)

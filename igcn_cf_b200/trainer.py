@@ -161,6 +161,7 @@ class BasicTrainer:
         self._mask_cache = {}
         self._eval_cache = {}
         self._last_rec = None
+        self._item_order = None
         self.test_users = torch.arange(self.dataset.n_users, dtype=torch.int64, device=self.device)
 
     def initialize_optimizer(self):
@@ -316,6 +317,22 @@ class BasicTrainer:
         from .graph import _pack_bits
         return 0, n, _pack_bits(flags, self.device)
 
+    def item_order(self):
+        """Scan order of the catalogue for the tensor-core ranking kernels: train popularity, most popular first
+        (engine.ItemOrder).  Static per dataset; trainer_config['item_order'] = 'natural' disables it."""
+        if self.config.get('item_order', 'popularity') != 'popularity':
+            return None
+        n_items = self.dataset.n_items
+        if self._item_order is None or len(self._item_order.perm_host) != n_items:
+            dg = getattr(self.dataset, 'device_graph', None)
+            if dg is not None:
+                deg = np.diff(dg.rowptr_host[dg.n_users:])
+            else:
+                from .graph import train_pairs_of
+                deg = np.bincount(train_pairs_of(self.dataset)[:, 1], minlength=n_items)
+            self._item_order = engine.ItemOrder.by_score(deg, self.device)
+        return self._item_order
+
     def recommend(self, val_or_test, banned_items=None, users=None, users_host=None):
         """Top-max(topks) item ids (device int32 [n, k]) and scores for `users` (default: all).
         users_host: the same ids as a numpy array when the caller has them (saves a D2H sync)."""
@@ -327,7 +344,7 @@ class BasicTrainer:
         lo, hi, bits = self._banned(banned_items)
         return engine.score_topk(rep, users, self.model.n_users, self.model.n_items, max(self.topks),
                                  mask=self._mask_csr(val_or_test), item_lo=lo, item_hi=hi, banned_bits=bits,
-                                 users_host=users_host, impl=self.config.get('score_impl', 'auto'))
+                                 users_host=users_host, impl=self.config.get('score_impl', 'auto'), order=self.item_order())
 
     def recommend_local(self, val_or_test, banned_items=None):
         """Top-k lists of the users this rank evaluates: all of them on one GPU, an even contiguous

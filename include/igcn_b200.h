@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define IGCN_ABI_VERSION 1
+#define IGCN_ABI_VERSION 2
 #define IGCN_MAX_ADD 8
 #define IGCN_MAX_PEERS 8
 #define IGCN_MEDIUM_NNZ 64
@@ -236,20 +236,14 @@ int igcn_score_topk_exact(const float *rep, const int64_t *user_ids, int64_t n_e
                           const int32_t *out_rows, const int32_t *n_eval_dev,
                           int32_t n_item_splits, uint64_t *split_keys, int64_t split_cap, void *stream);
 
-/* ---- EXPERIMENTAL: igcn_spmm (no peers) with the n_hot highest-degree rows of X staged in shared memory by one
- * persistent 1,024-thread CTA per SM (csrc/spmm_hot.cu).  col_enc = g->col with every hot column replaced by
- * -(slot + 1), hot_ids[slot] = that column; both built by the host (graph.CsrDevice.hot_plan).  D == 64 only,
- * n_hot <= 800.  Results are bit-identical to igcn_spmm.  Selected by the host with IGCN_SPMM_HOT=<n_hot>. */
-int igcn_spmm_hot(const igcn_csr *g, const int32_t *col_enc, const int32_t *hot_ids, int32_t n_hot,
-                  const float *X, float *Y, int32_t D, const float *const *add_host, int32_t n_add,
-                  const float *rowscale, float alpha, void *stream);
-
 /* ---- tensor-core scoring (tcgen05 / TMEM / bulk TMA), D <= 64, k <= 24 ------------------------
  * Same contract as igcn_score_topk_exact, split in three launches the host chains on one stream:
  *   igcn_tc_pack        fp32 rep rows -> fp16 operand images in the UMMA core-matrix layout, with one
  *                       extra K block carrying the rounding-error bound (c*|u| for users, |i| for items)
  *   igcn_tc_candidates  tcgen05.mma M128 x N256 tiles, accumulators in TMEM; the epilogue filters
- *                       s_hat >= running threshold and !masked into <= 96 candidates per (user, split)
+ *                       s_hat > running threshold and !masked into <= 96 candidates per (user, split)
+ *                       (a 3-input-max reduction and one warp vote per 32-column chunk; only chunks with a
+ *                       score above some row's threshold are compared column by column)
  *   igcn_tc_finalize    exact fp32 re-scoring (same FMA order as the exact kernel), top-k, and the
  *                       proof check; users that fail it are appended to (fb_users, fb_rows, fb_count)
  *                       for igcn_score_topk_exact.
@@ -261,23 +255,31 @@ int igcn_spmm_hot(const igcn_csr *g, const int32_t *col_enc, const int32_t *hot_
  * seen-item CSR bucketed by (user tile, item tile); dump (tests only) receives every s_hat.
  * n_head: the first n_head user tiles scan all item tiles in one CTA and use only list slot 0; the remaining
  * tiles are split n_splits ways -- the host sizes the split tail so that it fills the last wave of SMs
- * (0 = every user tile is split). */
+ * (0 = every user tile is split).
+ * item_perm (int32 [n_items], NULL = identity): the SCAN ORDER of the items -- position p of the item image is
+ * item item_perm[p].  Everything between pack and finalize is in position space (mask buckets, banned bitmap,
+ * item_lo / item_hi, candidate lists); igcn_tc_finalize maps positions back to item ids.  The order does not
+ * change the result (the final lists are proven exact or recomputed), it changes the cost: with the items most
+ * likely to rank high first (the host passes train popularity), the running thresholds tighten within the first
+ * tiles and the epilogue's compare-free path handles almost every later chunk.
+ * stats (uint64 [5], NULL = off; selects an instrumented copy of the kernel): 32-column chunks seen, chunks that
+ * left the compare-free path, 8-column groups compared, candidates appended, compactions. */
 int igcn_tc_workspace(int64_t n_eval, int64_t n_items, int32_t D, int32_t n_splits,
                       int64_t *a_img_bytes, int64_t *b_img_bytes, int64_t *cand_slots);
 int igcn_tc_pack(const float *rep, int64_t n_rep_elems, const int64_t *user_ids, int64_t n_eval,
-                 int64_t item_row0, int64_t n_items, int32_t D, uint32_t *maxabs_bits,
-                 uint8_t *a_img, uint8_t *b_img, float *center_sum, float *center_scratch,
-                 void *stream);
+                 int64_t item_row0, int64_t n_items, int32_t D, const int32_t *item_perm,
+                 uint32_t *maxabs_bits, uint8_t *a_img, uint8_t *b_img, float *center_sum,
+                 float *center_scratch, void *stream);
 int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, int64_t n_eval, int64_t n_items,
                        int32_t D, int32_t n_splits, int32_t n_head, int64_t item_lo,
                        int64_t item_hi,
                        const uint32_t *banned_bits, const int32_t *mask_tile_ptr,
                        const uint16_t *mask_entries, int32_t *cand_items, int32_t *cand_cnt,
-                       float *cand_thr, float *dump, void *stream);
+                       float *cand_thr, float *dump, unsigned long long *stats, void *stream);
 int igcn_tc_finalize(const float *rep, const int64_t *user_ids, int64_t n_eval, int64_t item_row0,
                      int32_t D, int32_t n_splits, const int32_t *cand_items,
                      const int32_t *cand_cnt, const float *cand_thr, const uint32_t *maxabs_bits,
-                     const float *center_sum, int64_t n_items,
+                     const float *center_sum, int64_t n_items, const int32_t *item_perm,
                      int32_t k, int32_t *out_items, float *out_scores, int32_t *fb_count,
                      int64_t *fb_users, int32_t *fb_rows, void *stream);
 

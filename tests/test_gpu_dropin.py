@@ -70,7 +70,7 @@ print('SAVED', saved, os.path.exists(saved), 'BEST', best)
 def test_reference_launcher_flow_through_the_aliases(tmp_path):
     from igcn_cf_b200 import synth
     full = synth.gen_named('tiny', seed=2021)
-    synth.write_split(full, str(tmp_path / 'time'))
+    synth.write_split(full, str(tmp_path / 'time_0'))          # igcn_dropui.py:26 strips '_dropui' from the path
     synth.write_split(synth.dropui(full), str(tmp_path / 'time_0_dropui'))
     out = subprocess.run([sys.executable, '-c', LAUNCHER, ROOT, os.path.join(ROOT, 'dropin'), str(tmp_path)],
                          capture_output=True, text=True, timeout=600)

@@ -111,27 +111,3 @@ def test_column_filter_layer_equals_full_layer_on_sparse_input():
     torch.cuda.synchronize()
     # skipped terms are exact zeros, so the sums agree exactly (up to the sign of zero)
     assert torch.equal(part + 0.0, full + 0.0)
-
-
-@pytest.mark.skipif(not os.environ.get('IGCN_EXPERIMENTAL'), reason='experimental kernel: set IGCN_EXPERIMENTAL=1')
-@pytest.mark.parametrize('shape,n_hot', [('small', 64), ('small', 800), ('yelp', 768)])
-def test_hot_row_staging_layer_is_bit_identical(shape, n_hot):
-    """igcn_spmm_hot (hottest rows of X in shared memory, persistent CTAs) against igcn_spmm: same bits, with
-    fused adds / alpha, on graphs that contain all three row classes."""
-    from igcn_cf_b200._lib import call, ptr, stream_ptr
-    split, adj = _graph(shape)
-    n = split.n_users + split.n_items
-    g = torch.Generator(device=DEV).manual_seed(8)
-    x = torch.randn(n, 64, device=DEV, generator=g)
-    add = torch.randn(n, 64, device=DEV, generator=g)
-    col_enc, hot_ids, coverage = adj.csr.hot_plan(n_hot)
-    assert 0.0 < coverage < 1.0
-    for adds, alpha in (([], 1.0), ([add, x], 0.25)):
-        want, got = torch.empty_like(x), torch.full_like(x, float('nan'))
-        _spmm('igcn_spmm', adj, x, want, adds, alpha)
-        arr = (C.c_void_p * max(1, len(adds)))(*[a.data_ptr() for a in adds])
-        for _ in range(2):                                            # twice: the chunk counters must reset themselves
-            call('igcn_spmm_hot', adj.csr.struct(64), ptr(col_enc), ptr(hot_ids), int(hot_ids.shape[0]), ptr(x), ptr(got), 64,
-                 arr, len(adds), None, alpha, stream_ptr())
-        torch.cuda.synchronize()
-        assert torch.equal(want + 0.0, got + 0.0)

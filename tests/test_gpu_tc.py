@@ -130,14 +130,71 @@ def test_tc_split_tail_plan(n_tiles):
     assert torch.equal(ex[0], tc[0]) and torch.equal(ex[1], tc[1])
 
 
-@pytest.mark.skipif(not __import__('os').environ.get('IGCN_EXPERIMENTAL'), reason='experimental kernel: set IGCN_EXPERIMENTAL=1')
+def _random_order(n_items, seed):
+    from igcn_cf_b200 import engine
+    return engine.ItemOrder(np.random.default_rng(seed).permutation(n_items), DEV)
+
+
 @pytest.mark.parametrize('n_users,n_items,D,k', [(300, 1000, 64, 20), (129, 257, 64, 5), (1000, 5000, 64, 20), (700, 20000, 32, 20)])
-def test_tc_threshold_in_mma_variant(monkeypatch, n_users, n_items, D, k):
-    """score_tc_kernel<7> (IGCN_TC_EXPERIMENT=7: the tensor core subtracts each row's threshold, the filter collects
-    sign bits): same lists and scores as the exact kernel; users whose top-k reaches into negative centred scores
-    go through the exact kernel, so only the answer is asserted, not the fallback count."""
-    monkeypatch.setenv('IGCN_TC_EXPERIMENT', '7')
-    rep, lists = _case(n_users, n_items, D, seed=n_items + 7)
-    ex, tc, fb = _both(rep, n_users, k, lists)
+def test_tc_scan_order_does_not_change_the_result(n_users, n_items, D, k):
+    """The items are scanned in a caller-supplied order (engine.ItemOrder; the trainers pass train popularity):
+    mask buckets, candidate lists and thresholds live in position space, the final lists must still be the exact
+    kernel's, bit for bit."""
+    from igcn_cf_b200 import engine
+    rep, lists = _case(n_users, n_items, D, seed=n_items + 3)
+    mask = engine.lists_to_csr(lists, DEV)
+    u = torch.arange(n_users, device=DEV)
+    ex = engine.score_topk(rep, u, n_users, n_items, k, mask, impl='exact')
+    for order in (_random_order(n_items, 1), engine.ItemOrder.by_score(rep[n_users:].norm(dim=1).cpu().numpy(), DEV)):
+        tc = engine.score_topk(rep, u, n_users, n_items, k, mask, impl='tc', order=order)
+        torch.cuda.synchronize()
+        assert torch.equal(ex[0], tc[0]) and torch.equal(ex[1], tc[1])
+
+
+@pytest.mark.parametrize('lo,hi,banned', [(300, 1000, None), (0, 700, range(0, 1000, 3)), (250, 260, None), (0, 1000, range(5, 900))])
+def test_tc_scan_order_with_ranges_and_banned_items(lo, hi, banned):
+    from igcn_cf_b200 import engine
+    from igcn_cf_b200.graph import _pack_bits
+    n_users, n_items = 150, 1000
+    rep, lists = _case(n_users, n_items, 64, seed=12)
+    mask = engine.lists_to_csr(lists, DEV)
+    bits = None
+    if banned is not None:
+        flags = np.zeros(n_items, dtype=bool)
+        flags[list(banned)] = True
+        bits = _pack_bits(flags, DEV)
+    u = torch.arange(n_users, device=DEV)
+    ex = engine.score_topk(rep, u, n_users, n_items, 20, mask, lo, hi, bits, impl='exact')
+    tc = engine.score_topk(rep, u, n_users, n_items, 20, mask, lo, hi, bits, impl='tc', order=_random_order(n_items, 2))
+    torch.cuda.synchronize()
     assert torch.equal(ex[0], tc[0]) and torch.equal(ex[1], tc[1])
-    assert fb < n_users                                     # the tensor-core path decided at least some users
+
+
+def test_tc_filter_statistics_and_popular_first_order():
+    """Structured scores (a few items every user likes): scanning them first must keep far more chunks on the
+    compare-free path than the natural order, with identical results; the counters are consistent."""
+    from igcn_cf_b200 import engine
+    n_users, n_items, D, k = 1024, 8192, 64, 20
+    g = torch.Generator().manual_seed(3)
+    rep = (torch.randn(n_users + n_items, D, generator=g) * 0.1)
+    direction = torch.randn(D, generator=g)
+    direction /= direction.norm()
+    pop = torch.rand(n_items, generator=g) ** 8                       # a handful of very popular items, spread over the ids
+    rep[:n_users] += 0.3 * direction
+    rep[n_users:] += pop[:, None] * 1.5 * direction
+    rep = rep.to(DEV)
+    u = torch.arange(n_users, device=DEV)
+    scorer = engine.TcScorer()
+    out = {}
+    for name, order in (('natural', None), ('popular', engine.ItemOrder.by_score(pop.numpy(), DEV))):
+        stats = torch.zeros(5, dtype=torch.int64, device=DEV)
+        items, scores = scorer.topk(rep, u, n_users, n_items, k, order=order, stats=stats)
+        torch.cuda.synchronize()
+        out[name] = (items.clone(), scores.clone(), stats.tolist())
+    ex = engine.score_topk(rep, u, n_users, n_items, k, impl='exact')
+    for name in out:
+        assert torch.equal(out[name][0], ex[0]) and torch.equal(out[name][1], ex[1])
+        chunks, slow, groups, hits, comp = out[name][2]
+        assert chunks == (n_users // 32) * (n_items // 32) and 0 < slow <= chunks and slow <= groups <= 4 * slow
+        assert hits >= n_users * k and comp <= slow
+    assert out['popular'][2][1] < 0.5 * out['natural'][2][1]          # far fewer chunks leave the compare-free path

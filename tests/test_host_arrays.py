@@ -2,6 +2,7 @@
 path, the inductive_eval restriction, the dataset CSR cache, the row-class / chunk plan and the per-rank row
 ranges of the sharded propagation."""
 import numpy as np
+import pytest
 import torch
 
 from igcn_cf_b200 import engine, graph
@@ -122,3 +123,40 @@ def test_popularity_and_identity_map_host_side():
     except KeyError:
         pass
     assert torch.equal(torch.arange(3), torch.arange(3))
+
+
+def test_item_order_positions_mask_tiles_and_position_bitmap():
+    """engine.ItemOrder: perm / pos are inverse permutations; ListCSR.tiles buckets the seen pairs by the item's
+    POSITION in the scan order; ranges and banned items become one bitmap over positions."""
+    import torch
+    from igcn_cf_b200 import engine
+    from igcn_cf_b200.graph import _pack_bits
+    rng = np.random.default_rng(0)
+    n_users, n_items = 300, 700
+    score = rng.integers(0, 50, size=n_items)
+    order = engine.ItemOrder.by_score(score, 'cpu')
+    assert np.array_equal(order.pos_host[order.perm_host], np.arange(n_items))
+    assert (np.diff(score[order.perm_host]) <= 0).all()                       # descending, ties by id (stable)
+    ties = np.nonzero(np.diff(score[order.perm_host]) == 0)[0]
+    assert (order.perm_host[ties] < order.perm_host[ties + 1]).all()
+    with pytest.raises(ValueError):
+        engine.ItemOrder(np.array([0, 0, 1]), 'cpu')
+    lists = [sorted(rng.choice(n_items, size=int(rng.integers(0, 9)), replace=False).tolist()) for _ in range(n_users)]
+    csr = engine.lists_to_csr(lists, 'cpu')
+    tile_ptr, ent = csr.tiles(n_items, None, order)
+    tile_ptr, ent = tile_ptr.numpy(), ent.numpy().view(np.uint16)
+    n_it = (n_items + 255) // 256
+    got = set()
+    for ut in range(tile_ptr.shape[0]):
+        for t in range(n_it):
+            for e in ent[tile_ptr[ut, t]:tile_ptr[ut, t + 1]]:
+                got.add((ut * 128 + (int(e) >> 8), int(order.perm_host[t * 256 + (int(e) & 255)])))
+    assert got == {(u, i) for u, l in enumerate(lists) for i in l}
+    flags = np.zeros(n_items, dtype=bool)
+    flags[::7] = True
+    bits = order.position_bits(n_items, 100, 650, _pack_bits(flags, 'cpu')).numpy().view(np.uint32)
+    for p in range(n_items):
+        item = order.perm_host[p]
+        want = item < 100 or item >= 650 or item % 7 == 0
+        assert bool((bits[p >> 5] >> (p & 31)) & 1) == want
+    assert order.position_bits(n_items, 0, n_items, None) is None

@@ -231,28 +231,6 @@ def test_scoring_cta_plan(monkeypatch):
     assert TcScorer.plan_ctas(588) == (0, 3)
 
 
-def test_hot_plan_encodes_the_most_gathered_columns():
-    """CsrDevice.hot_plan (operand of the experimental igcn_spmm_hot): decoding col_enc with hot_ids gives back
-    the column array, the hot set is the most frequent columns, and the reported coverage is their share."""
-    rng = np.random.default_rng(4)
-    n_rows, n_cols, H = 200, 300, 16
-    deg = rng.integers(0, 12, n_rows)
-    rowptr = np.r_[0, np.cumsum(deg)].astype(np.int64)
-    pop = 1.0 / (np.arange(n_cols) + 1.0)
-    col = np.concatenate([np.sort(rng.choice(n_cols, size=d, replace=False, p=pop / pop.sum())) for d in deg]).astype(np.int32)
-    csr = graph.CsrDevice(rowptr, col, None, n_cols, torch.device('cpu'))
-    enc, hot_ids, coverage = csr.hot_plan(H)
-    enc, hot_ids = enc.numpy(), hot_ids.numpy()
-    assert enc.dtype == np.int32 and hot_ids.dtype == np.int32 and len(hot_ids) == H and len(set(hot_ids.tolist())) == H
-    decoded = np.where(enc < 0, hot_ids[np.maximum(-enc - 1, 0)], enc)
-    assert np.array_equal(decoded, col)
-    counts = np.bincount(col, minlength=n_cols)
-    assert counts[hot_ids].min() >= np.sort(counts)[-H]                    # nothing more frequent was left out
-    assert abs(coverage - counts[hot_ids].sum() / len(col)) < 1e-12
-    assert (enc < 0).sum() == counts[hot_ids].sum()
-    assert csr.hot_plan(H)[0] is csr.hot_plan(H)[0]                        # cached
-
-
 def test_device_graph_builder_row_sharded_blocks_match():
     """Row-sharded construction (one user slice + one item slice per rank): the device builder cuts the same
     blocks with the same values as the scipy builder, for every rank of a 3-rank world."""
