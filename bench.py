@@ -651,7 +651,7 @@ def measure(env, name, args, main):
     D = 64
     # at N > 1 the step is timed BOTH ways: replicated on every rank (no exchange on the training path) and with the
     # propagation rows sharded (fused NVLink all-gather per layer); evaluation users are sharded in both
-    modes = [('single', False)] if env.world == 1 else [('replicated', 'users'), ('row_sharded', True)]
+    modes = [('single', False)] if env.world == 1 else [('replicated', 'users'), ('row_sharded', True), ('dim_sharded', 'dims')]
     built = {}
     for mode, shard in modes:
         model, trainer = build_model(ds, kind, dropout, l2_reg, env.dev, shard=shard)
@@ -662,21 +662,31 @@ def measure(env, name, args, main):
     # after one identical step); this is tests/dist_worker.py folded into the bench so every driver run proves it
     parity = None
     if env.world > 1:
-        (m_a, t_a), (m_b, t_b) = built['replicated'], built['row_sharded']
-        assert m_b._rows_sharded() and not m_a._rows_sharded()
-        ok = True
-        for m in (m_a, m_b):
-            m.eval()
+        m_a, t_a = built['replicated']
+        assert built['row_sharded'][0]._rows_sharded() and not m_a._rows_sharded() and built['dim_sharded'][1].step.dims
+        parity = {}
+        m_a.eval()
         with torch.no_grad():
-            ok &= torch.equal(m_a.get_rep(), m_b.get_rep())
-        for m, t in ((m_a, t_a), (m_b, t_b)):
-            m.train()
-            t.step.use_graph = False
-            t.step.run()
-            t.step.use_graph = True
-        ok &= torch.equal(m_a.embedding.weight.data, m_b.embedding.weight.data)
-        ok &= torch.equal(t_a.step.loss, t_b.step.loss)
-        parity = 'bit-identical' if env.all_true(bool(ok)) else 'MISMATCH'
+            rep_a = m_a.get_rep().clone()
+        m_a.train()
+        t_a.step.use_graph = False
+        t_a.step.run()
+        t_a.step.use_graph = True
+        for mode in ('row_sharded', 'dim_sharded'):
+            m_b, t_b = built[mode]
+            m_b.eval()
+            with torch.no_grad():
+                ok = torch.equal(rep_a, m_b.get_rep())
+            m_b.train()
+            t_b.step.use_graph = False
+            t_b.step.run()
+            t_b.step.use_graph = True
+            t_b.step.sync_params()
+            ok &= torch.equal(m_a.embedding.weight.data, m_b.embedding.weight.data)
+            ok &= torch.equal(t_a.step.loss, t_b.step.loss)
+            if kind == 'IGCN':
+                ok &= torch.equal(m_a.w.data, m_b.w.data)
+            parity[mode] = 'bit-identical' if env.all_true(bool(ok)) else 'MISMATCH'
 
     res = {}
     for mode, (model, trainer) in built.items():
@@ -708,7 +718,8 @@ def measure(env, name, args, main):
     # ---- per-kernel profile + rooflines of the dominant kernels (this rank's share of the work)
     n, nnz = model.n_users + model.n_items, model.norm_adj.nnz
     n_local, nnz_local = model.norm_adj.local_rows, model.norm_adj.local_nnz
-    summary, spmm_gbs, spmm_avg_ms, spmm_avg_bytes = profile_kernels(trainer, n_local, nnz_local, D, 10, n)
+    D_step = trainer.step.D                                  # D / world when the embedding columns are sharded
+    summary, spmm_gbs, spmm_avg_ms, spmm_avg_bytes = profile_kernels(trainer, n_local, nnz_local, D_step, 10, n)
     peak, tc_peak, peak_src = measured_peaks()
     traffic = measured_traffic(name) if env.world == 1 else {}
     ev_ms = profile_eval(t_ev)
@@ -740,9 +751,12 @@ def measure(env, name, args, main):
     if env.world > 1:
         block['ms_per_step_replicated'] = res['replicated']['ms_per_step']
         block['ms_per_step_row_sharded'] = res['row_sharded']['ms_per_step']
-        block['shard_parity'] = parity
+        block['ms_per_step_dim_sharded'] = res['dim_sharded']['ms_per_step']
+        block['shard_parity'] = ('bit-identical' if all(v == 'bit-identical' for v in parity.values())
+                                 else 'MISMATCH %s' % parity)
+        block['shard_parity_by_mode'] = parity
         block['eval']['ms_by_mode'] = {k: round(v[0], 4) for k, v in ev.items()}
-    block['_l2_inputs'] = (nnz_local, spmm_avg_ms)
+    block['_l2_inputs'] = (nnz_local * D_step // 64, spmm_avg_ms)
     if env.rank == 0 and env.world == 1 and not args.no_cpu_baseline:
         block['cpu_baseline'] = cpu_block(ds, name, args.cpu_steps if main else 2, 1)
     del built
@@ -793,11 +807,15 @@ def main():
                                 'parallelism': 'single GPU' if world == 1 else
                                 ('propagation rows sharded over %d GPUs (fused NVLink peer-store all-gather per layer), BPR step + Adam '
                                  'replicated, eval users sharded' % world) if b['step_mode'] == 'row_sharded' else
+                                ('embedding columns sharded over %d GPUs (every rank propagates and updates D/%d columns, per-triple partial '
+                                 'sums exchanged by peer stores, parameters all-gathered per epoch), eval users sharded' % (world, world))
+                                if b['step_mode'] == 'dim_sharded' else
                                 ('training step replicated on %d GPUs (faster than the row-sharded step on this graph, both timed), '
                                  'eval users sharded' % world)},
                 'e2e': b['e2e'], 'gpu_launches': b['launches_per_step'] * args.steps,
                 'eval_users_per_s': b['eval']['users_per_s'], 'eval_e2e_users_per_s': b['eval']['e2e_users_per_s']}
-        for k in ('step_mode', 'ms_per_step_replicated', 'ms_per_step_row_sharded', 'shard_parity', 'ms_per_step_regions',
+        for k in ('step_mode', 'ms_per_step_replicated', 'ms_per_step_row_sharded', 'ms_per_step_dim_sharded', 'shard_parity',
+                  'shard_parity_by_mode', 'ms_per_step_regions',
                   'eval', 'roofline', 'kernel_shares', 'kernel_ms_per_step_eager', 'cpu_baseline'):
             if k in b:
                 line[k] = b[k]

@@ -47,6 +47,9 @@ _SIGNATURES = {
                             c_void_p, c_void_p, c_void_p],
     'igcn_bpr_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p,
                      c_void_p, c_void_p, c_void_p],
+    'igcn_bpr_partial': [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, C.POINTER(c_void_p), c_int32, c_int32,
+                         c_int32, c_int64, c_void_p, c_void_p],
+    'igcn_bpr_combine': [c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'igcn_loss_finalize': [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_float, c_void_p,
                            c_void_p, c_void_p],
     'igcn_bpr_plan': [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
@@ -75,12 +78,15 @@ _SIGNATURES = {
                          c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'igcn_predict_scores': [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p],
     'igcn_hits': [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p],
+    'igcn_user_metrics': [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, C.POINTER(c_int32), c_int32, c_void_p, c_void_p,
+                          c_void_p],
     'igcn_peer_alloc': [c_int64, C.POINTER(c_void_p), c_void_p],
     'igcn_peer_open': [c_void_p, C.POINTER(c_void_p)],
     'igcn_peer_close': [c_void_p],
     'igcn_peer_free': [c_void_p],
     'igcn_peer_barrier': [C.POINTER(c_void_p), c_int32, c_int32, c_void_p, c_void_p, c_void_p],
     'igcn_peer_push': [C.POINTER(c_void_p), c_int32, c_int32, c_int64, c_int64, c_void_p],
+    'igcn_peer_push_cols': [C.POINTER(c_void_p), c_int32, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p],
 }
 EXPORTS = ['igcn_abi_version', 'igcn_last_error'] + sorted(_SIGNATURES)
 

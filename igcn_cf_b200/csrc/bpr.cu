@@ -39,10 +39,15 @@ __global__ void sample_kernel(const int64_t *__restrict__ rowptr, const int32_t 
 }
 
 // ------------------------------------------------------------------ forward
+// Sum over the LANES lanes of a group, smallest stride first: the result is a balanced binary tree over the lane
+// values in lane order -- ((l0 + l1) + (l2 + l3)) + ... -- so an aligned block of 2^j lanes holds ITS sum after j
+// steps.  That is what makes the column-sharded step (engine.TrainStep, shard 'dims') bit-identical to one GPU: a rank
+// that owns D / R columns computes exactly the subtree of its lanes (the other lanes contribute exact zeros) and
+// bpr_combine_kernel adds the R subtree sums in the same tree order.
 template <int LANES>
 __device__ __forceinline__ float group_sum(float v, uint32_t gmask) {
 #pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o, LANES);
+    for (int o = 1; o < LANES; o <<= 1) v += __shfl_xor_sync(gmask, v, o, LANES);
     return v;
 }
 
@@ -57,14 +62,12 @@ __device__ __forceinline__ float dot4(const float4 &a, const float4 &b) {
     return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
 }
 
+struct BprDots { float ps, ns, qa, qb, qc; };
+
+// <u * w, p>, <u * w, n> and the three squared norms of triple i over the D columns of T (group of LANES lanes)
 template <int LANES>
-__global__ void __launch_bounds__(kThreads) bpr_fwd_kernel(const float *__restrict__ T, const float *__restrict__ L2T,
-                                                           const float *__restrict__ w, const int64_t *__restrict__ tri,
-                                                           int64_t B, int64_t off, int D, float *sp, float *sig, float *l2) {
-    const int lane = threadIdx.x % LANES;
-    const uint32_t gmask = gmask_of<LANES>();
-    const int64_t i = (int64_t)blockIdx.x * (kThreads / LANES) + threadIdx.x / LANES;
-    if (i >= B) return;
+__device__ __forceinline__ BprDots bpr_dots(const float *__restrict__ T, const float *__restrict__ L2T, const float *__restrict__ w,
+                                            const int64_t *__restrict__ tri, int64_t i, int64_t off, int D, int lane, uint32_t gmask) {
     const bool active = lane * 4 < D;
     const int64_t u = tri[i * 3], p = tri[i * 3 + 1] + off, n = tri[i * 3 + 2] + off;
     float4 xu = f4zero(), xp = f4zero(), xn = f4zero(), ww = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -73,20 +76,96 @@ __global__ void __launch_bounds__(kThreads) bpr_fwd_kernel(const float *__restri
         if (w) ww = ld4(w + lane * 4);
     }
     const float4 uw = make_float4(xu.x * ww.x, xu.y * ww.y, xu.z * ww.z, xu.w * ww.w);
-    const float ps = group_sum<LANES>(dot4(uw, xp), gmask);
-    const float ns = group_sum<LANES>(dot4(uw, xn), gmask);
-    float q = 0.f;
+    BprDots d;
+    d.ps = group_sum<LANES>(dot4(uw, xp), gmask);
+    d.ns = group_sum<LANES>(dot4(uw, xn), gmask);
+    d.qa = d.qb = d.qc = 0.f;
     if (L2T) {
         float4 a = xu, b = xp, c = xn;
         if (L2T != T && active) { a = ld4(L2T + u * D + lane * 4); b = ld4(L2T + p * D + lane * 4); c = ld4(L2T + n * D + lane * 4); }
-        q = group_sum<LANES>(dot4(a, a), gmask) + group_sum<LANES>(dot4(b, b), gmask) + group_sum<LANES>(dot4(c, c), gmask);
+        d.qa = group_sum<LANES>(dot4(a, a), gmask);
+        d.qb = group_sum<LANES>(dot4(b, b), gmask);
+        d.qc = group_sum<LANES>(dot4(c, c), gmask);
     }
-    if (lane == 0) {
-        const float x = ns - ps;
-        sp[i] = x > 20.f ? x : log1pf(expf(x));      // F.softplus (beta 1, threshold 20)
-        sig[i] = 1.f / (1.f + expf(-x));
-        if (l2) l2[i] = q;
+    return d;
+}
+
+__device__ __forceinline__ void bpr_finish(const BprDots &d, bool has_l2, int64_t i, float *sp, float *sig, float *l2) {
+    const float x = d.ns - d.ps;
+    sp[i] = x > 20.f ? x : log1pf(expf(x));      // F.softplus (beta 1, threshold 20)
+    sig[i] = 1.f / (1.f + expf(-x));
+    if (l2) l2[i] = has_l2 ? (d.qa + d.qb) + d.qc : 0.f;
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(kThreads) bpr_fwd_kernel(const float *__restrict__ T, const float *__restrict__ L2T,
+                                                           const float *__restrict__ w, const int64_t *__restrict__ tri,
+                                                           int64_t B, int64_t off, int D, float *sp, float *sig, float *l2) {
+    const int lane = threadIdx.x % LANES;
+    const uint32_t gmask = gmask_of<LANES>();
+    const int64_t i = (int64_t)blockIdx.x * (kThreads / LANES) + threadIdx.x / LANES;
+    if (i >= B) return;
+    const BprDots d = bpr_dots<LANES>(T, L2T, w, tri, i, off, D, lane, gmask);
+    if (lane == 0) bpr_finish(d, L2T != nullptr, i, sp, sig, l2);
+}
+
+// ---- column-sharded step: every rank holds D / R columns of the tables.  bpr_partial_kernel writes this rank's five
+// partial sums of triple i into record i of EVERY rank's exchange buffer (peer stores over NVLink, 20 bytes per triple
+// and peer); after the device barrier bpr_combine_kernel adds the R partials in group_sum's tree order.
+// Buffer layout (floats): [2 step parities][R ranks][B triples][8]: slots 0..4 = ps, ns, qa, qb, qc of the main triples,
+// 5..6 = ps, ns of the auxiliary triples.  The parity (igcn_step_state.step & 1) double-buffers consecutive steps.
+struct PartArgs {
+    float *peer[IGCN_MAX_PEERS];
+    int n_peers, rank, slot0;
+    const igcn_step_state *state;
+    int64_t cap;                       // B capacity of the buffer (records per rank and parity)
+};
+
+template <int LANES>
+__global__ void __launch_bounds__(kThreads) bpr_partial_kernel(const float *__restrict__ T, const float *__restrict__ L2T,
+                                                               const float *__restrict__ w, const int64_t *__restrict__ tri,
+                                                               int64_t B, int64_t off, int D, const __grid_constant__ PartArgs pa) {
+    const int lane = threadIdx.x % LANES;
+    const uint32_t gmask = gmask_of<LANES>();
+    const int64_t i = (int64_t)blockIdx.x * (kThreads / LANES) + threadIdx.x / LANES;
+    if (i >= B) return;
+    const BprDots d = bpr_dots<LANES>(T, L2T, w, tri, i, off, D, lane, gmask);
+    if (lane != 0) return;
+    const int64_t parity = (int64_t)(pa.state->step & 1ULL);
+    const int64_t rec = ((parity * pa.n_peers + pa.rank) * pa.cap + i) * 8 + pa.slot0;
+    for (int p = 0; p < pa.n_peers; ++p) {
+        float *dst = pa.peer[p] + rec;
+        dst[0] = d.ps; dst[1] = d.ns;
+        if (L2T) { dst[2] = d.qa; dst[3] = d.qb; dst[4] = d.qc; }
     }
+}
+
+__device__ __forceinline__ float tree_sum(const float *v, int n) {      // n = 2, 4 or 8 partials, group_sum's order
+    float t[IGCN_MAX_PEERS];
+    for (int r = 0; r < n; ++r) t[r] = v[r];
+    for (int o = 1; o < n; o <<= 1)
+        for (int r = 0; r < n; r += 2 * o) t[r] = t[r] + t[r + o];
+    return t[0];
+}
+
+__global__ void __launch_bounds__(kThreads) bpr_combine_kernel(const float *__restrict__ parts, int64_t B, int64_t cap, int n_peers,
+                                                               int slot0, int has_l2, const igcn_step_state *__restrict__ state,
+                                                               float *sp, float *sig, float *l2) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const int64_t parity = (int64_t)(state->step & 1ULL);
+    float v[5][IGCN_MAX_PEERS];
+    const int nk = has_l2 ? 5 : 2;
+    for (int r = 0; r < n_peers; ++r) {
+        const float *rec = parts + ((parity * n_peers + r) * cap + i) * 8 + slot0;
+        for (int k = 0; k < nk; ++k) v[k][r] = __ldcg(rec + k);
+    }
+    BprDots d;
+    d.ps = tree_sum(v[0], n_peers);
+    d.ns = tree_sum(v[1], n_peers);
+    d.qa = d.qb = d.qc = 0.f;
+    if (has_l2) { d.qa = tree_sum(v[2], n_peers); d.qb = tree_sum(v[3], n_peers); d.qc = tree_sum(v[4], n_peers); }
+    bpr_finish(d, has_l2 != 0, i, sp, sig, l2);
 }
 
 // ------------------------------------------------------------------ loss finalisation (one CTA, fixed order)
@@ -468,6 +547,38 @@ extern "C" int igcn_bpr_fwd(const float *table, const float *l2_table, const flo
              [&] { bpr_fwd_kernel<8><<<(unsigned)((B + 31) / 32), kThreads, 0, st>>>(table, l2_table, w, triples, B, item_offset, D, sp, sig, l2); },
              [&] { bpr_fwd_kernel<16><<<(unsigned)((B + 15) / 16), kThreads, 0, st>>>(table, l2_table, w, triples, B, item_offset, D, sp, sig, l2); },
              [&] { bpr_fwd_kernel<32><<<(unsigned)((B + 7) / 8), kThreads, 0, st>>>(table, l2_table, w, triples, B, item_offset, D, sp, sig, l2); });
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_bpr_partial(const float *table, const float *l2_table, const float *w, const int64_t *triples, int64_t B,
+                                int64_t item_offset, int32_t D, float *const *parts_peer_host, int32_t n_peers, int32_t rank,
+                                int32_t slot0, int64_t cap, const igcn_step_state *state_dev, void *stream) {
+    IGCN_CHECK_ARG(table && triples && parts_peer_host && state_dev, "null pointer");
+    IGCN_CHECK_D(D);
+    IGCN_CHECK_ARG(n_peers == 2 || n_peers == 4 || n_peers == 8, "column sharding supports 2, 4 or 8 ranks");
+    IGCN_CHECK_ARG(rank >= 0 && rank < n_peers && B <= cap && slot0 >= 0 && slot0 + (l2_table ? 5 : 2) <= 8, "bad rank / capacity / slot");
+    if (B <= 0) return 0;
+    PartArgs pa{};
+    for (int p = 0; p < n_peers; ++p) pa.peer[p] = parts_peer_host[p];
+    pa.n_peers = n_peers; pa.rank = rank; pa.slot0 = slot0; pa.state = state_dev; pa.cap = cap;
+    cudaStream_t st = as_stream(stream);
+    by_lanes(D,
+             [&] { bpr_partial_kernel<8><<<(unsigned)((B + 31) / 32), kThreads, 0, st>>>(table, l2_table, w, triples, B, item_offset, D, pa); },
+             [&] { bpr_partial_kernel<16><<<(unsigned)((B + 15) / 16), kThreads, 0, st>>>(table, l2_table, w, triples, B, item_offset, D, pa); },
+             [&] { bpr_partial_kernel<32><<<(unsigned)((B + 7) / 8), kThreads, 0, st>>>(table, l2_table, w, triples, B, item_offset, D, pa); });
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_bpr_combine(const float *parts, int64_t B, int64_t cap, int32_t n_peers, int32_t slot0, int32_t has_l2,
+                                const igcn_step_state *state_dev, float *sp, float *sig, float *l2, void *stream) {
+    IGCN_CHECK_ARG(parts && state_dev && sp && sig, "null pointer");
+    IGCN_CHECK_ARG(n_peers == 2 || n_peers == 4 || n_peers == 8, "column sharding supports 2, 4 or 8 ranks");
+    IGCN_CHECK_ARG(B <= cap && slot0 >= 0 && slot0 + (has_l2 ? 5 : 2) <= 8, "bad capacity / slot");
+    if (B <= 0) return 0;
+    bpr_combine_kernel<<<(unsigned)((B + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream)>>>(parts, B, cap, n_peers, slot0,
+                                                                                                       has_l2, state_dev, sp, sig, l2);
     IGCN_CHECK_LAUNCH();
     return 0;
 }

@@ -279,9 +279,92 @@ __global__ void hits_kernel(const int32_t *__restrict__ rec, int64_t n, int k, c
     hit[idx] = (j >= 0 && lo < end && items[lo] == j) ? 1.f : 0.f;
 }
 
+// numpy's float32 add.reduce over a contiguous row of n <= 128 elements (numpy/core/src/umath/loops_utils.h,
+// pairwise_sum): fewer than 8 elements are added left to right; otherwise eight accumulators take elements j, j + 8,
+// ..., are combined as ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7)), and the n % 8 leftovers are added one by
+// one; the result is added to the zero-initialised output.  Verified against np.sum on this image for n = 1..50.
+__device__ __forceinline__ float numpy_row_sum(const float *a, int n) {
+    float res;
+    if (n < 8) {
+        res = 0.f;
+        for (int i = 0; i < n; ++i) res += a[i];
+    } else {
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+    }
+    return 0.f + res;
+}
+
+constexpr int kMetricsMaxK = 32, kMetricsMaxTopks = 8;
+struct MetricsArgs {
+    int32_t topks[kMetricsMaxTopks];
+    int n_topks, k;
+};
+
+// One thread per user: membership of its k recommended items in its eval list (the double loop of
+// calculate_metrics, trainer.py:111-115), then per cut-off the hit count and the DCG = sum_j hit_j / log2(j + 2)
+// with the reference's fp32 table and numpy's summation order, so that the per-user values -- and with them every
+// mean the host takes -- carry the reference's bits.  Only 2 x n_topks x U floats leave the device.
+__global__ void __launch_bounds__(256) user_metrics_kernel(const int32_t *__restrict__ rec, int64_t n, const int64_t *__restrict__ ptr,
+                                                           const int32_t *__restrict__ items, const float *__restrict__ log2_tab,
+                                                           const __grid_constant__ MetricsArgs ma, float *hit_num, float *dcg) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    const int k = ma.k;
+    float gain[kMetricsMaxK];
+    const int64_t lo0 = ptr[u], end = ptr[u + 1];
+    for (int j = 0; j < k; ++j) {
+        const int32_t it = rec[u * k + j];
+        int64_t lo = lo0, hi = end;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (items[mid] < it) lo = mid + 1; else hi = mid;
+        }
+        const float hit = (it >= 0 && lo < end && items[lo] == it) ? 1.f : 0.f;
+        gain[j] = hit;
+    }
+    for (int t = 0; t < ma.n_topks; ++t) {
+        const int kk = ma.topks[t];
+        float cnt = 0.f;
+        float a[kMetricsMaxK];
+        for (int j = 0; j < kk; ++j) {
+            cnt += gain[j];                                  // exact: small integers
+            a[j] = __fdiv_rn(gain[j], log2_tab[j]);          // hit / denominator, IEEE division like numpy's
+        }
+        hit_num[(int64_t)t * n + u] = cnt;
+        dcg[(int64_t)t * n + u] = numpy_row_sum(a, kk);
+    }
+}
+
 }  // namespace igcn
 
 using namespace igcn;
+
+extern "C" int igcn_user_metrics(const int32_t *rec, int64_t n_users, int32_t k, const int64_t *eval_ptr,
+                                 const int32_t *eval_items, const float *log2_table, const int32_t *topks_host,
+                                 int32_t n_topks, float *hit_num, float *dcg, void *stream) {
+    IGCN_CHECK_ARG(rec && eval_ptr && eval_items && log2_table && topks_host && hit_num && dcg, "null pointer");
+    IGCN_CHECK_ARG(k > 0 && k <= kMetricsMaxK, "k must be in [1, 32]");
+    IGCN_CHECK_ARG(n_topks > 0 && n_topks <= kMetricsMaxTopks, "at most 8 cut-offs");
+    MetricsArgs ma{};
+    for (int t = 0; t < n_topks; ++t) {
+        IGCN_CHECK_ARG(topks_host[t] > 0 && topks_host[t] <= k, "cut-off outside [1, k]");
+        ma.topks[t] = topks_host[t];
+    }
+    ma.n_topks = n_topks; ma.k = k;
+    if (n_users <= 0) return 0;
+    user_metrics_kernel<<<(unsigned)((n_users + 255) / 256), 256, 0, as_stream(stream)>>>(rec, n_users, eval_ptr, eval_items, log2_table,
+                                                                                           ma, hit_num, dcg);
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int igcn_score_topk_exact(const float *rep, const int64_t *user_ids, int64_t n_eval, int64_t item_row0,
                                      int64_t n_items, int32_t D, const int64_t *mask_ptr, const int32_t *mask_items,

@@ -46,6 +46,7 @@ constexpr int TC_BN = 256;        // items per tile     (UMMA N)
 constexpr int TC_CAP = 96;        // candidate slots per user row
 constexpr int TC_KEEP = 32;       // the threshold never rises above the TC_KEEP-th best upper bound
 constexpr int TC_STAGES = 2;      // item-tile smem stages
+constexpr int TC_MASKS = 4;       // ring of 128 x 256 mask bitmaps: the helper warp runs up to 4 tiles ahead of the epilogue
 constexpr int TC_THREADS = 7 * 32;
 constexpr int TC_STAGE_W = 12;    // words per row of the 8-score staging area (16 B aligned; 128-bit stores of 8 lanes hit 8 bank groups)
 
@@ -130,7 +131,7 @@ __device__ __forceinline__ void mbar_wait_helper(uint64_t *bar, uint32_t parity,
 }
 
 struct TcSmem {
-    uint64_t full[TC_STAGES], empty[TC_STAGES], a_full, tmem_full[2], tmem_empty[2], mask_full[2];
+    uint64_t full[TC_STAGES], empty[TC_STAGES], a_full, tmem_full[2], tmem_empty[2], mask_full[TC_MASKS], mask_empty[TC_MASKS];
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -197,7 +198,11 @@ __device__ __forceinline__ void compact_lanes(uint64_t *mybuf, int &cnt, float &
 // are NOT valid): 2 reads the accumulators but does not filter (TMA + MMA + TMEM-read floor), 3 filters against
 // thr = +inf (the compare-free path on every chunk, no hits, no compaction), 5 does not read TMEM at all (MMA
 // issue + the mbarrier hand-offs only).
-template <int VARIANT>
+// CL = 2: the grid is made of CTA PAIRS (thread-block clusters of two) that scan the same item tiles for two
+// different user tiles; each CTA fetches half of every item tile and multicasts it to both, a stage is released
+// when both CTAs' MMAs have read it.  A pair whose second user tile does not exist runs a dummy CTA (the last
+// user tile again, results discarded) so that the hand-offs stay symmetric.
+template <int VARIANT, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t a_bytes = (uint32_t)(TC_BM / 8) * a.kcores * 128;
@@ -206,38 +211,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
     uint8_t *sB = sA + a_bytes;
     uint64_t *cand = reinterpret_cast<uint64_t *>(sB + (size_t)TC_STAGES * b_bytes);
     uint32_t *bitmap = reinterpret_cast<uint32_t *>(cand + (size_t)TC_BM * (TC_CAP + 1));
-    uint32_t *stage = bitmap + 2 * TC_BM * 8;                       // [128 rows][TC_STAGE_W]: one 8-score group per row
+    uint32_t *stage = bitmap + TC_MASKS * TC_BM * 8;                // [128 rows][TC_STAGE_W]: one 8-score group per row
     TcSmem *sm = reinterpret_cast<TcSmem *>(stage + TC_BM * TC_STAGE_W);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // CTA -> (user tile, item split): head tiles scan every item tile in one CTA, the others are split n_splits ways
-    const bool head = (int)blockIdx.x < a.n_head;
-    const int rest = (int)blockIdx.x - a.n_head;
-    const int ut = head ? (int)blockIdx.x : a.n_head + rest / a.n_splits;
-    const int sp = head ? 0 : rest % a.n_splits;
-    const int ns = head ? 1 : a.n_splits;
+    bool head, dummy = false;
+    int ut, sp, ns;
+    const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
+    if (CL == 1) {
+        head = (int)blockIdx.x < a.n_head;
+        const int rest = (int)blockIdx.x - a.n_head;
+        ut = head ? (int)blockIdx.x : a.n_head + rest / a.n_splits;
+        sp = head ? 0 : rest % a.n_splits;
+    } else {
+        // pair P = blockIdx.x / 2 (n_head is even): head pairs take user tiles 2P, 2P + 1; tail pair P' = (tile pair, split)
+        const int P = (int)blockIdx.x >> 1, head_pairs = a.n_head >> 1;
+        head = P < head_pairs;
+        const int rest = P - head_pairs;
+        ut = head ? 2 * P + (int)crank : a.n_head + 2 * (rest / a.n_splits) + (int)crank;
+        sp = head ? 0 : rest % a.n_splits;
+        if (ut >= a.n_utiles) { dummy = true; ut = a.n_utiles - 1; }
+    }
+    ns = head ? 1 : a.n_splits;
     // item tiles intersecting [item_lo, item_hi), divided evenly over the splits
     const int64_t hi_eff = min(a.item_hi, a.n_items);
     const int t_first = (int)(max((int64_t)0, a.item_lo) / TC_BN);
     const int t_last = (int)((hi_eff + TC_BN - 1) / TC_BN);                 // exclusive
     const int n_t = max(0, t_last - t_first);
-    const int per = (n_t + ns - 1) / ns;
-    const int t0 = t_first + sp * per, t1 = min(t_last, t0 + per);
-    const int n_it = max(0, t1 - t0);
+    // split sp takes tiles t_first + sp, + ns, + 2 ns, ...: every split sees the head of the scan order (the
+    // popular items) first, so every list's threshold tightens early
+    const int t0 = t_first + sp;
+    const int n_it = sp < n_t ? (n_t - sp + ns - 1) / ns : 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], CL); }
         mbar_init(&sm->a_full, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm->tmem_full[i], 1); mbar_init(&sm->tmem_empty[i], 4); mbar_init(&sm->mask_full[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm->tmem_full[i], 1); mbar_init(&sm->tmem_empty[i], 4); }
+        for (int i = 0; i < TC_MASKS; ++i) { mbar_init(&sm->mask_full[i], 1); mbar_init(&sm->mask_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < 2 * TC_BM * 8; i += TC_THREADS) bitmap[i] = 0u;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();             // the peer's barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = sm->tmem_base;
 
@@ -251,7 +271,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
                 mbar_wait_helper(&sm->empty[s], ph ^ 1u, a.dbg & 1);
                 mbar_arrive_expect_tx(&sm->full[s], b_bytes);
-                bulk_g2s(sB + (size_t)s * b_bytes, a.b_img + (size_t)(t0 + it) * b_bytes, b_bytes, &sm->full[s]);
+                if (CL == 1) {
+                    bulk_g2s(sB + (size_t)s * b_bytes, a.b_img + (size_t)(t0 + it * ns) * b_bytes, b_bytes, &sm->full[s]);
+                } else {
+                    // my half of the tile goes to both CTAs; the other half arrives from the peer (same barrier, same phase)
+                    const uint32_t half = b_bytes / 2;
+                    bulk_g2s_multicast(sB + (size_t)s * b_bytes + crank * half, a.b_img + (size_t)(t0 + it * ns) * b_bytes + crank * half,
+                                       half, &sm->full[s], (uint16_t)3);
+                }
             }
         }
     } else if (warp == 1) {
@@ -270,55 +297,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 for (int ks = 0; ks < ksteps; ++ks)
                     tc_mma_f16(tmem_base + (uint32_t)acc * TC_BN, umma_desc(a0 + ks * 256, lbo, sbo), umma_desc(b0 + ks * 256, lbo, sbo),
                                idesc, ks > 0 ? 1u : 0u);
-                tc_commit(&sm->empty[s]);          // smem stage reusable once these MMAs retire
+                if (CL == 1) tc_commit(&sm->empty[s]);          // smem stage reusable once these MMAs retire
+                else tc_commit_multicast(&sm->empty[s], (uint16_t)3);      // ... in BOTH CTAs: either producer overwrites both
                 tc_commit(&sm->tmem_full[acc]);    // accumulator ready for the epilogue
             }
         }
     } else if (warp == 2) {
-        // ===== mask helper: seen-item bucket + banned bitmap + item range -> bitmap[acc][8 words][128 rows].
-        // The epilogue only reads the bitmap, so before building tile `it` the helper un-sets what it set for
-        // tile `it - 2` (same buffer): apply(t, false) stores zero words exactly where apply(t, true) OR-ed bits.
-        auto apply = [&](int t, bool set, uint32_t *bm) {
-            uint32_t common = 0;
-            if (lane < 8) {
-                const int64_t c0 = (int64_t)t * TC_BN + lane * 32;
-                if (c0 < a.item_lo) common |= (a.item_lo - c0 >= 32) ? 0xffffffffu : ((1u << (a.item_lo - c0)) - 1u);
-                if (c0 + 32 > hi_eff) common |= (c0 >= hi_eff) ? 0xffffffffu : ~((1u << (hi_eff - c0)) - 1u);
-                if (a.banned && c0 < a.n_items) common |= __ldg(a.banned + (c0 >> 5));
+        // ===== mask helper: seen-item bucket + banned bitmap + item range -> bitmap[ring slot][8 words][128 rows].
+        // The epilogue only reads the bitmaps.  The helper owns a ring of TC_MASKS of them and is NOT part of the
+        // accumulator hand-off chain: it zeroes a slot as soon as the epilogue has released it (mask_empty), ORs in
+        // the tile's entries -- whose global loads were issued one tile earlier, so the dependent chain tile_ptr ->
+        // entries (two L2 round trips, ~1,900 cycles per tile when it sat between tmem_empty and mask_full) is off
+        // the critical path -- and publishes it (mask_full) up to TC_MASKS tiles ahead of the epilogue.
+        const int32_t *tp = (a.mask_tile_ptr && !dummy) ? a.mask_tile_ptr + (size_t)ut * (a.n_itiles + 1) : nullptr;
+        auto bucket = [&](int it, int &e0, int &e1, uint32_t &first) {
+            e0 = e1 = 0; first = 0u;
+            if (tp && it < n_it) {
+                const int t = t0 + it * ns;
+                e0 = __ldg(tp + t); e1 = __ldg(tp + t + 1);
+                if (e0 + lane < e1) first = a.mask_entries[e0 + lane];
             }
-            if (__any_sync(0xffffffffu, common != 0u)) {
+        };
+        int e0, e1;
+        uint32_t first;
+        bucket(0, e0, e1, first);
+        for (int it = 0; it < n_it; ++it) {
+            const int slot = it % TC_MASKS, t = t0 + it * ns;
+            int n0, n1;
+            uint32_t nfirst;
+            bucket(it + 1, n0, n1, nfirst);                          // next tile's loads fly while this one is built
+            mbar_wait_helper(&sm->mask_empty[slot], ((uint32_t)(it / TC_MASKS) & 1u) ^ 1u, a.dbg & 2);
+            uint32_t *bm = bitmap + (size_t)slot * TC_BM * 8;
+            if (!(a.dbg & 4)) {
+                uint32_t common = 0;
+                if (lane < 8) {
+                    const int64_t c0 = (int64_t)t * TC_BN + lane * 32;
+                    if (c0 < a.item_lo) common |= (a.item_lo - c0 >= 32) ? 0xffffffffu : ((1u << (a.item_lo - c0)) - 1u);
+                    if (c0 + 32 > hi_eff) common |= (c0 >= hi_eff) ? 0xffffffffu : ~((1u << (hi_eff - c0)) - 1u);
+                    if (a.banned && c0 < a.n_items) common |= __ldg(a.banned + (c0 >> 5));
+                }
+                // word w of every row starts as the tile-wide word (item range, banned items), usually zero
+#pragma unroll
                 for (int w = 0; w < 8; ++w) {
                     const uint32_t cw = __shfl_sync(0xffffffffu, common, w);
-                    if (cw)
-                        for (int r = lane; r < TC_BM; r += 32) {
-                            if (set) bm[w * TC_BM + r] |= cw; else bm[w * TC_BM + r] = 0u;
-                        }
+                    const uint4 v4 = make_uint4(cw, cw, cw, cw);
+                    *reinterpret_cast<uint4 *>(bm + w * TC_BM + lane * 4) = v4;
                 }
                 __syncwarp();
-            }
-            if (a.mask_tile_ptr) {
-                const int32_t *p = a.mask_tile_ptr + (size_t)ut * (a.n_itiles + 1) + t;
-                const int e0 = __ldg(p), e1 = __ldg(p + 1);
-                for (int e = e0 + lane; e < e1; e += 32) {
+                if (e0 + lane < e1) atomicOr(bm + ((first & 255u) >> 5) * TC_BM + (first >> 8), 1u << (first & 31u));
+                for (int e = e0 + 32 + lane; e < e1; e += 32) {      // buckets beyond 32 entries (rare)
                     const uint32_t ent = a.mask_entries[e];
-                    uint32_t *w = bm + ((ent & 255u) >> 5) * TC_BM + (ent >> 8);
-                    if (set) atomicOr(w, 1u << (ent & 31u)); else *w = 0u;
+                    atomicOr(bm + ((ent & 255u) >> 5) * TC_BM + (ent >> 8), 1u << (ent & 31u));
                 }
+                __syncwarp();
+                __threadfence_block();
             }
-            __syncwarp();
-        };
-        for (int it = 0; it < n_it; ++it) {
-            const int acc = it & 1, t = t0 + it;
-            mbar_wait_helper(&sm->tmem_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u, a.dbg & 2);
-            if (a.dbg & 4) {
-                if (lane == 0) mbar_arrive(&sm->mask_full[acc]);
-                continue;
-            }
-            uint32_t *bm = bitmap + (size_t)acc * TC_BM * 8;
-            if (it >= 2) apply(t - 2, false, bm);
-            apply(t, true, bm);
-            __threadfence_block();
-            if (lane == 0) mbar_arrive(&sm->mask_full[acc]);
+            if (lane == 0) mbar_arrive(&sm->mask_full[slot]);
+            e0 = n0; e1 = n1; first = nfirst;
         }
     } else {
         // ===== epilogue: thread = user row (TMEM lane)
@@ -330,23 +365,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         int cnt = 0;
         uint32_t st_chunks = 0, st_slow = 0, st_groups = 0, st_hits = 0, st_compact = 0;     // VARIANT 4 only
         for (int it = 0; it < n_it; ++it) {
-            const int acc = it & 1, t = t0 + it;
+            const int acc = it & 1, t = t0 + it * ns, slot = it % TC_MASKS;
             const uint32_t ph = (uint32_t)(it >> 1) & 1u;
             mbar_wait(&sm->tmem_full[acc], ph);
-            mbar_wait(&sm->mask_full[acc], ph);
+            mbar_wait(&sm->mask_full[slot], (uint32_t)(it / TC_MASKS) & 1u);
             tc_fence_after();
             if (VARIANT == 5) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm->tmem_empty[acc]);
+                if (lane == 0) { mbar_arrive(&sm->tmem_empty[acc]); mbar_arrive(&sm->mask_empty[slot]); }
                 continue;
             }
-            const uint32_t *bm = bitmap + (size_t)acc * TC_BM * 8 + row;    // word w of this row at bm[w * 128]
+            const uint32_t *bm = bitmap + (size_t)slot * TC_BM * 8 + row;   // word w of this row at bm[w * 128]
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_BN;
-            uint32_t va[32], vb[32];
-            tc_ld32(taddr, va);
-            // two chunks per iteration so the next TMEM load is always in flight behind the filter
-            auto filter = [&](uint32_t (&v)[32], int ch) {
+            uint32_t va[64], vb[64];
+            tc_ld64(taddr, va);
+            // 64 columns per TMEM load, the next load always in flight behind the filter of the previous 64
+            auto filter = [&](const uint32_t *v, int ch) {
                 const uint32_t item0 = (uint32_t)(t * TC_BN + ch * 32);
                 if (VARIANT == 2) {
                     uint32_t x = 0;
@@ -399,21 +434,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 }
             };
 #pragma unroll 1
-            for (int ch = 0; ch < 8; ch += 2) {
+            for (int ch = 0; ch < 8; ch += 4) {
                 tc_wait_ld();
-                tc_ld32(taddr + (ch + 1) * 32, vb);
+                tc_ld64(taddr + (ch + 2) * 32, vb);
                 filter(va, ch);
+                filter(va + 32, ch + 1);
                 tc_wait_ld();
-                if (ch + 2 < 8) tc_ld32(taddr + (ch + 2) * 32, va);
-                filter(vb, ch + 1);
+                if (ch + 4 < 8) tc_ld64(taddr + (ch + 4) * 32, va);
+                filter(vb, ch + 2);
+                filter(vb + 32, ch + 3);
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm->tmem_empty[acc]);
+            if (lane == 0) { mbar_arrive(&sm->tmem_empty[acc]); mbar_arrive(&sm->mask_empty[slot]); }
         }
         // dump this row's candidates
         __syncwarp();
-        for (int r = 0; r < 32; ++r) {
+        for (int r = 0; r < 32 && !dummy; ++r) {
             const int64_t b = (int64_t)ut * TC_BM + q * 32 + r;
             if (b >= a.n_eval) break;
             const int n = __shfl_sync(0xffffffffu, cnt, r);
@@ -430,7 +467,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 a.cand_thr[b * a.n_splits + lane] = -INFINITY;
             }
         }
-        if (VARIANT == 4 && a.stats) {
+        if (VARIANT == 4 && a.stats && !dummy) {
             // chunk / group counters are per warp (lane 0 speaks), appended candidates per row (summed)
             const uint32_t hits = __reduce_add_sync(0xffffffffu, st_hits);
             if (lane == 0) {
@@ -444,6 +481,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();             // no CTA leaves while the peer can still signal or write into it
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
@@ -578,7 +616,14 @@ extern "C" int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, in
     if (n_eval <= 0) return 0;
     const int n_utiles = (int)((n_eval + TC_BM - 1) / TC_BM);
     IGCN_CHECK_ARG(n_head >= 0 && n_head <= n_utiles, "n_head must be in [0, number of user tiles]");
-    const unsigned n_ctas = (unsigned)(n_head + (n_utiles - n_head) * n_splits);
+    // CTA pairs (clusters of two) share the item stream; IGCN_TC_CLUSTER=1 selects the unpaired kernel (A/B timing)
+    static int cluster_env = -1;
+    if (cluster_env < 0) { const char *e = getenv("IGCN_TC_CLUSTER"); cluster_env = e ? atoi(e) : 2; }
+    const bool paired = cluster_env == 2 && n_utiles >= 2;
+    if (paired) n_head &= ~1;                           // head tiles come in pairs; an odd one joins the split tail
+    const int n_tail = n_utiles - n_head;
+    const unsigned n_ctas = paired ? 2u * (unsigned)(n_head / 2 + (n_tail + 1) / 2 * n_splits)
+                                   : (unsigned)(n_head + n_tail * n_splits);
     TcArgs a{};
     a.a_img = a_img; a.b_img = b_img;
     a.n_utiles = n_utiles;
@@ -588,17 +633,26 @@ extern "C" int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, in
     a.banned = banned_bits; a.mask_tile_ptr = mask_tile_ptr; a.mask_entries = mask_entries;
     a.cand_items = cand_items; a.cand_cnt = cand_cnt; a.cand_thr = cand_thr; a.dump = dump; a.stats = stats;
     const size_t smem = (size_t)(TC_BM / 8 + TC_STAGES * (TC_BN / 8)) * a.kcores * 128 + (size_t)TC_BM * (TC_CAP + 1) * 8 +
-                        2 * TC_BM * 8 * 4 + (size_t)TC_BM * TC_STAGE_W * 4 + sizeof(TcSmem) + 64;
+                        (size_t)TC_MASKS * TC_BM * 8 * 4 + (size_t)TC_BM * TC_STAGE_W * 4 + sizeof(TcSmem) + 64;
     const char *dbg_env = getenv("IGCN_TC_DEBUG");
     a.dbg = dbg_env ? atoi(dbg_env) : 0;
     const char *exp_env = getenv("IGCN_TC_EXPERIMENT");      // read per call: tools/tc_floor.py sweeps it in one process
     const int experiment = exp_env ? atoi(exp_env) : 0;
-    auto kern = dump ? score_tc_kernel<1> : stats ? score_tc_kernel<4>
-                : experiment == 2 ? score_tc_kernel<2> : experiment == 3 ? score_tc_kernel<3>
-                : experiment == 5 ? score_tc_kernel<5> : score_tc_kernel<0>;
+    const int variant = dump ? 1 : stats ? 4 : (experiment == 2 || experiment == 3 || experiment == 5) ? experiment : 0;
+    void (*kern)(TcArgs) = nullptr;
+#define IGCN_TC_PICK(V) case V: kern = paired ? score_tc_kernel<V, 2> : score_tc_kernel<V, 1>; break
+    switch (variant) { IGCN_TC_PICK(0); IGCN_TC_PICK(1); IGCN_TC_PICK(2); IGCN_TC_PICK(3); IGCN_TC_PICK(4); IGCN_TC_PICK(5); }
+#undef IGCN_TC_PICK
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("igcn_tc_candidates: %s", cudaGetErrorString(e)); return (int)e; }
-    kern<<<n_ctas, TC_THREADS, smem, as_stream(stream)>>>(a);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(n_ctas); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = paired ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, a);
+    if (e != cudaSuccess) { set_error("igcn_tc_candidates: %s", cudaGetErrorString(e)); return (int)e; }
     IGCN_CHECK_LAUNCH();
     return 0;
 }

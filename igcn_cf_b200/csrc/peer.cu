@@ -78,6 +78,29 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const __grid_constant__ 
     }
 }
 
+struct PushColsArgs {
+    float *peer[IGCN_MAX_PEERS];
+    int n_peers;
+    const float *src;                  // [rows, ds] contiguous
+    int64_t rows;
+    int ds, d, col0;                   // slice width, full row width, first column of the slice
+};
+
+// Column-sharded training: every rank owns columns [col0, col0 + ds) of a [rows, d] table.  This writes the rank's
+// slice into that column range of EVERY rank's full-width copy (its own included): the all-gather of the parameters
+// that an evaluation or a checkpoint needs, once per epoch.
+__global__ void __launch_bounds__(256) peer_push_cols_kernel(const __grid_constant__ PushColsArgs a) {
+    const int per_row = a.ds / 4;
+    const int64_t n4 = a.rows * per_row;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int64_t r = i / per_row;
+        const int c = (int)(i % per_row) * 4;
+        const float4 v = __ldcg(reinterpret_cast<const float4 *>(a.src + r * a.ds + c));
+        for (int p = 0; p < a.n_peers; ++p) __stcg(reinterpret_cast<float4 *>(a.peer[p] + r * a.d + a.col0 + c), v);
+    }
+}
+
 }  // namespace igcn
 
 using namespace igcn;
@@ -166,6 +189,22 @@ extern "C" int igcn_peer_push(float *const *peer_host, int32_t n_peers, int32_t 
     int64_t blocks = (a.n4 + 255) / 256;
     if (blocks > 148 * 4) blocks = 148 * 4;
     peer_push_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(a);
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_peer_push_cols(float *const *peer_host, int32_t n_peers, const float *src, int64_t rows, int32_t ds, int32_t d,
+                                   int32_t col0, void *stream) {
+    IGCN_CHECK_ARG(peer_host && src, "null pointer");
+    IGCN_CHECK_ARG(n_peers >= 1 && n_peers <= IGCN_MAX_PEERS, "bad peer count");
+    IGCN_CHECK_ARG(ds > 0 && !(ds & 3) && !(d & 3) && !(col0 & 3) && col0 >= 0 && col0 + ds <= d, "slice must be float4 aligned and inside the row");
+    if (rows <= 0) return 0;
+    PushColsArgs a{};
+    for (int p = 0; p < n_peers; ++p) a.peer[p] = peer_host[p];
+    a.n_peers = n_peers; a.src = src; a.rows = rows; a.ds = ds; a.d = d; a.col0 = col0;
+    int64_t blocks = (rows * (ds / 4) + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    peer_push_cols_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(a);
     IGCN_CHECK_LAUNCH();
     return 0;
 }

@@ -414,10 +414,15 @@ static int fill_drop(PropArgs &a, const igcn_dropout *drop) {
 }
 
 // ------------------------------------------------------------------ masked column sums
+// A CTA of GROUPS x LANES threads sums 256 rows: group g adds rows g, g + GROUPS, ... in order, then the GROUPS partials
+// are added in order.  GROUPS is the same for every width (the CTA size changes instead), so each column's sum is
+// formed in the same order whatever D is -- the column-sharded training step (D / ranks columns per GPU) has to
+// reproduce the single-GPU bits.
+constexpr int kColsumGroups = 16;
 template <int LANES>
-__global__ void __launch_bounds__(kThreads) colsum_stage1(const float *__restrict__ G, int64_t row_begin, int64_t row_end,
-                                                          int D, igcn_dropout drop, uint32_t thresh, float *scratch) {
-    constexpr int GROUPS = kThreads / LANES;
+__global__ void __launch_bounds__(kColsumGroups * LANES) colsum_stage1(const float *__restrict__ G, int64_t row_begin, int64_t row_end,
+                                                                      int D, igcn_dropout drop, uint32_t thresh, float *scratch) {
+    constexpr int GROUPS = kColsumGroups;
     __shared__ float4 sm[GROUPS][LANES];
     const int lane = threadIdx.x % LANES, grp = threadIdx.x / LANES;
     const bool active = lane * 4 < D;
@@ -550,9 +555,9 @@ extern "C" int igcn_colsum_masked(const float *G, int64_t row_begin, int64_t row
     cudaStream_t st = as_stream(stream);
     const int64_t n_blocks = (row_end - row_begin + 255) / 256;
     if (n_blocks > 0) {
-        if (D <= 32) colsum_stage1<8><<<(unsigned)n_blocks, kThreads, 0, st>>>(G, row_begin, row_end, D, a.drop, a.thresh, scratch);
-        else if (D <= 64) colsum_stage1<16><<<(unsigned)n_blocks, kThreads, 0, st>>>(G, row_begin, row_end, D, a.drop, a.thresh, scratch);
-        else colsum_stage1<32><<<(unsigned)n_blocks, kThreads, 0, st>>>(G, row_begin, row_end, D, a.drop, a.thresh, scratch);
+        if (D <= 32) colsum_stage1<8><<<(unsigned)n_blocks, kColsumGroups * 8, 0, st>>>(G, row_begin, row_end, D, a.drop, a.thresh, scratch);
+        else if (D <= 64) colsum_stage1<16><<<(unsigned)n_blocks, kColsumGroups * 16, 0, st>>>(G, row_begin, row_end, D, a.drop, a.thresh, scratch);
+        else colsum_stage1<32><<<(unsigned)n_blocks, kColsumGroups * 32, 0, st>>>(G, row_begin, row_end, D, a.drop, a.thresh, scratch);
     }
     colsum_stage2<<<1, 128, 0, st>>>(scratch, n_blocks, D, out);
     IGCN_CHECK_LAUNCH();

@@ -296,7 +296,16 @@ class TrainStep:
         self.use_graph = bool(use_graph)
         dev = model.embedding.weight.device
         self.device = dev
+        # column-sharded training (model_config['shard'] = 'dims'): this rank owns D / world columns of the parameters
+        # and of every layer buffer; the step runs the same kernels on the narrow tables
+        self.dims = getattr(model, '_dim_shard', None)
         D = model.embedding_size
+        if self.dims is not None:
+            rank, world = self.dims
+            if world not in (2, 4, 8) or D % (4 * world):
+                raise RuntimeError('column sharding needs 2, 4 or 8 ranks and embedding_size %% (4 * ranks) == 0')
+            self.D_full, D = D, D // world
+            self.col0 = rank * D
         self.D = D
         i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)
         f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
@@ -312,25 +321,84 @@ class TrainStep:
         self.state = opt.device_state(dev)                                # igcn_step_state
         n = model.n_users + model.n_items
         self.gprime = torch.zeros((n, D), dtype=torch.float32, device=dev)
-        prop = model._propagator()
-        self.shard = prop.shard
-        self.d_emb = prop.new_buffer(model.embedding.weight.shape[0])     # symmetric when row-sharded
-        self.d_emb.zero_()
-        self.emb_m, self.emb_v = opt.moments(model.embedding.weight)
+        if self.dims is None:
+            prop = model._propagator()
+            self.prop = None                                                  # looked up per step: the model may rebuild it
+            self.shard = prop.shard
+            self.d_emb = prop.new_buffer(model.embedding.weight.shape[0])     # symmetric when row-sharded
+            self.d_emb.zero_()
+            self.emb_m, self.emb_v = opt.moments(model.embedding.weight)
+        else:
+            self._init_dims(model, n, D, dev)
         if self.is_igcn:
             self.a_triples = torch.zeros((self.B, 3), dtype=torch.int64, device=dev)
             self.a_order, self.a_seg_start = i32(3 * self.B), i32(3 * self.B + 1)
             self.a_seg_row = torch.empty(3 * self.B, dtype=torch.int64, device=dev)
             self.a_n_seg = torch.zeros(1, dtype=torch.int32, device=dev)
             self.a_sp, self.a_sig = f32(self.B), f32(self.B)
-            self.d_w = torch.zeros_like(model.w.data)
+            self.d_w = torch.zeros(D, dtype=torch.float32, device=dev)
             self.dw_scratch = f32((self.B + 63) // 64, D)
-            self.w_m, self.w_v = opt.moments(model.w)
+            if self.dims is None:
+                self.w_m, self.w_v = opt.moments(model.w)
+            else:
+                self.w_s = torch.empty(D, dtype=torch.float32, device=dev)
+                self.w_m, self.w_v = torch.zeros_like(self.w_s), torch.zeros_like(self.w_s)
             self.colsum_scratch = colsum_scratch(n, D, dev)
         self._graphs = {}
         self._side = torch.cuda.Stream(device=dev)       # main scatter plan: joins before the last forward layer
         self._side2 = torch.cuda.Stream(device=dev)      # zeroed gradient buffers + auxiliary plan: joins before the gradient kernels
         self._side3 = torch.cuda.Stream(device=dev)      # loss value + running meter: nothing downstream reads them; joins at the end
+
+    # -- column-sharded training
+    def _init_dims(self, model, n, D, dev):
+        """Buffers of the column-sharded step: narrow parameter / moment / gradient tables, a private propagator of
+        width D / world (no exchange: the propagation acts on every column independently), the exchange buffer of
+        the per-triple partial sums and a symmetric staging copy for the parameter all-gather."""
+        rank, world = self.dims
+        peers = model._peers
+        rows = model.embedding.weight.shape[0]
+        self.prop = Propagator(n, D, model.n_layers, dev, None)
+        self.shard = None
+        z = lambda *sh: torch.zeros(sh, dtype=torch.float32, device=dev)
+        self.emb_s, self.emb_m, self.emb_v, self.d_emb = z(rows, D), z(rows, D), z(rows, D), z(rows, D)
+        self.parts = peers.alloc((2 * world * self.B * 8,), torch.float32)
+        self.gather = peers.alloc((rows + 1, self.D_full), torch.float32)     # last row: w
+        self._seen_epoch = None
+        self._dirty = False
+        model._param_sync = self.sync_params
+
+    def _reslice(self):
+        """Take this rank's columns of the model's (full-width) parameters; Adam moments restart only when the
+        parameters were replaced from outside (load / assignment), not after our own steps."""
+        m = self.model
+        c0, c1 = self.col0, self.col0 + self.D
+        self.emb_s.copy_(m.embedding.weight.data[:, c0:c1])
+        if self.is_igcn:
+            self.w_s.copy_(m.w.data[c0:c1])
+
+    def sync_params(self):
+        """All-gather of the column slices into model.embedding.weight (and w) on every rank: each rank writes its
+        columns into every rank's staging copy over NVLink (igcn_peer_push_cols), barrier, local copy.  Called by the
+        model before it needs full-width parameters (get_rep / save) and at the end of an epoch; collective."""
+        if self.dims is None or not self._dirty:
+            return
+        m, peers = self.model, self.model._peers
+        rank, world = self.dims
+        rows = m.embedding.weight.shape[0]
+        peers.barrier()                                  # nobody still reads the staging copy of the previous gather
+        arr = self.gather.peer_array(0)
+        call('igcn_peer_push_cols', arr, world, ptr(self.emb_s), rows, self.D, self.D_full, self.col0, stream_ptr())
+        if self.is_igcn:
+            arr_w = self.gather.peer_array(rows * self.D_full * 4)
+            call('igcn_peer_push_cols', arr_w, world, ptr(self.w_s), 1, self.D, self.D_full, self.col0, stream_ptr())
+        peers.barrier()
+        full = self.gather.tensor
+        m.embedding.weight.data.copy_(full[:rows])
+        if self.is_igcn:
+            m.w.data.copy_(full[rows])
+        self._dirty = False
+        m._bump()
+        self._seen_epoch = m._param_epoch
 
     # -- pieces
     def _sample(self, B):
@@ -345,9 +413,11 @@ class TrainStep:
 
     def _body(self, B, sample, drop):
         m, D, st = self.model, self.D, stream_ptr
-        prop = m._propagator()
+        dims = self.dims
+        prop = m._propagator() if dims is None else self.prop
         L = prop.n_layers
-        emb = m.embedding.weight.data
+        emb = m.embedding.weight.data if dims is None else self.emb_s
+        w = (m.w.data if dims is None else self.w_s) if self.is_igcn else None
         call('igcn_step_tick', ptr(self.state), self.lr, BETA1, BETA2, st())
         if sample:
             self._sample(B)
@@ -385,12 +455,29 @@ class TrainStep:
             l2_table = emb
         if L == 0:
             join()
-        call('igcn_bpr_fwd', ptr(rep), ptr(l2_table), None, ptr(self.triples), B, m.n_users, D, ptr(self.sp),
-             ptr(self.sig), ptr(self.l2), st())
-        if self.is_igcn:
-            t_u = m.feat_mat.t_users
-            call('igcn_bpr_fwd', ptr(emb), None, ptr(m.w.data), ptr(self.a_triples), B, t_u, D, ptr(self.a_sp),
-                 ptr(self.a_sig), None, st())
+        if dims is None:
+            call('igcn_bpr_fwd', ptr(rep), ptr(l2_table), None, ptr(self.triples), B, m.n_users, D, ptr(self.sp),
+                 ptr(self.sig), ptr(self.l2), st())
+            if self.is_igcn:
+                call('igcn_bpr_fwd', ptr(emb), None, ptr(w), ptr(self.a_triples), B, m.feat_mat.t_users, D, ptr(self.a_sp),
+                     ptr(self.a_sig), None, st())
+        else:
+            # the only cross-column quantities of the step: every rank's partial dot products / squared norms go to
+            # every rank (20 bytes per triple and peer), one device barrier, then the tree-ordered combine
+            rank, world = dims
+            arr = self.parts.peer_array(0)
+            call('igcn_bpr_partial', ptr(rep), ptr(l2_table), None, ptr(self.triples), B, m.n_users, D, arr, world, rank, 0,
+                 self.B, ptr(self.state), st())
+            if self.is_igcn:
+                call('igcn_bpr_partial', ptr(emb), None, ptr(w), ptr(self.a_triples), B, m.feat_mat.t_users, D, arr, world,
+                     rank, 5, self.B, ptr(self.state), st())
+            m._peers.barrier()
+            parts = self.parts.tensor
+            call('igcn_bpr_combine', ptr(parts), B, self.B, world, 0, 1, ptr(self.state), ptr(self.sp), ptr(self.sig),
+                 ptr(self.l2), st())
+            if self.is_igcn:
+                call('igcn_bpr_combine', ptr(parts), B, self.B, world, 5, 0, ptr(self.state), ptr(self.a_sp), ptr(self.a_sig),
+                     None, st())
         self._side3.wait_stream(main)
         with torch.cuda.stream(self._side3):
             if self.is_igcn:
@@ -412,7 +499,7 @@ class TrainStep:
             prop.backward(m.norm_adj, self.gprime, g_scaled, rowscale=feat.rowscale, alpha=inv_keep,
                           gprime_rows=self.touched)
             inmo_backward(feat, g_scaled, self.d_emb, drop, D, self.colsum_scratch, self.shard)
-            call('igcn_bpr_bwd', ptr(emb), ptr(m.w.data), ptr(self.a_triples), B, feat.t_users, D, ptr(self.a_sig),
+            call('igcn_bpr_bwd', ptr(emb), ptr(w), ptr(self.a_triples), B, feat.t_users, D, ptr(self.a_sig),
                  float(self.aux_reg), 0.0, 0, ptr(self.a_order), ptr(self.a_seg_start), ptr(self.a_seg_row),
                  ptr(self.a_n_seg), ptr(self.d_emb), 1, ptr(self.d_w), ptr(self.dw_scratch), st())
         else:
@@ -424,7 +511,6 @@ class TrainStep:
         call('igcn_adam', ptr(emb), ptr(self.d_emb), ptr(self.emb_m), ptr(self.emb_v), emb.numel(), self.lr,
              BETA1, BETA2, ADAM_EPS, 0, ptr(self.state), st())
         if self.is_igcn:
-            w = m.w.data
             call('igcn_adam', ptr(w), ptr(self.d_w), ptr(self.w_m), ptr(self.w_v), w.numel(), self.lr, BETA1,
                  BETA2, ADAM_EPS, 0, ptr(self.state), st())
         main.wait_stream(self._side3)
@@ -449,6 +535,9 @@ class TrainStep:
             self.triples[:B].copy_(triples)
             if self.is_igcn:
                 self.a_triples[:B].copy_(aux_triples)
+        if self.dims is not None and self._seen_epoch != self.model._param_epoch:
+            self.sync_params()                 # (no-op unless our own steps are pending)
+            self._reslice()                    # the full-width parameters were set from outside: take our columns again
         # the learning rate is a launch argument of igcn_step_tick / igcn_adam: follow the optimizer's param group
         # (schedulers, manual decay) like Adam.step() does; a new value re-captures the CUDA graph
         self.lr = float(self.opt.param_groups[0]['lr'])
@@ -472,6 +561,9 @@ class TrainStep:
             g.replay()
         self.opt.t += 1
         self.model._bump()
+        if self.dims is not None:
+            self._dirty = True
+            self._seen_epoch = self.model._param_epoch
         return self.loss
 
     def _capture(self, B, sample, d):
@@ -491,9 +583,10 @@ class TrainStep:
         return g
 
     def _snapshot(self):
-        ts = [self.model.embedding.weight.data, self.emb_m, self.emb_v, self.acc]
+        dims = self.dims is not None
+        ts = [self.emb_s if dims else self.model.embedding.weight.data, self.emb_m, self.emb_v, self.acc]
         if self.is_igcn:
-            ts += [self.model.w.data, self.w_m, self.w_v]
+            ts += [self.w_s if dims else self.model.w.data, self.w_m, self.w_v]
         return [(t, t.clone()) for t in ts]
 
     def _restore(self, snap, state_backup):

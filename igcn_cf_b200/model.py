@@ -59,6 +59,11 @@ class BasicModel(nn.Module):
         #   False   single-GPU behaviour on every rank
         #   'users' training step replicated, evaluation users sharded (no exchange anywhere on the training path)
         #   True    propagation rows sharded over the ranks (fused NVLink all-gather), eval users sharded
+        #   'dims'  training with the embedding COLUMNS sharded: every rank owns embedding_size / world columns of the
+        #           parameters, the optimizer state and every layer buffer.  The propagation is linear and acts on each
+        #           column independently, so no layer embedding ever crosses NVLink; the only exchange of a step is 20-28
+        #           bytes per triple (partial dot products), and the parameters are all-gathered once per epoch /
+        #           before an evaluation.  Bit-identical to one GPU.  Eval users sharded, eval propagation replicated.
         #   'auto'  (default) eval users always sharded; rows sharded only when every rank keeps at least
         #           SHARD_MIN_NNZ_PER_RANK non-zeros, i.e. when the per-layer exchange (N*D*4 bytes into every rank)
         #           pays off -- measured: Amazon-shaped on 2 GPUs yes (1.23x), on 8 no; Yelp/Gowalla-shaped never
@@ -67,11 +72,16 @@ class BasicModel(nn.Module):
         self._peers = dist.current() if mode else None
         self._shard_rows = mode is True
         self._shard_auto = mode == 'auto'
+        self._dim_shard = (self._peers.rank, self._peers.world) if (mode == 'dims' and self._peers is not None) else None
+        self._param_sync = None         # set by engine.TrainStep in 'dims' mode: all-gathers the column slices
 
     def predict(self, users):
         raise NotImplementedError
 
     def save(self, path):
+        sync = getattr(self, '_sync_params', None)
+        if callable(sync):
+            sync()
         torch.save(self.state_dict(), path)
 
     def load(self, path):
@@ -87,6 +97,12 @@ class _GraphModel(BasicModel):
     def _bump(self):
         """Tell the eval-mode cache that parameters were changed behind autograd's back."""
         self._param_epoch += 1
+
+    def _sync_params(self):
+        """Column-sharded training keeps the up-to-date parameters as per-rank column slices: gather them into
+        embedding.weight (collective, a no-op when nothing is pending) before anything reads full-width parameters."""
+        if self._param_sync is not None:
+            self._param_sync()
 
     def graph_version(self):
         """Identity of the graph objects the kernels read: their construction serial numbers (graph._Blocked.uid),
@@ -212,6 +228,7 @@ class LightGCN(_GraphModel):
 
     def get_rep(self):
         self._check_graph()
+        self._sync_params()
         require_cuda(self.embedding.weight, torch.float32, 'embedding.weight')
         return self._cached_rep(lambda: engine.LightGCNRep.apply(self.embedding.weight, self))
 
@@ -436,6 +453,7 @@ class IGCN(_GraphModel):
     def get_rep(self):
         """model.py:434-446."""
         self._check_graph()
+        self._sync_params()
         feat = self.feat_mat
         if feat.shape[0] != self.n_users + self.n_items or feat.shape[1] != self.embedding.weight.shape[0]:
             raise RuntimeError('feat_mat %s does not match nodes=%d / templates=%d'
@@ -454,6 +472,7 @@ class IGCN(_GraphModel):
 
     # ---- checkpoint (model.py:454-466; key spelling kept for file compatibility)
     def save(self, path):
+        self._sync_params()
         params = {'sate_dict': self.state_dict(), 'user_map': self.user_map,
                   'item_map': self.item_map, 'alpha': self.alpha}
         torch.save(params, path)

@@ -162,6 +162,7 @@ class BasicTrainer:
         self._eval_cache = {}
         self._last_rec = None
         self._item_order = None
+        self._metric_tables = {}
         self.test_users = torch.arange(self.dataset.n_users, dtype=torch.int64, device=self.device)
 
     def initialize_optimizer(self):
@@ -253,24 +254,39 @@ class BasicTrainer:
         return engine.lists_to_arrays(getattr(self.dataset, which + '_data'))
 
     def calculate_metrics(self, eval_data, rec_items):
-        """Precision / Recall / NDCG @k with the reference's dtypes: fp32 hit matrix and log2 table,
-        int32 list lengths, users without eval items excluded from the means."""
+        """Precision / Recall / NDCG @k with the reference's dtypes and bits (trainer.py:109-138): fp32 hits and log2
+        table, int32 list lengths, users without eval items excluded from the means.
+
+        The [U, k] part -- membership of every recommended item, per-user hit counts and DCGs -- runs on the device
+        (igcn_user_metrics: numpy's own float32 row-sum order, so the per-user values are the reference's bit for
+        bit); only 2 x len(topks) x U floats come back, and the remaining vector expressions are the reference's,
+        evaluated by numpy on [U] arrays.  rec_items: numpy array or device tensor [U, max(topks)]."""
         results = {'Precision': {}, 'Recall': {}, 'NDCG': {}}
         csr = self._eval_csr(eval_data)
-        if self._last_rec is not None and self._last_rec[0] is rec_items:
+        if torch.is_tensor(rec_items) and rec_items.is_cuda:
+            rec_dev = rec_items.to(torch.int32).contiguous()
+        elif self._last_rec is not None and self._last_rec[0] is rec_items:
             rec_dev = self._last_rec[1]
         else:
             rec_dev = torch.as_tensor(np.ascontiguousarray(rec_items), device=self.device).to(torch.int32).contiguous()
-        hit_matrix = engine.hit_matrix(rec_dev, csr).cpu().numpy()
+        n, k_rec = int(rec_dev.shape[0]), int(rec_dev.shape[1])
         eval_data_len = csr.lens.astype(np.int32)
-        for k in self.topks:
-            hit_num = np.sum(hit_matrix[:, :k], axis=1)
+        topks = list(self.topks)
+        if k_rec <= 32 and len(topks) <= 8 and max(topks) <= k_rec:
+            per_user = self._device_user_metrics(rec_dev, csr, topks, k_rec)
+        else:                                           # wide lists: the [U, k] hit matrix comes to the host
+            hit_matrix = engine.hit_matrix(rec_dev, csr).cpu().numpy()
+            per_user = {}
+            for k in topks:
+                denominator = np.log2(np.arange(2, k + 2, dtype=np.float32))[None, :]
+                per_user[k] = (np.sum(hit_matrix[:, :k], axis=1), np.sum(hit_matrix[:, :k] / denominator, axis=1))
+        for k in topks:
+            hit_num, dcgs = per_user[k]
             precisions = hit_num / k
             with np.errstate(invalid='ignore', divide='ignore'):
                 recalls = hit_num / eval_data_len
             max_hit_num = np.minimum(eval_data_len, k)
             denominator = np.log2(np.arange(2, k + 2, dtype=np.float32))[None, :]
-            dcgs = np.sum(hit_matrix[:, :k] / denominator, axis=1)
             # the ideal DCG of a user only depends on min(len, k): evaluate the reference's expression
             # (trainer.py:126-130) once per possible value -- same numpy row reduction, so the same bits -- and
             # look it up instead of building a second [U, k] matrix
@@ -283,6 +299,22 @@ class BasicTrainer:
             results['Recall'][k] = recalls[user_masks].mean()
             results['NDCG'][k] = ndcgs[user_masks].mean()
         return results
+
+    def _device_user_metrics(self, rec_dev, csr, topks, k_rec):
+        """{k: (hit_num fp32 [U], dcg fp32 [U])} from igcn_user_metrics; one D2H copy of 2 x len(topks) x U floats."""
+        import ctypes as C
+        n = int(rec_dev.shape[0])
+        table = self._metric_tables.get(k_rec)
+        if table is None:
+            # the reference's fp32 table, computed by numpy on the host exactly as trainer.py:128 does
+            table = torch.from_numpy(np.log2(np.arange(2, k_rec + 2, dtype=np.float32))).to(self.device)
+            self._metric_tables[k_rec] = table
+        out = torch.empty((2, len(topks), n), dtype=torch.float32, device=self.device)
+        ks = (C.c_int32 * len(topks))(*topks)
+        call('igcn_user_metrics', ptr(rec_dev), n, k_rec, ptr(csr.ptr), ptr(csr.items), ptr(table), ks, len(topks),
+             ptr(out[0]), ptr(out[1]), stream_ptr())
+        host = out.cpu().numpy()
+        return {k: (host[0, t], host[1, t]) for t, k in enumerate(topks)}
 
     # ---- evaluation (trainer.py:140-177)
     def _mask_csr(self, val_or_test):
@@ -375,10 +407,14 @@ class BasicTrainer:
         if peers is not None:
             # the top-k lists are gathered so that every rank reports the same metrics
             rec_dev = dist.gather_rows(rec_dev, self.dataset.n_users, peers.group)
-        rec_items = rec_dev.cpu().numpy()          # int32 ids; the hit matrix is computed from the device copy
-        self._last_rec = (rec_items, rec_dev)
-        metrics = self.calculate_metrics(eval_data, rec_items)
-        self._last_rec = None
+        if 'calculate_metrics' in self.__dict__:
+            # somebody wrapped calculate_metrics (the reference's signature takes the lists as a numpy array)
+            rec_items = rec_dev.cpu().numpy()
+            self._last_rec = (rec_items, rec_dev)
+            metrics = self.calculate_metrics(eval_data, rec_items)
+            self._last_rec = None
+        else:
+            metrics = self.calculate_metrics(eval_data, rec_dev)       # lists stay on the device
 
         return self.format_results(metrics), metrics
 
@@ -435,6 +471,7 @@ class _FusedBPRMixin:
             total, B = len(self.dataset), self.batch_size
             for lo in range(0, total, B):
                 self.step.run(batch=min(B, total - lo))
+        self.step.sync_params()             # column-sharded training: full-width parameters on every rank again
         return self.step.meter_avg()
 
 

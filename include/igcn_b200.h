@@ -166,6 +166,23 @@ int igcn_bpr_fwd(const float *table, const float *l2_table, const float *w,
                  const int64_t *triples, int64_t B, int64_t item_offset, int32_t D,
                  float *sp, float *sig, float *l2, void *stream);
 
+/* The same forward when the COLUMNS of the tables are sharded over n_peers = 2, 4 or 8 ranks (multi-GPU training
+ * without any exchange of layer embeddings: the propagation is linear and acts on every column independently, so a
+ * rank that owns D / n_peers columns of the parameters propagates just those; the only quantities that couple the
+ * columns are the dot products and squared norms of this step).  table / l2_table / w hold this rank's D columns.
+ *   igcn_bpr_partial   this rank's partial sums of every triple, stored into record i of EVERY rank's exchange buffer
+ *                      parts_peer_host[p] (float [2 parities][n_peers][cap][8]; slots slot0.. = pos, neg and, with
+ *                      l2_table, the three squared norms; the parity is igcn_step_state.step & 1)
+ *   igcn_bpr_combine   after a device barrier: adds the n_peers partials in the order of the single-GPU kernel's
+ *                      lane tree (bit-identical to igcn_bpr_fwd on the full-width tables) and finishes sp / sig / l2. */
+int igcn_bpr_partial(const float *table, const float *l2_table, const float *w, const int64_t *triples,
+                     int64_t B, int64_t item_offset, int32_t D, float *const *parts_peer_host,
+                     int32_t n_peers, int32_t rank, int32_t slot0, int64_t cap,
+                     const igcn_step_state *state_dev, void *stream);
+int igcn_bpr_combine(const float *parts, int64_t B, int64_t cap, int32_t n_peers, int32_t slot0,
+                     int32_t has_l2, const igcn_step_state *state_dev, float *sp, float *sig, float *l2,
+                     void *stream);
+
 /* loss[0] = mean(sp) + l2_reg * mean(l2) + aux_reg * mean(aux_sp)   (trainer.py:241-243, 313-314)
  * acc[0] += loss * B ; acc[1] += B   (the AverageMeter of utils.py:126-135, kept on device so
  * the per-step loss.item() sync of trainer.py:247/318 disappears).  l2 / aux_sp may be NULL. */
@@ -310,6 +327,10 @@ int igcn_peer_barrier(uint32_t *const *flags_host, int32_t n_peers, int32_t rank
  * (fp32, multiples of 4) to the same place in every other rank's copy.  peer_host as in igcn_spmm. */
 int igcn_peer_push(float *const *peer_host, int32_t n_peers, int32_t rank, int64_t elem_offset,
                    int64_t n_elems, void *stream);
+/* Column-sharded training: write this rank's [rows, ds] slice into columns [col0, col0 + ds) of EVERY rank's
+ * [rows, d] copy (its own included) -- the all-gather of the parameters before an evaluation or a checkpoint. */
+int igcn_peer_push_cols(float *const *peer_host, int32_t n_peers, const float *src, int64_t rows,
+                        int32_t ds, int32_t d, int32_t col0, void *stream);
 
 /* out[b][j] = <rep[user_ids[b]], rep[item_row0 + j]> (fp32 FMA chain, ascending d): the dense score block of
  * LightGCN.predict (model.py:118-123, torch.mm at :122) for callers that want raw scores; n_eval <= 65535 per
@@ -321,6 +342,16 @@ int igcn_predict_scores(const float *rep, const int64_t *user_ids, int64_t n_eva
  * the membership double loop of BasicTrainer.calculate_metrics (trainer.py:111-115). */
 int igcn_hits(const int32_t *rec, int64_t n_users, int32_t k, const int64_t *eval_ptr,
               const int32_t *eval_items, float *hit, void *stream);
+
+/* The per-user part of BasicTrainer.calculate_metrics (trainer.py:109-131) on the device: for every cut-off
+ * topks_host[t] <= k, hit_num[t][u] = number of u's first topks[t] recommendations found in its eval list and
+ * dcg[t][u] = sum_j hit_j / log2_table[j] -- log2_table is the reference's fp32 np.log2(arange(2, k + 2)) computed
+ * by the host, the division is IEEE and the sum follows numpy's pairwise float32 row reduction, so both arrays are
+ * bit-identical to what the reference's numpy expressions produce from the [U, k] hit matrix.  Only these
+ * 2 x n_topks x U floats have to leave the device; the host finishes with the reference's own vector expressions. */
+int igcn_user_metrics(const int32_t *rec, int64_t n_users, int32_t k, const int64_t *eval_ptr,
+                      const int32_t *eval_items, const float *log2_table, const int32_t *topks_host,
+                      int32_t n_topks, float *hit_num, float *dcg, void *stream);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,8 @@
 cpu: gloo, world_size N -- host-side sharding logic only (row bounds, user split, list gather).
 gpu: nccl, one rank per GPU -- the row-sharded propagation with fused peer-store all-gather, the
      replicated BPR step and the user-sharded evaluation must be BIT-IDENTICAL to the single-GPU path
-     run in the same process (`'shard': False`)."""
+     run in the same process (`'shard': False`); so must the column-sharded training step (`'shard': 'dims'`:
+     every rank owns embedding_size / world columns, per-triple partial sums exchanged, parameters all-gathered)."""
 import os
 import sys
 
@@ -101,6 +102,41 @@ def check_gpu(rank, world):
         r0, m0 = trainers[0].eval('val')
         r1, m1 = trainers[1].eval('val')
         assert r0 == r1 and m0 == m1, (r0, r1)
+        # column-sharded training against the same single-GPU run: 5 more steps on both, then weights / loss / eval
+        torch.manual_seed(5)
+        mcfg = dict(models[1].config, shard='dims')
+        mcfg.pop('dataset')
+        dm = get_model(mcfg, ds)
+        tcfg = {k: v for k, v in trainers[1].config.items() if k not in ('dataset', 'model')}
+        dt = get_trainer(tcfg, ds, dm)
+        assert dt.step.dims == (rank, world) and dt.step.D == 64 // world
+        with torch.no_grad():
+            dm.embedding.weight.copy_(single.embedding.weight)
+            if kind == 'IGCN':
+                dm.w.copy_(single.w)
+                dm.alpha = single.alpha
+                dm.update_feat_mat()
+        dm._bump()
+        # same optimizer state and step counter as the single-GPU trainer (moments in column slices)
+        c0, c1 = dt.step.col0, dt.step.col0 + dt.step.D
+        m_s, v_s = trainers[1].opt.moments(single.embedding.weight)
+        dt.step.emb_m.copy_(m_s[:, c0:c1]); dt.step.emb_v.copy_(v_s[:, c0:c1])
+        if kind == 'IGCN':
+            wm, wv = trainers[1].opt.moments(single.w)
+            dt.step.w_m.copy_(wm[c0:c1]); dt.step.w_v.copy_(wv[c0:c1])
+        dt.step.state.copy_(trainers[1].step.state)
+        dt.opt.t = trainers[1].opt.t
+        dm.train(); single.train()
+        l_d = [dt.step.run().item() for _ in range(5)]
+        l_s = [trainers[1].step.run().item() for _ in range(5)]
+        assert l_d == l_s, (kind, 'dims losses', l_d, l_s)
+        dt.step.sync_params()
+        assert torch.equal(dm.embedding.weight, single.embedding.weight), kind + ' weights differ (dims)'
+        if kind == 'IGCN':
+            assert torch.equal(dm.w, single.w)
+        r2, m2 = dt.eval('val')
+        r3, m3 = trainers[1].eval('val')
+        assert r2 == r3 and m2 == m3, (r2, r3)
         peers.check()
         if rank == 0:
             print('dist_worker: %s ok, world %d, %d barriers, %s' % (kind, world, peers.n_barriers, r0))

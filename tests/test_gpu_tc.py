@@ -188,7 +188,7 @@ def test_tc_filter_statistics_and_popular_first_order():
     out = {}
     for name, order in (('natural', None), ('popular', engine.ItemOrder.by_score(pop.numpy(), DEV))):
         stats = torch.zeros(5, dtype=torch.int64, device=DEV)
-        items, scores = scorer.topk(rep, u, n_users, n_items, k, order=order, stats=stats)
+        items, scores = scorer.topk(rep, u, n_users, n_items, k, order=order, stats=stats, n_splits=1)
         torch.cuda.synchronize()
         out[name] = (items.clone(), scores.clone(), stats.tolist())
     ex = engine.score_topk(rep, u, n_users, n_items, k, impl='exact')
@@ -198,3 +198,9 @@ def test_tc_filter_statistics_and_popular_first_order():
         assert chunks == (n_users // 32) * (n_items // 32) and 0 < slow <= chunks and slow <= groups <= 4 * slow
         assert hits >= n_users * k and comp <= slow
     assert out['popular'][2][1] < 0.5 * out['natural'][2][1]          # far fewer chunks leave the compare-free path
+    # item splits are strided over the scan order (every list sees the popular head first): still the same answer
+    stats = torch.zeros(5, dtype=torch.int64, device=DEV)
+    items, scores = scorer.topk(rep, u, n_users, n_items, k, order=engine.ItemOrder.by_score(pop.numpy(), DEV), stats=stats, n_splits=4)
+    torch.cuda.synchronize()
+    assert torch.equal(items, ex[0]) and torch.equal(scores, ex[1])
+    assert stats.tolist()[1] < out['natural'][2][1]
