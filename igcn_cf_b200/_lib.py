@@ -60,6 +60,7 @@ _SIGNATURES = {
     'igcn_bpr_bwd': [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_float, c_float,
                      c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
                      c_void_p, c_void_p],
+    'igcn_bpr_dw': [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_float, c_void_p, c_void_p, c_void_p],
     'igcn_l2_rows_bwd': [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_int64,
                          c_void_p],
     'igcn_adam': [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
@@ -126,7 +127,7 @@ def ptr(t):
 
 
 # kernels launched per entry point (igcn_bpr_bwd launches 2 more when dw is requested)
-KERNELS_PER_CALL = {'igcn_colsum_masked': 2, 'igcn_score_topk_exact': 3, 'igcn_tc_pack': 5, 'igcn_tc_workspace': 0, 'igcn_peer_alloc': 0,
+KERNELS_PER_CALL = {'igcn_colsum_masked': 2, 'igcn_bpr_dw': 2, 'igcn_score_topk_exact': 3, 'igcn_tc_pack': 5, 'igcn_tc_workspace': 0, 'igcn_peer_alloc': 0,
                     'igcn_peer_open': 0, 'igcn_peer_close': 0, 'igcn_peer_free': 0}
 launch_count = 0          # running total of kernel launches issued through this binding
 profile_hook = None       # optional callable(name, phase, args) used by bench.py to time launches

@@ -442,16 +442,29 @@ __global__ void __launch_bounds__(kThreads) bpr_bwd_kernel(const float *__restri
     st4(dst, acc);
 }
 
-// dw: stage 1 sums 64 triples per CTA in order, stage 2 adds the CTA partials in order.
+// dw: stage 1 sums 64 triples per CTA in order, stage 2 adds the CTA partials in order.  The gathers of 8 triples are
+// issued together (they do not depend on the running sum), the fused multiply-adds stay in triple order.
 __global__ void __launch_bounds__(128) dw_stage1(const float *__restrict__ T, const int64_t *__restrict__ tri, int64_t B, int64_t off,
                                                  int D, const float *__restrict__ sig, float cscale, float *scratch) {
     const int d = threadIdx.x;
     if (d >= D) return;
     const int64_t lo = (int64_t)blockIdx.x * 64, hi = min(B, lo + 64);
     float t = 0.f;
-    for (int64_t i = lo; i < hi; ++i) {
-        const int64_t u = tri[i * 3], p = tri[i * 3 + 1] + off, n = tri[i * 3 + 2] + off;
-        t = fmaf(cscale * sig[i] * T[u * D + d], T[n * D + d] - T[p * D + d], t);
+    for (int64_t i0 = lo; i0 < hi; i0 += 8) {
+        float a[8], b[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int64_t i = i0 + q;
+            a[q] = b[q] = 0.f;
+            if (i < hi) {
+                const int64_t u = tri[i * 3], p = tri[i * 3 + 1] + off, n = tri[i * 3 + 2] + off;
+                a[q] = cscale * sig[i] * T[u * D + d];
+                b[q] = T[n * D + d] - T[p * D + d];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (i0 + q < hi) t = fmaf(a[q], b[q], t);
     }
     scratch[(int64_t)blockIdx.x * D + d] = t;
 }
@@ -460,7 +473,14 @@ __global__ void dw_stage2(const float *__restrict__ scratch, int64_t n_blocks, i
     const int d = threadIdx.x;
     if (d >= D) return;
     float t = 0.f;
-    for (int64_t b = 0; b < n_blocks; ++b) t += scratch[b * D + d];
+    for (int64_t b0 = 0; b0 < n_blocks; b0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (b0 + q < n_blocks) ? scratch[(b0 + q) * D + d] : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (b0 + q < n_blocks) t += v[q];
+    }
     dw[d] += t;
 }
 
@@ -644,6 +664,19 @@ extern "C" int igcn_bpr_bwd(const float *table, const float *w, const int64_t *t
         dw_stage1<<<(unsigned)nb, 128, 0, st>>>(table, triples, B, item_offset, D, sig, cscale, dw_scratch);
         dw_stage2<<<1, 128, 0, st>>>(dw_scratch, nb, D, dw);
     }
+    IGCN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int igcn_bpr_dw(const float *table, const int64_t *triples, int64_t B, int64_t item_offset, int32_t D, const float *sig,
+                           float scale, float *dw, float *dw_scratch, void *stream) {
+    IGCN_CHECK_ARG(table && triples && sig && dw && dw_scratch, "null pointer");
+    IGCN_CHECK_D(D);
+    if (B <= 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    const int64_t nb = (B + 63) / 64;
+    dw_stage1<<<(unsigned)nb, 128, 0, st>>>(table, triples, B, item_offset, D, sig, scale / (float)B, dw_scratch);
+    dw_stage2<<<1, 128, 0, st>>>(dw_scratch, nb, D, dw);
     IGCN_CHECK_LAUNCH();
     return 0;
 }

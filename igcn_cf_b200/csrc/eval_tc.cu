@@ -198,11 +198,11 @@ __device__ __forceinline__ void compact_lanes(uint64_t *mybuf, int &cnt, float &
 // are NOT valid): 2 reads the accumulators but does not filter (TMA + MMA + TMEM-read floor), 3 filters against
 // thr = +inf (the compare-free path on every chunk, no hits, no compaction), 5 does not read TMEM at all (MMA
 // issue + the mbarrier hand-offs only).
-// CL = 2: the grid is made of CTA PAIRS (thread-block clusters of two) that scan the same item tiles for two
-// different user tiles; each CTA fetches half of every item tile and multicasts it to both, a stage is released
-// when both CTAs' MMAs have read it.  A pair whose second user tile does not exist runs a dummy CTA (the last
-// user tile again, results discarded) so that the hand-offs stay symmetric.
-template <int VARIANT, int CL>
+// (CTA pairs -- thread-block clusters of two that fetch half of every item tile each and multicast it into both CTAs'
+// shared memory -- were built and measured: bit-identical, 0.512 vs 0.507 ms on the Yelp shape, hand-off floor 0.366
+// vs 0.351 ms.  Halving the L2 reads changes nothing because every SM still has to take in 40 KB of item image per
+// 128 x 256 tile: the floor is the per-SM operand ingest (~42 B/cycle), not L2 bandwidth.  Removed again.)
+template <int VARIANT>
 __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t a_bytes = (uint32_t)(TC_BM / 8) * a.kcores * 128;
@@ -216,24 +216,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // CTA -> (user tile, item split): head tiles scan every item tile in one CTA, the others are split n_splits ways
-    bool head, dummy = false;
-    int ut, sp, ns;
-    const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
-    if (CL == 1) {
-        head = (int)blockIdx.x < a.n_head;
-        const int rest = (int)blockIdx.x - a.n_head;
-        ut = head ? (int)blockIdx.x : a.n_head + rest / a.n_splits;
-        sp = head ? 0 : rest % a.n_splits;
-    } else {
-        // pair P = blockIdx.x / 2 (n_head is even): head pairs take user tiles 2P, 2P + 1; tail pair P' = (tile pair, split)
-        const int P = (int)blockIdx.x >> 1, head_pairs = a.n_head >> 1;
-        head = P < head_pairs;
-        const int rest = P - head_pairs;
-        ut = head ? 2 * P + (int)crank : a.n_head + 2 * (rest / a.n_splits) + (int)crank;
-        sp = head ? 0 : rest % a.n_splits;
-        if (ut >= a.n_utiles) { dummy = true; ut = a.n_utiles - 1; }
-    }
-    ns = head ? 1 : a.n_splits;
+    const bool head = (int)blockIdx.x < a.n_head;
+    const int rest = (int)blockIdx.x - a.n_head;
+    const int ut = head ? (int)blockIdx.x : a.n_head + rest / a.n_splits;
+    const int sp = head ? 0 : rest % a.n_splits;
+    const int ns = head ? 1 : a.n_splits;
     // item tiles intersecting [item_lo, item_hi), divided evenly over the splits
     const int64_t hi_eff = min(a.item_hi, a.n_items);
     const int t_first = (int)(max((int64_t)0, a.item_lo) / TC_BN);
@@ -245,7 +232,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
     const int n_it = sp < n_t ? (n_t - sp + ns - 1) / ns : 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], CL); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
         mbar_init(&sm->a_full, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&sm->tmem_full[i], 1); mbar_init(&sm->tmem_empty[i], 4); }
         for (int i = 0; i < TC_MASKS; ++i) { mbar_init(&sm->mask_full[i], 1); mbar_init(&sm->mask_empty[i], 4); }
@@ -257,7 +244,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
     }
     tc_fence_before();
     __syncthreads();
-    if (CL == 2) cluster_sync_all();             // the peer's barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = sm->tmem_base;
 
@@ -271,14 +257,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
                 mbar_wait_helper(&sm->empty[s], ph ^ 1u, a.dbg & 1);
                 mbar_arrive_expect_tx(&sm->full[s], b_bytes);
-                if (CL == 1) {
-                    bulk_g2s(sB + (size_t)s * b_bytes, a.b_img + (size_t)(t0 + it * ns) * b_bytes, b_bytes, &sm->full[s]);
-                } else {
-                    // my half of the tile goes to both CTAs; the other half arrives from the peer (same barrier, same phase)
-                    const uint32_t half = b_bytes / 2;
-                    bulk_g2s_multicast(sB + (size_t)s * b_bytes + crank * half, a.b_img + (size_t)(t0 + it * ns) * b_bytes + crank * half,
-                                       half, &sm->full[s], (uint16_t)3);
-                }
+                bulk_g2s(sB + (size_t)s * b_bytes, a.b_img + (size_t)(t0 + it * ns) * b_bytes, b_bytes, &sm->full[s]);
             }
         }
     } else if (warp == 1) {
@@ -297,8 +276,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 for (int ks = 0; ks < ksteps; ++ks)
                     tc_mma_f16(tmem_base + (uint32_t)acc * TC_BN, umma_desc(a0 + ks * 256, lbo, sbo), umma_desc(b0 + ks * 256, lbo, sbo),
                                idesc, ks > 0 ? 1u : 0u);
-                if (CL == 1) tc_commit(&sm->empty[s]);          // smem stage reusable once these MMAs retire
-                else tc_commit_multicast(&sm->empty[s], (uint16_t)3);      // ... in BOTH CTAs: either producer overwrites both
+                tc_commit(&sm->empty[s]);          // smem stage reusable once these MMAs retire
                 tc_commit(&sm->tmem_full[acc]);    // accumulator ready for the epilogue
             }
         }
@@ -309,7 +287,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         // the tile's entries -- whose global loads were issued one tile earlier, so the dependent chain tile_ptr ->
         // entries (two L2 round trips, ~1,900 cycles per tile when it sat between tmem_empty and mask_full) is off
         // the critical path -- and publishes it (mask_full) up to TC_MASKS tiles ahead of the epilogue.
-        const int32_t *tp = (a.mask_tile_ptr && !dummy) ? a.mask_tile_ptr + (size_t)ut * (a.n_itiles + 1) : nullptr;
+        const int32_t *tp = a.mask_tile_ptr ? a.mask_tile_ptr + (size_t)ut * (a.n_itiles + 1) : nullptr;
         auto bucket = [&](int it, int &e0, int &e1, uint32_t &first) {
             e0 = e1 = 0; first = 0u;
             if (tp && it < n_it) {
@@ -450,7 +428,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         }
         // dump this row's candidates
         __syncwarp();
-        for (int r = 0; r < 32 && !dummy; ++r) {
+        for (int r = 0; r < 32; ++r) {
             const int64_t b = (int64_t)ut * TC_BM + q * 32 + r;
             if (b >= a.n_eval) break;
             const int n = __shfl_sync(0xffffffffu, cnt, r);
@@ -467,7 +445,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 a.cand_thr[b * a.n_splits + lane] = -INFINITY;
             }
         }
-        if (VARIANT == 4 && a.stats && !dummy) {
+        if (VARIANT == 4 && a.stats) {
             // chunk / group counters are per warp (lane 0 speaks), appended candidates per row (summed)
             const uint32_t hits = __reduce_add_sync(0xffffffffu, st_hits);
             if (lane == 0) {
@@ -481,7 +459,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
     }
     tc_fence_before();
     __syncthreads();
-    if (CL == 2) cluster_sync_all();             // no CTA leaves while the peer can still signal or write into it
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
@@ -616,14 +593,7 @@ extern "C" int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, in
     if (n_eval <= 0) return 0;
     const int n_utiles = (int)((n_eval + TC_BM - 1) / TC_BM);
     IGCN_CHECK_ARG(n_head >= 0 && n_head <= n_utiles, "n_head must be in [0, number of user tiles]");
-    // CTA pairs (clusters of two) share the item stream; IGCN_TC_CLUSTER=1 selects the unpaired kernel (A/B timing)
-    static int cluster_env = -1;
-    if (cluster_env < 0) { const char *e = getenv("IGCN_TC_CLUSTER"); cluster_env = e ? atoi(e) : 2; }
-    const bool paired = cluster_env == 2 && n_utiles >= 2;
-    if (paired) n_head &= ~1;                           // head tiles come in pairs; an odd one joins the split tail
-    const int n_tail = n_utiles - n_head;
-    const unsigned n_ctas = paired ? 2u * (unsigned)(n_head / 2 + (n_tail + 1) / 2 * n_splits)
-                                   : (unsigned)(n_head + n_tail * n_splits);
+    const unsigned n_ctas = (unsigned)(n_head + (n_utiles - n_head) * n_splits);
     TcArgs a{};
     a.a_img = a_img; a.b_img = b_img;
     a.n_utiles = n_utiles;
@@ -640,19 +610,12 @@ extern "C" int igcn_tc_candidates(const uint8_t *a_img, const uint8_t *b_img, in
     const int experiment = exp_env ? atoi(exp_env) : 0;
     const int variant = dump ? 1 : stats ? 4 : (experiment == 2 || experiment == 3 || experiment == 5) ? experiment : 0;
     void (*kern)(TcArgs) = nullptr;
-#define IGCN_TC_PICK(V) case V: kern = paired ? score_tc_kernel<V, 2> : score_tc_kernel<V, 1>; break
+#define IGCN_TC_PICK(V) case V: kern = score_tc_kernel<V>; break
     switch (variant) { IGCN_TC_PICK(0); IGCN_TC_PICK(1); IGCN_TC_PICK(2); IGCN_TC_PICK(3); IGCN_TC_PICK(4); IGCN_TC_PICK(5); }
 #undef IGCN_TC_PICK
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("igcn_tc_candidates: %s", cudaGetErrorString(e)); return (int)e; }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(n_ctas); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = paired ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, a);
-    if (e != cudaSuccess) { set_error("igcn_tc_candidates: %s", cudaGetErrorString(e)); return (int)e; }
+    kern<<<n_ctas, TC_THREADS, smem, as_stream(stream)>>>(a);
     IGCN_CHECK_LAUNCH();
     return 0;
 }

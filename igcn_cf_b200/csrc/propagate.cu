@@ -431,12 +431,18 @@ __global__ void __launch_bounds__(kColsumGroups * LANES) colsum_stage1(const flo
     const int64_t base = row_begin + (int64_t)blockIdx.x * 256;
     const int64_t stop = min(row_end, base + 256);
     float4 acc = f4zero();
-    for (int64_t r = base + grp; r < stop; r += GROUPS) {
-        bool keep = true;
-        if (drop.mode == 1) keep = edge_hash(seed, (uint32_t)r, kSelfCol) >= thresh;
-        if (drop.mode == 2) keep = (__ldg(drop.self_keep + (r >> 5)) >> (r & 31)) & 1u;
-        if (keep && active) add4(acc, ld4(G + r * D + lane * 4));
+    // the group's 16 rows are fetched together (independent loads), then added in row order
+    float4 v[256 / GROUPS];
+#pragma unroll
+    for (int q = 0; q < 256 / GROUPS; ++q) {
+        const int64_t r = base + grp + (int64_t)q * GROUPS;
+        bool keep = r < stop;
+        if (keep && drop.mode == 1) keep = edge_hash(seed, (uint32_t)r, kSelfCol) >= thresh;
+        if (keep && drop.mode == 2) keep = (__ldg(drop.self_keep + (r >> 5)) >> (r & 31)) & 1u;
+        v[q] = (keep && active) ? ld4(G + r * D + lane * 4) : f4zero();
     }
+#pragma unroll
+    for (int q = 0; q < 256 / GROUPS; ++q) add4(acc, v[q]);
     sm[grp][lane] = acc;
     __syncthreads();
     if (grp == 0 && active) {
@@ -450,7 +456,14 @@ __global__ void colsum_stage2(const float *__restrict__ scratch, int64_t n_block
     const int d = threadIdx.x;
     if (d >= D) return;
     float t = 0.f;
-    for (int64_t b = 0; b < n_blocks; ++b) t += scratch[b * D + d];
+    for (int64_t b0 = 0; b0 < n_blocks; b0 += 8) {           // 8 independent loads, added in block order
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (b0 + q < n_blocks) ? scratch[(b0 + q) * D + d] : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (b0 + q < n_blocks) t += v[q];
+    }
     out[d] = t;
 }
 

@@ -201,18 +201,29 @@ def inmo_forward(feat, emb, x0, drop, dim, shard=None):
         shard.ctx.barrier()
 
 
-def inmo_backward(feat, g_scaled, d_emb, drop, dim, scratch, shard=None):
+def inmo_backward(feat, g_scaled, d_emb, drop, dim, scratch, shard=None, side=None):
     """dE = F~^T dX0 given g_scaled = rowscale/(1-p) .* dX0 (autograd backward of model.py:430).
     Row-sharded: each rank produces the template rows of its own node block and stores them into every
-    rank's d_emb; the two global-template rows are column sums every rank computes for itself."""
+    rank's d_emb; the two global-template rows are column sums every rank computes for itself.
+    side: a stream for the two column sums (small, latency-bound, independent of the transposed product: they
+    write the two global-template rows only); the caller joins it before reading d_emb."""
     n, u = feat.shape[0], feat.n_users
     peers, n_peers = _peer_args(shard, d_emb, 0)
+    d = _drop_struct(drop)
+
+    def colsums():
+        call('igcn_colsum_masked', ptr(g_scaled), 0, u, dim, d, ptr(scratch), ptr(d_emb[feat.glob_user]), stream_ptr())
+        call('igcn_colsum_masked', ptr(g_scaled), u, n, dim, d, ptr(scratch), ptr(d_emb[feat.glob_item]), stream_ptr())
+
+    if side is not None:
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            colsums()
     for blk in feat.blocks:
         call('igcn_inmo_bwd', blk.csr.struct(dim), ptr(feat.tmpl), _drop_struct(drop), ptr(g_scaled), ptr(d_emb), dim,
              blk.row0, peers, n_peers, stream_ptr())
-    d = _drop_struct(drop)
-    call('igcn_colsum_masked', ptr(g_scaled), 0, u, dim, d, ptr(scratch), ptr(d_emb[feat.glob_user]), stream_ptr())
-    call('igcn_colsum_masked', ptr(g_scaled), u, n, dim, d, ptr(scratch), ptr(d_emb[feat.glob_item]), stream_ptr())
+    if side is None:
+        colsums()
     if shard is not None:
         shard.ctx.barrier()
 
@@ -348,6 +359,8 @@ class TrainStep:
         self._side = torch.cuda.Stream(device=dev)       # main scatter plan: joins before the last forward layer
         self._side2 = torch.cuda.Stream(device=dev)      # zeroed gradient buffers + auxiliary plan: joins before the gradient kernels
         self._side3 = torch.cuda.Stream(device=dev)      # loss value + running meter: nothing downstream reads them; joins at the end
+        self._side4 = torch.cuda.Stream(device=dev)      # gradient of the auxiliary weight vector: needs sig only; joins before Adam
+        self._side5 = torch.cuda.Stream(device=dev)      # column sums of the global-template gradient rows, beside the transposed INMO product
 
     # -- column-sharded training
     def _init_dims(self, model, n, D, dev):
@@ -401,15 +414,16 @@ class TrainStep:
         self._seen_epoch = m._param_epoch
 
     # -- pieces
-    def _sample(self, B):
+    def _sample_main(self, B):
         m = self.model
         rowptr, col = m.norm_adj.sampler_csr()
         call('igcn_sample_triples', ptr(rowptr), ptr(col), m.n_users, m.n_users, m.n_items, B, self.seed,
              0, ptr(self.state), ptr(self.triples), stream_ptr())
-        if self.is_igcn:
-            a = m.aux_csr()
-            call('igcn_sample_triples', ptr(a['rowptr']), ptr(a['col']), a['col_offset'], a['n_users'], a['n_items'], B,
-                 self.seed ^ 0x5bd1e995, 0, ptr(self.state), ptr(self.a_triples), stream_ptr())
+
+    def _sample_aux(self, B):
+        a = self.model.aux_csr()
+        call('igcn_sample_triples', ptr(a['rowptr']), ptr(a['col']), a['col_offset'], a['n_users'], a['n_items'], B,
+             self.seed ^ 0x5bd1e995, 0, ptr(self.state), ptr(self.a_triples), stream_ptr())
 
     def _body(self, B, sample, drop):
         m, D, st = self.model, self.D, stream_ptr
@@ -419,13 +433,13 @@ class TrainStep:
         emb = m.embedding.weight.data if dims is None else self.emb_s
         w = (m.w.data if dims is None else self.w_s) if self.is_igcn else None
         call('igcn_step_tick', ptr(self.state), self.lr, BETA1, BETA2, st())
-        if sample:
-            self._sample(B)
-        # the scatter plans depend on the triples only: sort them on a side stream while the forward
-        # propagation runs (one CTA each; joins before the gradient kernels)
+        # the triples and their scatter plans are needed by the LAST forward layer at the earliest: sample and sort
+        # them on side streams while the forward propagation runs (one or a few CTAs each)
         main = torch.cuda.current_stream()
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
+            if sample:
+                self._sample_main(B)
             call('igcn_bpr_plan', ptr(self.triples), B, m.n_users, m.n_users + m.n_items, ptr(self.order),
                  ptr(self.seg_start), ptr(self.seg_row), ptr(self.n_seg), ptr(self.touched), st())
         # second side stream: everything else the gradient kernels need that does not depend on the forward pass --
@@ -439,6 +453,8 @@ class TrainStep:
                     # template rows without a node in this graph get no gradient; zeroed long before any rank
                     # stores template rows into this copy (several barriers later)
                     self.d_emb.zero_()
+                if sample:
+                    self._sample_aux(B)
                 call('igcn_bpr_plan', ptr(self.a_triples), B, m.feat_mat.t_users, m.embedding.weight.shape[0],
                      ptr(self.a_order), ptr(self.a_seg_start), ptr(self.a_seg_row), ptr(self.a_n_seg), None, st())
         # forward: full layers 1..L-1, then the last layer + layer mean on the batch's rows only (the plan's
@@ -455,6 +471,7 @@ class TrainStep:
             l2_table = emb
         if L == 0:
             join()
+        main.wait_stream(self._side2)            # auxiliary triples, zeroed gradient buffers
         if dims is None:
             call('igcn_bpr_fwd', ptr(rep), ptr(l2_table), None, ptr(self.triples), B, m.n_users, D, ptr(self.sp),
                  ptr(self.sig), ptr(self.l2), st())
@@ -486,9 +503,14 @@ class TrainStep:
             else:
                 call('igcn_loss_finalize', ptr(self.sp), ptr(self.l2), None, B, 0, self.l2_reg, 0.0, ptr(self.loss),
                      ptr(self.acc), st())
+        if self.is_igcn:
+            # d_w depends on sig and the parameters only: beside the whole backward propagation
+            self._side4.wait_stream(main)
+            with torch.cuda.stream(self._side4):
+                call('igcn_bpr_dw', ptr(emb), ptr(self.a_triples), B, m.feat_mat.t_users, D, ptr(self.a_sig), float(self.aux_reg),
+                     ptr(self.d_w), ptr(self.dw_scratch), st())
         # backward
         main.wait_stream(self._side)
-        main.wait_stream(self._side2)
         call('igcn_bpr_bwd', ptr(rep), None, ptr(self.triples), B, m.n_users, D, ptr(self.sig), 1.0 / (L + 1),
              self.l2_reg if self.is_igcn else 0.0, 1 if self.is_igcn else 0, ptr(self.order), ptr(self.seg_start),
              ptr(self.seg_row), ptr(self.n_seg), ptr(self.gprime), 0, None, None, st())
@@ -498,10 +520,12 @@ class TrainStep:
             inv_keep = 1.0 if (drop is None or drop.get('mode', 0) == 0) else 1.0 / (1.0 - drop['p'])
             prop.backward(m.norm_adj, self.gprime, g_scaled, rowscale=feat.rowscale, alpha=inv_keep,
                           gprime_rows=self.touched)
-            inmo_backward(feat, g_scaled, self.d_emb, drop, D, self.colsum_scratch, self.shard)
+            inmo_backward(feat, g_scaled, self.d_emb, drop, D, self.colsum_scratch, self.shard, side=self._side5)
             call('igcn_bpr_bwd', ptr(emb), ptr(w), ptr(self.a_triples), B, feat.t_users, D, ptr(self.a_sig),
                  float(self.aux_reg), 0.0, 0, ptr(self.a_order), ptr(self.a_seg_start), ptr(self.a_seg_row),
-                 ptr(self.a_n_seg), ptr(self.d_emb), 1, ptr(self.d_w), ptr(self.dw_scratch), st())
+                 ptr(self.a_n_seg), ptr(self.d_emb), 1, None, None, st())
+            main.wait_stream(self._side5)
+            main.wait_stream(self._side4)
         else:
             prop.backward(m.norm_adj, self.gprime, self.d_emb, gprime_rows=self.touched)
             if self.l2_reg != 0.0:
@@ -779,18 +803,19 @@ class TcScorer:
 
     @staticmethod
     def pick_splits(n_groups, n_sm=148):
-        """Uniform item-range splits per user tile: enough CTAs (one per SM at a
-        time) for two waves when there are few user tiles, one split otherwise.  (Choosing uniform splits to fill
-        whole waves of 148 was tried: a third candidate list per user cost more in the epilogue and in
-        igcn_tc_finalize than the fuller last wave gained -- Gowalla-shaped 0.71 vs 0.68 ms.)"""
+        """Uniform item-range splits per user tile when there are fewer user tiles than SMs: enough CTAs for two
+        waves, at most 8."""
         return int(min(8, max(1, -(-2 * n_sm // max(1, int(n_groups))))))
 
     @classmethod
-    def plan_ctas(cls, n_groups, n_sm=148):
-        """(n_head, n_splits) of igcn_tc_candidates.  Every extra list costs a threshold warm-up in the epilogue, so
-        with at least one wave of user tiles only the TAIL (the tiles left over after whole waves of n_sm CTAs) is
-        split, just enough to fill the last wave: 297 tiles -> 296 unsplit + 1 tile in 8 splits = 2 1/8 waves
-        instead of 3.  Fewer user tiles than SMs: uniform splits (pick_splits)."""
+    def plan_ctas(cls, n_groups, n_itiles=None, n_sm=148):
+        """(n_head, n_splits) of igcn_tc_candidates.  Every extra list per user costs a threshold warm-up in the
+        epilogue and a longer igcn_tc_finalize, so with at least one wave of user tiles only the TAIL (the tiles left
+        over after whole waves of n_sm CTAs) is split, just enough to fill the last wave: 297 tiles -> 296 unsplit + 1
+        tile in 8 splits.  Fewer user tiles than SMs: uniform splits (pick_splits).
+        (A makespan model that also split whole waves -- Gowalla shape: 234 tiles as 148 + 86 x 5 instead of 234
+        unsplit in 1.58 waves -- was measured in round 2: igcn_tc_candidates 0.254 -> 0.272 ms and igcn_tc_finalize
+        0.091 -> 0.253 ms; five lists per user cost more than the fuller last wave gains.  Not used.)"""
         forced = int(os.environ.get('IGCN_TC_SPLITS', 0))
         if forced:
             return 0, forced
@@ -832,7 +857,7 @@ class TcScorer:
             c_lo, c_hi = 0, n_items
         n_head = 0
         if n_splits is None:
-            n_head, n_splits = self.plan_ctas((n_eval + 127) // 128)
+            n_head, n_splits = self.plan_ctas((n_eval + 127) // 128, (n_items + 255) // 256)
         ws = self._workspace(n_eval, n_items, D, n_splits, k, rep.device)
         st = stream_ptr
         call('igcn_tc_pack', ptr(rep), rep.numel(), ptr(user_ids), n_eval, n_users, n_items, D, ptr(perm), ptr(ws['maxabs']),

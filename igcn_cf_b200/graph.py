@@ -15,6 +15,7 @@ tmpl[N] int32 (only when some node is not a template) and rowscale[N] fp32.
 """
 import ctypes as C
 import itertools
+import os
 
 import numpy as np
 import scipy.sparse as sp
@@ -22,6 +23,7 @@ import torch
 
 from . import _lib
 
+ROW_ORDER = os.environ.get('IGCN_ROW_ORDER', 'degree')     # 'degree' | 'typed' (see CsrDevice)
 LONG_THRESHOLD = 256     # rows with more non-zeros than this are split ...
 CHUNK = 128              # ... into chunks of this many non-zeros
 MEDIUM_NNZ = 64          # IGCN_MEDIUM_NNZ: rows above it (and not long) get a whole warp
@@ -67,9 +69,10 @@ def chunk_plan(rowptr, threshold=LONG_THRESHOLD, chunk=CHUNK):
 class CsrDevice:
     """One CSR block on the GPU + chunk plan + per-D scratch; produces the `igcn_csr` struct."""
 
-    def __init__(self, rowptr, col, val, n_cols, device, threshold=LONG_THRESHOLD, chunk=CHUNK):
+    def __init__(self, rowptr, col, val, n_cols, device, threshold=LONG_THRESHOLD, chunk=CHUNK, split_at=None):
         """rowptr: host int64 array; col / val: host arrays, or tensors already on `device` (scale-out
-        graphs are generated on the GPU and never visit the host)."""
+        graphs are generated on the GPU and never visit the host).  split_at: local index of the first ITEM row of
+        this block (bipartite graphs: user rows gather item rows and vice versa), used by the visiting order."""
         self.device = torch.device(device)   # kernels need CUDA; a CPU device only supports the views
         self.n_rows = int(len(rowptr) - 1)
         self.n_cols = int(n_cols)
@@ -89,11 +92,21 @@ class CsrDevice:
         self.n_chunks = int(len(plan[0]))
         self._plan = [torch.from_numpy(np.ascontiguousarray(a)).to(self.device) for a in plan]
         self.counters = torch.zeros(max(1, self.n_chunks), dtype=torch.int32, device=self.device)
-        # visiting order: longest rows first, ties by row id (stable) -> rows sharing a warp are alike
+        # visiting order: the three row classes (long / medium / short) longest first -- rows sharing a warp are
+        # alike.  ROW_ORDER 'typed' additionally keeps the two halves of the bipartite graph apart INSIDE each class
+        # (item rows, then user rows): user rows gather from the item table, whose popular rows are hit again and
+        # again, item rows gather from the user table, which has no such head; visited together the cold user lines
+        # flush the hot item lines out of L1.  The order never changes a row's own sum (bit-identical results).
         deg = np.diff(self.rowptr_host)
-        self.row_order = torch.from_numpy(np.argsort(-deg, kind='stable').astype(np.int32)).to(self.device)
         self.n_long = int((deg > self.threshold).sum())
         self.n_medium = max(0, int((deg > MEDIUM_NNZ).sum()) - self.n_long)
+        if ROW_ORDER == 'typed' and split_at is not None and 0 < split_at < self.n_rows:
+            cls = np.where(deg > self.threshold, 0, np.where(deg > MEDIUM_NNZ, 1, 2))
+            is_user = (np.arange(self.n_rows) < split_at).astype(np.int64)
+            order = np.lexsort((np.arange(self.n_rows), -deg, is_user, cls))
+        else:
+            order = np.argsort(-deg, kind='stable')
+        self.row_order = torch.from_numpy(order.astype(np.int32)).to(self.device)
         self._partial = {}
         self._structs = {}
 
@@ -174,9 +187,10 @@ def _row_ranges(rowptr, n_users, shard):
     return [(int(ub[rank]), int(ub[rank + 1])), (int(ib[rank]), int(ib[rank + 1]))]
 
 
-def _block_csr(rowptr, col, val, row0, row1, n_cols, device):
+def _block_csr(rowptr, col, val, row0, row1, n_cols, device, n_users=None):
     lo, hi = int(rowptr[row0]), int(rowptr[row1])
-    return CsrDevice(rowptr[row0:row1 + 1] - lo, col[lo:hi], None if val is None else val[lo:hi], n_cols, device)
+    return CsrDevice(rowptr[row0:row1 + 1] - lo, col[lo:hi], None if val is None else val[lo:hi], n_cols, device,
+                     split_at=None if n_users is None else n_users - row0)
 
 
 _UID = itertools.count(1)
@@ -299,7 +313,7 @@ class NormAdj(_SparseView, _Blocked):
             left = d_inv[rows] if dg.mult is None else d_inv[rows] * dg.mult[lo:hi]
             val = left * d_inv[col.long()]
             del rows, left
-            blocks.append(RowBlock(row0, row1, CsrDevice(rp, col, val, n, dg.device)))
+            blocks.append(RowBlock(row0, row1, CsrDevice(rp, col, val, n, dg.device, split_at=dg.n_users - row0)))
         self._set_blocks(blocks)
         self._coo_cache = None
         self._sampler = (dg.rowptr[:dg.n_users + 1], dg.col[:dg.n_interactions])
@@ -342,7 +356,7 @@ class NormAdj(_SparseView, _Blocked):
         self.col_full = adj.indices.astype(np.int32)
         self.val_full = val
         self.nnz = int(self.rowptr_full[-1])
-        self._set_blocks([RowBlock(r0, r1, _block_csr(self.rowptr_full, self.col_full, val, r0, r1, adj.shape[0], device))
+        self._set_blocks([RowBlock(r0, r1, _block_csr(self.rowptr_full, self.col_full, val, r0, r1, adj.shape[0], device, n_users))
                           for r0, r1 in _row_ranges(self.rowptr_full, n_users, shard)])
         self._coo_cache = None
         self._sampler = None
@@ -401,7 +415,8 @@ class TemplateFeat(_SparseView, _Blocked):
         if adj is not None and list(adj.block_key()) == ranges:
             blocks = [RowBlock(b.row0, b.row1, b.csr.with_values(None)) for b in adj.blocks]
         else:
-            blocks = [RowBlock(r0, r1, CsrDevice(dg.block(r0, r1)[0], dg.block(r0, r1)[1], None, n, dg.device))
+            blocks = [RowBlock(r0, r1, CsrDevice(dg.block(r0, r1)[0], dg.block(r0, r1)[1], None, n, dg.device,
+                                                 split_at=dg.n_users - r0))
                       for r0, r1 in ranges]
         self._set_blocks(blocks)
         self.tmpl = None
@@ -420,7 +435,8 @@ class TemplateFeat(_SparseView, _Blocked):
         if adj is not None and list(adj.block_key()) == ranges:
             blocks = [RowBlock(b.row0, b.row1, b.csr.with_values(None)) for b in adj.blocks]
         else:
-            blocks = [RowBlock(r0, r1, CsrDevice(dg.block(r0, r1)[0], dg.block(r0, r1)[1], None, n, dg.device))
+            blocks = [RowBlock(r0, r1, CsrDevice(dg.block(r0, r1)[0], dg.block(r0, r1)[1], None, n, dg.device,
+                                                 split_at=dg.n_users - r0))
                       for r0, r1 in ranges]
         self._set_blocks(blocks)
         self.tmpl = torch.from_numpy(tmpl).to(self.device)
@@ -472,7 +488,7 @@ class TemplateFeat(_SparseView, _Blocked):
         row_sum = np.bincount(rows, weights=member, minlength=n).astype(np.float32) + np.float32(1.)
         self.rowptr_full = adj.indptr.astype(np.int64)
         self.col_full = adj.indices.astype(np.int32)
-        self._set_blocks([RowBlock(r0, r1, _block_csr(self.rowptr_full, self.col_full, None, r0, r1, n, device))
+        self._set_blocks([RowBlock(r0, r1, _block_csr(self.rowptr_full, self.col_full, None, r0, r1, n, device, n_users))
                           for r0, r1 in _row_ranges(self.rowptr_full, n_users, shard)])
         self.tmpl = None if identity else torch.from_numpy(tmpl).to(self.device)
         self.row_sum = torch.from_numpy(row_sum.astype(np.float32)).to(self.device)

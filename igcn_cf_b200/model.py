@@ -241,6 +241,72 @@ class LightGCN(_GraphModel):
         return rep[users, :], rep[self.n_users + pos_items, :], rep[self.n_users + neg_items, :], l2_norm_sq
 
 
+class MF(LightGCN):
+    """Matrix factorisation (model.py:52-72) as the zero-layer member of the family: get_rep is the embedding table
+    itself, bpr_forward is LightGCN's (raw rows, L2 over raw rows -- exactly MF.bpr_forward), so the fused BPR step and
+    the fused ranking kernels run it unchanged.  The reference keeps two tables; here they are the user and the item
+    half of ONE [U + I, D] table (what the kernels index), created with the reference's draw order (user table first)
+    and exposed under the reference's names: `user_embedding` / `item_embedding` (read-only views sharing storage with
+    `embedding`), and state_dict / load_state_dict use the reference's keys, so checkpoints are interchangeable."""
+
+    def __init__(self, model_config):
+        cfg = dict(model_config, n_layers=0)
+        _GraphModel.__init__(self, cfg)
+        self.config = model_config
+        self.embedding_size = model_config['embedding_size']
+        self.n_layers = 0
+        # same generator consumption as the reference constructor: both nn.Embedding inits, then both normal_ calls
+        user = nn.Embedding(self.n_users, self.embedding_size)
+        item = nn.Embedding(self.n_items, self.embedding_size)
+        normal_(user.weight, std=0.1)
+        normal_(item.weight, std=0.1)
+        self.embedding = nn.Embedding(self.n_users + self.n_items, self.embedding_size)
+        with torch.no_grad():
+            self.embedding.weight.copy_(torch.cat([user.weight, item.weight], dim=0))
+        self.norm_adj = self.generate_graph(model_config['dataset'])     # sampler CSR + touched-row plan of the step
+        self.to(device=self.device)
+
+    class _Half:
+        """`model.user_embedding.weight` / `model.user_embedding(ids)` of the reference, as a view of one half."""
+
+        def __init__(self, model, lo, hi):
+            self._m, self._lo, self._hi = model, lo, hi
+
+        @property
+        def weight(self):
+            return self._m.embedding.weight[self._lo:self._hi]
+
+        def __call__(self, ids):
+            return self._m.embedding(ids + self._lo)
+
+    @property
+    def user_embedding(self):
+        return MF._Half(self, 0, self.n_users)
+
+    @property
+    def item_embedding(self):
+        return MF._Half(self, self.n_users, self.n_users + self.n_items)
+
+    def bpr_forward(self, users, pos_items, neg_items):
+        """model.py:62-67."""
+        self._sync_params()
+        users_e = self.embedding(users)
+        pos_e, neg_e = self.embedding(self.n_users + pos_items), self.embedding(self.n_users + neg_items)
+        l2_norm_sq = (users_e ** 2).sum(dim=1) + (pos_e ** 2).sum(dim=1) + (neg_e ** 2).sum(dim=1)
+        return users_e, pos_e, neg_e, l2_norm_sq
+
+    def state_dict(self, *args, **kwargs):
+        self._sync_params()
+        w = self.embedding.weight.detach()
+        return {'user_embedding.weight': w[:self.n_users].clone(), 'item_embedding.weight': w[self.n_users:].clone()}
+
+    def load_state_dict(self, state, strict=True):
+        with torch.no_grad():
+            self.embedding.weight[:self.n_users].copy_(state['user_embedding.weight'])
+            self.embedding.weight[self.n_users:].copy_(state['item_embedding.weight'])
+        self._bump()
+
+
 class IdentityMap:
     """user_map / item_map of feature_ratio == 1 (model.py:392-401) without materialising n dict entries."""
 

@@ -215,6 +215,13 @@ int igcn_bpr_bwd(const float *table, const float *w, const int64_t *triples, int
                  const int64_t *seg_row, const int32_t *n_seg, float *G, int32_t accumulate,
                  float *dw, float *dw_scratch, void *stream);
 
+/* dw += scale / B * sum_i sig_i * T[u_i] .* (T[off+n_i] - T[off+p_i]): the gradient of the auxiliary loss with respect
+ * to the weight vector w (trainer.py:304-311) on its own -- the same two kernels igcn_bpr_bwd runs when it is given dw,
+ * so that the host can put them on a side stream (they depend on sig only, not on the backward propagation).
+ * Fixed summation order: 64 triples per block in order, block partials in order. */
+int igcn_bpr_dw(const float *table, const int64_t *triples, int64_t B, int64_t item_offset, int32_t D,
+                const float *sig, float scale, float *dw, float *dw_scratch, void *stream);
+
 /* dE[row] += coef * multiplicity(row) * E[row] for every touched row: gradient of
  * l2_reg * mean(|E[u]|^2 + |E[p]|^2 + |E[n]|^2) over RAW embedding rows (LightGCN.bpr_forward,
  * model.py:110-113), coef = 2 * l2_reg / B. */

@@ -18,6 +18,7 @@ Outputs (tests/golden/):
   tiny_igcn_dropui.npz     train on the dropui split, re-aggregate on the full graph, inductive_eval
   tiny_igcn_ratio.npz      feature_ratio 0.5 ('sort' ranking): maps, feat, rep
   tiny_siblings.npz        IMF (one epoch, evals) and Popularity (evals)
+  tiny_mf.npz              MF (model.py:52-72): predict, one epoch, evals      (python tests/golden/make_golden.py mf)
 """
 import os
 import sys
@@ -379,10 +380,42 @@ def golden_siblings(ds, out_path):
     print('wrote', out_path, len(out), 'arrays')
 
 
+def golden_mf(ds, out_path):
+    """MF (model.py:52-72) with BPRTrainer (config.py:6-10, Gowalla hyper-parameters): separate user / item tables,
+    one recorded epoch, evals -- the zero-layer member of the family on the same step and ranking kernels."""
+    out = {}
+    mcfg = {'name': 'MF', 'embedding_size': 64, 'device': DEV}
+    tcfg = {'name': 'BPRTrainer', 'optimizer': 'Adam', 'lr': 1.e-4, 'l2_reg': 1.e-3, 'device': DEV, 'n_epochs': 1,
+            'batch_size': 2048, 'dataloader_num_workers': 0, 'test_batch_size': 512, 'topks': [5, 20]}
+    R_utils.set_seed(SEED)
+    model = R_model.get_model(mcfg, ds)
+    trainer = R_trainer.get_trainer(tcfg, ds, model)
+    out['mf_user0'] = model.user_embedding.weight.detach().numpy().copy()
+    out['mf_item0'] = model.item_embedding.weight.detach().numpy().copy()
+    users = torch.arange(0, 64, dtype=torch.int64)
+    model.eval()
+    with torch.no_grad():
+        out['mf_scores0_users'] = users.numpy()
+        out['mf_scores0'] = model.predict(users).numpy().copy()
+    model.train()
+    R_utils.set_seed(SEED + 1)
+    with Recorder() as rec:
+        out['mf_epoch_loss'] = np.float64(trainer.train_one_epoch())
+    out['mf_epoch_triples'] = np.stack(rec.main)
+    out['mf_user1'] = model.user_embedding.weight.detach().numpy().copy()
+    out['mf_item1'] = model.item_embedding.weight.detach().numpy().copy()
+    eval_all(trainer, out, 'mf_e1')
+    np.savez_compressed(out_path, **out)
+    print('wrote', out_path, len(out), 'arrays')
+
+
 def main():
     split = synth.gen_named('tiny', seed=SEED)
     with tempfile.TemporaryDirectory() as tmp:
         ds = load_dataset(split, tmp, 'tiny')
+        if sys.argv[1:] == ['mf']:                      # only the fixture added in round 2 (the others stay as committed)
+            golden_mf(ds, os.path.join(HERE, 'tiny_mf.npz'))
+            return
         data = {'n_users': np.int64(ds.n_users), 'n_items': np.int64(ds.n_items)}
         for which in ('train', 'val', 'test'):
             data[which + '_ptr'], data[which + '_items'] = csr_of(getattr(ds, which + '_data'))
@@ -392,6 +425,7 @@ def main():
         golden_dropui(split, tmp, os.path.join(HERE, 'tiny_igcn_dropui.npz'))
         golden_ratio(ds, os.path.join(HERE, 'tiny_igcn_ratio.npz'))
         golden_siblings(ds, os.path.join(HERE, 'tiny_siblings.npz'))
+        golden_mf(ds, os.path.join(HERE, 'tiny_mf.npz'))
 
 
 if __name__ == '__main__':

@@ -428,6 +428,54 @@ def test_imf_epoch_and_eval(tiny):
     _check_evals(trainer, g, 'imf_e1', 'imf_rep1_eval')
 
 
+def test_mf_epoch_and_eval(tiny, tmp_path):
+    """MF (model.py:52-72; config.py:6-10 hyper-parameters) on the fused step and ranking kernels: predict, one
+    epoch on the reference's recorded triples, evals, and checkpoints with the reference's state_dict keys."""
+    from igcn_cf_b200.model import get_model
+    from igcn_cf_b200.trainer import get_trainer
+    g = load_golden('tiny_mf')
+    ds = _dataset(tiny)
+    model = get_model({'name': 'MF', 'embedding_size': 64, 'device': DEV}, ds)
+    with torch.no_grad():
+        model.embedding.weight.copy_(torch.from_numpy(np.concatenate([g['mf_user0'], g['mf_item0']])))
+    trainer = get_trainer({'name': 'BPRTrainer', 'optimizer': 'Adam', 'lr': 1e-4, 'l2_reg': 1e-3, 'device': DEV, 'n_epochs': 1,
+                           'batch_size': 2048, 'dataloader_num_workers': 0, 'test_batch_size': 512, 'topks': [5, 20],
+                           'cuda_graph': False}, ds, model)
+    assert model.user_embedding.weight.shape == (ds.n_users, 64) and model.item_embedding.weight.shape == (ds.n_items, 64)
+    model.eval()
+    with torch.no_grad():
+        scores = model.predict(_dev(g['mf_scores0_users']))
+    assert rel_err(scores.cpu().numpy(), g['mf_scores0']) < TOL
+    model.train()
+    tri = g['mf_epoch_triples']
+    trainer.step.reset_meter()
+    for lo in range(0, len(tri), 2048):
+        trainer.step.run(_dev(tri[lo:lo + 2048]))
+    assert abs(trainer.step.meter_avg() - float(g['mf_epoch_loss'])) < TOL
+    sd = model.state_dict()
+    assert sorted(sd) == ['item_embedding.weight', 'user_embedding.weight']            # the reference's keys
+    assert rel_err(sd['user_embedding.weight'].cpu().numpy(), g['mf_user1']) < TOL
+    assert rel_err(sd['item_embedding.weight'].cpu().numpy(), g['mf_item1']) < TOL
+    g['mf_rep1'] = np.concatenate([g['mf_user1'], g['mf_item1']])
+    _check_evals(trainer, g, 'mf_e1', 'mf_rep1')
+    path = str(tmp_path / 'mf.pth')
+    model.save(path)
+    other = get_model({'name': 'MF', 'embedding_size': 64, 'device': DEV}, ds)
+    other.load(path)
+    assert torch.equal(other.embedding.weight, model.embedding.weight)
+
+
+def test_mf_initialisation_follows_the_reference_draw_order(tiny):
+    """Same torch seed -> same initial tables as the reference constructor (user table first, model.py:56-60)."""
+    from igcn_cf_b200.model import get_model
+    from igcn_cf_b200.utils import set_seed
+    g = load_golden('tiny_mf')
+    set_seed(2021)
+    model = get_model({'name': 'MF', 'embedding_size': 64, 'device': DEV}, _dataset(tiny))
+    assert np.array_equal(model.user_embedding.weight.detach().cpu().numpy(), g['mf_user0'])
+    assert np.array_equal(model.item_embedding.weight.detach().cpu().numpy(), g['mf_item0'])
+
+
 def test_popularity_ranking(tiny):
     """Popularity (model.py:338-351) through BasicTrainer, as run/dropui/igcn_dropui.py:43-48 uses it."""
     from igcn_cf_b200.model import get_model

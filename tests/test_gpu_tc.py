@@ -120,7 +120,7 @@ def test_tc_split_tail_plan(n_tiles):
     from igcn_cf_b200 import engine
     n_users, n_items, D, k = (n_tiles - 1) * 128 + 3, 700, 32, 20
     rep, lists = _case(n_users, n_items, D, seed=11, mask_deg=3)
-    n_head, n_splits = engine.TcScorer.plan_ctas(n_tiles)
+    n_head, n_splits = engine.TcScorer.plan_ctas(n_tiles, (n_items + 255) // 256)
     assert 0 < n_head < n_tiles and n_splits > 1 and n_head % 148 == 0
     mask = engine.lists_to_csr(lists, DEV)
     u = torch.arange(n_users, device=DEV)

@@ -216,7 +216,7 @@ def test_scoring_cta_plan(monkeypatch):
     from igcn_cf_b200.engine import TcScorer
     monkeypatch.delenv('IGCN_TC_SPLITS', raising=False)
     for n in list(range(1, 700)) + [1175, 5000, 78125]:
-        n_head, n_splits = TcScorer.plan_ctas(n)
+        n_head, n_splits = TcScorer.plan_ctas(n, 167)
         assert 0 <= n_head <= n and 1 <= n_splits <= 8
         if n < 148:
             assert n_head == 0 and n_splits == TcScorer.pick_splits(n)

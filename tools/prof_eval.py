@@ -13,9 +13,12 @@ def main():
     shape, kind, l2_reg, dropout = bench.WORKLOADS[workload]
     dev = torch.device('cuda:0')
     ds = bench.build_dataset(shape, dev)
-    model, trainer = bench.build_model(ds, kind, dropout, l2_reg, dev, use_graph=False)
+    model, trainer = bench.build_model(ds, kind, dropout, l2_reg, dev, use_graph=True)
     if len(sys.argv) > 2:
         trainer.config['score_impl'] = sys.argv[2]
+    model.train()
+    for _ in range(int(os.environ.get('PROF_TRAIN_STEPS', 300))):      # evaluate a partly trained model, as the bench does
+        trainer.step.run()
     for _ in range(2):
         model._bump()
         print(trainer.eval('val')[0])

@@ -31,7 +31,7 @@ def main():
     users = torch.arange(n_users, device=dev)
     mask = trainer._mask_csr('val')
     scorer = engine.TcScorer()
-    n_head, n_splits = scorer.plan_ctas((n_users + 127) // 128)
+    n_head, n_splits = scorer.plan_ctas((n_users + 127) // 128, (n_items + 255) // 256)
     ws = scorer._workspace(n_users, n_items, D, n_splits, k, dev)
     for oname, order in (('natural', None), ('popularity', trainer.item_order())):
         tile_ptr, entries = mask.tiles(n_items, None, order)
