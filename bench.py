@@ -71,14 +71,20 @@ def measured_peaks():
 
 
 def measured_traffic(workload):
-    """DRAM bytes per launch of the dominant kernels from the committed ncu capture (profiles/*_traffic.json,
-    produced by tools/ncu_traffic.py); only valid for the workload the capture was taken on."""
+    """DRAM bytes per launch of the dominant kernels of `workload` from the committed ncu captures
+    (profiles/*_traffic.json: {'workloads': {name: {entry point: bytes per launch}}}); {} when this workload was not
+    captured."""
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_traffic.json')))
-    if not files or workload != 'yelp-lightgcn':
+    if not files:
         return {}
     with open(files[-1]) as f:
-        return {k: v['dram_bytes_per_launch'] for k, v in json.load(f)['kernels'].items()}
+        data = json.load(f)
+    if 'workloads' in data:
+        return dict(data['workloads'].get(workload, {}))
+    if workload != 'yelp-lightgcn':                      # round-1 file: one workload
+        return {}
+    return {k: v['dram_bytes_per_launch'] for k, v in data['kernels'].items()}
 
 
 def profile_eval(trainer, reps=5):

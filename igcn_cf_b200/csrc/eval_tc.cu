@@ -426,6 +426,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) { mbar_arrive(&sm->tmem_empty[acc]); mbar_arrive(&sm->mask_empty[slot]); }
         }
+        // one last compaction: the lists leave the SM at ~KEEP entries instead of up to 96, which is what
+        // igcn_tc_finalize has to re-score exactly and rank (its time more than halves); the threshold becomes the
+        // KEEP-th best upper bound, still a valid bound on everything that was dropped
+        if (VARIANT != 2 && VARIANT != 5 && n_it > 0) {
+            __syncwarp();
+            compact_lanes(mybuf, cnt, thr);
+        }
         // dump this row's candidates
         __syncwarp();
         for (int r = 0; r < 32; ++r) {

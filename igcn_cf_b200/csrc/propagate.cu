@@ -17,6 +17,12 @@
 // partials in chunk order.  The dependent-load chain of any unit is thus <= 8 batches, and how a row
 // is summed depends on its length only -- deterministic, independent of how rows are sharded over GPUs.
 //
+// Narrow tables (D = 16 or 8: the column-sharded training step on 4 / 8 GPUs) use 4 or 2 lanes per row instead of 8, so
+// that a warp instruction still moves useful bytes in every lane.  How a row is summed must not depend on that: the
+// pieces of a shared row are always cut for a TEAM of 4 subgroups on 8-non-zero boundaries (what the 8-lane kernel does),
+// a warp simply holds 2 or 4 teams; every output element then sees the same additions in the same order as in the
+// D = 64 kernel -- bit-identical column slices.
+//
 // Everything here is HBM/L2-bound gather work; there is no tensor-core shape to it.
 #include "common.cuh"
 
@@ -54,9 +60,19 @@ constexpr uint32_t kSelfCol = 0xffffffffu;
 template <int LPR>
 __device__ __forceinline__ uint32_t group_mask() {
     if (LPR == 32) return 0xffffffffu;
-    const uint32_t base = (LPR == 16) ? 0xffffu : 0xffu;
+    const uint32_t base = (LPR == 16) ? 0xffffu : (LPR == 8) ? 0xffu : (LPR == 4) ? 0xfu : 0x3u;
     return base << ((threadIdx.x & 31) & ~(LPR - 1));
 }
+
+// Subgroups that share one medium row / one chunk, and the alignment of their pieces: 4 subgroups on 8-non-zero
+// boundaries for every width up to 64 floats (LPR <= 8), the whole warp for the wide kernels.
+template <int LPR>
+struct Team {
+    static constexpr int SUB = 32 / LPR;                    // subgroups per warp
+    static constexpr int SIZE = SUB < 4 ? SUB : 4;          // subgroups per team
+    static constexpr int PER_WARP = SUB / SIZE;             // teams per warp
+    static constexpr int ALIGN = LPR < 8 ? 8 : LPR;         // piece boundaries
+};
 
 // Thread mapping: LPR lanes own one row, each lane carries V float4 accumulators; vector v of lane
 // l covers floats [v*LPR*4 + l*4, +4), so every load instruction of a group reads one contiguous
@@ -84,7 +100,8 @@ __device__ __forceinline__ void gather_range(const PropArgs &a, RowVec<LPR, V, E
     const int D = a.D;
     const float *__restrict__ Tl = a.X + lane * 4;
     constexpr bool COLS = (MODE == MODE_SPMM && DROP == 2);
-    constexpr int Q = (V == 1) ? 8 : 4;                 // neighbour rows in flight per group (8 x 16 B per lane)
+    constexpr int Q0 = (V == 1) ? 8 : 4;                // neighbour rows in flight per group (8 x 16 B per lane) ...
+    constexpr int Q = Q0 < LPR ? Q0 : LPR;              // ... but never more than one batch of column ids
     const int gshift = (threadIdx.x & 31) & ~(LPR - 1);
 
     int c_next = 0;
@@ -215,48 +232,54 @@ __device__ __forceinline__ void finish_row(const PropArgs &a, int64_t r, RowVec<
     }
 }
 
-// Ordered in-warp combine: subgroup 0 ends up with ((p0 + p1) + p2) + ... of the SUB subgroup accumulators.
+// Ordered in-team combine: subgroup 0 of the team ends up with ((p0 + p1) + p2) + ... of its subgroups' accumulators.
 template <int LPR, int V, bool EXACT>
-__device__ __forceinline__ void combine_subgroups(RowVec<LPR, V, EXACT> &acc, int lane, int sub) {
-    constexpr int SUB = 32 / LPR;
+__device__ __forceinline__ void combine_subgroups(RowVec<LPR, V, EXACT> &acc, int lane, int tsub, int team_base) {
+    constexpr int SIZE = Team<LPR>::SIZE;
+    // only the team's own lanes take part: the other teams of the warp may be on a different path or gone
+    const uint32_t tmask = (SIZE * LPR == 32) ? 0xffffffffu : (((1u << (SIZE * LPR)) - 1u) << team_base);
 #pragma unroll
-    for (int s = 1; s < SUB; ++s) {
+    for (int s = 1; s < SIZE; ++s) {
 #pragma unroll
         for (int i = 0; i < V; ++i) {
             float4 o;
-            o.x = __shfl_sync(0xffffffffu, acc.v[i].x, lane + s * LPR);
-            o.y = __shfl_sync(0xffffffffu, acc.v[i].y, lane + s * LPR);
-            o.z = __shfl_sync(0xffffffffu, acc.v[i].z, lane + s * LPR);
-            o.w = __shfl_sync(0xffffffffu, acc.v[i].w, lane + s * LPR);
-            if (sub == 0) add4(acc.v[i], o);
+            const int src = team_base + lane + s * LPR;
+            o.x = __shfl_sync(tmask, acc.v[i].x, src);
+            o.y = __shfl_sync(tmask, acc.v[i].y, src);
+            o.z = __shfl_sync(tmask, acc.v[i].z, src);
+            o.w = __shfl_sync(tmask, acc.v[i].w, src);
+            if (tsub == 0) add4(acc.v[i], o);
         }
     }
 }
 
-// This subgroup's slice of the non-zero range [beg, end) when a whole warp shares it (LPR-aligned pieces).
+// This subgroup's slice of the non-zero range [beg, end) when a team shares it (ALIGN-aligned pieces).
 template <int LPR>
-__device__ __forceinline__ void split_range(int64_t &beg, int64_t &end, int sub) {
-    constexpr int SUB = 32 / LPR;
-    const int64_t q = (((end - beg) + SUB - 1) / SUB + LPR - 1) & ~(int64_t)(LPR - 1);
-    const int64_t b = beg + sub * q;
+__device__ __forceinline__ void split_range(int64_t &beg, int64_t &end, int tsub) {
+    constexpr int SIZE = Team<LPR>::SIZE, ALIGN = Team<LPR>::ALIGN;
+    const int64_t q = (((end - beg) + SIZE - 1) / SIZE + ALIGN - 1) & ~(int64_t)(ALIGN - 1);
+    const int64_t b = beg + tsub * q;
     end = min(end, b + q);
     beg = min(b, end);
 }
 
-// Work units are WARPS, in this order (rows are visited by non-zero count, descending -- igcn_csr.row_order):
-//   [0, n_chunks)                 one chunk of a long row (> long_threshold non-zeros): the warp's subgroups share
-//                                 the chunk, the combined partial goes to g.partial and the last chunk of the row
-//                                 to finish adds the partials in chunk order
-//   [n_chunks, +n_medium_rows)    one medium row (> IGCN_MEDIUM_NNZ non-zeros) per warp, subgroups share it
+// Work units, in this order (rows are visited by non-zero count, descending -- igcn_csr.row_order):
+//   [0, n_chunks)                 one chunk of a long row (> long_threshold non-zeros) per TEAM (4 subgroups = one warp
+//                                 at 8 lanes per row): the subgroups share the chunk, the combined partial goes to
+//                                 g.partial and the last chunk of the row to finish adds the partials in chunk order
+//   [n_chunks, +n_medium_rows)    one medium row (> IGCN_MEDIUM_NNZ non-zeros) per team, subgroups share it
 //   the rest                      one short row per LPR-lane subgroup
 // How a row is summed depends on its length only, never on the grid, the row block or the GPU count.
 template <int LPR, int V, bool EXACT, int MODE, int DROP>
 __global__ void __launch_bounds__(kThreads, 4) prop_kernel(const __grid_constant__ PropArgs a) {
     constexpr int SUB = 32 / LPR;
+    constexpr int TSIZE = Team<LPR>::SIZE, TPW = Team<LPR>::PER_WARP;
     constexpr bool ROWS = (MODE == MODE_SPMM && DROP == 1);
     using Vec = RowVec<LPR, V, EXACT>;
     const int lane = threadIdx.x % LPR;
     const int sub = (threadIdx.x & 31) / LPR;
+    const int team = sub / TSIZE, tsub = sub % TSIZE;          // team of subgroups inside the warp, subgroup inside the team
+    const int team_base = team * TSIZE * LPR;
     const uint32_t gmask = group_mask<LPR>();
     const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
     const int64_t n_chunks = a.g.n_chunks;
@@ -267,9 +290,15 @@ __global__ void __launch_bounds__(kThreads, 4) prop_kernel(const __grid_constant
     Vec acc;
     acc.zero();
 
-    if (warp < n_chunks) {
+    // team units: [0, n_chunks) chunks of long rows, then (full kernel) the medium rows / (row-list kernel) the listed
+    // rows; they fill the first team_warps warps, TPW teams each.  Short rows of the full kernel follow, one per subgroup.
+    const int64_t n_shared = ROWS ? a.max_list : n_med;
+    const int64_t team_warps = (n_chunks + n_shared + TPW - 1) / TPW;
+    const int64_t unit = warp * TPW + team;
+
+    if (warp < team_warps && unit < n_chunks) {
         // ---- one chunk of a long row
-        const int ch = (int)warp;
+        const int ch = (int)unit;
         const int64_t r = a.g.chunk_row[ch];
         if (ROWS) {
             // is this long row on the list?  (ascending ids: binary search, same answer on every lane)
@@ -282,10 +311,10 @@ __global__ void __launch_bounds__(kThreads, 4) prop_kernel(const __grid_constant
             if (lo >= *a.n_list || __ldg(a.row_list + lo) != want) return;
         }
         int64_t beg = a.g.chunk_begin[ch], end = beg + a.g.chunk_len[ch];
-        split_range<LPR>(beg, end, sub);
+        split_range<LPR>(beg, end, tsub);
         gather_range<LPR, V, EXACT, MODE, DROP>(a, acc, beg, end, a.row0 + r, lane, gmask, seed);
-        combine_subgroups<LPR, V, EXACT>(acc, lane, sub);
-        if (sub != 0) return;
+        combine_subgroups<LPR, V, EXACT>(acc, lane, tsub, team_base);
+        if (tsub != 0) return;
         const int first = a.g.chunk_first[ch];
         const int count = a.g.chunk_count[ch];
 #pragma unroll
@@ -320,19 +349,22 @@ __global__ void __launch_bounds__(kThreads, 4) prop_kernel(const __grid_constant
     }
 
     int64_t r;
-    bool shared_row;                                    // does the whole warp work on row r?
-    if (ROWS) {
-        // one listed row per warp; its length decides how it is summed (same rule as the full kernel)
-        const int64_t idx = warp - n_chunks;
-        if (idx >= *a.n_list) return;
-        r = __ldg(a.row_list + idx) - a.row0;
-        if (r < 0 || r >= a.g.n_rows) return;           // another block's row
-        shared_row = true;
-    } else if (warp < n_chunks + n_med) {
-        r = __ldg(a.g.row_order + n_long + (warp - n_chunks));
+    bool shared_row;                                    // does the whole team work on row r?
+    if (warp < team_warps) {
+        const int64_t idx = unit - n_chunks;
+        if (idx >= n_shared) return;                    // idle team of the last team warp
+        if (ROWS) {
+            // one listed row per team; its length decides how it is summed (same rule as the full kernel)
+            if (idx >= *a.n_list) return;
+            r = __ldg(a.row_list + idx) - a.row0;
+            if (r < 0 || r >= a.g.n_rows) return;       // another block's row
+        } else {
+            r = __ldg(a.g.row_order + n_long + idx);
+        }
         shared_row = true;
     } else {
-        const int64_t idx = n_long + n_med + (warp - n_chunks - n_med) * SUB + sub;
+        if (ROWS) return;
+        const int64_t idx = n_long + n_med + (warp - team_warps) * SUB + sub;
         if (idx >= a.g.n_rows) return;
         r = a.g.row_order ? (int64_t)__ldg(a.g.row_order + idx) : idx;
         shared_row = false;
@@ -340,33 +372,38 @@ __global__ void __launch_bounds__(kThreads, 4) prop_kernel(const __grid_constant
     int64_t beg = __ldg(a.g.rowptr + r), end = __ldg(a.g.rowptr + r + 1);
     if (ROWS) {
         const int64_t nnz = end - beg;
-        if (n_chunks > 0 && nnz > a.g.long_threshold) return;          // the chunk warps own it
-        if (!(a.g.row_order && nnz > IGCN_MEDIUM_NNZ)) {                // short row: subgroup 0 alone, like the full kernel
-            if (sub != 0) return;
+        if (n_chunks > 0 && nnz > a.g.long_threshold) return;          // the chunk teams own it
+        if (!(a.g.row_order && nnz > IGCN_MEDIUM_NNZ)) {                // short row: subgroup 0 of the team alone, like the full kernel
+            if (tsub != 0) return;
             shared_row = false;
         }
     }
     if (shared_row) {
-        split_range<LPR>(beg, end, sub);
+        split_range<LPR>(beg, end, tsub);
         gather_range<LPR, V, EXACT, MODE, DROP>(a, acc, beg, end, a.row0 + r, lane, gmask, seed);
-        combine_subgroups<LPR, V, EXACT>(acc, lane, sub);
-        if (sub != 0) return;
+        combine_subgroups<LPR, V, EXACT>(acc, lane, tsub, team_base);
+        if (tsub != 0) return;
     } else {
         gather_range<LPR, V, EXACT, MODE, DROP>(a, acc, beg, end, a.row0 + r, lane, gmask, seed);
     }
     finish_row<LPR, V, EXACT, MODE, DROP>(a, r, acc, lane, seed);
 }
 
-static int64_t warp_units(const PropArgs &a, int sub, bool rows_variant) {
-    if (rows_variant) return a.g.n_chunks + a.max_list;
+template <int LPR>
+static int64_t warp_units(const PropArgs &a, bool rows_variant) {
+    constexpr int SUB = 32 / LPR, TPW = Team<LPR>::PER_WARP;
     const int64_t n_long = a.g.row_order ? a.g.n_long_rows : 0, n_med = a.g.row_order ? a.g.n_medium_rows : 0;
-    return a.g.n_chunks + n_med + (a.g.n_rows - n_long - n_med + sub - 1) / sub;
+    const int64_t n_shared = rows_variant ? a.max_list : n_med;
+    const int64_t team_warps = (a.g.n_chunks + n_shared + TPW - 1) / TPW;
+    if (rows_variant) return team_warps;
+    return team_warps + (a.g.n_rows - n_long - n_med + SUB - 1) / SUB;
 }
 
 template <int LPR, int V, bool EXACT, int MODE, int DROP>
 static void launch_one(const PropArgs &a, cudaStream_t st) {
-    const int64_t warps = warp_units(a, 32 / LPR, MODE == MODE_SPMM && DROP == 1);
+    const int64_t warps = warp_units<LPR>(a, MODE == MODE_SPMM && DROP == 1);
     constexpr int WPB = kThreads / 32;
+    if (warps <= 0) return;
     prop_kernel<LPR, V, EXACT, MODE, DROP><<<(unsigned)((warps + WPB - 1) / WPB), kThreads, 0, st>>>(a);
 }
 
@@ -376,6 +413,8 @@ static int launch_lanes(const PropArgs &a, cudaStream_t st) {
     const int D = a.D;
     if (D == 64) launch_one<8, 2, true, MODE, DROP>(a, st);
     else if (D == 32) launch_one<8, 1, true, MODE, DROP>(a, st);
+    else if (D == 16) launch_one<4, 1, true, MODE, DROP>(a, st);
+    else if (D == 8) launch_one<2, 1, true, MODE, DROP>(a, st);
     else if (D == 128) launch_one<16, 2, true, MODE, DROP>(a, st);
     else if (D < 32) launch_one<8, 1, false, MODE, DROP>(a, st);
     else if (D < 64) launch_one<8, 2, false, MODE, DROP>(a, st);

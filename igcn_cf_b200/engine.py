@@ -803,9 +803,12 @@ class TcScorer:
 
     @staticmethod
     def pick_splits(n_groups, n_sm=148):
-        """Uniform item-range splits per user tile when there are fewer user tiles than SMs: enough CTAs for two
-        waves, at most 8."""
-        return int(min(8, max(1, -(-2 * n_sm // max(1, int(n_groups))))))
+        """Uniform item-range splits per user tile when there are fewer user tiles than SMs: as many as fit in ONE
+        wave, at most 8 (147 tiles -> 1, 74 -> 2, 30 -> 4).  Round 1 filled two waves (better tail balance); with
+        the cheap epilogue of round 2 the lists are what costs -- every split is one more list per user for
+        igcn_tc_finalize to re-score and rank, and at N GPUs every rank is in this regime (4-GPU Yelp shape: 147 tiles
+        per rank in 3 splits spent as long in finalize, 0.17 ms, as in the candidate kernel)."""
+        return int(min(8, max(1, n_sm // max(1, int(n_groups)))))
 
     @classmethod
     def plan_ctas(cls, n_groups, n_itiles=None, n_sm=148):

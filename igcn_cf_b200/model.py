@@ -65,13 +65,16 @@ class BasicModel(nn.Module):
         #           bytes per triple (partial dot products), and the parameters are all-gathered once per epoch /
         #           before an evaluation.  Bit-identical to one GPU.  Eval users sharded, eval propagation replicated.
         #   'auto'  (default) eval users always sharded; rows sharded only when every rank keeps at least
-        #           SHARD_MIN_NNZ_PER_RANK non-zeros, i.e. when the per-layer exchange (N*D*4 bytes into every rank)
-        #           pays off -- measured: Amazon-shaped on 2 GPUs yes (1.23x), on 8 no; Yelp/Gowalla-shaped never
-        #           (DESIGN.md 7), so training runs as replicas there
+        #           SHARD_MIN_NNZ_PER_RANK non-zeros (graphs whose layer tables live in HBM: the scale-out class, where
+        #           one rank's propagation is tens of milliseconds); otherwise columns when 2, 4 or 8 ranks divide the
+        #           embedding size into multiples of 4 -- measured fastest on every paper-sized graph --
+        #           else replicated training
         mode = model_config.get('shard', 'auto')
         self._peers = dist.current() if mode else None
         self._shard_rows = mode is True
         self._shard_auto = mode == 'auto'
+        D = model_config.get('embedding_size', 0)
+        self._dims_ok = (self._peers is not None and self._peers.world in (2, 4, 8) and D and D % (4 * self._peers.world) == 0)
         self._dim_shard = (self._peers.rank, self._peers.world) if (mode == 'dims' and self._peers is not None) else None
         self._param_sync = None         # set by engine.TrainStep in 'dims' mode: all-gathers the column slices
 
@@ -111,7 +114,7 @@ class _GraphModel(BasicModel):
         return (getattr(self.norm_adj, 'uid', None), None if feat is None else getattr(feat, 'uid', None),
                 self.n_users, self.n_items)
 
-    SHARD_MIN_NNZ_PER_RANK = int(os.environ.get('IGCN_SHARD_MIN_NNZ_PER_RANK', 2_000_000))
+    SHARD_MIN_NNZ_PER_RANK = int(os.environ.get('IGCN_SHARD_MIN_NNZ_PER_RANK', 50_000_000))
 
     def _rows_sharded(self, dataset=None):
         if self._peers is None:
@@ -121,6 +124,8 @@ class _GraphModel(BasicModel):
             nnz = 2 * (dg.n_interactions if dg is not None else len(graph.train_pairs_of(dataset)))
             self._shard_rows = nnz >= self.SHARD_MIN_NNZ_PER_RANK * self._peers.world
             self._shard_auto = False                     # decided once per model: all graphs of a model agree
+            if not self._shard_rows and self._dims_ok:
+                self._dim_shard = (self._peers.rank, self._peers.world)
         return self._shard_rows
 
     def _shard_arg(self, dataset=None):

@@ -111,3 +111,83 @@ def test_column_filter_layer_equals_full_layer_on_sparse_input():
     torch.cuda.synchronize()
     # skipped terms are exact zeros, so the sums agree exactly (up to the sign of zero)
     assert torch.equal(part + 0.0, full + 0.0)
+
+
+def _spmm_w(name, adj, x, y, adds, alpha, *extra):
+    """_spmm for any width: D = x.shape[1]."""
+    from igcn_cf_b200._lib import call, ptr, stream_ptr
+    D = int(x.shape[1])
+    arr = (C.c_void_p * max(1, len(adds)))(*[a.data_ptr() for a in adds])
+    call(name, adj.csr.struct(D), ptr(x), ptr(y), D, arr, len(adds), None, alpha, *extra, None, 0, stream_ptr())
+
+
+@pytest.mark.parametrize('width', [32, 16, 8])
+def test_narrow_tables_reproduce_the_column_slices_of_the_full_width_layer(width):
+    """The column-sharded training step runs every propagation kernel on D / ranks columns (32, 16, 8 for 2, 4, 8
+    GPUs; 4 or 2 lanes per row below 32).  Each kernel variant on a contiguous column slice must give the bits of the
+    same slice of the D = 64 result: full layer with add operands, row-list layer, column-filter layer, INMO layer
+    forward (hash dropout) and its transpose, masked column sums."""
+    from igcn_cf_b200 import engine, graph
+    from igcn_cf_b200._lib import call, ptr, stream_ptr
+    split, adj = _graph()
+    n = split.n_users + split.n_items
+    assert adj.csr.n_chunks > 0 and adj.csr.n_medium > 0
+    g = torch.Generator(device=DEV).manual_seed(width)
+    x = torch.randn(n, 64, device=DEV, generator=g)
+    add = torch.randn(n, 64, device=DEV, generator=g)
+    rng = np.random.default_rng(width)
+    deg = np.diff(adj.rowptr_full)
+    rows = np.unique(np.r_[np.argsort(-deg)[:40], rng.integers(n, size=1500)]).astype(np.int64)
+    row_list = torch.from_numpy(rows).to(DEV)
+    n_list = torch.tensor([len(rows)], dtype=torch.int32, device=DEV)
+    touched = np.unique(np.r_[np.argsort(-deg)[:30], rng.integers(n, size=2000)])
+    flags = np.zeros(((n + 31) // 32) * 32, dtype=np.uint8)
+    flags[touched] = 1
+    bits = torch.from_numpy(np.packbits(flags, bitorder='little').view(np.int32).copy()).to(DEV)
+    xs = torch.zeros(n, 64, device=DEV)
+    xs[touched] = x[touched]
+
+    def run_all(xx, aa, xxs):
+        out = {}
+        y = torch.empty_like(xx)
+        _spmm_w('igcn_spmm', adj, xx, y, [aa, xx], 0.25)
+        out['full'] = y
+        y = torch.zeros_like(xx)
+        _spmm_w('igcn_spmm_rows', adj, xx, y, [aa, xx], 0.25, row_list.data_ptr(), n_list.data_ptr(), len(rows), 0)
+        out['rows'] = y
+        y = torch.empty_like(xx)
+        _spmm_w('igcn_spmm_cols', adj, xxs, y, [xxs], 1.0, bits.data_ptr())
+        out['cols'] = y
+        return out
+
+    want = run_all(x, add, xs)
+    for c0 in range(0, 64, width):
+        sl = slice(c0, c0 + width)
+        got = run_all(x[:, sl].contiguous(), add[:, sl].contiguous(), xs[:, sl].contiguous())
+        torch.cuda.synchronize()
+        for k in want:
+            assert torch.equal(got[k], want[k][:, sl]), (k, width, c0)
+
+    # INMO layer (identity templates, hash dropout) and its transpose + the masked column sums
+    pairs = np.stack([np.repeat(np.arange(split.n_users, dtype=np.int64), np.diff(split.csr('train')[0])), split.csr('train')[1]], axis=1)
+    feat = graph.TemplateFeat(split.n_users, split.n_items, pairs, np.arange(split.n_users), np.arange(split.n_items),
+                              split.n_users, split.n_items, DEV)
+    feat.set_alpha(0.9)
+    emb = torch.randn(n + 2, 64, device=DEV, generator=g)
+    gsc = torch.randn(n, 64, device=DEV, generator=g)
+    drop = {'mode': 1, 'p': 0.3, 'seed': 12345}
+
+    def inmo(e, gs):
+        D = int(e.shape[1])
+        x0 = torch.empty((n, D), device=DEV)
+        engine.inmo_forward(feat, e, x0, drop, D)
+        d_emb = torch.zeros_like(e)
+        engine.inmo_backward(feat, gs, d_emb, drop, D, engine.colsum_scratch(n, D, DEV))
+        return x0, d_emb
+
+    x0_w, de_w = inmo(emb, gsc)
+    for c0 in range(0, 64, width):
+        sl = slice(c0, c0 + width)
+        x0, de = inmo(emb[:, sl].contiguous(), gsc[:, sl].contiguous())
+        torch.cuda.synchronize()
+        assert torch.equal(x0, x0_w[:, sl]) and torch.equal(de, de_w[:, sl]), (width, c0)
