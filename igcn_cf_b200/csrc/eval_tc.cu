@@ -288,22 +288,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         // entries (two L2 round trips, ~1,900 cycles per tile when it sat between tmem_empty and mask_full) is off
         // the critical path -- and publishes it (mask_full) up to TC_MASKS tiles ahead of the epilogue.
         const int32_t *tp = a.mask_tile_ptr ? a.mask_tile_ptr + (size_t)ut * (a.n_itiles + 1) : nullptr;
-        auto bucket = [&](int it, int &e0, int &e1, uint32_t &first) {
-            e0 = e1 = 0; first = 0u;
-            if (tp && it < n_it) {
-                const int t = t0 + it * ns;
-                e0 = __ldg(tp + t); e1 = __ldg(tp + t + 1);
-                if (e0 + lane < e1) first = a.mask_entries[e0 + lane];
-            }
+        // Two-deep software pipeline of the bucket loads, so that no iteration waits for a load it has just issued:
+        // the bucket bounds tile_ptr[t], tile_ptr[t + 1] are fetched TWO tiles ahead, the first 32 entries ONE tile
+        // ahead (their address needs the bounds); with the bounds fetched one tile ahead the warp stalled an L2 round
+        // trip per tile on them.
+        auto bounds_of = [&](int it, int &b0, int &b1) {
+            b0 = b1 = 0;
+            if (tp && it < n_it) { const int t = t0 + it * ns; b0 = __ldg(tp + t); b1 = __ldg(tp + t + 1); }
         };
-        int e0, e1;
-        uint32_t first;
-        bucket(0, e0, e1, first);
+        auto first_of = [&](int b0, int b1) -> uint32_t { return (b0 + lane < b1) ? (uint32_t)a.mask_entries[b0 + lane] : 0u; };
+        int e0, e1, n0, n1;
+        bounds_of(0, e0, e1);
+        bounds_of(1, n0, n1);
+        uint32_t first = first_of(e0, e1);
         for (int it = 0; it < n_it; ++it) {
             const int slot = it % TC_MASKS, t = t0 + it * ns;
-            int n0, n1;
-            uint32_t nfirst;
-            bucket(it + 1, n0, n1, nfirst);                          // next tile's loads fly while this one is built
+            int q0, q1;
+            bounds_of(it + 2, q0, q1);                               // in flight for two tiles
+            const uint32_t nfirst = first_of(n0, n1);                // in flight for one tile
             mbar_wait_helper(&sm->mask_empty[slot], ((uint32_t)(it / TC_MASKS) & 1u) ^ 1u, a.dbg & 2);
             uint32_t *bm = bitmap + (size_t)slot * TC_BM * 8;
             if (!(a.dbg & 4)) {
@@ -332,6 +334,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             }
             if (lane == 0) mbar_arrive(&sm->mask_full[slot]);
             e0 = n0; e1 = n1; first = nfirst;
+            n0 = q0; n1 = q1;
         }
     } else {
         // ===== epilogue: thread = user row (TMEM lane)
@@ -358,32 +361,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_BN;
             uint32_t va[64], vb[64];
             tc_ld64(taddr, va);
-            // 64 columns per TMEM load, the next load always in flight behind the filter of the previous 64
-            auto filter = [&](const uint32_t *v, int ch) {
-                const uint32_t item0 = (uint32_t)(t * TC_BN + ch * 32);
-                if (VARIANT == 2) {
-                    uint32_t x = 0;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) x ^= v[c];
-                    if (x == 0x7fc12345u) cnt = 1;           // keeps the loads alive, never true in practice
-                    return;
-                }
-                if (VARIANT == 1) {
-                    float *d = a.dump + ((size_t)ut * TC_BM + row) * ((size_t)a.n_itiles * TC_BN) + item0;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) d[c] = __uint_as_float(v[c]);
-                }
-                // ---- compare-free path: maxima of the four 8-column groups (3-input FMNMX), one vote per chunk
-                float gm[4];
+            // 64 columns per TMEM load, the next load always in flight behind the filter of the previous 64.
+            // The compare-free test covers all 64 columns with ONE vote: the two 32-column maxima are independent
+            // FMNMX trees the compiler interleaves, so the dependent chain maxima -> compare -> vote -> branch (a
+            // single epilogue warp per scheduler cannot hide it) is paid once per 64 columns.
+            auto group_max = [&](const uint32_t *v, float (&gm)[4]) -> float {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     const uint32_t *f = &v[g * 8];
                     gm[g] = fmaxf(fmax3(f[0], f[1], f[2]), fmax3(f[3], f[4], fmax3(f[5], f[6], f[7])));
                 }
-                const float m = fmaxf(fmax3(gm[0], gm[1], gm[2]), gm[3]);
-                if (VARIANT == 4) ++st_chunks;
-                if (!__any_sync(0xffffffffu, m > thr)) return;
-                // ---- some row of the warp has a score above its threshold in this chunk
+                return fmaxf(fmax3(gm[0], gm[1], gm[2]), gm[3]);
+            };
+            // the compare path of one 32-column chunk some row of which may hold a hit
+            auto compare_chunk = [&](const uint32_t *v, const float (&gm)[4], int ch) {
+                const uint32_t item0 = (uint32_t)(t * TC_BN + ch * 32);
                 if (VARIANT == 4) ++st_slow;
                 if (__any_sync(0xffffffffu, cnt > TC_CAP - 32)) {
                     compact_lanes(mybuf, cnt, thr);
@@ -411,16 +403,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                     }
                 }
             };
+            auto filter64 = [&](const uint32_t *v, int ch) {          // columns [ch * 32, ch * 32 + 64)
+                if (VARIANT == 2) {
+                    uint32_t x = 0;
+#pragma unroll
+                    for (int c = 0; c < 64; ++c) x ^= v[c];
+                    if (x == 0x7fc12345u) cnt = 1;           // keeps the loads alive, never true in practice
+                    return;
+                }
+                if (VARIANT == 1) {
+                    float *d = a.dump + ((size_t)ut * TC_BM + row) * ((size_t)a.n_itiles * TC_BN) + (size_t)t * TC_BN + ch * 32;
+#pragma unroll
+                    for (int c = 0; c < 64; ++c) d[c] = __uint_as_float(v[c]);
+                }
+                float gm0[4], gm1[4];
+                const float m0 = group_max(v, gm0), m1 = group_max(v + 32, gm1);
+                if (VARIANT == 4) st_chunks += 2;
+                if (!__any_sync(0xffffffffu, fmaxf(m0, m1) > thr)) return;
+                // ---- some row of the warp has a score above its threshold in these 64 columns
+                if (__any_sync(0xffffffffu, m0 > thr)) compare_chunk(v, gm0, ch);
+                if (__any_sync(0xffffffffu, m1 > thr)) compare_chunk(v + 32, gm1, ch + 1);
+            };
 #pragma unroll 1
             for (int ch = 0; ch < 8; ch += 4) {
                 tc_wait_ld();
                 tc_ld64(taddr + (ch + 2) * 32, vb);
-                filter(va, ch);
-                filter(va + 32, ch + 1);
+                filter64(va, ch);
                 tc_wait_ld();
                 if (ch + 4 < 8) tc_ld64(taddr + (ch + 4) * 32, va);
-                filter(vb, ch + 2);
-                filter(vb + 32, ch + 3);
+                filter64(vb, ch + 2);
             }
             tc_fence_before();
             __syncwarp();

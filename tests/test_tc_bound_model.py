@@ -137,68 +137,3 @@ def test_bound_is_not_wastefully_loose():
         slack = float(frac_dot(hu, hi) + Fraction(float(bu)) * Fraction(float(bi)) - frac_dot(vu, vi))
         nu, ni = float(np.linalg.norm(vu.astype(np.float64))), float(np.linalg.norm(vi.astype(np.float64)))
         assert 0.0 <= slack <= 2.2e-3 * nu * ni + 1.0
-
-
-# ---------------------------------------------------------------- threshold-in-MMA filter (score_tc_kernel<7>)
-def _half_up_f32(x):
-    return np.float32(half_up(np.float32(x)))
-
-
-def _simulate_row(scores, keep=32, cap=96, tile=256, chunk=32, rng=None):
-    """Functional model of one user row of score_tc_kernel<7>: per tile parity p the tensor core subtracts
-    ta[p] = -fp16_up(-thr / 1024) * 1024 (the value the row wrote into the A tile two tiles earlier), the filter
-    keeps non-negative accumulators, the rare path rebuilds an upper bound, re-checks it against the exact
-    threshold, and the list is cut back to the `keep` best when fewer than `chunk` slots are free.
-    `scores` stands for s_sum - 80 * 2^-24 * mag, the value test_upper_bound_* above prove to be >= the exact
-    score whatever the accumulator rounds to; the hardware accumulator then lies anywhere between that minus
-    80 * 2^-24 |ta| (the rounding the subtracted term adds) and that plus 160 * 2^-24 mag + 80 * 2^-24 |ta| --
-    modelled as a random perturbation in that interval when rng is given."""
-    thr, ta = np.float32(0.0), [np.float32(0.0), np.float32(0.0)]
-    items, vals = [], []
-    n = len(scores)
-    for t in range((n + tile - 1) // tile):
-        p = t & 1
-        for c0 in range(t * tile, min(n, (t + 1) * tile), chunk):
-            if len(items) > cap - chunk:                               # compaction: threshold = keep-th best bound
-                order = np.argsort(-np.array(vals, dtype=np.float32), kind='stable')[:keep]
-                thr = np.float32(min(vals[i] for i in order))
-                order = [i for i in range(len(vals)) if vals[i] >= thr]
-                items, vals = [items[i] for i in order], [vals[i] for i in order]
-                assert len(items) <= cap - chunk, 'flat scores: the kernel would hand this row to the exact kernel'
-            for j in range(c0, min(n, c0 + chunk)):
-                err = 0.0
-                if rng is not None:
-                    err = 80 * 2.0 ** -24 * ((rng.random() * 2 - 1) * abs(float(ta[p])) + rng.random() * 2 * abs(float(scores[j])))
-                acc = np.float32(np.float64(scores[j]) - np.float64(ta[p]) + err)
-                if np.signbit(acc):
-                    continue                                           # dropped by the sign test
-                pad = np.float32(abs(ta[p]) * np.float32(2.0 ** -17))
-                s_up = np.nextafter(np.float32(np.float32(acc + ta[p]) + pad), np.float32(np.inf))   # >= both round-ups
-                if s_up > thr:
-                    items.append(j)
-                    vals.append(np.float32(s_up))
-        want = np.float32(-thr / np.float32(1024.0))
-        if thr > ta[p] and want <= 65504:
-            ta[p] = np.float32(-_half_up_f32(want) * np.float32(1024.0))
-            assert ta[p] <= thr
-    recorded = np.nextafter(np.float32(thr + np.float32(abs(thr) * np.float32(2.0 ** -17))), np.float32(np.inf))
-    return items, np.array(vals, dtype=np.float32), np.float32(recorded)
-
-
-@pytest.mark.parametrize('seed,scale,shift', [(0, 1.0e5, 0.0), (1, 3.0e6, 0.0), (2, 50.0, 0.0), (3, 1.0e5, -4.0e5), (4, 1.0e5, 2.0e5)])
-def test_threshold_in_mma_filter_never_loses_an_item_above_its_recorded_threshold(seed, scale, shift):
-    rng = np.random.default_rng(seed)
-    scores = (rng.standard_normal(6000) * scale + shift).astype(np.float32)       # upper bounds s_hat of one user's items
-    for err_rng in (None, np.random.default_rng(seed + 100)):
-        items, vals, recorded = _simulate_row(scores, rng=err_rng)
-        kept = np.zeros(len(scores), dtype=bool)
-        kept[items] = True
-        # the proof obligation of igcn_tc_finalize: every dropped item's bound is <= the recorded threshold
-        assert (scores[~kept] <= recorded).all(), float(scores[~kept].max() - recorded)
-        # stored bounds are upper bounds of the scores they stand for, and not wastefully above them
-        assert (vals >= scores[items]).all()
-        assert (vals <= scores[items] + np.abs(scores[items]) * 1e-4 + np.abs(recorded) * 1e-4 + 1e-3).all()
-        if (scores >= 0).sum() >= 32:
-            assert kept.sum() >= 32 and len(items) <= 96
-            # the 20 best are always among the candidates (what the path exists for)
-            assert kept[np.argsort(-scores)[:20]].all()
