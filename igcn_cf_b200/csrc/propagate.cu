@@ -24,6 +24,8 @@
 // D = 64 kernel -- bit-identical column slices.
 //
 // Everything here is HBM/L2-bound gather work; there is no tensor-core shape to it.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace igcn {
@@ -100,7 +102,7 @@ __device__ __forceinline__ void gather_range(const PropArgs &a, RowVec<LPR, V, E
     const int D = a.D;
     const float *__restrict__ Tl = a.X + lane * 4;
     constexpr bool COLS = (MODE == MODE_SPMM && DROP == 2);
-    constexpr int Q0 = (V == 1) ? 8 : 4;                // neighbour rows in flight per group (8 x 16 B per lane) ...
+    constexpr int Q0 = 8 / V;                           // neighbour rows in flight per group (8 x 16 B per lane) ...
     constexpr int Q = Q0 < LPR ? Q0 : LPR;              // ... but never more than one batch of column ids
     const int gshift = (threadIdx.x & 31) & ~(LPR - 1);
 
@@ -411,8 +413,11 @@ template <int MODE, int DROP>
 static int launch_lanes(const PropArgs &a, cudaStream_t st) {
     if (a.g.n_chunks + ((MODE == MODE_SPMM && DROP == 1) ? a.max_list : a.g.n_rows) == 0) return 0;
     const int D = a.D;
+    // D = 64: 8 lanes x 2 vectors per row.  (4 lanes x 4 vectors -- 8 rows per warp like the D = 32 shape below -- was
+    // measured: 16 accumulator + 32 in-flight registers per lane spill at the 64-register budget, Yelp-shaped step
+    // 0.406 -> 0.624 ms.)
     if (D == 64) launch_one<8, 2, true, MODE, DROP>(a, st);
-    else if (D == 32) launch_one<8, 1, true, MODE, DROP>(a, st);
+    else if (D == 32) launch_one<4, 2, true, MODE, DROP>(a, st);      // 8 rows per warp (2-GPU column shards: Amazon-shaped step 0.736 -> 0.626 ms against 8 lanes x 1 vector)
     else if (D == 16) launch_one<4, 1, true, MODE, DROP>(a, st);
     else if (D == 8) launch_one<2, 1, true, MODE, DROP>(a, st);
     else if (D == 128) launch_one<16, 2, true, MODE, DROP>(a, st);
