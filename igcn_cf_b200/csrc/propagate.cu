@@ -322,29 +322,52 @@ __global__ void __launch_bounds__(kThreads, 4) prop_kernel(const __grid_constant
 #pragma unroll
         for (int i = 0; i < V; ++i)
             if (Vec::on(i, lane, D)) st4(a.g.partial + (int64_t)ch * D + (i * LPR + lane) * 4, acc.v[i]);
-        __threadfence();
-        __syncwarp(gmask);
-        int old = 0;
-        if (lane == 0) old = atomicAdd(a.g.counters + first, 1);
-        old = __shfl_sync(gmask, old, 0, LPR);
-        if (old != count - 1) return;
-        __threadfence();
-        if (lane == 0) a.g.counters[first] = 0;   // self-reset for the next launch
-        acc.zero();
-        for (int k0 = 0; k0 < count; k0 += 4) {           // 4 partials in flight, added in chunk order
-            float4 pp[4][V];
+        // Two-level combine in a fixed order.  Chunks are grouped by kSuper = 32: the last chunk of a group to finish
+        // adds the group's partials in chunk order; a row of more than 32 chunks then adds its group sums in group
+        // order (again by whoever finishes last).  A single sequential pass over all partials -- 380 of them for the
+        // most popular item of the Amazon shape, four loads in flight -- was a 30 us serial tail, invisible behind a
+        // 100 us full-width layer but THE floor of the narrow layers of the column-sharded step.
+        constexpr int kSuper = 32;
+        auto last_to_arrive = [&](int32_t *counter, int expected) -> bool {
+            __threadfence();
+            __syncwarp(gmask);
+            int old = 0;
+            if (lane == 0) old = atomicAdd(counter, 1);
+            old = __shfl_sync(gmask, old, 0, LPR);
+            if (old != expected - 1) return false;
+            __threadfence();
+            if (lane == 0) *counter = 0;              // self-reset for the next launch
+            return true;
+        };
+        auto ordered_sum = [&](int64_t slot0, int n, int stride) {      // acc = p[slot0] + p[slot0 + stride] + ... in order
+            acc.zero();
+            for (int k0 = 0; k0 < n; k0 += 4) {           // 4 partials in flight, added in order
+                float4 pp[4][V];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+                for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int i = 0; i < V; ++i)
-                    pp[q][i] = (k0 + q < count && Vec::on(i, lane, D))
-                                   ? __ldcg(reinterpret_cast<const float4 *>(a.g.partial + (int64_t)(first + k0 + q) * D + (i * LPR + lane) * 4))
-                                   : f4zero();
+                    for (int i = 0; i < V; ++i)
+                        pp[q][i] = (k0 + q < n && Vec::on(i, lane, D))
+                                       ? __ldcg(reinterpret_cast<const float4 *>(a.g.partial + (slot0 + (int64_t)(k0 + q) * stride) * D + (i * LPR + lane) * 4))
+                                       : f4zero();
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (k0 + q < count)
+                for (int q = 0; q < 4; ++q)
+                    if (k0 + q < n)
 #pragma unroll
-                    for (int i = 0; i < V; ++i) add4(acc.v[i], pp[q][i]);
+                        for (int i = 0; i < V; ++i) add4(acc.v[i], pp[q][i]);
+            }
+        };
+        const int g0 = first + (ch - first) / kSuper * kSuper;          // first chunk of this chunk's group
+        const int g_count = min(kSuper, first + count - g0);
+        if (!last_to_arrive(a.g.counters + g0, g_count)) return;
+        ordered_sum(g0, g_count, 1);
+        if (count > kSuper) {
+#pragma unroll
+            for (int i = 0; i < V; ++i)                    // the group's sum replaces its first partial (all of them are consumed)
+                if (Vec::on(i, lane, D)) st4(a.g.partial + (int64_t)g0 * D + (i * LPR + lane) * 4, acc.v[i]);
+            const int n_groups = (count + kSuper - 1) / kSuper;
+            if (!last_to_arrive(a.g.counters + a.g.n_chunks + first, n_groups)) return;
+            ordered_sum(first, n_groups, kSuper);
         }
         finish_row<LPR, V, EXACT, MODE, DROP>(a, r, acc, lane, seed);
         return;

@@ -9,7 +9,7 @@ the kernels use (include/igcn_b200.h, `igcn_csr`).  They are built ONCE per gene
 `get_rep` as the reference's `dgl.graph(...)` is (model.py:99-100, 439-440).
 
 HBM layout: rowptr[N+1] int64 | col[nnz] int32 | val[nnz] fp32 | chunk plan (5 small int arrays)
-| partial[n_chunks, D] fp32 | counters[n_chunks] int32.  The INMO layer reuses rowptr/col (its
+| partial[n_chunks, D] fp32 | counters[2 * n_chunks] int32.  The INMO layer reuses rowptr/col (its
 pattern is the adjacency pattern filtered by template membership) and adds
 tmpl[N] int32 (only when some node is not a template) and rowscale[N] fp32.
 """
@@ -90,7 +90,7 @@ class CsrDevice:
         plan = chunk_plan(self.rowptr_host, threshold, chunk)
         self.n_chunks = int(len(plan[0]))
         self._plan = [torch.from_numpy(np.ascontiguousarray(a)).to(self.device) for a in plan]
-        self.counters = torch.zeros(max(1, self.n_chunks), dtype=torch.int32, device=self.device)
+        self.counters = torch.zeros(max(1, 2 * self.n_chunks), dtype=torch.int32, device=self.device)   # chunk groups + rows
         # visiting order: longest rows first, ties by row id (stable) -> rows sharing a warp are alike.
         # (Keeping the two halves of the bipartite graph apart inside each row class -- item rows, then user rows, so
         # that the cold user lines do not flush the popular item lines out of L1 -- was measured in round 2:

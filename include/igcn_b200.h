@@ -36,8 +36,10 @@ const char *igcn_last_error(void);
 /* CSR adjacency of one contiguous block of node rows, plus the long-row split plan that keeps
  * power-law rows from serialising on one half-warp.  Rows with more than `long_threshold`
  * non-zeros are cut into chunks (chunk_* arrays, one entry per chunk); each chunk's partial sum
- * goes to partial[chunk][D] and the last chunk to finish (counters[], self-resetting) adds the
- * partials IN CHUNK ORDER, so the result does not depend on scheduling or on the GPU count.
+ * goes to partial[chunk][D]; chunks are grouped by 32: the last chunk of a group to finish (counters[],
+ * self-resetting) adds the group's partials IN CHUNK ORDER, and for rows of more than 32 chunks the last
+ * group to finish adds the group sums IN GROUP ORDER, so the result does not depend on scheduling, on
+ * the GPU count or on the table width.
  * Built by igcn_cf_b200/graph.py from the same data LightGCN.generate_graph builds
  * (model.py:85-94): val[e] = fl32(d_r^-1/2 * d_c^-1/2), columns sorted inside each row. */
 typedef struct igcn_csr {
@@ -55,7 +57,7 @@ typedef struct igcn_csr {
     const int32_t *chunk_first; /* [n_chunks] index of the row's first chunk           */
     const int32_t *chunk_count; /* [n_chunks] number of chunks of the row              */
     float *partial;             /* [n_chunks, D] scratch                               */
-    int32_t *counters;          /* [n_chunks] scratch, must be zero before first use   */
+    int32_t *counters;          /* [2 * n_chunks] scratch, must be zero before first use */
     const int32_t *row_order;   /* [n_rows] visiting order (degree-descending) or NULL */
     int32_t n_long_rows;        /* leading entries of row_order with nnz > long_threshold          */
     int32_t n_medium_rows;      /* following entries with IGCN_MEDIUM_NNZ < nnz <= long_threshold:  */
