@@ -15,9 +15,10 @@ BASELINE.json's metric: full-ranking users/s (also at the top level as eval_user
 The default workload is the largest single-GPU configuration of BASELINE.json (configs[2], IGCN on the Amazon-book
 shape); configs[0] (Gowalla-shaped IGCN, the north-star target) and configs[1] (Yelp-shaped LightGCN) are measured in
 the same run and reported as sub-blocks under `configs`, each with its own ms_per_step, rooflines, eval and CPU sample.
-At N > 1 every workload's step is timed BOTH replicated and with the propagation rows sharded over the ranks
-(ms_per_step_replicated / ms_per_step_row_sharded; `value` is the better one, `step_mode` says which) and the sharded
-path is checked bit for bit against the replicated one (`shard_parity`).
+At N > 1 every workload's step is timed in all three modes -- replicated, propagation rows sharded over the ranks,
+embedding columns sharded over the ranks (ms_per_step_replicated / ms_per_step_row_sharded / ms_per_step_dim_sharded;
+`value` is the best one, `step_mode` says which) -- and both sharded paths are checked bit for bit against the
+replicated one (`shard_parity`).
 
 `roofline` describes the dominant kernel (the CSR SpMM) against the measured HBM peak, `eval.roofline` the tcgen05
 scoring kernel against the measured tensor peak (algorithmic flops 2 U I 64); `cpu_baseline` times the CPU oracle port of
