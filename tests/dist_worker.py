@@ -137,6 +137,17 @@ def check_gpu(rank, world):
         r2, m2 = dt.eval('val')
         r3, m3 = trainers[1].eval('val')
         assert r2 == r3 and m2 == m3, (r2, r3)
+        # the default ('auto') picks the column mode on paper-sized graphs and trains through the public epoch loop
+        torch.manual_seed(5)
+        am = get_model({k: v for k, v in models[1].config.items() if k not in ('dataset', 'shard')}, ds)
+        at = get_trainer(tcfg, ds, am)
+        assert am._dim_shard == (rank, world) and not am._rows_sharded() and at.step.dims == (rank, world)
+        am.train()
+        loss_auto = at.train_one_epoch()
+        assert np.isfinite(loss_auto) and not at.step._dirty                 # the epoch ends with the parameter all-gather
+        gathered = [None] * world
+        dist.all_gather_object(gathered, float(am.embedding.weight.detach().double().sum().item()))
+        assert all(g == gathered[0] for g in gathered), gathered            # every rank holds the same full-width weights
         peers.check()
         if rank == 0:
             print('dist_worker: %s ok, world %d, %d barriers, %s' % (kind, world, peers.n_barriers, r0))
