@@ -286,6 +286,49 @@ class IGCNRep(torch.autograd.Function):
         return (d_emb if prop.shard is None else d_emb.clone()), None, None
 
 
+class ColumnRep:
+    """Evaluation-mode get_rep of a column-sharded model (model_config['shard'] = 'dims' / 'auto'): every rank runs the
+    template layer and the L propagation layers on ITS embedding_size / world columns only -- the propagation is linear
+    and acts on each column independently, so nothing is exchanged between layers -- then stores its slice of the
+    layer mean into the column range of every rank's full-width copy over NVLink (igcn_peer_push_cols) and one
+    device-side barrier closes the all-gather.  Same kernels, same per-row summation order as the full-width
+    propagation: bit-identical to one GPU (bench.py `shard_parity`, tests/dist_worker.py)."""
+
+    def __init__(self, model):
+        rank, world = model._dim_shard
+        self.peers = model._peers
+        self.world, self.D_full = world, model.embedding_size
+        self.D = self.D_full // world
+        self.col0 = rank * self.D
+        self.n = model.n_users + model.n_items
+        self.rows = model.embedding.weight.shape[0]
+        dev = model.embedding.weight.device
+        self.prop = Propagator(self.n, self.D, model.n_layers, dev, None)
+        self.emb_s = torch.empty((self.rows, self.D), dtype=torch.float32, device=dev)
+        self.full = self.peers.alloc((self.n, self.D_full), torch.float32)
+        self.key = self.key_of(model)
+
+    @staticmethod
+    def key_of(model):
+        return (model.n_users + model.n_items, model.embedding.weight.shape[0], model.embedding_size, model.n_layers)
+
+    def run(self, model):
+        """Collective: every rank calls it for the same parameters and graph."""
+        self.emb_s.copy_(model.embedding.weight.data[:, self.col0:self.col0 + self.D])
+        feat = getattr(model, 'feat_mat', None)
+        if feat is None:
+            x0 = self.emb_s
+        else:
+            x0 = self.prop.x0_buffer()
+            inmo_forward(feat, self.emb_s, x0, None, self.D)
+        rep = self.prop.forward(model.norm_adj, x0)
+        self.peers.barrier()                             # every rank is done reading the copy of the previous evaluation
+        call('igcn_peer_push_cols', self.full.peer_array(0), self.world, ptr(rep), self.n, self.D, self.D_full, self.col0,
+             stream_ptr())
+        self.peers.barrier()
+        return self.full.tensor.clone()                  # callers keep the representation; the symmetric copy is reused
+
+
 # --------------------------------------------------------------------------- fused training step
 class TrainStep:
     """One BPR training step with no autograd tape (trainer.py:233-247 and 296-318).

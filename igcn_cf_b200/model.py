@@ -63,7 +63,7 @@ class BasicModel(nn.Module):
         #           parameters, the optimizer state and every layer buffer.  The propagation is linear and acts on each
         #           column independently, so no layer embedding ever crosses NVLink; the only exchange of a step is 20-28
         #           bytes per triple (partial dot products), and the parameters are all-gathered once per epoch /
-        #           before an evaluation.  Bit-identical to one GPU.  Eval users sharded, eval propagation replicated.
+        #           before an evaluation.  Bit-identical to one GPU.  Eval users sharded, eval propagation column-sharded too.
         #   'auto'  (default) eval users always sharded; rows sharded only when every rank keeps at least
         #           SHARD_MIN_NNZ_PER_RANK non-zeros (graphs whose layer tables live in HBM: the scale-out class, where
         #           one rank's propagation is tens of milliseconds); otherwise columns when 2, 4 or 8 ranks divide the
@@ -181,6 +181,16 @@ class _GraphModel(BasicModel):
             raise RuntimeError('norm_adj has %d rows but the model has %d nodes; regenerate the graph'
                                % (self.norm_adj.shape[0], n))
 
+    _col_rep = None
+
+    def _column_rep(self):
+        """Column-sharded models evaluate column-sharded too (engine.ColumnRep): each rank propagates its
+        embedding_size / world columns and the slices are all-gathered over NVLink.  Collective."""
+        c = self._col_rep
+        if c is None or c.key != engine.ColumnRep.key_of(self):
+            c = self._col_rep = engine.ColumnRep(self)
+        return c.run(self)
+
     def _cached_rep(self, compute):
         """Eval mode: the representation is a pure function of parameters and graph (model.py:264-265
         makes dropout the identity), so compute it once."""
@@ -188,7 +198,8 @@ class _GraphModel(BasicModel):
             return compute()
         key = self._cache_key()
         if self._rep_cache is None or self._rep_cache[0] != key:
-            self._rep_cache = (key, compute())
+            sharded = self._dim_shard is not None and (self.n_layers > 0 or hasattr(self, 'feat_mat'))
+            self._rep_cache = (key, self._column_rep() if sharded else compute())
         return self._rep_cache[1]
 
     def load(self, path):

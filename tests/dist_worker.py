@@ -134,6 +134,12 @@ def check_gpu(rank, world):
         assert torch.equal(dm.embedding.weight, single.embedding.weight), kind + ' weights differ (dims)'
         if kind == 'IGCN':
             assert torch.equal(dm.w, single.w)
+        # evaluation-mode representation of the column-sharded model: propagated per column slice, all-gathered
+        dm.eval(); single.eval()
+        with torch.no_grad():
+            rep_d = dm.get_rep()
+            assert dm._col_rep is not None and dm._col_rep.D == 64 // world
+            assert torch.equal(rep_d, single.get_rep()), kind + ' column-sharded eval rep differs'
         r2, m2 = dt.eval('val')
         r3, m3 = trainers[1].eval('val')
         assert r2 == r3 and m2 == m3, (r2, r3)
