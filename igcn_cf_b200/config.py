@@ -5,19 +5,23 @@ keeps its index here (reference config.py:6-72, 81-147, 156-222):
 
     0 MF   1 LightGCN   2 IGCN   3 ItemKNN   4 NGCF   5 MultiVAE   6 IMF   7 IMCGAE   8 IDCF_LGCN   9 NeuMF
 
-Slots 0, 1, 2 and 6 are the models on the B200 hot path and carry the reference's hyper-parameters per dataset.
-The other slots name baseline models that are out of scope; they are present so that the positions
-stay right, and `get_model` answers them with a clear error instead of an IndexError.
+Slots 0, 1, 2 and 6 are the models on the B200 hot path; slots 4 and 7 (NGCF, IMCGAE) are the sibling models that
+reuse its propagation and ranking kernels (igcn_cf_b200/siblings.py).  All six carry the reference's hyper-parameters
+per dataset.  The other slots name baseline models that are out of scope; they are present so that
+the positions stay right, and `get_model` answers them with a clear error instead of an IndexError.
 """
 
-OUT_OF_SCOPE = ('ItemKNN', 'NGCF', 'MultiVAE', 'IMCGAE', 'IDCF_LGCN', 'NeuMF')
+OUT_OF_SCOPE = ('ItemKNN', 'MultiVAE', 'IDCF_LGCN', 'NeuMF')
 _SLOTS = ('MF', 'LightGCN', 'IGCN', 'ItemKNN', 'NGCF', 'MultiVAE', 'IMF', 'IMCGAE', 'IDCF_LGCN', 'NeuMF')
 
-# per dataset: MF (lr, l2), LightGCN l2, IGCN dropout, IMF (dropout, aux_reg)
+# per dataset: MF (lr, l2), LightGCN l2, IGCN dropout, IMF (dropout, aux_reg), NGCF (dropout, l2), IMCGAE dropout
 _HYPER = {
-    'gowalla': {'path': 'data/Gowalla/time', 'mf': (1.e-4, 1.e-3), 'lgcn_l2': 1.e-4, 'igcn_dropout': 0.3, 'imf': (0.1, 0.1)},
-    'yelp': {'path': 'data/Yelp/time', 'mf': (1.e-3, 1.e-3), 'lgcn_l2': 1.e-4, 'igcn_dropout': 0.3, 'imf': (0.5, 0.01)},
-    'amazon': {'path': 'data/Amazon/time', 'mf': (1.e-3, 1.e-4), 'lgcn_l2': 1.e-5, 'igcn_dropout': 0.0, 'imf': (0.3, 0.1)},
+    'gowalla': {'path': 'data/Gowalla/time', 'mf': (1.e-4, 1.e-3), 'lgcn_l2': 1.e-4, 'igcn_dropout': 0.3, 'imf': (0.1, 0.1),
+                'ngcf': (0.1, 1.e-3), 'imcgae': 0.3},
+    'yelp': {'path': 'data/Yelp/time', 'mf': (1.e-3, 1.e-3), 'lgcn_l2': 1.e-4, 'igcn_dropout': 0.3, 'imf': (0.5, 0.01),
+             'ngcf': (0.3, 1.e-3), 'imcgae': 0.3},
+    'amazon': {'path': 'data/Amazon/time', 'mf': (1.e-3, 1.e-4), 'lgcn_l2': 1.e-5, 'igcn_dropout': 0.0, 'imf': (0.3, 0.1),
+               'ngcf': (0.3, 1.e-4), 'imcgae': 0.9},
 }
 
 
@@ -36,6 +40,8 @@ def _table(device, dataset_config, h):
                  trainer('IGCNTrainer', l2_reg=0., aux_reg=0.01)),
         'IMF': (dict(emb, name='IMF', n_layers=0, dropout=h['imf'][0], feature_ratio=1.),
                 trainer('IGCNTrainer', l2_reg=1.e-5, aux_reg=h['imf'][1])),
+        'NGCF': (dict(emb, name='NGCF', layer_sizes=[64, 64, 64], dropout=h['ngcf'][0]), trainer('BPRTrainer', l2_reg=h['ngcf'][1])),
+        'IMCGAE': (dict(emb, name='IMCGAE', n_layers=3, dropout=h['imcgae']), trainer('BPRTrainer', l2_reg=0.)),
     }
     out = []
     for name in _SLOTS:

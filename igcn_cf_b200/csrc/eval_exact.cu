@@ -84,13 +84,17 @@ struct ExactArgs {
     uint64_t *split_keys;        // [split_cap, n_item_splits, k] partial top-k keys, merged by exact_merge_kernel
 };
 
-// smem: Us[BM][D+4] | Is[BN][min(D,64)+4] | keys[BM][CAP] (u64) | cnt[BM] | thr[BM]
+// Dimensions of the item tile held in shared memory at a time: 64, or 32 for the wide representations of the sibling
+// models (IMCGAE 192, NGCF 256 columns) so that the user tile [BM][D+4] still fits beside the candidate keys.
+__host__ __device__ inline int exact_kc(int D) { return D > 128 ? 32 : (D < 64 ? D : 64); }
+
+// smem: Us[BM][D+4] | Is[BN][exact_kc(D)+4] | keys[BM][CAP] (u64) | cnt[BM] | thr[BM]
 __global__ void __launch_bounds__(EX_THREADS, 1) score_topk_exact_kernel(const __grid_constant__ ExactArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = a.D, DP = D + 4;
     float *Us = reinterpret_cast<float *>(smem_raw);
     float *Is = Us + BM * DP;
-    uint64_t *keys = reinterpret_cast<uint64_t *>(Is + BN * (min(D, 64) + 4));
+    uint64_t *keys = reinterpret_cast<uint64_t *>(Is + BN * (exact_kc(D) + 4));
     int *cnt = reinterpret_cast<int *>(keys + BM * CAP);
     float *thr = reinterpret_cast<float *>(cnt + BM);
     __shared__ int need_compact;
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) score_topk_exact_kernel(const _
     const int64_t j_end = min(a.n_items, a.item_hi);
     const int64_t n_tiles = (max(j_end, j_first) - j_first + BN - 1) / BN, per = (n_tiles + n_splits - 1) / n_splits;
     const int64_t j_begin = j_first + split * per * BN, j_stop = min(j_end, j_begin + per * BN);
-    const int KC = min(D, 64), KCP = KC + 4;      // item tile holds at most 64 dims at a time
+    const int KC = exact_kc(D), KCP = KC + 4;     // item tile holds at most 64 dims at a time
     for (int64_t j0 = j_begin; j0 < j_stop; j0 += BN) {
         float acc[4][8];
 #pragma unroll
@@ -373,7 +377,7 @@ extern "C" int igcn_score_topk_exact(const float *rep, const int64_t *user_ids, 
                                      const int32_t *n_eval_dev, int32_t n_item_splits, uint64_t *split_keys,
                                      int64_t split_cap, void *stream) {
     IGCN_CHECK_ARG(rep && user_ids && out_items && out_scores, "null pointer");
-    IGCN_CHECK_ARG(D > 0 && D <= 128 && !(D & 3), "embedding size unsupported (need D % 4 == 0, D <= 128)");
+    IGCN_CHECK_ARG(D > 0 && D <= 256 && !(D & 3), "embedding size unsupported (need D % 4 == 0, D <= 256)");
     IGCN_CHECK_ARG(k > 0 && k <= CAP - BN, "k must be in [1, 128]");
     IGCN_CHECK_ARG(!mask_ptr || mask_items, "mask_ptr without mask_items");
     IGCN_CHECK_ARG(n_items > 0 && n_items < 0x7fffffff, "n_items out of range");
@@ -382,7 +386,7 @@ extern "C" int igcn_score_topk_exact(const float *rep, const int64_t *user_ids, 
     IGCN_CHECK_ARG(n_item_splits == 1 || (split_keys && split_cap > 0), "item splitting needs the split_keys scratch");
     ExactArgs a{rep, user_ids, n_eval, item_row0, n_items, D, mask_ptr, mask_items, item_lo, item_hi, banned_bits, k,
                 out_items, out_scores, out_rows, n_eval_dev, n_item_splits, split_cap, split_keys};
-    const size_t smem = ((size_t)BM * (D + 4) + (size_t)BN * ((D < 64 ? D : 64) + 4)) * sizeof(float) + (size_t)BM * CAP * sizeof(uint64_t) + BM * 8;
+    const size_t smem = ((size_t)BM * (D + 4) + (size_t)BN * (exact_kc(D) + 4)) * sizeof(float) + (size_t)BM * CAP * sizeof(uint64_t) + BM * 8;
     cudaError_t e = cudaFuncSetAttribute(score_topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("igcn_score_topk_exact: %s", cudaGetErrorString(e)); return (int)e; }
     const int64_t blocks = (n_eval + BM - 1) / BM;

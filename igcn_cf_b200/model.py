@@ -32,7 +32,7 @@ def get_model(config, dataset):
     cls = getattr(sys.modules[__name__], config['name'], None)
     if cls is None or config.get('out_of_scope'):
         raise NotImplementedError('model %r is a baseline outside the B200 hot path (SURVEY.md 2.1); implemented: '
-                                  'LightGCN, IGCN, IMF, MF, Popularity' % config['name'])
+                                  'LightGCN, IGCN, IMF, MF, NGCF, IMCGAE, Popularity' % config['name'])
     return cls(config)
 
 
@@ -577,3 +577,6 @@ class IMF(IGCN):
     def __init__(self, model_config):
         super().__init__(model_config)
         self.n_layers = 0
+
+
+from .siblings import IMCGAE, NGCF  # noqa: E402,F401  (get_model dispatches on this module's namespace; siblings imports _GraphModel)

@@ -21,6 +21,7 @@ import time
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 from torch.utils.data import DataLoader
 
 from . import dist, engine
@@ -445,6 +446,57 @@ class BasicTrainer:
             print('{:s} result. {:s}'.format(title, results))
 
 
+class AutogradStep:
+    """One BPR step of BPRTrainer.train_one_epoch (trainer.py:233-247) for the sibling models that have no fused step
+    (model.fused_step is False: NGCF, IMCGAE): the model's own bpr_forward under autograd -- every propagation hop is
+    an autograd node on igcn_spmm (siblings.SpMM) --, the loss as the reference writes it, igcn_adam through
+    Adam.step.  Triples come from the device sampler (igcn_sample_triples, same counter-based stream as the fused
+    step) unless the caller passes them.  Same interface as engine.TrainStep as far as the epoch loop uses it; the
+    running loss stays on the device (one read per epoch instead of the reference's loss.item() per step)."""
+
+    dims = None
+
+    def __init__(self, model, opt, l2_reg, batch_size=2048, seed=0):
+        self.model, self.opt, self.l2_reg = model, opt, float(l2_reg)
+        self.B, self.seed = int(batch_size), int(seed)
+        dev = model.embedding.weight.device
+        self.triples = torch.zeros((self.B, 3), dtype=torch.int64, device=dev)
+        self.acc = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+
+    def run(self, triples=None, aux_triples=None, drop='auto', batch=None):
+        m = self.model
+        if triples is None:
+            B = self.B if batch is None else int(batch)
+            rowptr, col = m.norm_adj.sampler_csr()
+            call('igcn_sample_triples', ptr(rowptr), ptr(col), m.n_users, m.n_users, m.n_items, B, self.seed,
+                 self.opt.t + 1, None, ptr(self.triples), stream_ptr())
+            triples = self.triples[:B]
+        users, pos_items, neg_items = triples[:, 0], triples[:, 1], triples[:, 2]
+        users_r, pos_r, neg_r, l2_norm_sq = m.bpr_forward(users, pos_items, neg_items)
+        pos_scores = torch.sum(users_r * pos_r, dim=1)
+        neg_scores = torch.sum(users_r * neg_r, dim=1)
+        loss = F.softplus(neg_scores - pos_scores).mean() + self.l2_reg * l2_norm_sq.mean()
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+        self.loss = loss.detach()
+        n = triples.shape[0]
+        self.acc[0] += self.loss.double() * n
+        self.acc[1] += n
+        return self.loss
+
+    def sync_params(self):
+        pass
+
+    def reset_meter(self):
+        self.acc.zero_()
+
+    def meter_avg(self):
+        s, n = self.acc.tolist()
+        return s / max(n, 1.)
+
+
 class _FusedBPRMixin:
     """Epoch loop shared by BPRTrainer and IGCNTrainer on top of engine.TrainStep."""
 
@@ -453,6 +505,9 @@ class _FusedBPRMixin:
         self.batch_size = trainer_config['batch_size']
         self.sampler = trainer_config.get('sampler', 'device')
         self.initialize_optimizer()
+        if not getattr(self.model, 'fused_step', True):
+            self.step = AutogradStep(self.model, self.opt, self.l2_reg, self.batch_size, trainer_config.get('seed', 0))
+            return
         self.step = engine.TrainStep(self.model, self.opt, self.l2_reg, aux_reg=aux_reg, batch_size=self.batch_size,
                                      seed=trainer_config.get('seed', 0),
                                      use_graph=trainer_config.get('cuda_graph', True))

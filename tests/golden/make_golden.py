@@ -19,6 +19,8 @@ Outputs (tests/golden/):
   tiny_igcn_ratio.npz      feature_ratio 0.5 ('sort' ranking): maps, feat, rep
   tiny_siblings.npz        IMF (one epoch, evals) and Popularity (evals)
   tiny_mf.npz              MF (model.py:52-72): predict, one epoch, evals      (python tests/golden/make_golden.py mf)
+  tiny_ngcf_imcgae.npz     NGCF (model.py:232-299) and IMCGAE (model.py:546-585): graph, rep, one fwd/bwd, one epoch
+                           with every dropout mask recorded, evals             (python tests/golden/make_golden.py wide)
 """
 import os
 import sys
@@ -46,8 +48,9 @@ class Recorder:
     """Wraps torch.rand and BasicDataset.__getitem__ (no reference code is changed)."""
 
     def __init__(self):
-        self.rands, self.main, self.aux = [], [], []
+        self.rands, self.main, self.aux, self.dense = [], [], [], []
         self._rand = torch.rand
+        self._dropout = torch.nn.functional.dropout
         self._getitem = R_dataset.BasicDataset.__getitem__
 
     def __enter__(self):
@@ -63,12 +66,21 @@ class Recorder:
             (rec.aux if isinstance(ds, R_dataset.AuxiliaryDataset) else rec.main).append(out[0].copy())
             return out
 
+        def dropout(inp, p=0.5, training=True, inplace=False):
+            # F.dropout (NGCF model.py:287, IMCGAE model.py:574): the keep mask is what survives, the scale is 1/(1-p)
+            out = rec._dropout(inp, p=p, training=training, inplace=False)
+            if training:
+                rec.dense.append(((out != 0) | (inp == 0)).detach().numpy().copy())
+            return out
+
         torch.rand = rand
+        torch.nn.functional.dropout = dropout
         R_dataset.BasicDataset.__getitem__ = getitem
         return self
 
     def __exit__(self, *exc):
         torch.rand = self._rand
+        torch.nn.functional.dropout = self._dropout
         R_dataset.BasicDataset.__getitem__ = self._getitem
 
 
@@ -409,12 +421,84 @@ def golden_mf(ds, out_path):
     print('wrote', out_path, len(out), 'arrays')
 
 
+def golden_wide(ds, out_path):
+    """NGCF (model.py:232-299; Gowalla hyper-parameters config.py:30-34) and IMCGAE (model.py:546-585; config.py:51-55):
+    the sibling models whose propagation is the same gspmm.  Every random draw of a train-mode forward pass is
+    recorded: torch.rand of NGCF.dropout_sp_mat and the keep mask of every F.dropout call (bit-packed)."""
+    out = {}
+    cfgs = {'ngcf': ({'name': 'NGCF', 'embedding_size': 64, 'layer_sizes': [64, 64, 64], 'device': DEV, 'dropout': 0.1}, 1.e-3),
+            'imcgae': ({'name': 'IMCGAE', 'embedding_size': 64, 'n_layers': 3, 'device': DEV, 'dropout': 0.3}, 0.)}
+    for px, (mcfg, l2) in cfgs.items():
+        tcfg = {'name': 'BPRTrainer', 'optimizer': 'Adam', 'lr': 1.e-3, 'l2_reg': l2, 'device': DEV, 'n_epochs': 1,
+                'batch_size': 2048, 'dataloader_num_workers': 0, 'test_batch_size': 512, 'topks': [5, 20]}
+        R_utils.set_seed(SEED)
+        model = R_model.get_model(mcfg, ds)
+        trainer = R_trainer.get_trainer(tcfg, ds, model)
+        names = [k for k, _ in model.named_parameters()]
+        out[px + '_param_names'] = np.array(names)
+        for k, v in model.named_parameters():
+            out['%s_p0_%s' % (px, k)] = v.detach().numpy().copy()
+        if px == 'ngcf':
+            out['ngcf_adj_idx'], out['ngcf_adj_val'] = sparse_parts(model.norm_adj)
+        users = torch.arange(0, 64, dtype=torch.int64)
+        model.eval()
+        with torch.no_grad():
+            out[px + '_rep0_eval_every5'] = model.get_rep().numpy()[::5].copy()      # every 5th node row (fixture size)
+            out[px + '_scores0'] = model.predict(users).numpy().copy()
+
+        def masks(rec, key):
+            for s, r in enumerate(rec.rands):
+                out['%s_%s_rand_%d' % (px, key, s)] = r
+            for s, m in enumerate(rec.dense):
+                out['%s_%s_dense_%d' % (px, key, s)] = np.packbits(m.reshape(-1))
+                out['%s_%s_dense_%d_shape' % (px, key, s)] = np.array(m.shape, dtype=np.int64)
+            out['%s_%s_n_rand' % (px, key)] = np.int64(len(rec.rands))
+            out['%s_%s_n_dense' % (px, key)] = np.int64(len(rec.dense))
+
+        # one train-mode forward/backward on fixed triples (BPRTrainer.train_one_epoch body, trainer.py:236-245)
+        model.train()
+        tri = fixed_triples(ds, 256, SEED + 7)
+        out[px + '_fb_triples'] = tri
+        t = torch.tensor(tri)
+        R_utils.set_seed(SEED + 3)
+        with Recorder() as rec:
+            u_r, p_r, n_r, l2n = model.bpr_forward(t[:, 0], t[:, 1], t[:, 2])
+        masks(rec, 'fb')
+        bpr = torch.nn.functional.softplus((u_r * n_r).sum(1) - (u_r * p_r).sum(1)).mean()
+        loss = bpr + l2 * l2n.mean()
+        model.zero_grad()
+        loss.backward()
+        out[px + '_fb_loss'] = np.float64(loss.item())
+        out[px + '_fb_l2_norm_sq'] = l2n.detach().numpy().copy()
+        for k, v in model.named_parameters():
+            out['%s_fb_grad_%s' % (px, k)] = v.grad.detach().numpy().copy()
+        model.zero_grad()
+
+        # one recorded epoch
+        R_utils.set_seed(SEED + 1)
+        with Recorder() as rec:
+            out[px + '_epoch_loss'] = np.float64(trainer.train_one_epoch())
+        out[px + '_epoch_triples'] = np.stack(rec.main)
+        masks(rec, 'epoch')
+        for k, v in model.named_parameters():
+            out['%s_p1_%s' % (px, k)] = v.detach().numpy().copy()
+        model.eval()
+        with torch.no_grad():
+            out[px + '_rep1_eval'] = model.get_rep().numpy().copy()      # the tie checker recomputes the reference's scores
+        eval_all(trainer, out, px + '_e1')
+    np.savez_compressed(out_path, **out)
+    print('wrote', out_path, len(out), 'arrays')
+
+
 def main():
     split = synth.gen_named('tiny', seed=SEED)
     with tempfile.TemporaryDirectory() as tmp:
         ds = load_dataset(split, tmp, 'tiny')
         if sys.argv[1:] == ['mf']:                      # only the fixture added in round 2 (the others stay as committed)
             golden_mf(ds, os.path.join(HERE, 'tiny_mf.npz'))
+            return
+        if sys.argv[1:] == ['wide']:
+            golden_wide(ds, os.path.join(HERE, 'tiny_ngcf_imcgae.npz'))
             return
         data = {'n_users': np.int64(ds.n_users), 'n_items': np.int64(ds.n_items)}
         for which in ('train', 'val', 'test'):
@@ -426,6 +510,7 @@ def main():
         golden_ratio(ds, os.path.join(HERE, 'tiny_igcn_ratio.npz'))
         golden_siblings(ds, os.path.join(HERE, 'tiny_siblings.npz'))
         golden_mf(ds, os.path.join(HERE, 'tiny_mf.npz'))
+        golden_wide(ds, os.path.join(HERE, 'tiny_ngcf_imcgae.npz'))
 
 
 if __name__ == '__main__':

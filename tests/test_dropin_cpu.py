@@ -43,13 +43,13 @@ def test_config_slots_and_hyperparameters_match_the_reference_table():
     """reference config.py:6-72, 81-147, 156-222: positions and the hot-path hyper-parameters."""
     from igcn_cf_b200 import config as C
     names = ['MF', 'LightGCN', 'IGCN', 'ItemKNN', 'NGCF', 'MultiVAE', 'IMF', 'IMCGAE', 'IDCF_LGCN', 'NeuMF']
-    want = {'gowalla': ((1e-4, 1e-3), 1e-4, 0.3, (0.1, 0.1), 'data/Gowalla/time'),
-            'yelp': ((1e-3, 1e-3), 1e-4, 0.3, (0.5, 0.01), 'data/Yelp/time'),
-            'amazon': ((1e-3, 1e-4), 1e-5, 0.0, (0.3, 0.1), 'data/Amazon/time')}
+    want = {'gowalla': ((1e-4, 1e-3), 1e-4, 0.3, (0.1, 0.1), 'data/Gowalla/time', (0.1, 1e-3), 0.3),
+            'yelp': ((1e-3, 1e-3), 1e-4, 0.3, (0.5, 0.01), 'data/Yelp/time', (0.3, 1e-3), 0.3),
+            'amazon': ((1e-3, 1e-4), 1e-5, 0.0, (0.3, 0.1), 'data/Amazon/time', (0.3, 1e-4), 0.9)}
     for key, fn in (('gowalla', C.get_gowalla_config), ('yelp', C.get_yelp_config), ('amazon', C.get_amazon_config)):
         cfg = fn('cuda')
         assert [m['name'] for _, m, _ in cfg] == names
-        mf, l2, drop, imf, path = want[key]
+        mf, l2, drop, imf, path, ngcf, imcgae = want[key]
         assert all(d == {'name': 'ProcessedDataset', 'path': path, 'device': 'cuda'} for d, _, _ in cfg)
         assert (cfg[0][2]['lr'], cfg[0][2]['l2_reg'], cfg[0][2]['name']) == (mf[0], mf[1], 'BPRTrainer')
         assert cfg[1][1] == {'name': 'LightGCN', 'embedding_size': 64, 'n_layers': 3, 'device': 'cuda'}
@@ -58,7 +58,12 @@ def test_config_slots_and_hyperparameters_match_the_reference_table():
                              'feature_ratio': 1.}
         assert (cfg[2][2]['l2_reg'], cfg[2][2]['aux_reg'], cfg[2][2]['topks']) == (0., 0.01, [20])
         assert (cfg[6][1]['dropout'], cfg[6][2]['aux_reg'], cfg[6][2]['l2_reg'], cfg[6][1]['n_layers']) == (imf[0], imf[1], 1e-5, 0)
-        assert all(cfg[i][1].get('out_of_scope') for i in (3, 4, 5, 7, 8, 9))
+        # reference config.py:30-34, 51-55 (and the Yelp / Amazon counterparts): the sibling models on the same kernels
+        assert cfg[4][1] == {'name': 'NGCF', 'embedding_size': 64, 'layer_sizes': [64, 64, 64], 'device': 'cuda', 'dropout': ngcf[0]}
+        assert (cfg[4][2]['name'], cfg[4][2]['l2_reg'], cfg[4][2]['lr']) == ('BPRTrainer', ngcf[1], 1e-3)
+        assert cfg[7][1] == {'name': 'IMCGAE', 'embedding_size': 64, 'n_layers': 3, 'device': 'cuda', 'dropout': imcgae}
+        assert (cfg[7][2]['name'], cfg[7][2]['l2_reg']) == ('BPRTrainer', 0.)
+        assert all(cfg[i][1].get('out_of_scope') for i in (3, 5, 8, 9))
     from igcn_cf_b200.model import get_model
     with pytest.raises(NotImplementedError, match='outside the B200 hot path'):
         get_model(C.get_gowalla_config('cuda')[3][1], None)

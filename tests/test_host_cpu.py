@@ -251,3 +251,39 @@ def test_device_graph_builder_row_sharded_blocks_match():
         assert fh.block_key() == fd.block_key() and torch.equal(fh.row_sum, fd.row_sum)
         for bh, bd in zip(fh.blocks, fd.blocks):
             assert torch.equal(bh.csr.col, bd.csr.col) and bd.csr.val is None
+
+
+def test_row_normalised_adjacency_of_ngcf_matches_reference(tiny):
+    """siblings.RowNormAdj = normalize(A + I, 'l1') of NGCF.generate_graph (reference model.py:255-261): indices and
+    values bit-equal to the reference's coalesced COO, the stored transpose values are those of A^T, and a restatement
+    of NGCF.get_rep (model.py:277-291, eval mode) on that matrix reproduces the reference's representation."""
+    from igcn_cf_b200.siblings import RowNormAdj
+    g = load_golden('tiny_ngcf_imcgae')
+    dg = graph.DeviceGraph.from_pairs(tiny['n_users'], tiny['n_items'], tiny['pairs'], 'cpu')
+    adj = RowNormAdj(dg)
+    n = tiny['n_users'] + tiny['n_items']
+    assert tuple(adj.shape) == (n, n) and adj._nnz() == g['ngcf_adj_idx'].shape[1]
+    assert np.array_equal(adj.indices().numpy(), g['ngcf_adj_idx'])
+    assert np.array_equal(adj.values().numpy(), g['ngcf_adj_val'])
+    r, c = adj.indices()
+    dense, dense_t = torch.zeros(n, n), torch.zeros(n, n)
+    dense[r, c] = adj.csr_fwd.val
+    dense_t[r, c] = adj.csr_bwd.val
+    assert torch.equal(dense_t, dense.t()) and torch.equal(dense.sum(1), dense.sum(1))
+    assert float((dense.sum(1) - 1).abs().max()) < 1e-6
+    fwd, bwd = adj.pair(torch.arange(adj.nnz) % 3 != 0, 0.25)                      # edge dropout keeps the pair consistent
+    dense[r, c], dense_t[r, c] = fwd.val, bwd.val
+    assert torch.equal(dense_t, dense.t())
+    # restated eval-mode forward on the golden parameters
+    dense[r, c] = adj.csr_fwd.val
+    p = lambda k: torch.from_numpy(g['ngcf_p0_' + k])
+    rep = p('embedding.weight')
+    hops = [rep]
+    for l in range(3):
+        m0 = dense @ rep
+        m1 = rep * m0
+        rep = torch.nn.functional.leaky_relu(m0 @ p('gc_layers.%d.weight' % l).t() + p('gc_layers.%d.bias' % l)
+                                             + m1 @ p('bi_layers.%d.weight' % l).t() + p('bi_layers.%d.bias' % l), 0.2)
+        hops.append(torch.nn.functional.normalize(rep, p=2, dim=1))
+    got = torch.cat(hops, 1).numpy()[::5]
+    assert np.abs(got - g['ngcf_rep0_eval_every5']).max() < 1e-5
