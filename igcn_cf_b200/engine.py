@@ -114,9 +114,20 @@ class Propagator:
             self._add_arrays[key] = arr
         return arr
 
+    def _partials(self, n_rows):
+        """Two [n_rows, dim] ping-pong buffers for the partial results of a column-blocked layer."""
+        key = (n_rows, self.dim)
+        if getattr(self, '_partial_key', None) != key:
+            self._partial_key = key
+            self._partial_bufs = [torch.empty((n_rows, self.dim), dtype=torch.float32, device=self.device) for _ in range(2)]
+        return self._partial_bufs
+
     def spmm(self, adj, x, y, adds=(), rowscale=None, alpha=1.0, rows=None, cols=None):
         """One layer.  rows = (row_list int64, n_list int32[1], max_list): compute the listed rows only
-        (igcn_spmm_rows); cols = bitmap of the columns whose X row is non-zero (igcn_spmm_cols)."""
+        (igcn_spmm_rows); cols = bitmap of the columns whose X row is non-zero (igcn_spmm_cols).
+        Row blocks that carry column blocks (graph.column_blocks: tables far larger than L2) run once per column
+        range, every pass adding the previous partial result; the last pass applies adds / rowscale / alpha and the
+        exchange."""
         sh = self.shard
         pushes = []
         for blk in adj.blocks:
@@ -128,8 +139,22 @@ class Propagator:
                 pushes.append((row0, blk.csr.n_rows))
             else:
                 peers, n_peers = _peer_args(sh, y, off)
-            head = (blk.csr.struct(self.dim), ptr(x), ptr(y) + off, self.dim, self._adds(adds, off), len(adds),
-                    None if rowscale is None else ptr(rowscale) + row0 * 4, float(alpha))
+            rs = None if rowscale is None else ptr(rowscale) + row0 * 4
+            cbs = blk.col_blocks if (rows is None and cols is None) else None
+            if cbs and len(cbs) > 1:
+                bufs = self._partials(blk.csr.n_rows)
+                prev = None
+                for b, csr in enumerate(cbs[:-1]):
+                    dst = bufs[b & 1]
+                    padd = (C.c_void_p * 1)(*([] if prev is None else [prev.data_ptr()]))
+                    call('igcn_spmm', csr.struct(self.dim), ptr(x), ptr(dst), self.dim, padd, 0 if prev is None else 1, None, 1.0,
+                         None, 0, stream_ptr())
+                    prev = dst
+                last = (C.c_void_p * (len(adds) + 1))(prev.data_ptr(), *[t.data_ptr() + off for t in adds])
+                call('igcn_spmm', cbs[-1].struct(self.dim), ptr(x), ptr(y) + off, self.dim, last, len(adds) + 1, rs, float(alpha),
+                     peers, n_peers, stream_ptr())
+                continue
+            head = (blk.csr.struct(self.dim), ptr(x), ptr(y) + off, self.dim, self._adds(adds, off), len(adds), rs, float(alpha))
             if rows is not None:
                 call('igcn_spmm_rows', *head, ptr(rows[0]), ptr(rows[1]), int(rows[2]), row0, peers, n_peers, stream_ptr())
             elif cols is not None:

@@ -158,10 +158,58 @@ class _SparseView:
 
 
 class RowBlock:
-    """Rows [row0, row1) of a graph as their own CSR."""
+    """Rows [row0, row1) of a graph as their own CSR.  col_blocks: the same rows cut into column ranges (one CsrDevice
+    each, ascending), present only when the table these rows gather from is far larger than L2 (column_blocks)."""
 
-    def __init__(self, row0, row1, csr):
+    def __init__(self, row0, row1, csr, col_blocks=None):
         self.row0, self.row1, self.csr = int(row0), int(row1), csr
+        self.col_blocks = col_blocks
+
+
+# Column blocking (BASELINE.json configs[4], the HBM-resident graphs): the item rows of the scale-out graph gather
+# 496 M rows of 256 bytes out of a 2.6 GB user table, far more than L2 holds.  Cutting the columns into ranges whose
+# slice of the table stays in L2 and running the layer once per range, each pass adding to the previous partial result,
+# turns the DRAM gathers into one streaming read of the table plus a read-modify-write of the (10x smaller) output per
+# pass.  Measured (profiles/r02_colblocks.log, one layer, item rows): unblocked 19.4 ms; 26 ranges of 96 MB 17.5 ms,
+# 51 x 48 MB 20.8 ms, 102 x 24 MB 30.8 ms, 204 x 12 MB 50.4 ms = 11 ms + 0.19 ms per pass: with the table slice in L2
+# the gathers still move nnz x 256 B = 127 GB through the L2 -> SM fabric, whose ~11.5 TB/s is the floor (the user
+# rows, which gather from a 256 MB item table, run at 9.3 TB/s without any blocking).  So blocking buys 10 %, not
+# the 3x the DRAM traffic ratio suggests; 96 MB ranges are the default.
+# Ranges are global column intervals of a fixed width, so a row's partial sums are the same whatever the row
+# sharding: results stay GPU-count independent (they differ in the last bits from the unblocked order, which is why
+# blocking is decided by table size alone, never by rank count).
+COL_BLOCK_BYTES = int(os.environ.get('IGCN_COL_BLOCK_MB', 96)) << 20       # slice of the gathered table per pass
+COL_BLOCK_MIN_TABLE = int(os.environ.get('IGCN_COL_BLOCK_MIN_TABLE_MB', 1024)) << 20   # tables below this are not blocked
+
+
+def column_block_width(n_table_rows, row_bytes=256):
+    """Rows of the gathered table per column block, or 0 = do not block."""
+    if COL_BLOCK_BYTES <= 0 or n_table_rows * row_bytes < COL_BLOCK_MIN_TABLE:
+        return 0
+    return max(1, COL_BLOCK_BYTES // row_bytes)
+
+
+def column_blocks(rowptr_host, col, val, col_lo, col_hi, width, n_cols, device):
+    """Cut a CSR (host rowptr int64 [rows + 1], device col int32 / val fp32, columns sorted inside a row) into the
+    column ranges [col_lo + b * width, +width): one CsrDevice per range over the SAME rows, entries in row-major,
+    column-ascending order.  One stable sort by range id, one histogram, one scan per range."""
+    n_rows = len(rowptr_host) - 1
+    nb = max(1, -(-(col_hi - col_lo) // width))
+    bid = torch.div(col - col_lo, width, rounding_mode='floor').to(torch.int16 if nb < 32768 else torch.int32)
+    order = torch.sort(bid, stable=True)[1]
+    counts = torch.diff(torch.from_numpy(np.ascontiguousarray(rowptr_host)).to(device))
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=device, dtype=torch.int32), counts)
+    per = torch.bincount(bid.long() * n_rows + rows.long(), minlength=nb * n_rows).view(nb, n_rows)
+    del rows, bid
+    sizes = per.sum(dim=1).cpu().numpy()
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    out = []
+    for b in range(nb):
+        rp = np.zeros(n_rows + 1, dtype=np.int64)
+        np.cumsum(per[b].cpu().numpy(), out=rp[1:])
+        idx = order[int(starts[b]):int(starts[b + 1])]
+        out.append(CsrDevice(rp, col[idx].contiguous(), None if val is None else val[idx].contiguous(), n_cols, device))
+    return out
 
 
 def _row_ranges(rowptr, n_users, shard):
@@ -285,7 +333,8 @@ class NormAdj(_SparseView, _Blocked):
     @classmethod
     def from_device(cls, dg, shard=None):
         """Same object from a DeviceGraph: values computed on the GPU with the reference's rounding order
-        ((d_r * 1) * d_c in fp32), only this rank's row block is kept."""
+        ((d_r * 1) * d_c in fp32), only this rank's row block is kept.  When the user table is far larger than L2
+        the item rows are additionally cut into column blocks (RowBlock.col_blocks, see column_blocks)."""
         self = object.__new__(cls)
         n = dg.n_users + dg.n_items
         self.n_users, self.n_items = dg.n_users, dg.n_items
@@ -297,7 +346,11 @@ class NormAdj(_SparseView, _Blocked):
         deg = np.maximum(np.float32(1.), dg.degrees_host())
         d_inv = torch.from_numpy(np.power(deg, np.float32(-0.5)).astype(np.float32)).to(dg.device)
         blocks = []
-        for row0, row1 in _row_ranges(self.rowptr_full, dg.n_users, shard):
+        width = column_block_width(dg.n_users)
+        ranges = _row_ranges(self.rowptr_full, dg.n_users, shard)
+        if width and shard is None:
+            ranges = [(0, dg.n_users), (dg.n_users, n)]      # the item rows become a block of their own
+        for row0, row1 in ranges:
             rp, col, lo, hi = dg.block(row0, row1)
             rows = torch.repeat_interleave(torch.arange(row0, row1, device=dg.device),
                                            dg.rowptr[row0 + 1:row1 + 1] - dg.rowptr[row0:row1])
@@ -305,7 +358,10 @@ class NormAdj(_SparseView, _Blocked):
             left = d_inv[rows] if dg.mult is None else d_inv[rows] * dg.mult[lo:hi]
             val = left * d_inv[col.long()]
             del rows, left
-            blocks.append(RowBlock(row0, row1, CsrDevice(rp, col, val, n, dg.device, split_at=dg.n_users - row0)))
+            cbs = None
+            if width and row0 >= dg.n_users and row1 > row0:
+                cbs = column_blocks(rp, col, val, 0, dg.n_users, width, n, dg.device)
+            blocks.append(RowBlock(row0, row1, CsrDevice(rp, col, val, n, dg.device, split_at=dg.n_users - row0), cbs))
         self._set_blocks(blocks)
         self._coo_cache = None
         self._sampler = (dg.rowptr[:dg.n_users + 1], dg.col[:dg.n_interactions])

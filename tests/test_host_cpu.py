@@ -287,3 +287,32 @@ def test_row_normalised_adjacency_of_ngcf_matches_reference(tiny):
         hops.append(torch.nn.functional.normalize(rep, p=2, dim=1))
     got = torch.cat(hops, 1).numpy()[::5]
     assert np.abs(got - g['ngcf_rep0_eval_every5']).max() < 1e-5
+
+
+def test_column_blocks_partition_a_csr():
+    """graph.column_blocks: every entry lands in exactly one range, rows keep their column order, empty ranges and
+    empty rows survive (pure index work: runs on the CPU)."""
+    rng = np.random.default_rng(4)
+    n_rows, n_cols, width = 50, 1000, 300
+    rows = []
+    for r in range(n_rows):
+        k = 0 if r % 7 == 0 else int(rng.integers(1, 40))
+        rows.append(np.sort(rng.choice(np.arange(100, 900), size=k, replace=False)))     # columns 900.. stay empty
+    rowptr = np.zeros(n_rows + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in rows], out=rowptr[1:])
+    col = torch.from_numpy(np.concatenate(rows).astype(np.int32))
+    val = torch.arange(len(col), dtype=torch.float32)
+    blocks = graph.column_blocks(rowptr, col, val, 0, n_cols, width, n_cols, 'cpu')
+    assert len(blocks) == 4 and blocks[3].nnz == 0
+    seen = [[] for _ in range(n_rows)]
+    for b, c in enumerate(blocks):
+        assert c.n_rows == n_rows and c.n_cols == n_cols
+        for r in range(n_rows):
+            lo, hi = c.rowptr_host[r], c.rowptr_host[r + 1]
+            cc = c.col[lo:hi].numpy()
+            assert ((cc >= b * width) & (cc < (b + 1) * width)).all() and (np.diff(cc) > 0).all()
+            seen[r] += list(zip(cc.tolist(), c.val[lo:hi].tolist()))
+    for r in range(n_rows):
+        lo, hi = rowptr[r], rowptr[r + 1]
+        assert seen[r] == list(zip(col[lo:hi].tolist(), val[lo:hi].tolist()))
+    assert graph.column_block_width(10_000_000) == graph.COL_BLOCK_BYTES // 256 and graph.column_block_width(100_000) == 0
