@@ -342,12 +342,15 @@ def run_scaleout(args):
     ds = get_dataset({'name': 'DeviceSyntheticDataset', 'shape': SCALEOUT[args.workload], 'seed': 2021, 'device': dev})
     torch.cuda.synchronize()
     gen_s = time.perf_counter() - t0
+    shard = {'auto': 'auto', 'rows': True, 'dims': 'dims', 'users': 'users'}[args.shard]
+    torch.manual_seed(2021)                     # same parameters on every rank and in every run (rep_checksum is comparable)
     model = get_model({'name': 'IGCN', 'embedding_size': 64, 'n_layers': 3, 'device': dev, 'dropout': 0.3,
-                       'feature_ratio': 1.}, ds)
+                       'feature_ratio': 1., 'shard': shard}, ds)
     trainer = BasicTrainer({'name': 'BasicTrainer', 'device': dev, 'n_epochs': 0, 'topks': [20], 'test_batch_size': 512,
                             'dataset': ds, 'model': model})
     model.eval()
     n, nnz, D, L = ds.n_users + ds.n_items, model.norm_adj.nnz, 64, 3
+    mode = 'single' if world == 1 else ('rows' if model._rows_sharded() else 'columns' if model._dim_shard else 'replicated')
     lo, hi = idist.split_range(ds.n_users, rank, world)
     if args.eval_users:
         hi = min(hi, lo + args.eval_users)
@@ -384,14 +387,16 @@ def run_scaleout(args):
     sampler = ClockSampler(local)
     sampler.start()
     prop_ms = timed(propagate, steps)
+    rep_sum = float(propagate().double().sum().item())          # the same number on every rank and in every sharding mode
     score_ms = timed(lambda: trainer.recommend('train', users=users), steps)
     clocks = sampler.stop()
     peak, tc_peak, peak_src = measured_peaks()
     n_local, nnz_local = model.norm_adj.local_rows, model.norm_adj.local_nnz
     # algorithmic bytes of one propagation on this rank: INMO layer + L adjacency layers + mean
-    b_adj = nnz_local * 8 + (n_local + 1) * 8 + n * D * 4 + n_local * D * 4
-    b_feat = nnz_local * 4 + (n_local + 1) * 8 + n_local * 4 + (n + 2) * D * 4 + n_local * D * 4
-    alg = b_feat + L * b_adj + L * n_local * D * 4
+    Dl = D // world if mode == 'columns' else D             # columns mode: all rows, D / world columns per rank
+    b_adj = nnz_local * 8 + (n_local + 1) * 8 + n * Dl * 4 + n_local * Dl * 4
+    b_feat = nnz_local * 4 + (n_local + 1) * 8 + n_local * 4 + (n + 2) * Dl * 4 + n_local * Dl * 4
+    alg = b_feat + L * b_adj + L * n_local * Dl * 4
     n_scored = int(users.shape[0])
     total_scored = n_scored * world if args.eval_users else ds.n_users
     flops = 2.0 * n_scored * ds.n_items * D               # algorithmic 2 U I D
@@ -403,8 +408,8 @@ def run_scaleout(args):
                            'interactions': len(ds), 'nnz_adj': nnz, 'dim': D, 'layers': L, 'users_scored': total_scored,
                            'generated_on_device_s': round(gen_s, 2),
                            'l2': 'inputs larger than L2 (layer table %d MB)' % (n * D * 4 // 2 ** 20),
-                           'parallelism': 'single GPU' if world == 1 else 'rows and users sharded over %d GPUs' % world},
-                'propagate_ms': prop_ms, 'score_topk_ms': score_ms,
+                           'parallelism': 'single GPU' if world == 1 else 'propagation %s, users sharded over %d GPUs' % (mode, world)},
+                'propagate_ms': prop_ms, 'score_topk_ms': score_ms, 'propagate_mode': mode, 'rep_checksum': repr(rep_sum),
                 'roofline': {'kernel': 'propagation (igcn_inmo_fwd + %d x igcn_spmm)' % L, 'bound': 'hbm', 'achieved': alg / (prop_ms * 1e-3) / 1e9,
                              'peak': peak, 'unit': 'GB/s', 'frac': alg / (prop_ms * 1e-3) / 1e9 / peak, 'traffic': None,
                              'peak_source': peak_src, 'algorithmic_bytes': alg,
@@ -781,6 +786,8 @@ def main():
                     help='comma-separated workloads reported as sub-blocks `configs` of the same JSON line ("" = none)')
     ap.add_argument('--repeats', type=int, default=10, help='timed regions of K steps each; the median is reported')
     ap.add_argument('--eval-users', type=int, default=None, help='scale-out: users scored per rank (default: all of its share)')
+    ap.add_argument('--shard', default='auto', choices=['auto', 'rows', 'dims', 'users'],
+                    help='scale-out: what the propagation divides over the ranks (model_config shard)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-steps', type=int, default=4)
