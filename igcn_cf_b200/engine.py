@@ -40,6 +40,27 @@ class Shard:
     def __init__(self, ctx):
         self.ctx = ctx
         self._bufs = {}
+        self._side = None
+        self._pending = False
+
+    def push_behind(self, t, row0, n_rows, dim):
+        """Bulk push of a finished row block on a side stream: it leaves over NVLink while the main stream already
+        computes the rank's next row block (user slice out while the item slice is computed).  join() before the
+        barrier."""
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            self.push(t, row0, n_rows, dim)
+        self._pending = True
+
+    def join(self):
+        # only when a push was forked since the last join (inside a CUDA-graph capture the side stream must have been
+        # forked from the capturing stream)
+        if self._pending:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._pending = False
 
     def bulk(self, n_rows, dim):
         return n_rows * dim * 4 >= self.PUSH_BYTES
@@ -129,14 +150,13 @@ class Propagator:
         range, every pass adding the previous partial result; the last pass applies adds / rowscale / alpha and the
         exchange."""
         sh = self.shard
-        pushes = []
         for blk in adj.blocks:
             row0 = blk.row0
             off = row0 * self.dim * 4
-            if sh is not None and sh.bulk(blk.csr.n_rows, self.dim) and rows is None:
+            bulk = sh is not None and sh.bulk(blk.csr.n_rows, self.dim) and rows is None
+            if bulk:
                 sh.peers(y, off)                                   # must be a symmetric buffer all the same
                 peers, n_peers = None, 0
-                pushes.append((row0, blk.csr.n_rows))
             else:
                 peers, n_peers = _peer_args(sh, y, off)
             rs = None if rowscale is None else ptr(rowscale) + row0 * 4
@@ -153,6 +173,8 @@ class Propagator:
                 last = (C.c_void_p * (len(adds) + 1))(prev.data_ptr(), *[t.data_ptr() + off for t in adds])
                 call('igcn_spmm', cbs[-1].struct(self.dim), ptr(x), ptr(y) + off, self.dim, last, len(adds) + 1, rs, float(alpha),
                      peers, n_peers, stream_ptr())
+                if bulk:
+                    sh.push_behind(y, row0, blk.csr.n_rows, self.dim)
                 continue
             head = (blk.csr.struct(self.dim), ptr(x), ptr(y) + off, self.dim, self._adds(adds, off), len(adds), rs, float(alpha))
             if rows is not None:
@@ -161,9 +183,10 @@ class Propagator:
                 call('igcn_spmm_cols', *head, ptr(cols), peers, n_peers, stream_ptr())
             else:
                 call('igcn_spmm', *head, peers, n_peers, stream_ptr())
-        for row0, n_rows in pushes:
-            sh.push(y, row0, n_rows, self.dim)
+            if bulk:
+                sh.push_behind(y, row0, blk.csr.n_rows, self.dim)      # overlaps the next row block's kernels
         if sh is not None:
+            sh.join()
             sh.ctx.barrier()
 
     def forward(self, adj, x0, out=None, rows=None, before_last=None):
@@ -208,21 +231,21 @@ class Propagator:
 
 def inmo_forward(feat, emb, x0, drop, dim, shard=None):
     """X0 = F~ E with dropout fused (model.py:423-432 after model.py:435)."""
-    pushes = []
     for blk in feat.blocks:
         row0 = blk.row0
         off = row0 * dim * 4
-        if shard is not None and shard.bulk(blk.csr.n_rows, dim):
+        bulk = shard is not None and shard.bulk(blk.csr.n_rows, dim)
+        if bulk:
             shard.peers(x0, off)
             peers, n_peers = None, 0
-            pushes.append((row0, blk.csr.n_rows))
         else:
             peers, n_peers = _peer_args(shard, x0, off)
         call('igcn_inmo_fwd', blk.csr.struct(dim), ptr(feat.tmpl), ptr(feat.rowscale) + row0 * 4, _drop_struct(drop),
              ptr(emb), ptr(x0) + off, dim, row0, feat.n_users, feat.glob_user, feat.glob_item, peers, n_peers, stream_ptr())
-    for row0, n_rows in pushes:
-        shard.push(x0, row0, n_rows, dim)
+        if bulk:
+            shard.push_behind(x0, row0, blk.csr.n_rows, dim)          # leaves while the next row block is computed
     if shard is not None:
+        shard.join()
         shard.ctx.barrier()
 
 

@@ -79,6 +79,14 @@ def check_gpu(rank, world):
             m.eval()
         with torch.no_grad():
             assert torch.equal(sharded.get_rep(), single.get_rep()), kind + ' rep differs'
+        # bulk form of the exchange (what the scale-out graph uses): every finished row block leaves through
+        # igcn_peer_push on a side stream while the next block is computed
+        from igcn_cf_b200 import engine as _engine
+        keep_bytes, _engine.Shard.PUSH_BYTES = _engine.Shard.PUSH_BYTES, 0
+        sharded._bump()
+        with torch.no_grad():
+            assert torch.equal(sharded.get_rep(), single.get_rep()), kind + ' rep differs (bulk push)'
+        _engine.Shard.PUSH_BYTES = keep_bytes
         # autograd bridge
         for m in models:
             m.train()
