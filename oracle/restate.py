@@ -21,6 +21,9 @@ torch.optim.Adam) -- what these reference functions compute:
   trainer.py:140-167  BasicTrainer.eval                          -> masked_topk / evaluate
   trainer.py:109-138  BasicTrainer.calculate_metrics             -> calculate_metrics
   dataset.py:119-131  BasicDataset.__getitem__                   -> sample_triples
+  model.py:255-261    NGCF.generate_graph                        -> row_normalized_adjacency
+  model.py:277-291    NGCF.get_rep                               -> ngcf_rep
+  model.py:560-581    IMCGAE.get_rep                             -> imcgae_rep
 
 It is pinned against outputs of the reference itself (tests/golden/*.npz, produced by
 tests/golden/make_golden.py in the build container through oracle/ref_loader.py); see
@@ -105,6 +108,59 @@ def dropout_sparse(mat, p, rand):
     idx = mat.indices()[:, keep]
     val = mat.values()[keep] / (1. - p)
     return torch.sparse_coo_tensor(idx, val, mat.shape).coalesce()
+
+
+def row_normalized_adjacency(n_users, n_items, train_pairs):
+    """normalize(A + I, norm='l1', axis=1) as a coalesced torch COO (NGCF.generate_graph, model.py:255-261).  sp.eye is
+    float64, so the division happens in float64 and the values are rounded to float32 at the very end."""
+    adj = bipartite_adjacency(n_users, n_items, train_pairs)
+    adj = (adj + sp.eye(adj.shape[0], format='csr')).tocsr()
+    inv = 1.0 / np.asarray(adj.sum(axis=1)).reshape(-1)
+    return to_coalesced(sp.diags(inv).dot(adj))
+
+
+# --------------------------------------------------------------------------- sibling models (SURVEY.md 8f rank 4)
+def ngcf_rep(adj, emb, gc, bi, p=0., edge_keep=None, dense_keep=None):
+    """NGCF.get_rep (model.py:277-291).  adj: row_normalized_adjacency; gc / bi: lists of (weight, bias) of the two
+    dense layers per hop.  Train mode: edge_keep (bool per non-zero, model.py:263-275) and dense_keep (one bool
+    [N, size] mask per hop, the F.dropout draw of model.py:287) with rate p; eval mode: both None."""
+    if edge_keep is not None:
+        adj = torch.sparse_coo_tensor(adj.indices()[:, edge_keep], adj.values()[edge_keep] / (1. - p), adj.shape).coalesce()
+    rep = emb
+    hops = [rep]
+    for l in range(len(gc)):
+        m0 = torch.sparse.mm(adj, rep)
+        m1 = rep * m0
+        rep = F.leaky_relu(F.linear(m0, *gc[l]) + F.linear(m1, *bi[l]), negative_slope=0.2)
+        if dense_keep is not None:
+            rep = rep * dense_keep[l].to(rep.dtype) / (1. - p)
+        hops.append(F.normalize(rep, p=2, dim=1))
+    return torch.cat(hops, dim=1)
+
+
+def imcgae_rep(norm_adj, emb, n_users, n_items, n_layers, p=0., node_keep=None):
+    """IMCGAE.get_rep (model.py:560-581).  emb: [U + I + 3, D] (personal rows, then identical / general-user /
+    general-item); node_keep: per hop a bool [U + I] mask drawn with rate p - 0.1 * hop (train mode) or None."""
+    U, I = n_users, n_items
+    ident, gen_u, gen_i = emb[U + I], emb[U + I + 1], emb[U + I + 2]
+    u_rep = torch.cat([emb[:U], gen_u[None, :].expand(U, -1), ident[None, :].expand(U, -1)], dim=1)
+    i_rep = torch.cat([emb[U:U + I], gen_i[None, :].expand(I, -1), ident[None, :].expand(I, -1)], dim=1)
+    rep = torch.cat([u_rep, i_rep], dim=0)
+    layers = [rep]
+    for l in range(n_layers):
+        if node_keep is not None:
+            rep = rep * (node_keep[l].to(rep.dtype) / (1. - (p - 0.1 * l)))[:, None]
+        rep = torch.sparse.mm(norm_adj, rep)
+        layers.append(rep / float(l + 2))
+    return torch.stack(layers, dim=0).sum(dim=0)
+
+
+def rep_bpr_loss(rep, n_users, users, pos, neg, l2_reg):
+    """BPRTrainer's loss on a propagated representation with NGCF.bpr_forward's L2 term (model.py:293-299;
+    trainer.py:238-243)."""
+    u, p_, n_ = rep[users], rep[n_users + pos], rep[n_users + neg]
+    l2 = torch.norm(u, p=2, dim=1) ** 2 + torch.norm(p_, p=2, dim=1) ** 2 + torch.norm(n_, p=2, dim=1) ** 2
+    return F.softplus((u * n_).sum(1) - (u * p_).sum(1)).mean() + l2_reg * l2.mean()
 
 
 # --------------------------------------------------------------------------- propagation

@@ -161,3 +161,60 @@ def test_initialisation_follows_the_reference_draw_order(tiny):
         model = get_model(CFG[px][0], _dataset(tiny))
         for k, p in model.named_parameters():
             assert np.array_equal(p.detach().cpu().numpy(), g['%s_p0_%s' % (px, k)]), (px, k)
+
+
+@pytest.mark.parametrize('px', ['ngcf', 'imcgae'])
+def test_against_the_oracle_on_a_larger_graph(px):
+    """'small' shape (3000 x 4000, ~90 K interactions, rows long enough for the chunked-row path): eval representation,
+    one train-mode forward/backward with seeded masks injected into both sides, and the top-20 of 512 users against
+    oracle/restate.py (pinned to the reference by tests/test_oracle_golden.py)."""
+    from igcn_cf_b200 import synth
+    from igcn_cf_b200.dataset import get_dataset
+    from igcn_cf_b200.model import get_model
+    from igcn_cf_b200 import engine
+    from conftest import check_topk_lists
+    from oracle import restate as R
+    ds = get_dataset({'name': 'SyntheticDataset', 'split': synth.gen_named('small', seed=11), 'device': DEV})
+    U, I = ds.n_users, ds.n_items
+    torch.manual_seed(4)
+    mcfg, l2 = CFG[px]
+    model = get_model(mcfg, ds)
+    P = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.named_parameters()}
+    gen = torch.Generator().manual_seed(9)
+    tri = torch.from_numpy(np.stack([np.arange(512) % U, [ds.train_data[u % U][0] for u in range(512)],
+                                     (np.arange(512) * 7919) % I], axis=1).astype(np.int64))
+    if px == 'ngcf':
+        adj = R.row_normalized_adjacency(U, I, ds.train_pairs)
+        gc = [(P['gc_layers.%d.weight' % l], P['gc_layers.%d.bias' % l]) for l in range(3)]
+        bi = [(P['bi_layers.%d.weight' % l], P['bi_layers.%d.bias' % l]) for l in range(3)]
+        edge = torch.rand(adj._nnz(), generator=gen) >= 0.1
+        dense = [torch.rand(U + I, 64, generator=gen) >= 0.1 for _ in range(3)]
+        oracle_rep = lambda train: R.ngcf_rep(adj, P['embedding.weight'], gc, bi, p=0.1, edge_keep=edge if train else None,
+                                              dense_keep=dense if train else None)
+        injected = {'edge': edge.to(DEV), 'dense': [d.to(DEV) for d in dense]}
+    else:
+        adj = R.normalized_adjacency(U, I, ds.train_pairs)
+        node = [torch.rand(U + I, generator=gen) >= 0.3 - 0.1 * l for l in range(3)]
+        oracle_rep = lambda train: R.imcgae_rep(adj, P['embedding.weight'], U, I, 3, p=0.3, node_keep=node if train else None)
+        injected = {'dense': [d.to(DEV) for d in node]}
+    model.eval()
+    with torch.no_grad():
+        mine = model.get_rep()
+        want = oracle_rep(False)
+    assert rel_err(mine.cpu().numpy(), want.numpy()) < TOL
+    users = torch.arange(512, device=DEV)
+    rec, _ = engine.score_topk(mine.contiguous(), users, U, I, 20)
+    ref = torch.topk(want[:512] @ want[U:].t(), 20, dim=1)[1].numpy()
+    check_topk_lists(rec.cpu().numpy(), ref, want.numpy(), U, rep_mine=mine.cpu().numpy(), scale_tol=TOL)
+    model.train()
+    model.injected = injected
+    t = tri.to(DEV)
+    u_r, p_r, n_r, l2n = model.bpr_forward(t[:, 0], t[:, 1], t[:, 2])
+    loss = torch.nn.functional.softplus((u_r * n_r).sum(1) - (u_r * p_r).sum(1)).mean() + l2 * l2n.mean()
+    model.zero_grad()
+    loss.backward()
+    ref_loss = R.rep_bpr_loss(oracle_rep(True), U, tri[:, 0], tri[:, 1], tri[:, 2], l2)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < TOL
+    for k, p in model.named_parameters():
+        assert rel_err(p.grad.cpu().numpy(), P[k].grad.numpy()) < TOL, k

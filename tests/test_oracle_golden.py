@@ -158,3 +158,54 @@ def test_imf_is_igcn_without_layers(tiny):
     for which in ('train', 'val', 'test'):
         metrics, rec = R.evaluate(m, which, tiny['train'], tiny['val'], tiny[which], [5, 20])
         assert np.array_equal(rec, g['imf_e1_%s_rec' % which])
+
+
+def _unpack(g, key):
+    shape = tuple(g[key + '_shape'])
+    return _t(np.unpackbits(g[key])[:int(np.prod(shape))].reshape(shape).astype(bool))
+
+
+def test_ngcf_restatement(tiny):
+    """NGCF (model.py:232-299): graph bit-equal, eval representation, and the train-mode forward/backward with the
+    reference's recorded edge and feature dropout draws -- loss and the gradient of every parameter."""
+    g = load_golden('tiny_ngcf_imcgae')
+    U, I = tiny['n_users'], tiny['n_items']
+    adj = R.row_normalized_adjacency(U, I, tiny['pairs'])
+    assert np.array_equal(adj.indices().numpy(), g['ngcf_adj_idx'])
+    assert np.array_equal(adj.values().numpy(), g['ngcf_adj_val'])
+    P = {k: _t(g['ngcf_p0_' + k]).clone().requires_grad_(True) for k in g['ngcf_param_names']}
+    gc = [(P['gc_layers.%d.weight' % l], P['gc_layers.%d.bias' % l]) for l in range(3)]
+    bi = [(P['bi_layers.%d.weight' % l], P['bi_layers.%d.bias' % l]) for l in range(3)]
+    with torch.no_grad():
+        rep = R.ngcf_rep(adj, P['embedding.weight'], gc, bi)
+    assert rel_err(rep.numpy()[::5], g['ngcf_rep0_eval_every5']) < TOL
+    assert rel_err((rep[:64] @ rep[U:].t()).numpy(), g['ngcf_scores0']) < TOL
+    keep = torch.floor(np.float32(0.9) + _t(g['ngcf_fb_rand_0'])).bool()
+    rep = R.ngcf_rep(adj, P['embedding.weight'], gc, bi, p=0.1, edge_keep=keep,
+                     dense_keep=[_unpack(g, 'ngcf_fb_dense_%d' % l) for l in range(3)])
+    tri = _t(g['ngcf_fb_triples'])
+    loss = R.rep_bpr_loss(rep, U, tri[:, 0], tri[:, 1], tri[:, 2], 1e-3)
+    loss.backward()
+    assert abs(loss.item() - float(g['ngcf_fb_loss'])) < TOL
+    for k, v in P.items():
+        assert rel_err(v.grad.numpy(), g['ngcf_fb_grad_' + k]) < TOL, k
+
+
+def test_imcgae_restatement(tiny):
+    """IMCGAE (model.py:546-585): eval representation / scores and the train-mode forward/backward with the recorded
+    node-dropout masks (rates 0.3, 0.2, 0.1)."""
+    g = load_golden('tiny_ngcf_imcgae')
+    U, I = tiny['n_users'], tiny['n_items']
+    adj = R.normalized_adjacency(U, I, tiny['pairs'])
+    emb = _t(g['imcgae_p0_embedding.weight']).clone().requires_grad_(True)
+    with torch.no_grad():
+        rep = R.imcgae_rep(adj, emb, U, I, 3)
+    assert rep.shape == (U + I, 192)
+    assert rel_err(rep.numpy()[::5], g['imcgae_rep0_eval_every5']) < TOL
+    assert rel_err((rep[:64] @ rep[U:].t()).numpy(), g['imcgae_scores0']) < TOL
+    rep = R.imcgae_rep(adj, emb, U, I, 3, p=0.3, node_keep=[_unpack(g, 'imcgae_fb_dense_%d' % l) for l in range(3)])
+    tri = _t(g['imcgae_fb_triples'])
+    loss = R.rep_bpr_loss(rep, U, tri[:, 0], tri[:, 1], tri[:, 2], 0.)
+    loss.backward()
+    assert abs(loss.item() - float(g['imcgae_fb_loss'])) < TOL
+    assert rel_err(emb.grad.numpy(), g['imcgae_fb_grad_embedding.weight']) < TOL
