@@ -10,8 +10,9 @@ autograd step (trainer.AutogradStep): no fused step, no sharded training -- at N
 like everywhere else.  Evaluation goes through the same fused score + mask + top-k kernel (exact CUDA-core form: the
 representations are 256 / 192 columns wide, the tensor-core form stops at 64).
 
-Random draws: train-mode dropout masks come from torch's CUDA generator; `model.injected` (a test facility) replays
-masks recorded from the reference -- {'edge': bool [nnz] in the reference's coalesced COO order, 'dense': [bool
+Random draws: train-mode dropout masks come from torch's CUDA generator -- at N > 1 the training replicas stay identical
+only if every rank seeds it alike (the reference launchers call set_seed(2021) first); `model.injected` (a test
+facility) replays masks recorded from the reference -- {'edge': bool [nnz] in the reference's coalesced COO order, 'dense': [bool
 tensors, one per F.dropout call of a forward pass]}."""
 import ctypes as C
 
