@@ -16,7 +16,6 @@ facility) replays masks recorded from the reference -- {'edge': bool [nnz] in th
 tensors, one per F.dropout call of a forward pass]}."""
 import ctypes as C
 
-import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
