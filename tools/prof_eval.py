@@ -19,10 +19,15 @@ def main():
     model.train()
     for _ in range(int(os.environ.get('PROF_TRAIN_STEPS', 300))):      # evaluate a partly trained model, as the bench does
         trainer.step.run()
-    for _ in range(2):
+    for i in range(2):
         model._bump()
+        torch.cuda.synchronize()
+        if i == 1:
+            torch.cuda.nvtx.range_push('eval')           # ncu --nvtx --nvtx-include "eval/" captures this evaluation only
         print(trainer.eval('val')[0])
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        if i == 1:
+            torch.cuda.nvtx.range_pop()
 
 
 if __name__ == '__main__':
